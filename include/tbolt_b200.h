@@ -1,0 +1,236 @@
+/*
+ * tbolt_b200.h -- C ABI of libtbolt_b200.so: the B200-native (sm_100a) monodomain hot path that
+ * replaces Thunderbolt.jl's ext/CuThunderboltExt.jl behind the solver/operator dispatch points.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / opaque handles, returns an
+ * int32 status (TB_OK = 0) and never throws.  The message of the last failure is available from
+ * tb_last_error().  Host pointers are borrowed for the duration of the call only; device memory is
+ * owned by the library behind the handles and released by the matching *_destroy.  A tb_ctx is
+ * used from one host thread at a time; all work is ordered on the context's CUDA stream; only
+ * *_download, tb_cg_solve, tb_monodomain_step (they return scalars) and tb_sync block the host.
+ *
+ * Each declaration cites the reference interface (file:line under JuliaHealth/Thunderbolt.jl
+ * v0.0.4) that a Julia `ccall` of it replaces; INTEGRATION.md shows those bindings.
+ *
+ * Layout contracts shared with the reference:
+ *   - state vectors are state-blocked (SoA): state s of point i is u[s*N + i] on the host side
+ *     (src/modeling/solution_variables.jl:60-63); on the device each state column is padded to a
+ *     multiple of 32 doubles so 128-bit loads stay aligned -- invisible through this API.
+ *   - matrices are CSR with the reference's pattern (Ferrite allocate_matrix, sorted columns,
+ *     diagonal included; src/solver/interface.jl:159-168).  Values are exchanged in CSR nonzero
+ *     order (`nonzeros(A)`); on the device they live in a sliced-ELL (SELL-32) image of that
+ *     pattern, again invisible through this API.
+ *   - K is assembled NEGATIVE semi-definite exactly like the reference (diffusion.jl:28-50), so the
+ *     backward-Euler operator is A = M - dt*K (euler.jl:104-116).
+ */
+#ifndef TBOLT_B200_H
+#define TBOLT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_OK 0
+#define TB_ERR_INVALID 1     /* bad argument (null handle, size mismatch, unsupported enum) */
+#define TB_ERR_CUDA 2        /* a CUDA runtime call or kernel failed */
+#define TB_ERR_NOMEM 3       /* device or host allocation failed */
+#define TB_ERR_COMM 4        /* NCCL failure */
+#define TB_ERR_UNSUPPORTED 5 /* valid request the library does not implement */
+
+/* cell types (Ferrite Quadrilateral / Hexahedron / Triangle / Tetrahedron, Lagrange order 1) */
+#define TB_QUAD4 0
+#define TB_HEX8 1
+#define TB_TRI3 2
+#define TB_TET4 3
+
+/* ionic models: src/modeling/cells/fhn.jl:6-13 (6 parameters a,b,c,d,e,f) and
+ * src/modeling/cells/pcg2019.jl:4-48 (36 parameters in declaration order g_Na .. E_Ca) */
+#define TB_FHN 0
+#define TB_PCG2019 1
+
+/* diffusion coefficient kinds, D = kappa/(Cm*chi)  (src/modeling/core/coefficients.jl:152-162)
+ *   SCALAR   data[0]                                   ConstantCoefficient(number)
+ *   TENSOR   data[dim*dim] row-major symmetric tensor  ConstantCoefficient(SymmetricTensor) :106-120
+ *   SPECTRAL data = lambda[3], then for every cell and local node a: f[3], s[3], n[3]
+ *            SpectralTensorCoefficient over an OrthotropicMicrostructureModel of FieldCoefficients
+ *            (coefficients.jl:36-99,451-488; microstructure.jl:136-187) */
+#define TB_D_SCALAR 0
+#define TB_D_TENSOR 1
+#define TB_D_SPECTRAL 2
+
+/* built-in stimulus families f(x,t); a Julia closure cannot cross a C ABI, so either one of these
+ * or host-evaluated values per quadrature point (tb_assemble_source_qp).  prm[]:
+ *   BOX    max_d x_d < p0 && t < p1 ? p2 : 0   bak/examples/conduction-velocity-benchmark.jl:47-50
+ *   BALL   |x| < p0 && t < p1 ? p2 : 0         test/integration/test_electrophysiology.jl:83
+ *   COSEXP cos(2 pi t) exp(-|x|^2)             benchmarks/benchmarks-cuda-linear-form.jl:4-18
+ *   NORMT  |x| + t                             benchmarks/benchmarks-linear-form.jl:16-21
+ *   ENDO   t <= p1 && x0 < p0 ? p2/p3*exp(t/p3) : 0   docs/src/literate-tutorials/ep04_geselowitz-ecg.jl:15-26 */
+#define TB_SRC_NONE 0
+#define TB_SRC_BOX 1
+#define TB_SRC_BALL 2
+#define TB_SRC_COSEXP 3
+#define TB_SRC_NORMT 4
+#define TB_SRC_ENDO 5
+
+typedef struct tb_ctx tb_ctx;
+typedef struct tb_vec tb_vec;
+typedef struct tb_mesh tb_mesh;
+typedef struct tb_csr tb_csr;
+typedef struct tb_monodomain tb_monodomain;
+
+/* ---- context --------------------------------------------------------------------------------
+ * Replaces the device selection of src/devices.jl:1-4 / ext/CuThunderboltExt.jl (CudaDevice).
+ * `stream` may be NULL (library creates its own non-blocking stream) or an existing cudaStream_t. */
+int32_t tb_version(void);
+const char *tb_last_error(void);
+int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out);
+int32_t tb_ctx_destroy(tb_ctx *ctx);
+int32_t tb_sync(tb_ctx *ctx);
+int32_t tb_device_info(tb_ctx *ctx, int32_t *sm_count, int64_t *total_mem_bytes, int32_t *cc_major, int32_t *cc_minor);
+/* CUDA-event timer on the context's stream (the stream every kernel of this library launches on) */
+int32_t tb_timer_start(tb_ctx *ctx);
+int32_t tb_timer_stop(tb_ctx *ctx, double *elapsed_ms);
+/* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
+int32_t tb_launch_count(tb_ctx *ctx, int64_t *count);
+/* overwrite a buffer larger than L2 so that the next timed kernel starts cold */
+int32_t tb_l2_flush(tb_ctx *ctx);
+/* multi-GPU: join a communicator of `nranks` one-process-per-GPU peers.  `nccl_unique_id` is the
+ * 128-byte ncclUniqueId created by tb_comm_unique_id on rank 0 and shipped by the host (e.g.
+ * torch.distributed).  The reference has no counterpart (shared-memory only). */
+int32_t tb_comm_unique_id(void *out128);
+int32_t tb_ctx_comm_init(tb_ctx *ctx, int32_t rank, int32_t nranks, const void *nccl_unique_id);
+int32_t tb_comm_barrier(tb_ctx *ctx);
+int32_t tb_comm_allreduce_max(tb_ctx *ctx, double *value_inout);
+
+/* ---- vectors --------------------------------------------------------------------------------
+ * create_system_vector / adapt_vector_type (src/solver/interface.jl:175-181, src/utils.jl:425-427;
+ * ext/CuThunderboltExt.jl:126-127,144-146).  A tb_vec has n rows and ncols state columns. */
+int32_t tb_vec_create(tb_ctx *ctx, int64_t n, int32_t ncols, tb_vec **out);
+int32_t tb_vec_destroy(tb_vec *v);
+int32_t tb_vec_sizes(const tb_vec *v, int64_t *n, int32_t *ncols);
+/* host layout: column c occupies host[c*n .. c*n+n) (the reference's flat SoA vector) */
+int32_t tb_vec_upload(tb_vec *v, const double *host);
+int32_t tb_vec_download(const tb_vec *v, double *host);
+int32_t tb_vec_upload_col(tb_vec *v, int32_t col, const double *host, int64_t offset, int64_t count);
+int32_t tb_vec_download_col(const tb_vec *v, int32_t col, double *host, int64_t offset, int64_t count);
+int32_t tb_vec_fill(tb_vec *v, int32_t col, double value);
+int32_t tb_vec_copy(tb_vec *dst, int32_t dcol, const tb_vec *src, int32_t scol);
+/* y[:,ycol] += a * x[:,xcol]   (add!(b, S) of euler.jl:88-91 is the a = 1 case) */
+int32_t tb_vec_axpy(tb_vec *y, int32_t ycol, double a, const tb_vec *x, int32_t xcol);
+/* raw device pointer of a column and the padded column stride (for interop with torch/CuArray) */
+int32_t tb_vec_devptr(const tb_vec *v, int32_t col, void **ptr, int64_t *ld);
+
+/* ---- mesh -----------------------------------------------------------------------------------
+ * What Ferrite hands the operators: cells (node ids), node coordinates, celldofs of the closed
+ * DofHandler (src/discretization/fem.jl:180-182).  index_base is 1 for Julia callers. */
+int32_t tb_mesh_create(tb_ctx *ctx, int32_t celltype, int64_t ncells, int64_t nnodes, const int64_t *conn,
+                       const double *coords, const int64_t *celldofs, int64_t ndofs, int32_t index_base,
+                       tb_mesh **out);
+/* device-side generate_grid + DofHandler close! for synthetic benchmarks (src/mesh/generators.jl:942):
+ * Ferrite's node/cell order and first-touch DoF numbering, built in HBM without a host mesh. */
+int32_t tb_mesh_generate_grid(tb_ctx *ctx, int32_t celltype, const int64_t *nel3, const double *left3,
+                              const double *right3, tb_mesh **out);
+int32_t tb_mesh_destroy(tb_mesh *m);
+int32_t tb_mesh_sizes(const tb_mesh *m, int64_t *ncells, int64_t *nnodes, int64_t *ndofs, int32_t *nv, int32_t *dim);
+/* any of the three may be NULL; ids come back 0-based */
+int32_t tb_mesh_download(const tb_mesh *m, int64_t *conn, double *coords, int64_t *celldofs);
+/* coordinates at the dof locations, ndofs x dim (evaluate_coefficient_at_dof_locations of a
+ * CartesianCoordinateSystem, src/modeling/core/coefficients.jl:199-245) */
+int32_t tb_mesh_dof_coords(const tb_mesh *m, double *host);
+/* multi-GPU: keep the cells that touch dofs [dof_lo, dof_hi) of `global` and renumber: owned dofs
+ * first (global id - dof_lo), ghosts after them sorted by global id.  ghost_global (nullable) gets
+ * the ghosts' global ids; *nghost their count. */
+int32_t tb_mesh_extract_local(const tb_mesh *global, int64_t dof_lo, int64_t dof_hi, tb_mesh **out, int64_t *nghost);
+int32_t tb_mesh_ghosts(const tb_mesh *local, int64_t *ghost_global);
+
+/* ---- CSR operators ----------------------------------------------------------------------------
+ * create_system_matrix (src/solver/interface.jl:159-173; ext/CuThunderboltExt.jl:129-139). */
+int32_t tb_csr_create(tb_ctx *ctx, int64_t nrows, int64_t ncols, const int64_t *rowptr, const int64_t *colidx,
+                      int32_t index_base, tb_csr **out);
+/* device-side allocate_matrix(dh): all dof pairs sharing a cell, diagonal included, sorted.  Rows are
+ * the mesh's owned dofs, columns all its dofs. */
+int32_t tb_csr_create_from_mesh(tb_ctx *ctx, const tb_mesh *mesh, tb_csr **out);
+/* a second operator on the same pattern (M, K and A share one pattern in the reference: euler.jl:134-146) */
+int32_t tb_csr_create_like(const tb_csr *pattern_of, tb_csr **out);
+int32_t tb_csr_destroy(tb_csr *a);
+int32_t tb_csr_sizes(const tb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+int32_t tb_csr_download_pattern(const tb_csr *a, int64_t *rowptr, int64_t *colidx, int32_t index_base);
+int32_t tb_csr_values_download(const tb_csr *a, double *vals); /* nonzeros(A), CSR order */
+int32_t tb_csr_values_upload(tb_csr *a, const double *vals);
+int32_t tb_csr_zero(tb_csr *a);
+/* nz(A) = nz(M) - dt*nz(K)   (_implicit_euler_heat_solver_update_system_matrix!, euler.jl:104-116) */
+int32_t tb_csr_axpby_values(tb_csr *A, const tb_csr *M, const tb_csr *K, double dt);
+/* y = A x   (mul!(y, ::ThreadedSparseMatrixCSR, x), src/utils.jl:210-231): sequential left-to-right
+ * row sums, so the result is bitwise the reference's */
+int32_t tb_spmv(tb_ctx *ctx, const tb_csr *A, const tb_vec *x, int32_t xcol, tb_vec *y, int32_t ycol);
+/* multi-GPU halo plan of a row-partitioned operator: for each neighbour rank the local rows whose x
+ * entries it needs, and where its entries land in our ghost block.  send_ptr/recv_ptr have nneigh+1
+ * entries; recv offsets are relative to the first ghost. */
+int32_t tb_csr_set_halo(tb_csr *A, int32_t nneigh, const int32_t *neigh_ranks, const int64_t *send_ptr,
+                        const int64_t *send_rows, const int64_t *recv_ptr);
+
+/* ---- assembly ---------------------------------------------------------------------------------
+ * update_operator!(op, t) of the FerriteOperators element loop (called at euler.jl:173-175) with the
+ * element kernels of src/modeling/core/mass.jl:28-43, diffusion.jl:28-50,
+ * analytical_coefficient.jl:80-101.  Values are zeroed, then every element matrix/vector is
+ * scattered into the fixed pattern. */
+int32_t tb_quadrature(int32_t celltype, int32_t qorder, int32_t *nq, double *pts, double *weights);
+int32_t tb_assemble_mass(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, double rho, tb_csr *M);
+int32_t tb_assemble_diffusion(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, int32_t kind, const double *data,
+                              int64_t ndata, double cm_chi, tb_csr *K);
+int32_t tb_assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, int32_t kind, const double *prm,
+                           int32_t nprm, double t, tb_vec *b, int32_t bcol);
+/* general closure path: fq[cell*nq + q] = f(x_q, t) evaluated by the host */
+int32_t tb_assemble_source_qp(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, const double *fq, tb_vec *b,
+                              int32_t bcol);
+/* deterministic variant of the scatter: 0 = fp64 atomics (default), 1 = greedy element colouring */
+int32_t tb_assembly_set_mode(tb_ctx *ctx, int32_t mode);
+
+/* ---- linear solve -----------------------------------------------------------------------------
+ * LinearSolve.solve!(cache) with KrylovJL_CG (euler.jl:10,94,155-156): unpreconditioned CG from
+ * x0 = 0, stop when |r| <= atol + rtol*|r0|, at most itmax iterations.  Non-convergence is NOT an
+ * error status: it comes back as *converged = 0 so the caller can report ReturnCode.MaxIters and
+ * euler.jl:95-100 returns false. */
+int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol, double atol,
+                    double rtol, int64_t itmax, int64_t *iters, double *rnorm, int32_t *converged);
+
+/* ---- cell sweep -------------------------------------------------------------------------------
+ * _pointwise_step_outer_kernel! (src/solver/time/partitioned_solver.jl:38-52; the method
+ * ext/CuThunderboltExt.jl:111-124 provided for CuVector).  substeps <= 1: ForwardEulerCellSolver
+ * (:80-99); substeps > 1: AdaptiveForwardEulerSubstepper (:196-234) with `reaction_threshold`.
+ * `u` holds num_states columns; phi_idx is the 0-based state column of the transmembrane potential.
+ * max_dphi (nullable) receives max_i du[i, phi] of the first rhs evaluation (rtc.jl:64-67). */
+int32_t tb_cell_step(tb_ctx *ctx, int32_t model, const double *params, int32_t nparams, tb_vec *u, int32_t phi_idx,
+                     double t, double dt, int32_t substeps, double reaction_threshold, double *max_dphi);
+
+/* ---- fused LieTrotterGodunov step -------------------------------------------------------------
+ * One OS.LieTrotterGodunov((BackwardEulerSolver, cell solver)) step (operatorsplitting-interface.jl:23-232;
+ * perform_backward_euler_step!, euler.jl:71-101; partitioned_solver.jl:14-21): refresh A when dt
+ * changed, b = M*phi (+ bS), CG, phi <- x, cell sweep -- without returning to the host in between. */
+int32_t tb_monodomain_create(tb_ctx *ctx, const tb_csr *M, const tb_csr *K, int32_t model, const double *params,
+                             int32_t nparams, int32_t phi_idx, tb_monodomain **out);
+int32_t tb_monodomain_destroy(tb_monodomain *md);
+int32_t tb_monodomain_set_cg(tb_monodomain *md, double atol, double rtol, int64_t itmax);
+int32_t tb_monodomain_set_cell_solver(tb_monodomain *md, int32_t substeps, double reaction_threshold);
+/* bS (nullable): the source operator's vector, added to b as is (euler.jl:88-91).  Borrowed. */
+int32_t tb_monodomain_set_source(tb_monodomain *md, const tb_vec *bS, int32_t col);
+/* after the system matrix is formed K's values may be released to save HBM when dt is fixed */
+int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
+                           int32_t *converged);
+/* `nsteps` steps back to back with one host round trip at the end (iters = total, converged = all) */
+int32_t tb_monodomain_run(tb_monodomain *md, tb_vec *u, double t0, double dt, int64_t nsteps, int64_t *iters_total,
+                          int32_t *all_converged);
+/* end-to-end variant on HOST buffers: uploads u_in, steps, downloads into u_out (may alias u_in) */
+int32_t tb_monodomain_step_host(tb_monodomain *md, tb_vec *u_dev, const double *u_in, double *u_out, double t, double dt,
+                                int64_t *iters, double *rnorm, int32_t *converged);
+/* per-section CUDA-event timings of the last step, ms: [0] "b = M u", [1] "inner solve",
+ * [2] "reaction solve" (the reference's TimerOutputs labels, euler.jl:85,94; partitioned_solver.jl:20) */
+int32_t tb_monodomain_section_ms(tb_monodomain *md, double *ms3);
+int32_t tb_monodomain_enable_timing(tb_monodomain *md, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBOLT_B200_H */

@@ -1,0 +1,154 @@
+"""The reference's own known-answer checks for the path, run against the oracle.
+Each test names the reference test it restates."""
+import numpy as np
+import pytest
+
+from conftest import DISTORTED_HEX
+
+
+def test_backward_euler_steady_state(oracle):
+    """test/test_time_integrator.jl:13-41: 4x4 Q1 grid, D = I, pure Neumann, u = 1 is steady."""
+    O = oracle
+    m = O.generate_grid(O.QUAD4, (4, 4), (0.0, 0.0), (1.0, 1.0))
+    rp, ci = m.pattern()
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, [1.0, 0.0, 0.0, 1.0])
+    A = O.axpby_values(M, K, 0.1)
+    u = np.ones(m.ndofs)
+    b = O.spmv(rp, ci, M, u)
+    u, it, rn, conv = O.cg(rp, ci, A, b)
+    assert conv and np.allclose(u, 1.0, atol=1e-4)
+    for _ in range(9):                       # solve! to t = 1 with dt = 0.1
+        b = O.spmv(rp, ci, M, u)
+        u, it, rn, conv = O.cg(rp, ci, A, b)
+        assert conv
+    assert np.allclose(u, 1.0, atol=1e-4)
+
+
+def test_substepper_evaluates_each_substep_at_its_own_time(oracle):
+    """test/test_time_integrator.jl:275-294: closed form with t0 = 2, dt = 0.4, 4 substeps."""
+    O = oracle
+    t0, dt, sub = 2.0, 0.4, 4
+    u = np.zeros(1)
+    # threshold 0 forces the substepping branch regardless of |du| (the reference's default 0.1 is also exceeded)
+    O.cell_step(O.TIMEPROBE, [0.0], u, 1, t0, dt, substeps=sub, threshold=0.1)
+    dts = dt / sub
+    assert u[0] == pytest.approx(sum(dts * (1.0 + np.sin(t0 + s * dts)) for s in range(sub)), rel=1e-15)
+
+
+def test_pcg2019_default_initial_state(oracle):
+    """src/modeling/cells/pcg2019.jl:137-152 / test/test_solution_variables.jl:100-111."""
+    O = oracle
+    p = O.default_params(O.PCG2019)
+    u0 = O.default_initial_state(O.PCG2019)
+    sig = lambda phi, E, k, s: 1.0 / (1.0 + np.exp(s * (phi - E) / k))
+    assert u0[0] == -85.0
+    expect = [sig(-85.0, -78.7, 5.93, 1.0), sig(-85.0, -52.244, 6.5472, -1.0), sig(-85.0, -15.7, 4.6, 1.0),
+              sig(-85.0, -47.9286, 4.9314, 1.0), sig(-85.0, 24.6, 12.1, -1.0), sig(-85.0, -26.6, 6.5, -1.0)]
+    assert np.allclose(u0[1:], expect, rtol=1e-15)
+    # resting state: gates sit at their infinity values, so only phi moves
+    du = O.cell_rhs(O.PCG2019, p, u0)
+    assert np.all(np.abs(du[1:]) < 1e-12)
+
+
+def test_fhn_rhs_values(oracle):
+    """src/modeling/cells/fhn.jl:21-34 with defaults a=.1 b=.5 c=1 d=0 e=.01 f=1."""
+    O = oracle
+    du = O.cell_rhs(O.FHN, O.default_params(O.FHN), [0.5, 0.2])
+    assert du[0] == pytest.approx(0.5 * 0.5 * 0.4 - 0.2)
+    assert du[1] == pytest.approx(0.01 * (0.25 - 0.2))
+
+
+def test_layout_is_state_blocked(oracle):
+    """test/test_solution_variables.jl:113-127: state s of point i lives at u[s*N + i]."""
+    O = oracle
+    n = 5
+    u = np.zeros(2 * n)
+    u[:n] = np.linspace(0.0, 1.0, n)          # phi block
+    u[n:] = 0.1                                # s block
+    ref = u.copy()
+    O.cell_step(O.FHN, O.default_params(O.FHN), u, n, 0.0, 0.5)
+    for i in range(n):
+        du = O.cell_rhs(O.FHN, O.default_params(O.FHN), [ref[i], ref[n + i]])
+        assert u[i] == ref[i] + 0.5 * du[0] and u[n + i] == ref[n + i] + 0.5 * du[1]
+
+
+def test_forward_euler_and_adaptive_agree_but_differ(oracle):
+    """test/integration/test_electrophysiology.jl:76-95: 8x8 quads on [-2.5,2.5]^2, FHN, stimulus
+    |x| < 0.1 && t < 2 -> 0.01, initial condition phi0 = max(1 - |x|, 0) (simple_initializer!, :8-27),
+    tspan (0,10), dt = 1: FE and adaptive agree to 1e-2 and differ at 1e-8."""
+    O = oracle
+    m = O.generate_grid(O.QUAD4, (8, 8), (-2.5, -2.5), (2.5, 2.5))
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, [4.5e-4, 0, 0, 2.0e-4])
+    x = m.dof_coords
+    res = []
+    for sub in (1, 10):
+        orc = O.MonodomainOracle(m, O.FHN, O.default_params(O.FHN), M, K, substeps=sub)
+        u = np.zeros(2 * m.ndofs)
+        u[:m.ndofs] = np.maximum(1.0 - np.linalg.norm(x, axis=1), 0.0)
+        for s in range(10):
+            t = float(s)
+            if 0.0 <= t + 1.0 <= 2.1:
+                orc.bS = O.assemble_source(m, 2, O.SRC_BALL, [0.1, 2.0, 0.01], t + 1.0)
+            it, rn, conv = orc.step(u, t, 1.0)
+            assert conv
+        res.append(u.copy())
+    assert np.allclose(res[0], res[1], rtol=1e-2, atol=1e-2 * np.abs(res[0]).max())
+    assert not np.allclose(res[0], res[1], rtol=1e-8, atol=0)
+
+
+def test_distorted_hex_geometry(oracle):
+    """test/test_coefficients.jl:239-279 compares two implementations of the mapping on this fixture;
+    here: partition of unity, gradient of a linear field, detJ*w sums to the volume (independent facts)."""
+    O = oracle
+    pts, w = O.quadrature(O.HEX8, 2)
+    assert pts.shape == (8, 3) and np.allclose(w, 1.0)
+    vol = 0.0
+    lin = DISTORTED_HEX @ np.array([0.3, -1.2, 0.7]) + 2.0      # u(x) = a.x + c at the vertices
+    for q in range(8):
+        det, N, G = O.map_qp(O.HEX8, DISTORTED_HEX, pts[q])
+        assert det > 0
+        assert N.sum() == pytest.approx(1.0, abs=1e-15)
+        assert np.allclose(G.sum(axis=0), 0.0, atol=1e-14)
+        assert np.allclose(lin @ G, [0.3, -1.2, 0.7], atol=1e-13)    # isoparametric map reproduces linear fields
+        assert np.allclose(N @ DISTORTED_HEX, _trilinear(DISTORTED_HEX, pts[q]), atol=1e-15)
+        vol += det * w[q]
+    # volume by a much finer rule
+    p4, w4 = O.quadrature(O.HEX8, 4)
+    vol4 = sum(O.map_qp(O.HEX8, DISTORTED_HEX, p)[0] * ww for p, ww in zip(p4, w4))
+    assert vol == pytest.approx(vol4, rel=1e-12)
+
+
+def _trilinear(X, xi):
+    sx = np.array([-1, 1, 1, -1, -1, 1, 1, -1.0]); sy = np.array([-1, -1, 1, 1, -1, -1, 1, 1.0]); sz = np.array([-1, -1, -1, -1, 1, 1, 1, 1.0])
+    N = 0.125 * (1 + sx * xi[0]) * (1 + sy * xi[1]) * (1 + sz * xi[2])
+    return N @ X
+
+
+def test_conductivity_to_diffusivity(oracle):
+    """test/test_coefficients.jl:164-188: ConductivityToDiffusivityCoefficient(kappa, Cm=2, chi=0.5) == kappa."""
+    O = oracle
+    X = DISTORTED_HEX
+    k = [1.0, 0.2, 0.0, 0.2, 2.0, 0.1, 0.0, 0.1, 0.5]
+    K1 = O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, k, cmchi=2.0 * 0.5)
+    K2 = O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, k, cmchi=1.0)
+    assert np.array_equal(K1, K2)
+    K3 = O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, k, cmchi=2.0)
+    assert np.allclose(K3, K1 / 2.0, rtol=1e-15)
+
+
+def test_ltg_order_heat_then_cells(oracle):
+    """test/test_os_gearing.jl:471-508 idea: LTG advances children sequentially, each from the previous
+    child's result.  With K = 0 the heat child is the identity (A = M), so one LTG step must equal one
+    cell step to CG tolerance; with the cell model frozen (dt_cell effect zero at rest) it is pure BE."""
+    O = oracle
+    m = O.generate_grid(O.QUAD4, (3, 3), (0, 0), (1, 1))
+    M = O.assemble_mass(m, 2)
+    prm = O.default_params(O.FHN)
+    u = np.concatenate([np.linspace(0, 1, m.ndofs), np.full(m.ndofs, 0.05)])
+    u_ref = u.copy()
+    orc = O.MonodomainOracle(m, O.FHN, prm, M, np.zeros_like(M), atol=1e-15, rtol=1e-15)
+    orc.step(u, 0.0, 0.25)
+    O.cell_step(O.FHN, prm, u_ref, m.ndofs, 0.0, 0.25)
+    assert np.allclose(u, u_ref, rtol=1e-12, atol=1e-14)

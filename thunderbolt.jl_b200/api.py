@@ -1,0 +1,821 @@
+"""Host-side mirror of Thunderbolt.jl's public API for the monodomain path.
+
+Names, argument meaning and error behaviour follow the reference so that tests read like the
+reference's own (`!` becomes a trailing underscore: `step!` -> `step_`).  Everything numerical is a
+call into libtbolt_b200.so; this module only carries the plumbing the reference does in Julia:
+
+  models / protocols            src/modeling/electrophysiology.jl:240-381, cells/fhn.jl, cells/pcg2019.jl
+  coefficients                  src/modeling/core/coefficients.jl, microstructure.jl
+  semidiscretize + index sets   src/discretization/fem.jl:170-196,371-419; solution_variables.jl:53-68
+  solver structs + caches       src/solver/time/euler.jl:4-179, partitioned_solver.jl:57-269
+  operators                     src/solver/interface.jl:17-94, src/discretization/operator.jl:2-32
+  integrator                    src/solver/time/integrator/type.jl:79-498, operatorsplitting-interface.jl:23-232
+"""
+from __future__ import annotations
+
+import enum
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from . import core
+from .core import B200CSRMatrix, B200Device, B200Vector, DeviceMesh, SQRT_EPS
+
+# ---------------------------------------------------------------------------------------------
+# cells
+# ---------------------------------------------------------------------------------------------
+Quadrilateral, Hexahedron, Triangle, Tetrahedron = L.QUAD4, L.HEX8, L.TRI3, L.TET4
+
+
+@dataclass
+class ParametrizedFHNModel:
+    """src/modeling/cells/fhn.jl:6-13"""
+    a: float = 0.1
+    b: float = 0.5
+    c: float = 1.0
+    d: float = 0.0
+    e: float = 0.01
+    f: float = 1.0
+    model_id = L.FHN
+
+    def params(self):
+        return np.array([self.a, self.b, self.c, self.d, self.e, self.f])
+
+
+FHNModel = ParametrizedFHNModel
+
+_PCG_FIELDS = ("g_Na E_m k_m tau_m E_h k_h delta_h tau_h0 g_K1 E_z k_z g_to E_r k_r E_s k_s tau_s g_CaL E_d k_d E_f k_f "
+               "tau_f g_Kr E_xr k_xr tau_xr E_y k_y g_Ks E_xs k_xs tau_xs E_Na E_K E_Ca").split()
+_PCG_DEFAULTS = (12.0, -52.244, 6.5472, 0.12, -78.7, 5.93, 0.799163, 6.80738, 0.73893, -91.9655, 12.4997, 0.1688, 14.3116,
+                 11.462, -47.9286, 4.9314, 9.90669, 0.11503, 0.7, 4.3, -15.7, 4.6, 30.0, 0.056, -26.6, 6.5, 334.0, -49.6,
+                 23.5, 0.008, 24.6, 12.1, 628.0, 65.0, -85.0, 50.0)
+
+
+class ParametrizedPCG2019Model:
+    """src/modeling/cells/pcg2019.jl:4-48 (36 parameters, declaration order)."""
+    model_id = L.PCG2019
+
+    def __init__(self, **kw):
+        vals = dict(zip(_PCG_FIELDS, _PCG_DEFAULTS))
+        for k, v in kw.items():
+            if k not in vals:
+                raise TypeError(f"unknown PCG2019 parameter {k}")
+            vals[k] = float(v)
+        self.__dict__.update(vals)
+
+    def params(self):
+        return np.array([getattr(self, k) for k in _PCG_FIELDS])
+
+
+PCG2019 = ParametrizedPCG2019Model
+
+
+def num_states(ion) -> int:
+    return 2 if ion.model_id == L.FHN else 7
+
+
+def state_symbols(ion):
+    return ("φₘ", "s") if ion.model_id == L.FHN else ("φₘ", "h", "m", "f", "s", "xs", "xr")
+
+
+def transmembranepotential_index(ion) -> int:
+    """1-based like the reference (electrophysiology.jl:107-153)."""
+    return 1
+
+
+def default_initial_state(ion) -> np.ndarray:
+    """fhn.jl:19, pcg2019.jl:137-152"""
+    if ion.model_id == L.FHN:
+        return np.zeros(2)
+    p = ion
+
+    def sig(phi, E, k, sign):
+        return 1.0 / (1.0 + math.exp(sign * (phi - E) / k))
+
+    u0 = np.zeros(7)
+    u0[0] = p.E_K
+    u0[1] = sig(u0[0], p.E_h, p.k_h, 1.0)
+    u0[2] = sig(u0[0], p.E_m, p.k_m, -1.0)
+    u0[3] = sig(u0[0], p.E_f, p.k_f, 1.0)
+    u0[4] = sig(u0[0], p.E_s, p.k_s, 1.0)
+    u0[5] = sig(u0[0], p.E_xs, p.k_xs, -1.0)
+    u0[6] = sig(u0[0], p.E_xr, p.k_xr, -1.0)
+    return u0
+
+
+# ---------------------------------------------------------------------------------------------
+# coefficients, protocols, models
+# ---------------------------------------------------------------------------------------------
+def SymmetricTensor(dim: int, data: Sequence[float]) -> np.ndarray:
+    """Tensors.jl SymmetricTensor{2,dim}(data): lower triangle, column major ((11,21,22) / (11,21,31,22,32,33))."""
+    T = np.zeros((dim, dim))
+    k = 0
+    for j in range(dim):
+        for i in range(j, dim):
+            T[i, j] = T[j, i] = data[k]
+            k += 1
+    return T
+
+
+@dataclass
+class ConstantCoefficient:
+    """coefficients.jl:106-120"""
+    val: object
+
+
+@dataclass
+class FieldCoefficient:
+    """coefficients.jl:36-99: elementwise_data[cell, local node, component]."""
+    elementwise_data: np.ndarray
+
+
+@dataclass
+class OrthotropicMicrostructureModel:
+    """microstructure.jl:140-187"""
+    fiber_coefficient: object
+    sheetlet_coefficient: object
+    normal_coefficient: object
+
+
+@dataclass
+class SpectralTensorCoefficient:
+    """coefficients.jl:451-488"""
+    eigenvectors: OrthotropicMicrostructureModel
+    eigenvalues: ConstantCoefficient
+
+
+class CartesianCoordinateSystem:
+    def __init__(self, mesh=None):
+        self.mesh = mesh
+
+
+@dataclass
+class AnalyticalCoefficient:
+    """analytical_coefficient.jl:7-39: f(x, t) evaluated in a coordinate system.
+
+    `f` is either a Python callable (evaluated on the host at the quadrature points) or one of the
+    built-in families below (evaluated inside the assembly kernel)."""
+    f: object
+    coordinate_system: object = None
+
+
+@dataclass
+class BoxStimulus:
+    """maximum(x) < xmax && t < tmax ? amplitude : 0   (bak/examples/conduction-velocity-benchmark.jl:47-50)"""
+    xmax: float
+    tmax: float
+    amplitude: float
+    kind = L.SRC_BOX
+
+    def prm(self):
+        return [self.xmax, self.tmax, self.amplitude]
+
+    def __call__(self, x, t):
+        return self.amplitude if (max(x) < self.xmax and t < self.tmax) else 0.0
+
+
+@dataclass
+class BallStimulus:
+    """norm(x) < radius && t < tmax ? amplitude : 0   (test/integration/test_electrophysiology.jl:83)"""
+    radius: float
+    tmax: float
+    amplitude: float
+    kind = L.SRC_BALL
+
+    def prm(self):
+        return [self.radius, self.tmax, self.amplitude]
+
+    def __call__(self, x, t):
+        return self.amplitude if (math.sqrt(sum(v * v for v in x)) < self.radius and t < self.tmax) else 0.0
+
+
+@dataclass
+class UniformEndocardialActivation:
+    """docs/src/literate-tutorials/ep04_geselowitz-ecg.jl:15-26"""
+    transmural_depth: float = 0.15
+    tmax: float = 2.0
+    amplitude: float = 0.5
+    tau: float = 0.25
+    kind = L.SRC_ENDO
+
+    def prm(self):
+        return [self.transmural_depth, self.tmax, self.amplitude, self.tau]
+
+
+class NoStimulationProtocol:
+    """electrophysiology.jl:251-255"""
+
+
+@dataclass
+class AnalyticalTransmembraneStimulationProtocol:
+    """electrophysiology.jl:260-283"""
+    f: AnalyticalCoefficient
+    nonzero_intervals: Sequence[tuple]
+
+
+@dataclass
+class MonodomainModel:
+    """electrophysiology.jl:338-368"""
+    χ: ConstantCoefficient
+    Cₘ: ConstantCoefficient
+    κ: object
+    stim: object
+    ion: object
+    transmembrane_solution_symbol: str = "φₘ"
+    internal_state_symbol: str = "s"
+    cell_coordinates: object = None
+
+
+@dataclass
+class ReactionDiffusionSplit:
+    """electrophysiology.jl:379-381"""
+    model: MonodomainModel
+
+
+@dataclass
+class TransientDiffusionModel:
+    """core/diffusion.jl:62-70"""
+    κ: object
+    source: object
+    solution_variable_symbol: str
+
+
+@dataclass
+class ConductivityToDiffusivityCoefficient:
+    """coefficients.jl:122-162: κ/(Cₘ χ)"""
+    conductivity_tensor_coefficient: object
+    capacitance_coefficient: ConstantCoefficient
+    χ_coefficient: ConstantCoefficient
+
+
+# ---------------------------------------------------------------------------------------------
+# discretization
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class LagrangeCollection:
+    order: int = 1
+
+
+@dataclass
+class QuadratureRuleCollection:
+    order: int = 2
+
+
+@dataclass
+class ElementAssemblyStrategy:
+    device: object = None
+
+
+SequentialAssemblyStrategy = PerColorAssemblyStrategy = ElementAssemblyStrategy
+
+
+class FiniteElementDiscretization:
+    """fem.jl:19-47"""
+
+    def __init__(self, interpolations: dict, dbcs=(), qrcs=None, fqrcs=None, assembly_strategy=None):
+        self.interpolations = interpolations
+        self.dbcs = list(dbcs)
+        self.qrcs = qrcs or {}
+        self.fqrcs = fqrcs or {}
+        self.assembly_strategy = assembly_strategy or ElementAssemblyStrategy()
+
+
+def _extract_qrc(ipc):
+    """fem.jl:52-55: QuadratureRuleCollection(max(2*order-1, 2))"""
+    if isinstance(ipc, tuple):
+        return ipc[1]
+    return QuadratureRuleCollection(max(2 * ipc.order - 1, 2))
+
+
+_default_device: B200Device | None = None
+
+
+def default_device() -> B200Device:
+    global _default_device
+    if _default_device is None:
+        _default_device = B200Device(0)
+    return _default_device
+
+
+def set_default_device(dev: B200Device):
+    global _default_device
+    _default_device = dev
+
+
+def generate_mesh(celltype, nel, left, right, device: B200Device | None = None) -> DeviceMesh:
+    """generate_mesh = to_mesh ∘ generate_grid (src/mesh/generators.jl:942), built in HBM."""
+    return DeviceMesh.generate_grid(device or default_device(), celltype, nel, left, right)
+
+
+def close_dofs(conn: np.ndarray) -> tuple[np.ndarray, int]:
+    """Ferrite DofHandler close! for one Lagrange-1 field on a host grid: first-touch numbering."""
+    flat = np.asarray(conn, dtype=np.int64).ravel()
+    uniq, first = np.unique(flat, return_index=True)
+    order = np.argsort(first, kind="stable")
+    node2dof = np.full(flat.max() + 1, -1, dtype=np.int64)
+    node2dof[uniq[order]] = np.arange(uniq.size)
+    return node2dof[flat].reshape(np.asarray(conn).shape), int(uniq.size)
+
+
+def to_mesh(celltype, cells, nodes, device: B200Device | None = None, index_base=0) -> DeviceMesh:
+    """to_mesh(Grid(cells, nodes)) for a host grid (src/mesh/simple_meshes.jl:181-247)."""
+    cells = np.asarray(cells, dtype=np.int64) - index_base
+    celldofs, ndofs = close_dofs(cells)
+    return DeviceMesh.from_host(device or default_device(), celltype, cells, nodes, celldofs, ndofs)
+
+
+@dataclass
+class BilinearMassIntegrator:
+    ρ: ConstantCoefficient
+    qrc: QuadratureRuleCollection
+    sym: str
+
+
+@dataclass
+class BilinearDiffusionIntegrator:
+    D: object
+    qrc: QuadratureRuleCollection
+    sym: str
+
+
+@dataclass
+class LinearIntegrator:
+    integrand: object
+    qrc: QuadratureRuleCollection
+
+
+@dataclass
+class AffineODEFunction:
+    """functions.jl:79-88"""
+    mass_term: BilinearMassIntegrator
+    bilinear_term: BilinearDiffusionIntegrator
+    source_term: LinearIntegrator
+    dh: DeviceMesh
+    strategy: object = None
+
+
+@dataclass
+class PointwiseODEFunction:
+    """functions.jl:46-65"""
+    ode: object
+    x: object
+    associated_states: range
+    state_symbol: str = "s"
+
+
+@dataclass
+class GenericSplitFunction:
+    functions: tuple
+    solution_indices: tuple
+
+
+def solution_size(f) -> int:
+    if isinstance(f, GenericSplitFunction):
+        return max(int(np.max(ix)) if not isinstance(ix, range) else ix.stop - 1 for ix in f.solution_indices)
+    if isinstance(f, AffineODEFunction):
+        return f.dh.ndofs
+    return len(f.associated_states)
+
+
+def semidiscretize(model, discretization: FiniteElementDiscretization, mesh: DeviceMesh):
+    """fem.jl:170-196 (TransientDiffusionModel) and :371-411 (ReactionDiffusionSplit{MonodomainModel})."""
+    if isinstance(model, TransientDiffusionModel):
+        if discretization.dbcs:
+            raise AssertionError("Dirichlet conditions not supported yet for TransientDiffusionProblem")
+        sym = model.solution_variable_symbol
+        if sym not in discretization.interpolations:
+            raise KeyError(f"no interpolation for field {sym} in the discretization")
+        ipc = discretization.interpolations[sym]
+        qrc = _extract_qrc(ipc)
+        ipc = ipc[0] if isinstance(ipc, tuple) else ipc
+        if ipc.order != 1:
+            raise NotImplementedError("only LagrangeCollection{1} is on the B200 path")
+        return AffineODEFunction(
+            BilinearMassIntegrator(ConstantCoefficient(1.0), discretization.qrcs.get("mass", qrc), sym),
+            BilinearDiffusionIntegrator(model.κ, qrc, sym), LinearIntegrator(model.source, qrc), mesh,
+            discretization.assembly_strategy)
+    if isinstance(model, ReactionDiffusionSplit):
+        ep = model.model
+        heatfun = semidiscretize(
+            TransientDiffusionModel(ConductivityToDiffusivityCoefficient(ep.κ, ep.Cₘ, ep.χ), ep.stim,
+                                    ep.transmembrane_solution_symbol), discretization, mesh)
+        n = mesh.ndofs
+        ns = num_states(ep.ion)
+        odefun = PointwiseODEFunction(ep.ion, None, range(1, ns * n + 1), ep.internal_state_symbol)
+        φidx = transmembranepotential_index(ep.ion)
+        heat_dofrange = (φidx - 1) * n + np.arange(1, n + 1)      # 1-based, as fem.jl:399-402
+        return GenericSplitFunction((heatfun, odefun), (heat_dofrange, range(1, ns * n + 1)))
+    raise TypeError(f"no semidiscretize method for {type(model).__name__}")
+
+
+def create_initial_condition(f) -> np.ndarray:
+    """functions.jl:312-339: zeros + every model's default_initial_state, state blocked."""
+    if isinstance(f, GenericSplitFunction):
+        odefun = f.functions[1]
+        n = len(odefun.associated_states) // num_states(odefun.ode)
+        u = np.zeros(solution_size(f))
+        for s, v in enumerate(default_initial_state(odefun.ode)):
+            u[s * n:(s + 1) * n] = v
+        return u
+    return np.zeros(solution_size(f))
+
+
+def setvariable_(u0: np.ndarray, f: GenericSplitFunction, sym: str, fn: Callable):
+    """setvariable!(u0, odeform, :sym) do x ... end  (ep01_spiral-wave.jl:113-118)."""
+    heatfun, odefun = f.functions
+    n = heatfun.dh.ndofs
+    syms = state_symbols(odefun.ode)
+    names = {heatfun.mass_term.sym: 0}
+    names.update({s: i for i, s in enumerate(syms)})
+    names[odefun.state_symbol] = 1
+    if sym not in names:
+        raise KeyError(f"unknown solution variable {sym}")
+    s = names[sym]
+    x = heatfun.dh.dof_coords()
+    u0[s * n:(s + 1) * n] = [fn(xi) for xi in x]
+    return u0
+
+
+# ---------------------------------------------------------------------------------------------
+# operators (setup_operator / update_operator! / needs_update)
+# ---------------------------------------------------------------------------------------------
+def _diffusion_data(D, mesh: DeviceMesh):
+    """Lower a coefficient tree to (kind, data, cm_chi) of the C ABI."""
+    cmchi = 1.0
+    if isinstance(D, ConductivityToDiffusivityCoefficient):
+        cmchi = float(D.capacitance_coefficient.val) * float(D.χ_coefficient.val)
+        D = D.conductivity_tensor_coefficient
+    if isinstance(D, ConstantCoefficient):
+        v = np.asarray(D.val, dtype=np.float64)
+        if v.ndim == 0:
+            return L.D_SCALAR, v.reshape(1), cmchi
+        if v.shape != (mesh.dim, mesh.dim):
+            raise ValueError(f"conductivity tensor must be {mesh.dim}x{mesh.dim}")
+        return L.D_TENSOR, v.ravel(), cmchi
+    if isinstance(D, SpectralTensorCoefficient):
+        ms = D.eigenvectors
+        lam = np.asarray(D.eigenvalues.val, dtype=np.float64).ravel()
+        if lam.size != 3:
+            raise ValueError("orthotropic spectral coefficient needs three eigenvalues")
+
+        def field(c):
+            if isinstance(c, ConstantCoefficient):
+                return np.broadcast_to(np.asarray(c.val, dtype=np.float64), (mesh.ncells, mesh.nv, 3))
+            if isinstance(c, FieldCoefficient):
+                return np.asarray(c.elementwise_data, dtype=np.float64).reshape(mesh.ncells, mesh.nv, 3)
+            raise TypeError("fibre coefficient must be ConstantCoefficient or FieldCoefficient")
+
+        fsn = np.stack([field(ms.fiber_coefficient), field(ms.sheetlet_coefficient), field(ms.normal_coefficient)], axis=2)
+        return L.D_SPECTRAL, np.concatenate([lam, fsn.ravel()]), cmchi
+    raise TypeError(f"unsupported diffusion coefficient {type(D).__name__}")
+
+
+class BilinearOperator:
+    """FerriteOperators BilinearFerriteOperator: fields .A, .integrator, .dh"""
+
+    def __init__(self, integrator, dh: DeviceMesh, A: B200CSRMatrix):
+        self.integrator, self.dh, self.A = integrator, dh, A
+
+
+class LinearOperator:
+    """FerriteOperators LinearFerriteOperator: fields .b, .integrator, .dh"""
+
+    def __init__(self, integrator, dh: DeviceMesh, b: B200Vector):
+        self.integrator, self.dh, self.b = integrator, dh, b
+
+
+class LinearNullOperator:
+    """interface.jl:17-64: source operator of a NoStimulationProtocol"""
+    b = None
+
+
+def setup_operator(strategy, integrator, solver, dh: DeviceMesh, pattern_of: B200CSRMatrix | None = None):
+    if isinstance(integrator, LinearIntegrator) and isinstance(integrator.integrand, NoStimulationProtocol):
+        return LinearNullOperator()
+    dev = dh.dev
+    if isinstance(integrator, LinearIntegrator):
+        return LinearOperator(integrator, dh, B200Vector(dev, dh.ndofs, 1))
+    A = pattern_of.like() if pattern_of is not None else B200CSRMatrix.from_mesh(dev, dh)
+    return BilinearOperator(integrator, dh, A)
+
+
+def needs_update(op, t) -> bool:
+    """src/discretization/operator.jl:2-32: closed intervals."""
+    if isinstance(op, LinearNullOperator):
+        return False
+    proto = op.integrator.integrand
+    if isinstance(proto, NoStimulationProtocol):
+        return False
+    return any(a <= t <= b for a, b in proto.nonzero_intervals)
+
+
+def update_operator_(op, t):
+    """update_operator!(op, t): THE assembly."""
+    if isinstance(op, LinearNullOperator):
+        return
+    dh, dev = op.dh, op.dh.dev
+    q = op.integrator.qrc.order
+    if isinstance(op, BilinearOperator):
+        if isinstance(op.integrator, BilinearMassIntegrator):
+            core.assemble_mass(dev, dh, op.A, q, float(op.integrator.ρ.val))
+        else:
+            kind, data, cmchi = _diffusion_data(op.integrator.D, dh)
+            core.assemble_diffusion(dev, dh, op.A, q, kind, data, cmchi)
+        return
+    f = op.integrator.integrand.f.f
+    if hasattr(f, "kind"):
+        core.assemble_source(dev, dh, op.b, q, f.kind, f.prm(), t)
+    else:
+        # arbitrary closure: evaluate at the quadrature points on the host (a closure cannot cross the C ABI)
+        conn, coords, _ = dh.download()
+        pts, _w = core.quadrature(dh.celltype, q)
+        N = _shape_values(dh.celltype, pts)                       # nq x nv
+        xq = np.einsum("qa,cad->cqd", N, coords[conn])            # ncells x nq x dim
+        fq = np.array([[f(xq[c, k], t) for k in range(xq.shape[1])] for c in range(xq.shape[0])])
+        core.assemble_source_qp(dev, dh, op.b, q, fq)
+
+
+def _shape_values(celltype, pts):
+    pts = np.asarray(pts)
+    if celltype == L.QUAD4:
+        sx, sy = np.array([-1, 1, 1, -1.0]), np.array([-1, -1, 1, 1.0])
+        return 0.25 * (1 + pts[:, :1] * sx) * (1 + pts[:, 1:2] * sy)
+    if celltype == L.HEX8:
+        sx, sy, sz = (np.array([-1, 1, 1, -1, -1, 1, 1, -1.0]), np.array([-1, -1, 1, 1, -1, -1, 1, 1.0]),
+                      np.array([-1, -1, -1, -1, 1, 1, 1, 1.0]))
+        return 0.125 * (1 + pts[:, :1] * sx) * (1 + pts[:, 1:2] * sy) * (1 + pts[:, 2:3] * sz)
+    if celltype == L.TET4:
+        return np.stack([1 - pts.sum(1), pts[:, 0], pts[:, 1], pts[:, 2]], axis=1)
+    return np.stack([pts[:, 0], pts[:, 1], 1 - pts.sum(1)], axis=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# solvers
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class B200CG:
+    """Stands where LinearSolve.KrylovJL_CG(atol=…, rtol=…) stands (euler.jl:10); defaults are LinearSolve's."""
+    atol: float = SQRT_EPS
+    rtol: float = SQRT_EPS
+    maxiters: int | None = None
+
+
+KrylovJL_CG = B200CG
+
+
+@dataclass
+class BackwardEulerSolver:
+    """euler.jl:4-15"""
+    inner_solver: B200CG = field(default_factory=B200CG)
+    solution_vector_type: type = B200Vector
+    system_matrix_type: type = B200CSRMatrix
+    monitor: object = None
+
+
+@dataclass
+class ForwardEulerCellSolver:
+    """partitioned_solver.jl:57-60"""
+    solution_vector_type: type = B200Vector
+    batch_size_hint: int = 32
+
+
+@dataclass
+class AdaptiveForwardEulerSubstepper:
+    """partitioned_solver.jl:169-175"""
+    substeps: int = 10
+    reaction_threshold: float = 0.1
+    solution_vector_type: type = B200Vector
+    batch_size_hint: int = 32
+
+
+@dataclass
+class LieTrotterGodunov:
+    """OS.LieTrotterGodunov((heat, cell))"""
+    inner_algs: tuple
+
+
+class ReturnCode(enum.Enum):
+    Default = 0
+    Success = 1
+    MaxIters = 2
+    DtNaN = 3
+    Unstable = 4
+    ConvergenceFailure = 5
+    Failure = 6
+
+
+@dataclass
+class OperatorSplittingProblem:
+    f: GenericSplitFunction
+    u0: object
+    tspan: tuple
+
+
+@dataclass
+class ODEProblem:
+    f: object
+    u0: object
+    tspan: tuple
+
+
+PointwiseODEProblem = ODEProblem
+
+
+@dataclass
+class IntegratorStats:
+    """type.jl:1-7"""
+    naccept: int = 0
+    nreject: int = 0
+
+
+@dataclass
+class Solution:
+    retcode: ReturnCode = ReturnCode.Default
+
+
+class BackwardEulerSolverCache:
+    """euler.jl:21-69,122-179: M, K, source, A, Δt_last + the linear solver cache."""
+
+    def __init__(self, f: AffineODEFunction, solver: BackwardEulerSolver, t0, u: B200Vector, ucol=0):
+        dh, dev = f.dh, f.dh.dev
+        self.f, self.solver, self.dev, self.uₙ, self.ucol = f, solver, dev, u, ucol
+        self.M = setup_operator(f.strategy, f.mass_term, solver, dh)
+        self.K = setup_operator(f.strategy, f.bilinear_term, solver, dh, pattern_of=self.M.A)
+        self.source_term = setup_operator(ElementAssemblyStrategy(dev), f.source_term, solver, dh)
+        self.A = self.M.A.like()
+        self.b = B200Vector(dev, dh.ndofs, 1)
+        self.uprev = B200Vector(dev, dh.ndofs, 1)
+        self.Δt_last = 0.0
+        self.iters, self.resid = [], []
+        update_operator_(self.M, t0)          # "initial assembly", euler.jl:172-176
+        update_operator_(self.K, t0)
+        update_operator_(self.source_term, t0)
+
+
+class PointwiseSolverCache:
+    def __init__(self, f: PointwiseODEFunction, solver, u: B200Vector):
+        self.f, self.solver, self.uₙ = f, solver, u
+        self.substeps = getattr(solver, "substeps", 1) if isinstance(solver, AdaptiveForwardEulerSubstepper) else 1
+        self.threshold = getattr(solver, "reaction_threshold", 0.1)
+
+
+def setup_solver_cache(f, solver, t0, u: B200Vector, ucol=0):
+    if isinstance(f, AffineODEFunction):
+        return BackwardEulerSolverCache(f, solver, t0, u, ucol)
+    return PointwiseSolverCache(f, solver, u)
+
+
+def _isapprox(a, b):
+    return a == b or abs(a - b) <= SQRT_EPS * max(abs(a), abs(b))
+
+
+def perform_step_(f, cache, t, Δt) -> bool:
+    """perform_step!(f, cache, t, Δt) -> Bool for the two (function, solver) pairs on the path."""
+    if isinstance(cache, BackwardEulerSolverCache):
+        dev = cache.dev
+        if not _isapprox(Δt, cache.Δt_last):                         # euler.jl:82
+            cache.A.axpby_values(cache.M.A, cache.K.A, Δt)
+            cache.Δt_last = Δt
+        cache.uprev.copy_from(cache.uₙ, scol=cache.ucol)              # forward_sync of the OS child
+        cache.M.A.mul(cache.b, cache.uprev)                           # b = M uprev, euler.jl:85
+        if needs_update(cache.source_term, t + Δt):                  # euler.jl:118-120
+            update_operator_(cache.source_term, t + Δt)
+        if not isinstance(cache.source_term, LinearNullOperator):    # add!(b, S) is unconditional, euler.jl:88-91
+            _add(dev, cache.b, cache.source_term.b)
+        s = cache.solver.inner_solver
+        it, rn, conv = core.cg_solve(dev, cache.A, cache.b, cache.uₙ, s.atol, s.rtol, s.maxiters, xcol=cache.ucol)
+        cache.iters.append(it)
+        cache.resid.append(rn)
+        return conv
+    ion = f.ode
+    core.cell_step(cache.uₙ.dev, ion.model_id, ion.params(), cache.uₙ, t, Δt, cache.substeps, cache.threshold)
+    return True
+
+
+def _add(dev, b: B200Vector, s: B200Vector):
+    """add!(b, S): b .+= S.b"""
+    b.axpy(1.0, s)
+
+
+class ThunderboltTimeIntegrator:
+    """type.jl:79-126 + the OS outer integrator for LieTrotterGodunov: fields u, t, dt, stats, sol."""
+
+    def __init__(self, prob, alg, dt, fused=True, maxiters=10**9):
+        if dt is None or not (dt == dt):
+            self.sol = Solution(ReturnCode.DtNaN)
+            raise ValueError("dt must be given and finite")
+        self.prob, self.alg = prob, alg
+        self.t, self.dt = float(prob.tspan[0]), float(dt)
+        self.tstop = float(prob.tspan[1])
+        self.stats = IntegratorStats()
+        self.sol = Solution()
+        self.maxiters = maxiters
+        self.iter = 0
+        f = prob.f
+        dev = self._device_of(f)
+        self.dev = dev
+        if isinstance(f, GenericSplitFunction):
+            heatfun, odefun = f.functions
+            ns = num_states(odefun.ode)
+            self.u = prob.u0 if isinstance(prob.u0, B200Vector) else B200Vector.from_host(dev, prob.u0, ns)
+            self.uprev = B200Vector(dev, self.u.n, self.u.ncols)
+            heat_alg, cell_alg = alg.inner_algs
+            φcol = transmembranepotential_index(odefun.ode) - 1
+            self.caches = (setup_solver_cache(heatfun, heat_alg, self.t, self.u, φcol),
+                           setup_solver_cache(odefun, cell_alg, self.t, self.u))
+            self.fused = None
+            if fused:
+                hc, cc = self.caches
+                st = core.MonodomainStepper(dev, hc.M.A, hc.K.A, odefun.ode.model_id, odefun.ode.params(), φcol)
+                s = heat_alg.inner_solver
+                st.set_cg(s.atol, s.rtol, s.maxiters)
+                st.set_cell_solver(cc.substeps, cc.threshold)
+                self.fused = st
+        elif isinstance(f, AffineODEFunction):
+            self.u = prob.u0 if isinstance(prob.u0, B200Vector) else B200Vector.from_host(dev, prob.u0, 1)
+            self.uprev = B200Vector(dev, self.u.n, 1)
+            self.caches = (setup_solver_cache(f, alg, self.t, self.u, 0),)
+            self.fused = None
+        else:
+            ns = num_states(f.ode)
+            self.u = prob.u0 if isinstance(prob.u0, B200Vector) else B200Vector.from_host(dev, prob.u0, ns)
+            self.uprev = B200Vector(dev, self.u.n, ns)
+            self.caches = (setup_solver_cache(f, alg, self.t, self.u),)
+            self.fused = None
+
+    @staticmethod
+    def _device_of(f):
+        if isinstance(f, GenericSplitFunction):
+            return f.functions[0].dh.dev
+        if isinstance(f, AffineODEFunction):
+            return f.dh.dev
+        return default_device()
+
+    @property
+    def cg_iterations(self):
+        hc = self.caches[0]
+        return hc.iters if isinstance(hc, BackwardEulerSolverCache) else []
+
+    def _functions(self):
+        f = self.prob.f
+        return f.functions if isinstance(f, GenericSplitFunction) else (f,)
+
+    def _step_once(self) -> bool:
+        """One accepted-or-rejected step (type.jl:189-218; rollback type.jl:510-532)."""
+        t, dt = self.t, self.dt
+        if self.tstop - t < dt * (1 - 1e-12):
+            dt = self.tstop - t                      # land exactly on the tstop
+        for c in range(self.u.ncols):
+            self.uprev.copy_from(self.u, scol=c, dcol=c)
+        ok = True
+        if self.fused is not None:
+            hc = self.caches[0]
+            src = hc.source_term
+            if needs_update(src, t + dt):
+                update_operator_(src, t + dt)
+            self.fused.set_source(None if isinstance(src, LinearNullOperator) else src.b)
+            it, rn, ok = self.fused.step(self.u, t, dt)
+            hc.iters.append(it)
+            hc.resid.append(rn)
+        else:
+            for f, cache in zip(self._functions(), self.caches):     # children in tuple order: heat, then cells
+                if not perform_step_(f, cache, t, dt):
+                    ok = False
+                    break
+        self.iter += 1
+        if ok:
+            self.stats.naccept += 1
+            self.t = t + dt
+        else:
+            self.stats.nreject += 1
+            for c in range(self.u.ncols):
+                self.u.copy_from(self.uprev, scol=c, dcol=c)
+            self.sol.retcode = ReturnCode.ConvergenceFailure       # non-adaptive: diffeq-interface.jl:347-354
+        return ok
+
+
+def init(prob, alg, dt=None, **kw) -> ThunderboltTimeIntegrator:
+    unsupported = set(kw) - {"verbose", "maxiters", "fused"}
+    if unsupported:
+        raise TypeError(f"unsupported keyword arguments: {sorted(unsupported)}")
+    return ThunderboltTimeIntegrator(prob, alg, dt, fused=kw.get("fused", True), maxiters=kw.get("maxiters", 10**9))
+
+
+def step_(integ: ThunderboltTimeIntegrator) -> bool:
+    """SciMLBase.step!(integrator)"""
+    return integ._step_once()
+
+
+def solve_(integ: ThunderboltTimeIntegrator) -> Solution:
+    """SciMLBase.solve!(integrator)"""
+    while integ.t < integ.tstop * (1 - 1e-15) - 1e-300 or (integ.tstop == 0 and integ.t < 0):
+        if integ.iter >= integ.maxiters:
+            integ.sol.retcode = ReturnCode.MaxIters
+            return integ.sol
+        if not integ._step_once():
+            return integ.sol
+    integ.sol.retcode = ReturnCode.Success
+    return integ.sol

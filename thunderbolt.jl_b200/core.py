@@ -1,0 +1,369 @@
+"""Handle objects over the C ABI: B200Device, B200Vector, DeviceMesh, B200CSRMatrix, MonodomainStepper.
+
+These are the Python twins of the Julia types INTEGRATION.md introduces (`B200Device`,
+`B200Vector{Float64}`, `B200CSRMatrix{Float64,Int32}`); every method is one C call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
+
+
+class B200Device:
+    """A CUDA context on one B200 (`src/devices.jl:1-4` maps devices to backends; this is the new one)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        L.call("tb_ctx_create", int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        self.h = h
+        self.device = int(device)
+        self.rank, self.nranks = 0, 1
+
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().tb_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        L.call("tb_sync", self.h)
+
+    def info(self):
+        sm, mem, ma, mi = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        L.call("tb_device_info", self.h, C.byref(sm), C.byref(mem), C.byref(ma), C.byref(mi))
+        return {"sm_count": sm.value, "total_mem": mem.value, "cc": (ma.value, mi.value)}
+
+    def timer_start(self):
+        L.call("tb_timer_start", self.h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        L.call("tb_timer_stop", self.h, C.byref(ms))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        L.call("tb_launch_count", self.h, C.byref(n))
+        return n.value
+
+    def l2_flush(self):
+        L.call("tb_l2_flush", self.h)
+
+    # ---- multi-GPU --------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        L.call("tb_comm_unique_id", buf)
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        L.call("tb_ctx_comm_init", self.h, int(rank), int(nranks), buf)
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def barrier(self):
+        L.call("tb_comm_barrier", self.h)
+
+    def allreduce_max(self, v: float) -> float:
+        x = C.c_double(v)
+        L.call("tb_comm_allreduce_max", self.h, C.byref(x))
+        return x.value
+
+
+class B200Vector:
+    """Device vector with `ncols` state columns of `n` rows (host image: column c = host[c*n:(c+1)*n])."""
+
+    def __init__(self, dev: B200Device, n: int, ncols: int = 1):
+        h = C.c_void_p()
+        L.call("tb_vec_create", dev.h, int(n), int(ncols), C.byref(h))
+        self.h, self.dev, self.n, self.ncols = h, dev, int(n), int(ncols)
+
+    @classmethod
+    def from_host(cls, dev, host, ncols: int = 1):
+        host = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        assert host.size % ncols == 0
+        v = cls(dev, host.size // ncols, ncols)
+        v.upload(host)
+        return v
+
+    def __len__(self):
+        return self.n * self.ncols
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        if host.size != self.n * self.ncols:
+            raise ValueError(f"host vector has {host.size} entries, device vector {self.n * self.ncols}")
+        L.call("tb_vec_upload", self.h, L.ptr(host))
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.n * self.ncols)
+        L.call("tb_vec_download", self.h, L.ptr(out))
+        return out
+
+    def column(self, col: int) -> np.ndarray:
+        out = np.empty(self.n)
+        L.call("tb_vec_download_col", self.h, int(col), L.ptr(out), 0, self.n)
+        return out
+
+    def set_column(self, col: int, host):
+        host = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        L.call("tb_vec_upload_col", self.h, int(col), L.ptr(host), 0, host.size)
+
+    def fill(self, value: float, col: int = 0):
+        L.call("tb_vec_fill", self.h, int(col), float(value))
+
+    def copy_from(self, src: "B200Vector", scol: int = 0, dcol: int = 0):
+        L.call("tb_vec_copy", self.h, int(dcol), src.h, int(scol))
+
+    def axpy(self, a: float, x: "B200Vector", xcol: int = 0, ycol: int = 0):
+        """self[:, ycol] += a * x[:, xcol]"""
+        L.call("tb_vec_axpy", self.h, int(ycol), float(a), x.h, int(xcol))
+
+    def devptr(self, col: int = 0):
+        p, ld = C.c_void_p(), C.c_int64()
+        L.call("tb_vec_devptr", self.h, int(col), C.byref(p), C.byref(ld))
+        return p.value, ld.value
+
+    def free(self):
+        if getattr(self, "h", None):
+            L.lib().tb_vec_destroy(self.h)
+            self.h = None
+
+
+class DeviceMesh:
+    """Grid + closed DofHandler (one Lagrange-1 scalar field) resident in HBM."""
+
+    def __init__(self, dev, h):
+        self.dev, self.h = dev, h
+        nc, nn, nd, nv, dim = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        L.call("tb_mesh_sizes", h, C.byref(nc), C.byref(nn), C.byref(nd), C.byref(nv), C.byref(dim))
+        self.ncells, self.nnodes, self.ndofs, self.nv, self.dim = nc.value, nn.value, nd.value, nv.value, dim.value
+        self.celltype = None
+        self.ndofs_owned = self.ndofs
+        self.dof_lo = 0
+        self.ghost_global = np.empty(0, dtype=np.int64)
+
+    @classmethod
+    def generate_grid(cls, dev, celltype, nel, left, right):
+        dim = 2 if celltype in (L.QUAD4, L.TRI3) else 3
+        nel3 = np.ones(3, dtype=np.int64)
+        nel3[:dim] = nel
+        l3, r3 = np.zeros(3), np.ones(3)
+        l3[:dim], r3[:dim] = left, right
+        h = C.c_void_p()
+        L.call("tb_mesh_generate_grid", dev.h, int(celltype), nel3, l3, r3, C.byref(h))
+        m = cls(dev, h)
+        m.celltype = int(celltype)
+        return m
+
+    @classmethod
+    def from_host(cls, dev, celltype, conn, coords, celldofs, ndofs, index_base=0):
+        conn = np.ascontiguousarray(conn, dtype=np.int64)
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        celldofs = np.ascontiguousarray(celldofs, dtype=np.int64)
+        nv = {L.QUAD4: 4, L.HEX8: 8, L.TRI3: 3, L.TET4: 4}[celltype]
+        dim = 2 if celltype in (L.QUAD4, L.TRI3) else 3
+        h = C.c_void_p()
+        L.call("tb_mesh_create", dev.h, int(celltype), conn.size // nv, coords.size // dim, conn.ravel(), coords.ravel(),
+               celldofs.ravel(), int(ndofs), int(index_base), C.byref(h))
+        m = cls(dev, h)
+        m.celltype = int(celltype)
+        return m
+
+    def extract_local(self, dof_lo: int, dof_hi: int) -> "DeviceMesh":
+        h, ng = C.c_void_p(), C.c_int64()
+        L.call("tb_mesh_extract_local", self.h, int(dof_lo), int(dof_hi), C.byref(h), C.byref(ng))
+        m = DeviceMesh(self.dev, h)
+        m.celltype = self.celltype
+        m.ndofs_owned = int(dof_hi - dof_lo)
+        m.dof_lo = int(dof_lo)
+        m.ghost_global = np.empty(ng.value, dtype=np.int64)
+        if ng.value:
+            L.call("tb_mesh_ghosts", h, m.ghost_global)
+        return m
+
+    def download(self):
+        conn = np.empty((self.ncells, self.nv), dtype=np.int64)
+        coords = np.empty((self.nnodes, self.dim))
+        celldofs = np.empty((self.ncells, self.nv), dtype=np.int64)
+        L.call("tb_mesh_download", self.h, L.ptr(conn), L.ptr(coords), L.ptr(celldofs))
+        return conn, coords, celldofs
+
+    def dof_coords(self) -> np.ndarray:
+        x = np.empty((self.ndofs, self.dim))
+        L.call("tb_mesh_dof_coords", self.h, x.reshape(-1))
+        return x
+
+    def free(self):
+        if getattr(self, "h", None):
+            L.lib().tb_mesh_destroy(self.h)
+            self.h = None
+
+
+class B200CSRMatrix:
+    """CSR operator (SELL-32 in HBM) with the reference's sparsity pattern."""
+
+    def __init__(self, dev, h):
+        self.dev, self.h = dev, h
+        nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        L.call("tb_csr_sizes", h, C.byref(nr), C.byref(nc), C.byref(nnz))
+        self.nrows, self.ncols, self.nnz = nr.value, nc.value, nnz.value
+
+    @classmethod
+    def from_pattern(cls, dev, rowptr, colidx, ncols=None, index_base=0):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int64)
+        n = rowptr.size - 1
+        h = C.c_void_p()
+        L.call("tb_csr_create", dev.h, n, int(n if ncols is None else ncols), rowptr, colidx, int(index_base), C.byref(h))
+        return cls(dev, h)
+
+    @classmethod
+    def from_mesh(cls, dev, mesh: DeviceMesh):
+        h = C.c_void_p()
+        L.call("tb_csr_create_from_mesh", dev.h, mesh.h, C.byref(h))
+        return cls(dev, h)
+
+    def like(self) -> "B200CSRMatrix":
+        h = C.c_void_p()
+        L.call("tb_csr_create_like", self.h, C.byref(h))
+        return B200CSRMatrix(self.dev, h)
+
+    def pattern(self, index_base=0):
+        rowptr = np.empty(self.nrows + 1, dtype=np.int64)
+        colidx = np.empty(self.nnz, dtype=np.int64)
+        L.call("tb_csr_download_pattern", self.h, rowptr, colidx, int(index_base))
+        return rowptr, colidx
+
+    def nonzeros(self) -> np.ndarray:
+        vals = np.empty(self.nnz)
+        L.call("tb_csr_values_download", self.h, vals)
+        return vals
+
+    def set_nonzeros(self, vals):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        if vals.size != self.nnz:
+            raise ValueError("wrong number of nonzeros")
+        L.call("tb_csr_values_upload", self.h, vals)
+
+    def zero(self):
+        L.call("tb_csr_zero", self.h)
+
+    def axpby_values(self, M: "B200CSRMatrix", K: "B200CSRMatrix", dt: float):
+        """nonzeros(self) .= nonzeros(M) .- dt .* nonzeros(K)   (euler.jl:104-116)."""
+        L.call("tb_csr_axpby_values", self.h, M.h, K.h, float(dt))
+
+    def mul(self, y: B200Vector, x: B200Vector, xcol=0, ycol=0):
+        """mul!(y, A, x)."""
+        L.call("tb_spmv", self.dev.h, self.h, x.h, int(xcol), y.h, int(ycol))
+
+    def set_halo(self, neigh_ranks, send_ptr, send_rows, recv_ptr):
+        nr = np.ascontiguousarray(neigh_ranks, dtype=np.int32)
+        sp = np.ascontiguousarray(send_ptr, dtype=np.int64)
+        sr = np.ascontiguousarray(send_rows, dtype=np.int64)
+        rp = np.ascontiguousarray(recv_ptr, dtype=np.int64)
+        L.call("tb_csr_set_halo", self.h, int(nr.size), L.ptr(nr), L.ptr(sp), L.ptr(sr), L.ptr(rp))
+
+    def free(self):
+        if getattr(self, "h", None):
+            L.lib().tb_csr_destroy(self.h)
+            self.h = None
+
+
+def quadrature(celltype, qorder):
+    nq = C.c_int32()
+    L.call("tb_quadrature", int(celltype), int(qorder), C.byref(nq), None, None)
+    dim = 2 if celltype in (L.QUAD4, L.TRI3) else 3
+    pts, w = np.empty((nq.value, dim)), np.empty(nq.value)
+    L.call("tb_quadrature", int(celltype), int(qorder), C.byref(nq), L.ptr(pts), L.ptr(w))
+    return pts, w
+
+
+def assemble_mass(dev, mesh, M: B200CSRMatrix, qorder=2, rho=1.0):
+    L.call("tb_assemble_mass", dev.h, mesh.h, int(qorder), float(rho), M.h)
+
+
+def assemble_diffusion(dev, mesh, K: B200CSRMatrix, qorder, kind, data, cm_chi=1.0):
+    data = np.ascontiguousarray(np.atleast_1d(np.asarray(data, dtype=np.float64)).ravel())
+    L.call("tb_assemble_diffusion", dev.h, mesh.h, int(qorder), int(kind), data, data.size, float(cm_chi), K.h)
+
+
+def assemble_source(dev, mesh, b: B200Vector, qorder, kind, prm, t, col=0):
+    prm = np.ascontiguousarray(np.atleast_1d(np.asarray(prm, dtype=np.float64)).ravel())
+    L.call("tb_assemble_source", dev.h, mesh.h, int(qorder), int(kind), L.ptr(prm), prm.size, float(t), b.h, int(col))
+
+
+def assemble_source_qp(dev, mesh, b: B200Vector, qorder, fq, col=0):
+    fq = np.ascontiguousarray(fq, dtype=np.float64).ravel()
+    L.call("tb_assemble_source_qp", dev.h, mesh.h, int(qorder), fq, b.h, int(col))
+
+
+def cg_solve(dev, A: B200CSRMatrix, b: B200Vector, x: B200Vector, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, bcol=0,
+             xcol=0):
+    it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()
+    itmax = A.nrows if itmax is None else itmax
+    L.call("tb_cg_solve", dev.h, A.h, b.h, int(bcol), x.h, int(xcol), float(atol), float(rtol), int(itmax), C.byref(it),
+           C.byref(rn), C.byref(cv))
+    return it.value, rn.value, bool(cv.value)
+
+
+def cell_step(dev, model, params, u: B200Vector, t, dt, substeps=1, threshold=0.1, phi_idx=0, want_max=False):
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    mx = C.c_double()
+    L.call("tb_cell_step", dev.h, int(model), params, params.size, u.h, int(phi_idx), float(t), float(dt), int(substeps),
+           float(threshold), C.byref(mx) if want_max else None)
+    return mx.value if want_max else None
+
+
+class MonodomainStepper:
+    """tb_monodomain_*: the fused LieTrotterGodunov step."""
+
+    def __init__(self, dev, M: B200CSRMatrix, K: B200CSRMatrix, model, params, phi_idx=0):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        h = C.c_void_p()
+        L.call("tb_monodomain_create", dev.h, M.h, K.h, int(model), params, params.size, int(phi_idx), C.byref(h))
+        self.h, self.dev, self.M, self.K = h, dev, M, K
+        self._bS = None
+
+    def set_cg(self, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None):
+        L.call("tb_monodomain_set_cg", self.h, float(atol), float(rtol), int(self.M.nrows if itmax is None else itmax))
+
+    def set_cell_solver(self, substeps=1, threshold=0.1):
+        L.call("tb_monodomain_set_cell_solver", self.h, int(substeps), float(threshold))
+
+    def set_source(self, bS: B200Vector | None, col=0):
+        self._bS = bS
+        L.call("tb_monodomain_set_source", self.h, bS.h if bS is not None else None, int(col))
+
+    def enable_timing(self, on=True):
+        L.call("tb_monodomain_enable_timing", self.h, int(on))
+
+    def section_ms(self):
+        ms = (C.c_double * 3)()
+        L.call("tb_monodomain_section_ms", self.h, ms)
+        return list(ms)
+
+    def step(self, u: B200Vector, t, dt):
+        it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()
+        L.call("tb_monodomain_step", self.h, u.h, float(t), float(dt), C.byref(it), C.byref(rn), C.byref(cv))
+        return it.value, rn.value, bool(cv.value)
+
+    def run(self, u: B200Vector, t0, dt, nsteps):
+        it, cv = C.c_int64(), C.c_int32()
+        L.call("tb_monodomain_run", self.h, u.h, float(t0), float(dt), int(nsteps), C.byref(it), C.byref(cv))
+        return it.value, bool(cv.value)
+
+    def step_host(self, u_dev: B200Vector, u_in: np.ndarray, u_out: np.ndarray, t, dt):
+        it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()
+        L.call("tb_monodomain_step_host", self.h, u_dev.h, L.ptr(u_in), L.ptr(u_out), float(t), float(dt), C.byref(it),
+               C.byref(rn), C.byref(cv))
+        return it.value, rn.value, bool(cv.value)
+
+    def free(self):
+        if getattr(self, "h", None):
+            L.lib().tb_monodomain_destroy(self.h)
+            self.h = None

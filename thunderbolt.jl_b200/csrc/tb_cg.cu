@@ -1,0 +1,265 @@
+// Conjugate gradients on the SELL-32 operator, all scalars device-resident.
+// Replaces LinearSolve.solve!(cache) with KrylovJL_CG (src/solver/time/euler.jl:10,94,155-156), i.e.
+// Krylov.jl 0.10.9 cg! with LinearSolve 3.87.0 defaults: x0 = 0, r = b, p = r, gamma = r.r,
+// eps = atol + rtol*sqrt(gamma); loop { Ap; alpha = gamma/p.Ap; x += alpha p; r -= alpha Ap;
+// gamma' = r.r; solved = sqrt(gamma') <= eps; if !solved { beta = gamma'/gamma; p = r + beta p };
+// iter++ } until solved or iter >= itmax.
+//
+// One iteration = three kernels, no host round trip:
+//   k_cg_spmv_dot : Ap = A p fused with the p.Ap reduction (warp shuffles -> block -> last-block)
+//   k_cg_xr       : x += alpha p, r -= alpha Ap fused with the r.r reduction          (48 B/row)
+//   k_cg_p        : p = r + beta p                                                   (24 B/row)
+// alpha, beta, gamma, |r|, iter and the `done` flag live in a CGState in HBM; the last block of each
+// reducing kernel (ticket counter) finishes the reduction in a fixed order -- deterministic run to
+// run -- and advances the scalars.  Kernels launched after convergence see done = 1 and return at
+// once, so the host enqueues iterations ahead and polls the flag only every few iterations.
+// Algorithmic bytes per iteration and row: SpMV (nnzr*12 + 24) + 72.
+#include "tb_internal.cuh"
+#include "tb_spmv.cuh"
+
+#define TB_DEV(ctx) TB_CUDA(cudaSetDevice((ctx)->device))
+
+// ---- scalar recurrences (run by one thread) ------------------------------------------------------
+__device__ __forceinline__ void cg_after_init(CGState *st, double gamma) {
+    st->gamma = gamma;
+    const double rn = sqrt(gamma);
+    st->rnorm = rn;
+    st->eps = st->atol + st->rtol * rn;
+    st->solved = rn <= st->eps;
+    st->iter = 0;
+    st->done = st->solved || (st->iter >= st->itmax);
+}
+__device__ __forceinline__ void cg_after_pAp(CGState *st, double pAp) {
+    st->pAp = pAp;
+    st->alpha = st->gamma / pAp;
+}
+__device__ __forceinline__ void cg_after_rr(CGState *st, double gnext) {
+    st->gamma_next = gnext;
+    const double rn = sqrt(gnext);
+    st->rnorm = rn;
+    const int solved = rn <= st->eps;
+    st->solved = solved;
+    if (!solved) {
+        st->beta = gnext / st->gamma;
+        st->gamma = gnext;
+    }
+    st->iter += 1;
+    st->done = solved || (st->iter >= st->itmax);
+}
+
+// which: 0 init, 1 pAp, 2 rr.  Used on the multi-GPU path after the NCCL all-reduce of st->local[0].
+__global__ void k_cg_scalar(CGState *st, int which) {
+    if (which != 0 && st->done) return;
+    if (which == 0) cg_after_init(st, st->local[0]);
+    else if (which == 1) cg_after_pAp(st, st->local[0]);
+    else cg_after_rr(st, st->local[0]);
+}
+
+__global__ void k_cg_set_tol(CGState *st, double atol, double rtol, long long itmax) {
+    st->atol = atol;
+    st->rtol = rtol;
+    st->itmax = itmax;
+    st->done = 0;
+    st->solved = 0;
+    st->iter = 0;
+}
+
+// finishing step shared by the reducing kernels: single GPU -> advance the scalars here;
+// multi GPU -> leave the rank-local sum for the all-reduce
+template <int WHICH>
+__device__ __forceinline__ void cg_finish(double block_value, CGState *st, double *partials, unsigned *ticket, double *sm,
+                                          bool dist) {
+    double total;
+    if (tb_grid_sum(block_value, partials, ticket, sm, &total) && threadIdx.x == 0) {
+        if (dist) st->local[0] = total;
+        else if (WHICH == 0) cg_after_init(st, total);
+        else if (WHICH == 1) cg_after_pAp(st, total);
+        else cg_after_rr(st, total);
+    }
+}
+
+// ---- init from a given right-hand side: x = 0, r = p = b, gamma = b.b ------------------------------
+__global__ void __launch_bounds__(256) k_cg_init_b(const double *__restrict__ b, double *__restrict__ x,
+                                                   double *__restrict__ r, double *__restrict__ p, int64_t n, CGState *st,
+                                                   double *partials, unsigned *ticket, bool dist) {
+    __shared__ double sm[32];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = b[i];
+        x[i] = 0.0;
+        r[i] = v;
+        p[i] = v;
+        acc += v * v;
+    }
+    const double bs = tb_block_sum(acc, sm);
+    cg_finish<0>(bs, st, partials, ticket, sm, dist);
+}
+
+// ---- init fused with the backward-Euler right-hand side: r = p = M*phi (+ bS), x = 0 ----------------
+// ("b = M u_{n-1}" + add!(b, source), src/solver/time/euler.jl:85-91)
+__global__ void __launch_bounds__(256)
+    k_cg_init_Mphi(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ Mval,
+                   const double *__restrict__ phi, const double *__restrict__ bS, double *__restrict__ x,
+                   double *__restrict__ r, double *__restrict__ p, int64_t nrows, int64_t nslices, CGState *st,
+                   double *partials, unsigned *ticket, bool dist) {
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    for (int64_t s = warp; s < nslices; s += nwarps) {
+        double v = tb_sell_row(slice_ptr, col, Mval, phi, s, lane);
+        const int64_t row = s * TB_SLICE + lane;
+        if (row < nrows) {
+            if (bS) v += bS[row];
+            x[row] = 0.0;
+            r[row] = v;
+            p[row] = v;
+            acc += v * v;
+        }
+    }
+    const double bs = tb_block_sum(acc, sm);
+    cg_finish<0>(bs, st, partials, ticket, sm, dist);
+}
+
+// ---- Ap = A p, p.Ap -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_cg_spmv_dot(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ val,
+                  const double *__restrict__ p, double *__restrict__ Ap, int64_t nrows, int64_t nslices, CGState *st,
+                  double *partials, unsigned *ticket, bool dist) {
+    if (st->done) return;
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    for (int64_t s = warp; s < nslices; s += nwarps) {
+        const double v = tb_sell_row(slice_ptr, col, val, p, s, lane);
+        const int64_t row = s * TB_SLICE + lane;
+        if (row < nrows) {
+            Ap[row] = v;
+            acc += p[row] * v;
+        }
+    }
+    const double bs = tb_block_sum(acc, sm);
+    cg_finish<1>(bs, st, partials, ticket, sm, dist);
+}
+
+// ---- x += alpha p; r -= alpha Ap; r.r  (128-bit loads/stores) --------------------------------------
+__global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                                               const double *__restrict__ Ap, int64_t n, CGState *st, double *partials,
+                                               unsigned *ticket, bool dist) {
+    if (st->done) return;
+    __shared__ double sm[32];
+    const double alpha = st->alpha;
+    const int64_t n2 = n >> 1;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 xv = reinterpret_cast<double2 *>(x)[i], rv = reinterpret_cast<double2 *>(r)[i];
+        const double2 pv = reinterpret_cast<const double2 *>(p)[i], av = reinterpret_cast<const double2 *>(Ap)[i];
+        xv.x += alpha * pv.x;
+        xv.y += alpha * pv.y;
+        rv.x -= alpha * av.x;
+        rv.y -= alpha * av.y;
+        reinterpret_cast<double2 *>(x)[i] = xv;
+        reinterpret_cast<double2 *>(r)[i] = rv;
+        acc += rv.x * rv.x;
+        acc += rv.y * rv.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * Ap[i];
+        x[i] = xn;
+        r[i] = rn;
+        acc += rn * rn;
+    }
+    const double bs = tb_block_sum(acc, sm);
+    cg_finish<2>(bs, st, partials, ticket, sm, dist);
+}
+
+// ---- p = r + beta p ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cg_p(const double *__restrict__ r, double *__restrict__ p, int64_t n,
+                                              const CGState *st) {
+    if (st->done) return;
+    const double beta = st->beta;
+    const int64_t n2 = n >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 rv = reinterpret_cast<const double2 *>(r)[i];
+        double2 pv = reinterpret_cast<double2 *>(p)[i];
+        pv.x = rv.x + beta * pv.x;
+        pv.y = rv.y + beta * pv.y;
+        reinterpret_cast<double2 *>(p)[i] = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+}
+
+static int32_t cg_allreduce_then(tb_ctx *ctx, int which) {
+    TB_NCCL(ncclAllReduce(ctx->d_cg->local, ctx->d_cg->local, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    TB_LAUNCH(ctx, k_cg_scalar, 1, 1, 0, ctx->d_cg, which);
+    return TB_OK;
+}
+
+// b != NULL: solve A x = b.  b == NULL: right-hand side is M*phi (+ bS), built inside the init kernel.
+int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
+                       double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
+                       int32_t *converged) {
+    const tb_pattern *pat = A->pat;
+    const int64_t n = pat->nrows;
+    TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
+    double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
+    CGState *st = ctx->d_cg;
+    const bool dist = ctx->has_comm && ctx->nranks > 1;
+    double *part = ctx->d_partials;
+    unsigned *tick = ctx->d_ticket;
+    const int grid_v = tb_grid_for(ctx, n / 2 + 1, 256, 8);
+    const int grid_s = tb_grid_for(ctx, pat->nslices * 32, 256, 8);
+
+    TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);
+    if (b) {
+        TB_LAUNCH(ctx, k_cg_init_b, grid_v, 256, 0, b, x, r, p, n, st, part, tick, dist);
+    } else {
+        if (M->pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, M->pat, phi));
+        TB_LAUNCH(ctx, k_cg_init_Mphi, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
+                  pat->nslices, st, part, tick, dist);
+    }
+    if (dist) TB_TRY(cg_allreduce_then(ctx, 0));
+
+    int64_t enq = 0;
+    int64_t chunk = ctx->last_cg_iters + 1;
+    if (chunk < 2) chunk = 2;
+    CGState *h = ctx->h_cg;
+    for (;;) {
+        if (chunk > itmax - enq) chunk = itmax - enq;
+        for (int64_t k = 0; k < chunk; k++) {
+            if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));
+            TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n, pat->nslices,
+                      st, part, tick, dist);
+            if (dist) TB_TRY(cg_allreduce_then(ctx, 1));
+            TB_LAUNCH(ctx, k_cg_xr, grid_v, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist);
+            if (dist) TB_TRY(cg_allreduce_then(ctx, 2));
+            TB_LAUNCH(ctx, k_cg_p, grid_v, 256, 0, r, p, n, st);
+        }
+        enq += chunk;
+        TB_CUDA(cudaMemcpyAsync(h, st, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h->done || enq >= itmax) break;
+        chunk = 4;
+    }
+    ctx->last_cg_iters = h->iter;
+    if (iters) *iters = h->iter;
+    if (rnorm) *rnorm = h->rnorm;
+    if (converged) *converged = h->solved;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol,
+                               double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
+                               int32_t *converged) {
+    TB_REQUIRE(ctx && A && b && x, "tb_cg_solve: NULL argument");
+    TB_REQUIRE(bcol >= 0 && bcol < b->ncols && xcol >= 0 && xcol < x->ncols, "tb_cg_solve: column out of range");
+    TB_REQUIRE(b->n >= A->pat->nrows && x->n >= A->pat->nrows, "tb_cg_solve: vector shorter than the operator");
+    TB_REQUIRE(itmax >= 0, "tb_cg_solve: itmax must be >= 0");
+    TB_DEV(ctx);
+    return tb_cg_run_impl(ctx, A, b->d + (size_t)bcol * b->ld, nullptr, nullptr, nullptr, x->d + (size_t)xcol * x->ld, atol,
+                          rtol, itmax, iters, rnorm, converged);
+}

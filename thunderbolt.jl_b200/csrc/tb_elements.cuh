@@ -1,0 +1,331 @@
+// Element kernels of the three weak forms, as host/device inline templates:
+//   mass       Me[i][j] += rho (Ni Nj) dOmega                    src/modeling/core/mass.jl:28-43
+//   diffusion  Ke[i][j] -= ((gradNj . D) . gradNi) dOmega        src/modeling/core/diffusion.jl:28-50, utils.jl:409
+//   source     be[j]    += f(x_q,t) Nj dOmega                    src/modeling/core/analytical_coefficient.jl:80-101
+// with the geometry mapping of Ferrite's reinit! (device twin src/ferrite-addons/PR883.jl:254-291,367-387):
+//   J = sum_a x_a (x) dM_a/dxi,  dOmega = det(J) w_q,  gradN_a = dN_a/dxi . J^-1.
+// Quadrature/shape tables follow Ferrite 1.6.0 (QuadratureRule, Lagrange{refshape,1}); see tb_build_tables.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TB_HD __host__ __device__ __forceinline__
+#else
+#define TB_HD inline
+#endif
+
+#define TB_MAXQ 64
+
+struct tb_elem_tables {
+    int nv, dim, nq, pad;
+    double w[TB_MAXQ];
+    double N[TB_MAXQ * 8];        // N[q*nv + a]
+    double dN[TB_MAXQ * 8 * 3];   // dN[(q*nv + a)*dim + d]
+    double xi[TB_MAXQ * 3];       // reference points (for tb_quadrature)
+};
+
+// ---- host-side table construction --------------------------------------------------------------
+static inline int tb_gauss_1d(int order, double *p, double *w) {
+    switch (order) {
+    case 1: p[0] = 0.0; w[0] = 2.0; return 1;
+    case 2: p[0] = -0.5773502691896257645; p[1] = 0.5773502691896257645; w[0] = w[1] = 1.0; return 2;
+    case 3:
+        p[0] = -0.7745966692414833770; p[1] = 0.0; p[2] = 0.7745966692414833770;
+        w[0] = w[2] = 0.5555555555555555556; w[1] = 0.8888888888888888889; return 3;
+    case 4:
+        p[0] = -0.8611363115940525752; p[1] = -0.3399810435848562648;
+        p[2] = 0.3399810435848562648;  p[3] = 0.8611363115940525752;
+        w[0] = w[3] = 0.3478548451374538574; w[1] = w[2] = 0.6521451548625461426; return 4;
+    default: return 0;
+    }
+}
+
+// celltype: 0 quad, 1 hex, 2 tri, 3 tet.  Returns 0 on success.
+static inline int tb_build_tables(int celltype, int qorder, tb_elem_tables *T) {
+    const int dim = (celltype == 0 || celltype == 2) ? 2 : 3;
+    const int nv = celltype == 0 ? 4 : celltype == 1 ? 8 : celltype == 2 ? 3 : 4;
+    T->nv = nv;
+    T->dim = dim;
+    T->pad = 0;
+    int nq = 0;
+    if (celltype == 0 || celltype == 1) {
+        double p1[4], w1[4];
+        const int n = tb_gauss_1d(qorder, p1, w1);
+        if (!n) return 1;
+        for (int k = 0; k < (dim == 3 ? n : 1); k++)
+            for (int j = 0; j < n; j++)
+                for (int i = 0; i < n; i++) {   // first coordinate fastest
+                    T->xi[nq * dim + 0] = p1[i];
+                    T->xi[nq * dim + 1] = p1[j];
+                    if (dim == 3) T->xi[nq * dim + 2] = p1[k];
+                    T->w[nq] = dim == 3 ? w1[i] * w1[j] * w1[k] : w1[i] * w1[j];
+                    nq++;
+                }
+    } else if (celltype == 3) {
+        if (qorder == 1) {
+            T->xi[0] = T->xi[1] = T->xi[2] = 0.25;
+            T->w[0] = 1.0 / 6.0;
+            nq = 1;
+        } else if (qorder == 2) {
+            const double a = 0.1381966011250105, b = 0.5854101966249685;
+            const double P[4][3] = {{a, a, a}, {a, a, b}, {a, b, a}, {b, a, a}};
+            for (int q = 0; q < 4; q++) {
+                for (int d = 0; d < 3; d++) T->xi[q * 3 + d] = P[q][d];
+                T->w[q] = 1.0 / 24.0;
+            }
+            nq = 4;
+        } else return 1;
+    } else {
+        if (qorder == 1) {
+            T->xi[0] = T->xi[1] = 1.0 / 3.0;
+            T->w[0] = 0.5;
+            nq = 1;
+        } else if (qorder == 2) {
+            const double P[3][2] = {{1.0 / 6.0, 1.0 / 6.0}, {2.0 / 3.0, 1.0 / 6.0}, {1.0 / 6.0, 2.0 / 3.0}};
+            for (int q = 0; q < 3; q++) {
+                T->xi[q * 2] = P[q][0];
+                T->xi[q * 2 + 1] = P[q][1];
+                T->w[q] = 1.0 / 6.0;
+            }
+            nq = 3;
+        } else return 1;
+    }
+    T->nq = nq;
+    for (int q = 0; q < nq; q++) {
+        const double *xi = T->xi + q * dim;
+        double *N = T->N + q * nv, *dN = T->dN + q * nv * dim;
+        if (celltype == 0) {
+            const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+            for (int a = 0; a < 4; a++) {
+                N[a] = 0.25 * (1 + sx[a] * xi[0]) * (1 + sy[a] * xi[1]);
+                dN[a * 2 + 0] = 0.25 * sx[a] * (1 + sy[a] * xi[1]);
+                dN[a * 2 + 1] = 0.25 * (1 + sx[a] * xi[0]) * sy[a];
+            }
+        } else if (celltype == 1) {
+            const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1},
+                         sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+            for (int a = 0; a < 8; a++) {
+                const double fx = 1 + sx[a] * xi[0], fy = 1 + sy[a] * xi[1], fz = 1 + sz[a] * xi[2];
+                N[a] = 0.125 * fx * fy * fz;
+                dN[a * 3 + 0] = 0.125 * sx[a] * fy * fz;
+                dN[a * 3 + 1] = 0.125 * fx * sy[a] * fz;
+                dN[a * 3 + 2] = 0.125 * fx * fy * sz[a];
+            }
+        } else if (celltype == 3) {
+            N[0] = 1 - xi[0] - xi[1] - xi[2]; N[1] = xi[0]; N[2] = xi[1]; N[3] = xi[2];
+            const double g[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            for (int a = 0; a < 4; a++)
+                for (int d = 0; d < 3; d++) dN[a * 3 + d] = g[a][d];
+        } else {
+            N[0] = xi[0]; N[1] = xi[1]; N[2] = 1 - xi[0] - xi[1];
+            const double g[3][2] = {{1, 0}, {0, 1}, {-1, -1}};
+            for (int a = 0; a < 3; a++)
+                for (int d = 0; d < 2; d++) dN[a * 2 + d] = g[a][d];
+        }
+    }
+    return 0;
+}
+
+// ---- geometry at one quadrature point --------------------------------------------------------------
+// X[(a*DIM+d)*XS]: vertex coordinates (XS = element stride of the staging buffer, 1 on the host).
+// dNq: dN/dxi of this point [a*DIM+d].  G (nullable): spatial gradients [a*DIM+d].  Returns det J.
+template <int NV, int DIM, int XS, bool WANT_G>
+TB_HD double tb_map_qp(const double *X, const double *dNq, double *G) {
+    double J[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < DIM * DIM; i++) J[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NV; a++)
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+            const double xa = X[(a * DIM + i) * XS];
+#pragma unroll
+            for (int j = 0; j < DIM; j++) J[i * DIM + j] += xa * dNq[a * DIM + j];
+        }
+    double det;
+    double Ji[DIM * DIM];
+    if constexpr (DIM == 2) {
+        det = J[0] * J[3] - J[1] * J[2];
+        if (WANT_G) {
+            Ji[0] = J[3] / det; Ji[1] = -J[1] / det; Ji[2] = -J[2] / det; Ji[3] = J[0] / det;
+        }
+    } else {
+        const double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+        det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+        if (WANT_G) {
+            Ji[0] = c00 / det; Ji[1] = (J[2] * J[7] - J[1] * J[8]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+            Ji[3] = c01 / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (J[2] * J[3] - J[0] * J[5]) / det;
+            Ji[6] = c02 / det; Ji[7] = (J[1] * J[6] - J[0] * J[7]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+        }
+    }
+    if (WANT_G) {
+#pragma unroll
+        for (int a = 0; a < NV; a++)
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < DIM; j++) s += dNq[a * DIM + j] * Ji[j * DIM + i];
+                G[a * DIM + i] = s;
+            }
+    }
+    return det;
+}
+
+// index of (i,j), i <= j, in the packed upper triangle
+template <int NV> TB_HD constexpr int tb_sym(int i, int j) { return i * NV - (i * (i - 1)) / 2 + (j - i); }
+
+// ---- diffusion tensor at a quadrature point ---------------------------------------------------------
+// kind 0 scalar, 1 constant tensor, 2 spectral (lambda[3] + per cell per node f,s,n); see tbolt_b200.h.
+// D = kappa/(Cm*chi) (coefficients.jl:152-162).  Spectral: FieldCoefficient interpolation
+// (coefficients.jl:88-99), orthogonalize_system (microstructure.jl:176-187, utils.jl:131-139),
+// sum lambda_i v_i (x) v_i (microstructure.jl:136-138).
+template <int NV, int DIM>
+TB_HD void tb_eval_D(int kind, const double *data, double cmchi, int64_t cell, const double *Nq, double *D) {
+    if (kind == 0) {
+#pragma unroll
+        for (int i = 0; i < DIM * DIM; i++) D[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; i++) D[i * DIM + i] = data[0] / cmchi;
+    } else if (kind == 1) {
+#pragma unroll
+        for (int i = 0; i < DIM * DIM; i++) D[i] = data[i] / cmchi;
+    } else if constexpr (DIM == 3) {
+        const double *lam = data;
+        const double *fsn = data + 3 + cell * NV * 9;
+        double v[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) v[m][d] = 0.0;
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int a = 0; a < NV; a++)
+#pragma unroll
+                for (int d = 0; d < 3; d++) v[m][d] += Nq[a] * fsn[a * 9 + m * 3 + d];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const double nrm = sqrt(v[m][0] * v[m][0] + v[m][1] * v[m][1] + v[m][2] * v[m][2]);
+#pragma unroll
+            for (int d = 0; d < 3; d++) v[m][d] /= nrm;
+        }
+        double w1[3], w2[3], w3[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) w1[d] = v[0][d];
+        const double d12 = w1[0] * v[1][0] + w1[1] * v[1][1] + w1[2] * v[1][2];
+#pragma unroll
+        for (int d = 0; d < 3; d++) w2[d] = v[1][d] - d12 * w1[d];
+        const double d13 = w1[0] * v[2][0] + w1[1] * v[2][1] + w1[2] * v[2][2];
+        const double d23 = w2[0] * v[2][0] + w2[1] * v[2][1] + w2[2] * v[2][2];
+#pragma unroll
+        for (int d = 0; d < 3; d++) w3[d] = v[2][d] - d13 * w1[d] - d23 * w2[d];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                D[i * DIM + j] = (lam[0] * w1[i] * w1[j] + lam[1] * w2[i] * w2[j] + lam[2] * w3[i] * w3[j]) / cmchi;
+    }
+}
+
+// ---- element matrices (packed upper triangle, NV*(NV+1)/2 entries) -----------------------------------
+template <int NV, int DIM, int XS>
+TB_HD void tb_element_mass(const tb_elem_tables *T, const double *X, double rho, double *acc) {
+#pragma unroll
+    for (int i = 0; i < NV * (NV + 1) / 2; i++) acc[i] = 0.0;
+    for (int q = 0; q < T->nq; q++) {
+        const double *Nq = T->N + q * NV;
+        const double dO = tb_map_qp<NV, DIM, XS, false>(X, T->dN + q * NV * DIM, nullptr) * T->w[q];
+#pragma unroll
+        for (int i = 0; i < NV; i++)
+#pragma unroll
+            for (int j = i; j < NV; j++) acc[tb_sym<NV>(i, j)] += rho * (Nq[i] * Nq[j]) * dO;
+    }
+}
+
+template <int NV, int DIM, int XS>
+TB_HD void tb_element_diffusion(const tb_elem_tables *T, const double *X, int kind, const double *data, double cmchi,
+                                int64_t cell, double *acc) {
+#pragma unroll
+    for (int i = 0; i < NV * (NV + 1) / 2; i++) acc[i] = 0.0;
+    for (int q = 0; q < T->nq; q++) {
+        double G[NV * DIM], D[DIM * DIM];
+        const double dO = tb_map_qp<NV, DIM, XS, true>(X, T->dN + q * NV * DIM, G) * T->w[q];
+        tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T->N + q * NV, D);
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            if (kind == 0) {
+                // _inner_product_helper(a, B::AbstractFloat, c) = a . c * B
+#pragma unroll
+                for (int i = 0; i <= j; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) s += G[j * DIM + d] * G[i * DIM + d];
+                    acc[tb_sym<NV>(i, j)] -= (s * D[0]) * dO;
+                }
+            } else {
+                double gD[DIM];   // gradNj . D
+#pragma unroll
+                for (int l = 0; l < DIM; l++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) s += G[j * DIM + k] * D[k * DIM + l];
+                    gD[l] = s;
+                }
+#pragma unroll
+                for (int i = 0; i <= j; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < DIM; l++) s += gD[l] * G[i * DIM + l];
+                    acc[tb_sym<NV>(i, j)] -= s * dO;
+                }
+            }
+        }
+    }
+}
+
+// ---- built-in stimulus families (see tbolt_b200.h TB_SRC_*) --------------------------------------------
+template <int DIM> TB_HD double tb_source_eval(int kind, const double *prm, const double *x, double t) {
+    double n2 = 0.0, mx = -INFINITY;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        n2 += x[d] * x[d];
+        mx = x[d] > mx ? x[d] : mx;
+    }
+    switch (kind) {
+    case 1: return (mx < prm[0] && t < prm[1]) ? prm[2] : 0.0;
+    case 2: return (sqrt(n2) < prm[0] && t < prm[1]) ? prm[2] : 0.0;
+    case 3: return cos(2.0 * 3.14159265358979323846 * t) * exp(-n2);
+    case 4: return sqrt(n2) + t;
+    case 5: return (t <= prm[1] && x[0] < prm[0]) ? prm[2] / prm[3] * exp(t / prm[3]) : 0.0;
+    default: return 0.0;
+    }
+}
+
+// fq != nullptr: host-evaluated f at this cell's quadrature points
+template <int NV, int DIM, int XS>
+TB_HD void tb_element_source(const tb_elem_tables *T, const double *X, int kind, const double *prm, double t,
+                             const double *fq, double *be) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) be[j] = 0.0;
+    for (int q = 0; q < T->nq; q++) {
+        const double *Nq = T->N + q * NV;
+        const double dO = tb_map_qp<NV, DIM, XS, false>(X, T->dN + q * NV * DIM, nullptr) * T->w[q];
+        double fx;
+        if (fq) {
+            fx = fq[q];
+        } else {
+            double x[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) x[d] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NV; a++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) x[d] += Nq[a] * X[(a * DIM + d) * XS];
+            fx = tb_source_eval<DIM>(kind, prm, x, t);
+        }
+#pragma unroll
+        for (int j = 0; j < NV; j++) be[j] += fx * Nq[j] * dO;
+    }
+}

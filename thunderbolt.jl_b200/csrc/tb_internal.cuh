@@ -1,0 +1,248 @@
+// Internal declarations shared by the translation units of libtbolt_b200.so.
+// Nothing in here is part of the ABI; the ABI is include/tbolt_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/tbolt_b200.h"
+
+#define TB_SLICE 32            // SELL slice height = warp size
+#define TB_MAX_PARTIALS 4096   // upper bound on blocks of any reducing kernel
+#define TB_MAXROW 128          // max nonzeros per row the device pattern builder supports
+
+int32_t tb_fail(int32_t code, const char *fmt, ...);
+
+#define TB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return tb_fail(e__ == cudaErrorMemoryAllocation ? TB_ERR_NOMEM : TB_ERR_CUDA, "%s:%d: %s -> %s", \
+                           __FILE__, __LINE__, #call, cudaGetErrorString(e__));                         \
+    } while (0)
+
+#define TB_NCCL(call)                                                                                   \
+    do {                                                                                                \
+        ncclResult_t r__ = (call);                                                                      \
+        if (r__ != ncclSuccess)                                                                         \
+            return tb_fail(TB_ERR_COMM, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+    } while (0)
+
+#define TB_REQUIRE(cond, ...)                                  \
+    do {                                                       \
+        if (!(cond)) return tb_fail(TB_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define TB_TRY(call)                   \
+    do {                               \
+        int32_t s__ = (call);          \
+        if (s__ != TB_OK) return s__;  \
+    } while (0)
+
+// launch bookkeeping: every kernel launch of the library goes through TB_LAUNCH so that
+// tb_launch_count() is an honest count and launch errors surface immediately.
+#define TB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+    do {                                                                                \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+        (ctx)->launches++;                                                              \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess)                                                         \
+            return tb_fail(TB_ERR_CUDA, "%s:%d: launch of %s failed: %s", __FILE__, __LINE__, #kernel, \
+                           cudaGetErrorString(e__));                                    \
+    } while (0)
+
+struct tb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    size_t total_mem = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    // scratch for deterministic two-stage reductions (block partials + last-block ticket)
+    double *d_partials = nullptr;   // 4 * TB_MAX_PARTIALS
+    unsigned *d_ticket = nullptr;   // 8 tickets
+    // CG workspace (grown on demand): r, p, Ap as one tb_vec-like allocation
+    double *d_cgwork = nullptr;
+    int64_t cgwork_ld = 0;
+    struct CGState *d_cg = nullptr;   // device scalars of the running solve
+    struct CGState *h_cg = nullptr;   // pinned mirror
+    double *d_scalar = nullptr;       // small device scratch (16 doubles)
+    double *h_scalar = nullptr;       // pinned
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+    int assembly_mode = 0;
+    int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
+    // communicator
+    bool has_comm = false;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+};
+
+// device-resident scalars of a CG solve; mirrors the locals of Krylov.jl's cg!
+struct CGState {
+    double gamma;       // r.r of the current iterate
+    double pAp;
+    double alpha;
+    double beta;
+    double gamma_next;
+    double rnorm;
+    double eps;         // atol + rtol*|r0|
+    double atol, rtol;
+    double local[2];    // per-rank partial sums awaiting the allreduce (multi-GPU)
+    long long iter;
+    long long itmax;
+    int done;           // solved || tired
+    int solved;
+    int pad[2];
+};
+
+struct tb_vec {
+    tb_ctx *ctx;
+    int64_t n;
+    int ncols;
+    int64_t ld;   // padded column stride (multiple of 32 doubles)
+    double *d;
+};
+
+struct tb_mesh {
+    tb_ctx *ctx;
+    int celltype, nv, dim;
+    int64_t ncells, nnodes;
+    int64_t ndofs;        // all dofs referenced by celldofs (owned + ghosts)
+    int64_t ndofs_owned;  // rows this rank owns (== ndofs on one GPU)
+    int *d_conn = nullptr;      // ncells*nv node ids
+    int *d_celldofs = nullptr;  // ncells*nv dof ids
+    double *d_coords = nullptr; // nnodes*dim
+    int *d_node2dof = nullptr;  // nnodes, -1 if the node carries no dof
+    int64_t *d_ghost_global = nullptr;
+    int64_t nghost = 0;
+    int64_t dof_lo = 0;         // global id of local dof 0
+};
+
+struct tb_halo {
+    int nneigh = 0;
+    std::vector<int> ranks;
+    std::vector<int64_t> send_ptr, recv_ptr;
+    int *d_send_rows = nullptr;   // concatenated local row ids to pack
+    double *d_sendbuf = nullptr;
+    int64_t nsend = 0, nrecv = 0;
+};
+
+// sparsity pattern shared by M, K and A (sliced ELL image of the reference's CSR pattern)
+struct tb_pattern {
+    tb_ctx *ctx;
+    int64_t nrows, ncols, nnz;
+    int64_t nslices;
+    int64_t sell_len;             // padded number of stored entries
+    int64_t *d_rowptr = nullptr;  // nrows+1 (CSR row pointers, 0-based)
+    int64_t *d_slice_ptr = nullptr; // nslices+1 offsets into col/val, multiples of 32
+    int *d_col = nullptr;         // sell_len column ids (padding: a valid column, value 0)
+    int refcount = 1;
+    tb_halo halo;
+    // element colouring cache (assembly mode 1)
+};
+
+struct tb_csr {
+    tb_pattern *pat;
+    double *d_val;   // sell_len
+};
+
+struct tb_monodomain {
+    tb_ctx *ctx;
+    const tb_csr *M, *K;
+    tb_csr *A;
+    int model;
+    double params[40];
+    int nparams;
+    int phi_idx;
+    double atol, rtol;
+    int64_t itmax;
+    int substeps;
+    double threshold;
+    const tb_vec *bS;
+    int bS_col;
+    double dt_last;
+    tb_vec *b, *x;
+    bool timing;
+    cudaEvent_t ev[4];
+    double section_ms[3];
+};
+
+static inline int64_t tb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ double tb_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double tb_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Sum over the block; result valid in every thread of warp 0.  `sm` has >= 32 doubles.
+__device__ __forceinline__ double tb_block_sum(double v, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = tb_warp_sum(v);
+    __syncthreads();   // protect sm against a previous use
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    v = (warp == 0 && lane < nw) ? sm[lane] : 0.0;
+    if (warp == 0) v = tb_warp_sum(v);
+    return v;
+}
+__device__ __forceinline__ double tb_block_max(double v, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = tb_warp_max(v);
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    v = (warp == 0 && lane < nw) ? sm[lane] : -INFINITY;
+    if (warp == 0) v = tb_warp_max(v);
+    return v;
+}
+
+// Deterministic grid reduction: every block deposits its partial, the last block to arrive
+// (ticket) sums all partials in a fixed order.  Returns true in ALL threads of the last block,
+// with *total valid in thread 0 of that block.  The ticket resets itself for the next launch.
+__device__ __forceinline__ bool tb_grid_sum(double block_value /* valid in thread 0 */, double *partials,
+                                            unsigned *ticket, double *sm, double *total) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = block_value;
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    double s = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += ((volatile double *)partials)[i];
+    s = tb_block_sum(s, sm);
+    if (threadIdx.x == 0) *total = s;
+    return true;
+}
+
+// internal cross-TU helpers
+int32_t tb_pattern_release(tb_pattern *p);
+int32_t tb_ctx_ensure_cgwork(tb_ctx *ctx, int64_t n);
+int32_t tb_halo_exchange(tb_ctx *ctx, const tb_pattern *pat, double *x);
+int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
+                       double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
+                       int32_t *converged);
+int32_t tb_spmv_raw(tb_ctx *ctx, const tb_csr *A, double *x, double *y);
+int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int nparams, double *u, int64_t n, int64_t ld,
+                         int phi_idx, const double *phi_src, double t, double dt, int substeps, double thr,
+                         double *max_dphi);
+int tb_grid_for(tb_ctx *ctx, int64_t work_items, int block, int blocks_per_sm);
