@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- monodomain DoF*steps/s on B200 (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c1] [--impl b200|reference]
+
+A "step" is one LieTrotterGodunov step (backward-Euler diffusion solved with CG + ionic cell sweep)
+over the whole mesh.  Default workload = BASELINE config 5, the configuration the headline target is
+quoted on: 3D hexahedral slab 512x512x384 (101,320,065 nodes), FHN, fp64 -- it fits one 180 GB B200.
+N > 1 (torchrun, one rank per GPU) partitions the SAME mesh by dof ownership (z-slabs): strong scaling.
+
+Printed JSON line (rank 0): see the contract in the task statement; additional keys `roofline`
+(dominant kernel = SpMV inside CG, timed live with CUDA events on the library's stream),
+`cpu_baseline` (the oracle = CPU restatement of the reference's algorithm, timed on this box's host
+cores on a bounded z-slab of the same mesh) and `e2e` (same metric through tb_monodomain_step_host:
+pinned host buffers, H2D + D2H of the state every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
+
+# kappa chosen so that kappa*dt/h^2 equals the tutorial's (ep01_spiral-wave.jl: 4.5e-5, 2e-5 on h = 2.5/256, dt = 1)
+WORKLOADS = {
+    "c5": dict(name="C5 3D hex slab 512x512x384 FHN (BASELINE config 5)", celltype="hex", nel=(512, 512, 384), h=0.25,
+               model="fhn", kappa=(0.0295, 0.0131, 0.0131), dt=1.0, substeps=1),
+    "c2": dict(name="C2 3D hex slab 128x128x32 PCG2019 (BASELINE config 2)", celltype="hex", nel=(128, 128, 32), h=0.25,
+               model="pcg2019", kappa=(0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24), 0.019 * 0.24 / (0.019 + 0.24)),
+               dt=0.01, substeps=1),
+    "c1": dict(name="C1 2D quad 256x256 FHN spiral wave (BASELINE config 1)", celltype="quad", nel=(256, 256), h=2.5 / 256,
+               model="fhn", kappa=(4.5e-5, 2.0e-5), dt=1.0, substeps=1),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def initial_state(x, model, lengths, tb):
+    """Spiral-wave style initial condition of the tutorial (ep01_spiral-wave.jl:113-118) scaled to the box."""
+    n = x.shape[0]
+    if model == "fhn":
+        u = np.zeros(2 * n)
+        u[:n] = np.where((x[:, 0] <= 0.5 * lengths[0]) & (x[:, 1] <= 0.5 * lengths[1]), 1.0, 0.0)
+        u[n:] = np.where(x[:, 1] >= 0.5 * lengths[1], 0.1, 0.0)
+        return u
+    u = np.repeat(tb.default_initial_state(tb.PCG2019()), n)
+    u[:n] = np.where(np.all(x < 1.5, axis=1), 20.0, u[:n])   # a depolarised corner instead of a stimulus current
+    return u
+
+
+def bytes_per_row(nnz, n):
+    """SpMV = nnzr*12 + 8 (rowptr) + 8 (x) + 8 (y) per row."""
+    return nnz / n * 12.0 + 24.0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import thunderbolt_jl_b200 as tb
+
+    W = WORKLOADS[args.workload]
+    nel = tuple(int(v) for v in args.grid.split(",")) if args.grid else W["nel"]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = tb.B200Device(local)
+    tb.set_default_device(dev)
+    if world > 1:
+        from thunderbolt_jl_b200 import dist as tbd
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        tbd.init_comm(dev, dist)
+
+    ct = tb.Hexahedron if W["celltype"] == "hex" else tb.Quadrilateral
+    dim = len(nel)
+    lengths = tuple(n * W["h"] for n in nel)
+    t_setup = time.time()
+    mesh = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
+    N_global = mesh.ndofs
+    ion = tb.FHNModel() if W["model"] == "fhn" else tb.PCG2019()
+    ns = tb.num_states(ion)
+    if world > 1:
+        part = tbd.partition_mesh(dev, mesh, dist)          # z-slab ownership, halo plan
+        mesh.free()
+        mesh = part.mesh
+    M = tb.B200CSRMatrix.from_mesh(dev, mesh)
+    K = M.like()
+    tb.core.assemble_mass(dev, mesh, M, 2, 1.0)
+    D = np.diag(W["kappa"][:dim])
+    tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_TENSOR, D, 1.0)
+    if world > 1:
+        part.attach_halo(M)
+    st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+    st.set_cg(SQRT_EPS, SQRT_EPS, None)
+    st.set_cell_solver(W["substeps"], 0.1)
+    x = mesh.dof_coords()
+    n_local = mesh.ndofs                                    # owned + ghosts
+    n_owned = mesh.ndofs_owned
+    u0 = initial_state(x, W["model"], lengths, tb)
+    del x
+    u = tb.B200Vector.from_host(dev, u0, ns)
+    nnz = M.nnz
+    dev.sync()
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        dev.sync()
+        if world > 1:
+            dist.barrier()
+        dev.sync()
+
+    t, dt = 0.0, W["dt"]
+    iters = []
+    for _ in range(args.warmup):
+        it, rn, conv = st.step(u, t, dt)
+        t += dt
+    # ---- timed region: exactly K steps, device timer, max over ranks ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev.profile_enable(True)
+    launches0 = dev.launch_count()
+    barrier()
+    dev.timer_start()
+    conv_all = True
+    for _ in range(args.steps):
+        it, rn, conv = st.step(u, t, dt)
+        t += dt
+        iters.append(it)
+        conv_all &= conv
+    ms = dev.timer_stop()
+    barrier()
+    launches = dev.launch_count() - launches0
+    spmv_ms, spmv_n = dev.profile_get()
+    dev.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = N_global * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (SpMV + fused p.Ap inside CG) ----
+    peak, peak_src = peaks()
+    rows_local = n_owned
+    spmv_bytes = bytes_per_row(nnz, rows_local) * rows_local
+    avg_spmv_ms = spmv_ms / max(spmv_n, 1)
+    achieved = spmv_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None
+    k_mean = float(np.mean(iters))
+    step_bytes = (2 * ns * 8 + bytes_per_row(nnz, rows_local) * (1 + k_mean) + 72.0 * k_mean) * rows_local
+    roofline = {"bound": "hbm", "kernel": "k_cg_spmv_dot (SELL-32 SpMV fused with p.Ap)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms, "launches_timed": spmv_n,
+                "spmv_share_of_step": spmv_ms / ms if ms else None,
+                "step_bytes_per_dof": step_bytes / rows_local,
+                "step_achieved_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 * 1.0,
+                "step_frac_of_peak": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak}
+
+    # ---- e2e: same step through the host-buffer entry point (pinned host memory, H2D + D2H every step) ----
+    e2e = None
+    if world == 1:
+        hin = torch.empty(ns * n_local, dtype=torch.float64, pin_memory=True)
+        hout = torch.empty(ns * n_local, dtype=torch.float64, pin_memory=True)
+        hin.numpy()[:] = u.to_host()
+        ke = max(1, min(args.steps, args.e2e_steps))
+        st.step_host(u, hin.numpy(), hout.numpy(), t, dt)            # warm-up
+        dev.sync()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            st.step_host(u, hin.numpy(), hout.numpy(), t, dt)
+            hin, hout = hout, hin
+            t += dt
+        dev.sync()
+        te = time.perf_counter() - t0
+        e2e = {"value": N_global * ke / te, "unit": "DoF*steps/s", "h2d_bytes_per_step": ns * n_local * 8,
+               "d2h_bytes_per_step": ns * n_local * 8, "steps": ke, "api": "tb_monodomain_step_host (C ABI, pinned host buffers)"}
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded z-slab of the same mesh ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args, W, nel)
+
+    if rank == 0:
+        line = {
+            "metric": "monodomain DoF*steps/s", "value": value, "unit": "DoF*steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": W["name"] if not args.grid else f"{W['name']} [grid override {nel}]", "nel": list(nel),
+                       "dofs": N_global, "nnz": int(nnz) if world == 1 else None, "cell_model": W["model"], "dt": dt,
+                       "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "iters_per_step_mean": k_mean,
+                              "iters_min": int(min(iters)), "iters_max": int(max(iters)), "all_converged": bool(conv_all)},
+                       "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
+                       "parallelism": "single GPU" if world == 1 else f"dof-ownership z-slabs x{world}, NCCL halo + allreduce",
+                       "l2": "working set (matrix + vectors) is far larger than the 126 MB L2, no flush needed"
+                             if nnz * 12 > 4e8 else "working set fits L2: tb_l2_flush not applied between steps (steady-state regime)",
+                       "setup_s": t_setup},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, W, nel, all_threads=True):
+    """Oracle (CPU restatement of the reference's algorithm, threads over nodes/rows like the reference)
+    on a thin z-slab (or sub-square) of the SAME mesh spacing/physics: ~10-30 s of CPU work."""
+    import oracle as O
+    dim = len(nel)
+    if dim == 3:
+        snel = (min(nel[0], 512), min(nel[1], 512), min(nel[2], args.cpu_layers))
+        ct = O.HEX8
+    else:
+        snel = (min(nel[0], 256), min(nel[1], 256))
+        ct = O.QUAD4
+    lengths = tuple(n * W["h"] for n in snel)
+    m = O.generate_grid(ct, snel, (0.0,) * dim, lengths)
+    Mv = O.assemble_mass(m, 2)
+    Kv = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag(W["kappa"][:dim]))
+    model = O.FHN if W["model"] == "fhn" else O.PCG2019
+
+    class _T:
+        default_initial_state = staticmethod(lambda ion: O.default_initial_state(O.PCG2019))
+        PCG2019 = staticmethod(lambda: None)
+    u = initial_state(m.dof_coords, W["model"], lengths, _T)
+    # variant B of BASELINE.md: threaded vector ops (the stronger baseline); variant A (serial BLAS-1,
+    # what Krylov.jl does on Vector{Float64}) is reported beside it
+    out = {}
+    for name, thr in (("threaded_blas1", True), ("serial_blas1", False)):
+        orc = O.MonodomainOracle(m, model, O.default_params(model), Mv, Kv, substeps=W["substeps"], threaded_blas1=thr)
+        v = u.copy()
+        orc.step(v, 0.0, W["dt"])                       # warm-up (builds A)
+        t0 = time.perf_counter()
+        nst = args.cpu_steps
+        for s in range(nst):
+            orc.step(v, (s + 1) * W["dt"], W["dt"])
+        dtw = time.perf_counter() - t0
+        out[name] = m.ndofs * nst / dtw
+        out[name + "_iters"] = float(np.mean(orc.iters[1:]))
+    return {"value": out["threaded_blas1"], "unit": "DoF*steps/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{'x'.join(map(str, snel))} cells ({m.ndofs} DoFs) of the same mesh, {args.cpu_steps} steps after 1 warm-up; "
+                      f"oracle = C/OpenMP restatement of the reference's CPU algorithm (not Julia)",
+            "serial_blas1_value": out["serial_blas1"], "cg_iters_mean": out["threaded_blas1_iters"]}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is pure Julia
+    and there is no julia binary in this image (and nothing to compile into oracle/_ref), so this arm
+    times the oracle port with all host threads on a bounded sample, as the task statement prescribes."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    W = WORKLOADS[args.workload]
+    nel = tuple(int(v) for v in args.grid.split(",")) if args.grid else W["nel"]
+    import oracle as O
+    dim = len(nel)
+    snel = (min(nel[0], 512), min(nel[1], 512), min(nel[2], args.cpu_layers)) if dim == 3 else (min(nel[0], 256), min(nel[1], 256))
+    ct = O.HEX8 if dim == 3 else O.QUAD4
+    lengths = tuple(n * W["h"] for n in snel)
+    m = O.generate_grid(ct, snel, (0.0,) * dim, lengths)
+    Mv = O.assemble_mass(m, 2)
+    Kv = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag(W["kappa"][:dim]))
+    model = O.FHN if W["model"] == "fhn" else O.PCG2019
+
+    class _T:
+        default_initial_state = staticmethod(lambda ion: O.default_initial_state(O.PCG2019))
+        PCG2019 = staticmethod(lambda: None)
+    u = initial_state(m.dof_coords, W["model"], lengths, _T)
+    orc = O.MonodomainOracle(m, model, O.default_params(model), Mv, Kv, substeps=W["substeps"], threaded_blas1=True)
+    t = 0.0
+    for _ in range(args.warmup):
+        orc.step(u, t, W["dt"]); t += W["dt"]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.step(u, t, W["dt"]); t += W["dt"]
+    el = time.perf_counter() - t0
+    value = m.ndofs * args.steps / el
+    sample = f"{'x'.join(map(str, snel))} cells ({m.ndofs} DoFs) of the same mesh spacing and physics"
+    print(json.dumps({
+        "impl": "reference", "metric": "monodomain DoF*steps/s", "value": value, "unit": "DoF*steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": W["name"], "nel": list(nel), "sample": sample,
+                   "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "iters_per_step_mean": float(np.mean(orc.iters[-args.steps:]))}},
+        "cpu_baseline": {"value": value, "unit": "DoF*steps/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "DoF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--grid", default="", help="override cells per direction, e.g. 128,128,32")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-layers", type=int, default=2, help="z-layers of cells in the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        print("note: the timing rules ask for >= 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,10 @@ int32_t tb_timer_start(tb_ctx *ctx);
 int32_t tb_timer_stop(tb_ctx *ctx, double *elapsed_ms);
 /* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
 int32_t tb_launch_count(tb_ctx *ctx, int64_t *count);
+/* per-kernel timing of the dominant kernel (the SpMV inside CG): CUDA events around every launch that
+ * did work, accumulated since the last tb_profile_enable(ctx, 1).  bench.py's roofline.achieved. */
+int32_t tb_profile_enable(tb_ctx *ctx, int32_t on);
+int32_t tb_profile_get(tb_ctx *ctx, double *spmv_ms_total, int64_t *spmv_launches);
 /* overwrite a buffer larger than L2 so that the next timed kernel starts cold */
 int32_t tb_l2_flush(tb_ctx *ctx);
 /* multi-GPU: join a communicator of `nranks` one-process-per-GPU peers.  `nccl_unique_id` is the

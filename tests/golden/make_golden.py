@@ -1,0 +1,97 @@
+"""Generates the golden fixtures in this directory FROM THE ORACLE (the reference is pure Julia and
+cannot run in this image, so there is nothing else to generate them from -- see DESIGN.md "Oracle").
+They pin the oracle against accidental change and give the GPU tests input/output vectors that do
+not need /root/reference or the oracle build at run time.
+
+    python tests/golden/make_golden.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+import oracle as O  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+
+
+def activation_steps(phi_hist, thr):
+    """first step index n with phi(t_n) >= thr after having been below it; -1 if never."""
+    act = np.full(phi_hist.shape[1], -1, dtype=np.int64)
+    below = phi_hist[0] < thr
+    for n in range(1, phi_hist.shape[0]):
+        hit = (phi_hist[n] >= thr) & below & (act < 0)
+        act[hit] = n
+        below |= phi_hist[n] < thr
+    return act
+
+
+def c1_small():
+    """config 1 (ep01_spiral-wave.jl) on 32x32 quads: FHN, kappa scaled to keep kappa*dt/h^2 of the
+    256x256 tutorial grid, spiral initial condition, dt = 1, default sqrt(eps) tolerances."""
+    n = 32
+    s = (256 / n) ** 2
+    m = O.generate_grid(O.QUAD4, (n, n), (0.0, 0.0), (2.5, 2.5))
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, [4.5e-5 * s, 0, 0, 2.0e-5 * s])
+    x = m.dof_coords
+    N = m.ndofs
+    u = np.zeros(2 * N)
+    u[:N] = np.where((x[:, 0] <= 1.25) & (x[:, 1] <= 1.25), 1.0, 0.0)
+    u[N:] = np.where(x[:, 1] >= 1.25, 0.1, 0.0)
+    out = {"u0": u.copy(), "kappa": np.array([4.5e-5 * s, 2.0e-5 * s])}
+    for name, sub in (("fe", 1), ("adaptive", 10)):
+        orc = O.MonodomainOracle(m, O.FHN, O.default_params(O.FHN), M, K, substeps=sub)
+        v = u.copy()
+        hist = [v[:N].copy()]
+        for step in range(200):
+            it, rn, conv = orc.step(v, float(step), 1.0)
+            assert conv
+            hist.append(v[:N].copy())
+            if step == 0:
+                out[f"u1_{name}"] = v.copy()
+        out[f"u200_{name}"] = v.copy()
+        out[f"iters_{name}"] = np.array(orc.iters)
+        out[f"act_{name}"] = activation_steps(np.array(hist), 0.5)
+    np.savez_compressed(HERE / "c1_small.npz", **out)
+
+
+def c2_small():
+    """config 2 (conduction-velocity-benchmark.jl) on 16x16x4 hexes, h = 0.25: PCG2019, corner stimulus."""
+    m = O.generate_grid(O.HEX8, (16, 16, 4), (0, 0, 0), (4.0, 4.0, 1.0))
+    k1 = 0.17 * 0.62 / (0.17 + 0.62)
+    kr = 0.019 * 0.24 / (0.019 + 0.24)
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag([k1, kr, kr]))
+    N = m.ndofs
+    u = np.repeat(O.default_initial_state(O.PCG2019), N)
+    out = {"u0": u.copy()}
+    dt = 0.01
+    for name, sub in (("fe", 1), ("adaptive", 10)):
+        orc = O.MonodomainOracle(m, O.PCG2019, O.default_params(O.PCG2019), M, K, substeps=sub)
+        v = u.copy()
+        hist = [v[:N].copy()]
+        t = 0.0
+        for step in range(300):
+            if 0.0 <= t + dt <= 2.1:
+                orc.bS = O.assemble_source(m, 2, O.SRC_BOX, [1.5, 2.0, 0.5], t + dt)
+            it, rn, conv = orc.step(v, t, dt)
+            assert conv
+            t += dt
+            hist.append(v[:N].copy())
+            if step == 0:
+                out[f"u1_{name}"] = v.copy()
+        out[f"u300_{name}"] = v.copy()
+        out[f"iters_{name}"] = np.array(orc.iters)
+        out[f"act_{name}"] = activation_steps(np.array(hist), 0.0)
+    np.savez_compressed(HERE / "c2_small.npz", **out)
+
+
+if __name__ == "__main__":
+    c1_small()
+    c2_small()
+    for f in sorted(HERE.glob("*.npz")):
+        d = np.load(f)
+        print(f.name, {k: d[k].shape for k in d.files})

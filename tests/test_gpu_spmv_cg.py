@@ -1,0 +1,90 @@
+"""-m gpu: SpMV, A = M - dt K, and CG through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(tb, dev, O, ct, nel, dt, kappa):
+    dim = len(nel)
+    mo = O.generate_grid(ct, nel, (0.0,) * dim, tuple(0.25 * n for n in nel))
+    md = tb.DeviceMesh.from_host(dev, ct, mo.conn, mo.coords, mo.celldofs, mo.ndofs)
+    M = tb.B200CSRMatrix.from_mesh(dev, md)
+    K, A = M.like(), M.like()
+    Mo, Ko = O.assemble_mass(mo, 2), O.assemble_diffusion(mo, 2, O.D_TENSOR, np.diag(kappa[:dim]))
+    # upload the oracle's values so that SpMV/CG are compared on IDENTICAL operators
+    M.set_nonzeros(Mo); K.set_nonzeros(Ko)
+    A.axpby_values(M, K, dt)
+    Ao = O.axpby_values(Mo, Ko, dt)
+    return mo, md, M, K, A, Mo, Ko, Ao
+
+
+@pytest.mark.parametrize("ct,nel", [(0, (31, 17)), (1, (9, 8, 7)), (3, (6, 5, 4)), (2, (12, 9))])
+def test_axpby_and_spmv_bitwise(tb, dev, oracle, ct, nel):
+    O = oracle
+    mo, md, M, K, A, Mo, Ko, Ao = _system(tb, dev, O, ct, nel, 0.37, (0.13, 0.02, 0.02))
+    assert np.array_equal(A.nonzeros(), Ao)                           # a - dt*b without fma: bitwise
+    rp, ci = mo.pattern()
+    x = np.random.default_rng(0).standard_normal(mo.ndofs)
+    xd, yd = tb.B200Vector.from_host(dev, x), tb.B200Vector(dev, mo.ndofs)
+    for mat, vals in ((A, Ao), (M, Mo), (K, Ko)):
+        mat.mul(yd, xd)
+        assert np.array_equal(yd.to_host(), O.spmv(rp, ci, vals, x))  # sequential row sums, no fma: bitwise
+    with pytest.raises(tb.TBError):
+        A.mul(xd, xd)                                                 # aliasing refused
+    for h in (M, K, A, xd, yd, md):
+        h.free()
+
+
+@pytest.mark.parametrize("ct,nel,dt", [(0, (40, 40), 1.0), (1, (12, 10, 8), 0.5), (3, (6, 6, 6), 0.5), (1, (16, 16, 4), 0.01)])
+def test_cg_matches_oracle(tb, dev, oracle, ct, nel, dt):
+    O = oracle
+    mo, md, M, K, A, Mo, Ko, Ao = _system(tb, dev, O, ct, nel, dt, (0.13, 0.02, 0.02))
+    rp, ci = mo.pattern()
+    rng = np.random.default_rng(1)
+    u = rng.standard_normal(mo.ndofs)
+    b = O.spmv(rp, ci, Mo, u)
+    bd, xd = tb.B200Vector.from_host(dev, b), tb.B200Vector(dev, mo.ndofs)
+    xd.fill(123.0)                                                    # x0 = 0 regardless of what x holds
+    for atol, rtol in ((O.SQRT_EPS, O.SQRT_EPS), (1e-6, 1e-5), (1e-14, 1e-14)):
+        xo, ito, rno, convo = O.cg(rp, ci, Ao, b, atol, rtol)
+        it, rn, conv = tb.core.cg_solve(dev, A, bd, xd, atol, rtol)
+        assert conv == convo and abs(it - ito) <= 1, (it, ito)       # north star: iteration counts within +-1
+        if it == ito:
+            assert rn == pytest.approx(rno, rel=1e-6)
+            x = xd.to_host()
+            assert np.abs(x - xo).max() <= 1e-12 * np.abs(xo).max()
+    # run-to-run determinism of the two-stage reductions
+    it1, rn1, _ = tb.core.cg_solve(dev, A, bd, xd)
+    x1 = xd.to_host()
+    it2, rn2, _ = tb.core.cg_solve(dev, A, bd, xd)
+    assert it1 == it2 and rn1 == rn2 and np.array_equal(x1, xd.to_host())
+    for h in (M, K, A, bd, xd, md):
+        h.free()
+
+
+def test_cg_failure_is_a_flag_not_an_error(tb, dev, oracle):
+    """Non-convergence must come back as converged = False (-> ReturnCode.MaxIters, euler.jl:95-100)."""
+    O = oracle
+    mo, md, M, K, A, Mo, Ko, Ao = _system(tb, dev, O, 0, (30, 30), 50.0, (0.13, 0.02, 0.02))
+    rp, ci = mo.pattern()
+    b = np.sin(np.arange(mo.ndofs) * 0.1)
+    bd, xd = tb.B200Vector.from_host(dev, b), tb.B200Vector(dev, mo.ndofs)
+    for itmax in (0, 1, 3):
+        xo, ito, rno, convo = O.cg(rp, ci, Ao, b, itmax=itmax)
+        it, rn, conv = tb.core.cg_solve(dev, A, bd, xd, itmax=itmax)
+        assert (it, conv) == (ito, convo) == (itmax, False)
+        assert np.abs(xd.to_host() - xo).max() <= 1e-13 * max(np.abs(xo).max(), 1.0)
+        assert rn == pytest.approx(rno, rel=1e-10)
+    # zero right-hand side: solved at iteration 0
+    bd.fill(0.0)
+    it, rn, conv = tb.core.cg_solve(dev, A, bd, xd)
+    assert (it, rn, conv) == (0, 0.0, True) and not xd.to_host().any()
+    # NaN in the operator: no hang, no error status, just not converged
+    bad = Ao.copy(); bad[5] = np.nan
+    A.set_nonzeros(bad)
+    bd.upload(b)
+    it, rn, conv = tb.core.cg_solve(dev, A, bd, xd, itmax=20)
+    assert not conv and it == 20
+    for h in (M, K, A, bd, xd, md):
+        h.free()

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "tb_timer_stop": [_vp, _pf64],
     "tb_launch_count": [_vp, _pi64],
     "tb_l2_flush": [_vp],
+    "tb_profile_enable": [_vp, C.c_int32],
+    "tb_profile_get": [_vp, _pf64, _pi64],
     "tb_comm_unique_id": [_vp],
     "tb_ctx_comm_init": [_vp, C.c_int32, C.c_int32, _vp],
     "tb_comm_barrier": [_vp],

@@ -53,6 +53,15 @@ class B200Device:
     def l2_flush(self):
         L.call("tb_l2_flush", self.h)
 
+    def profile_enable(self, on=True):
+        L.call("tb_profile_enable", self.h, int(on))
+
+    def profile_get(self):
+        """(total ms, launches) of the SpMV-in-CG kernel since profile_enable(True)."""
+        ms, n = C.c_double(), C.c_int64()
+        L.call("tb_profile_get", self.h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
     # ---- multi-GPU --------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -232,8 +232,11 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
         if (chunk > itmax - enq) chunk = itmax - enq;
         for (int64_t k = 0; k < chunk; k++) {
             if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));
+            const bool prof = ctx->profile && enq + k < TB_PROF_MAX;
+            if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k)], ctx->stream));
             TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n, pat->nslices,
                       st, part, tick, dist);
+            if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k) + 1], ctx->stream));
             if (dist) TB_TRY(cg_allreduce_then(ctx, 1));
             TB_LAUNCH(ctx, k_cg_xr, grid_v, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist);
             if (dist) TB_TRY(cg_allreduce_then(ctx, 2));
@@ -246,6 +249,16 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
         chunk = 4;
     }
     ctx->last_cg_iters = h->iter;
+    if (ctx->profile) {
+        // only launches that did work: iteration k ran its SpMV iff k < iter (later ones saw done = 1)
+        const int64_t nreal = h->iter < TB_PROF_MAX ? h->iter : TB_PROF_MAX;
+        for (int64_t k = 0; k < nreal && k < enq; k++) {
+            float ms = 0.f;
+            TB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * k], ctx->prof_ev[2 * k + 1]));
+            ctx->prof_spmv_ms += ms;
+            ctx->prof_spmv_n += 1;
+        }
+    }
     if (iters) *iters = h->iter;
     if (rnorm) *rnorm = h->rnorm;
     if (converged) *converged = h->solved;

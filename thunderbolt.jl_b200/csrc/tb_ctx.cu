@@ -78,6 +78,8 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_flush);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 2 * TB_PROF_MAX; i++)
+        if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TB_OK;
@@ -265,6 +267,23 @@ extern "C" int32_t tb_vec_devptr(const tb_vec *v, int32_t col, void **ptr, int64
     TB_REQUIRE(col >= 0 && col < v->ncols, "tb_vec_devptr: column out of range");
     *ptr = v->d + (size_t)col * v->ld;
     if (ld) *ld = v->ld;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_profile_enable(tb_ctx *ctx, int32_t on) {
+    TB_REQUIRE(ctx, "tb_profile_enable: ctx is NULL");
+    if (on && !ctx->prof_ev[0])
+        for (int i = 0; i < 2 * TB_PROF_MAX; i++) TB_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+    ctx->profile = on != 0;
+    ctx->prof_spmv_ms = 0.0;
+    ctx->prof_spmv_n = 0;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_profile_get(tb_ctx *ctx, double *spmv_ms_total, int64_t *spmv_launches) {
+    TB_REQUIRE(ctx && spmv_ms_total && spmv_launches, "tb_profile_get: NULL argument");
+    *spmv_ms_total = ctx->prof_spmv_ms;
+    *spmv_launches = ctx->prof_spmv_n;
     return TB_OK;
 }
 

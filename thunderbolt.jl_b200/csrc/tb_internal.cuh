@@ -16,6 +16,7 @@
 #define TB_SLICE 32            // SELL slice height = warp size
 #define TB_MAX_PARTIALS 4096   // upper bound on blocks of any reducing kernel
 #define TB_MAXROW 128          // max nonzeros per row the device pattern builder supports
+#define TB_PROF_MAX 256        // SpMV launches per solve that the profiler brackets with events
 
 int32_t tb_fail(int32_t code, const char *fmt, ...);
 
@@ -80,6 +81,11 @@ struct tb_ctx {
     size_t flush_bytes = 0;
     int assembly_mode = 0;
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
+    // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
+    bool profile = false;
+    cudaEvent_t prof_ev[2 * TB_PROF_MAX] = {};
+    double prof_spmv_ms = 0.0;
+    int64_t prof_spmv_n = 0;
     // communicator
     bool has_comm = false;
     int rank = 0, nranks = 1;
