@@ -130,7 +130,7 @@ def run_b200(args):
     ion = tb.FHNModel() if W["model"] == "fhn" else tb.PCG2019()
     ns = tb.num_states(ion)
     if world > 1:
-        part = tbd.partition_mesh(dev, mesh, dist)          # z-slab ownership, halo plan
+        part = tbd.partition_mesh(dev, mesh, dist, plane=(nel[0] + 1) * (nel[1] + 1) if dim == 3 else nel[0] + 1)
         mesh.free()
         mesh = part.mesh
     M = tb.B200CSRMatrix.from_mesh(dev, mesh)

@@ -107,8 +107,9 @@ def test_c2_small_against_golden(tb, dev, variant, sub):
 
 
 def test_fused_and_unfused_paths_agree(tb, dev):
-    """The fused tb_monodomain_step and the operator-by-operator path (perform_step! per child) are
-    the same arithmetic: bitwise equal states, equal iteration counts."""
+    """The fused tb_monodomain_step and the operator-by-operator path (perform_step! per child) are the
+    same algorithm; only the block partition of the first dot product differs (the fused init kernel
+    reduces per SELL slice), so states agree to rounding and iteration counts within +-1."""
     g = np.load(GOLD / "c1_small.npz")
     res = []
     for fused in (True, False):
@@ -121,7 +122,8 @@ def test_fused_and_unfused_paths_agree(tb, dev):
         sol = tb.solve_(integ)
         assert sol.retcode == tb.ReturnCode.Success and integ.t == 20.0
         res.append((integ.u.to_host(), list(integ.cg_iterations)))
-    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    assert np.abs(res[0][0] - res[1][0]).max() <= 1e-9 * np.abs(res[0][0]).max()
+    assert np.abs(np.array(res[0][1]) - np.array(res[1][1])).max() <= 1
 
 
 def test_backward_euler_steady_state(tb, dev):
