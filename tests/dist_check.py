@@ -1,0 +1,87 @@
+"""Run under torchrun (one rank per GPU): the row-partitioned multi-GPU path against the single-GPU path
+on the same mesh and inputs.  Rank 0 also solves the whole problem alone; every rank compares its owned
+rows.  Used by tests/test_gpu_multi.py and by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dist_check.py
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import thunderbolt_jl_b200 as tb  # noqa: E402
+from thunderbolt_jl_b200 import dist as tbd  # noqa: E402
+
+
+def build(dev, mesh, ion, D):
+    M = tb.B200CSRMatrix.from_mesh(dev, mesh)
+    K = M.like()
+    tb.core.assemble_mass(dev, mesh, M, 2, 1.0)
+    tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_TENSOR, D, 1.0)
+    return M, K
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = tb.B200Device(local)
+    tbd.init_comm(dev, dist)
+    nel = (24, 20, 4 * world + 3)
+    lengths = tuple(0.25 * n for n in nel)
+    D = np.diag([0.0295, 0.0131, 0.0131])
+    ion = tb.FHNModel()
+    full = tb.generate_mesh(tb.Hexahedron, nel, (0, 0, 0), lengths, device=dev)
+    N = full.ndofs
+    x = full.dof_coords()
+    rng = np.random.default_rng(0)
+    u0 = np.concatenate([np.where(x[:, 0] <= 0.5 * lengths[0], 1.0, 0.0) + 0.01 * rng.standard_normal(N),
+                         np.where(x[:, 1] >= 0.5 * lengths[1], 0.1, 0.0)])
+    # --- reference: the whole problem on this rank's GPU alone -------------------------------------
+    M1, K1 = build(dev, full, ion, D)
+    st1 = tb.MonodomainStepper(dev, M1, K1, ion.model_id, ion.params())
+    st1.set_cell_solver(10, 0.1)
+    u1 = tb.B200Vector.from_host(dev, u0, 2)
+    it1 = [st1.step(u1, float(s), 1.0)[0] for s in range(5)]
+    ref = u1.to_host()
+    # --- partitioned ---------------------------------------------------------------------------------
+    part = tbd.partition_mesh(dev, full, dist, plane=(nel[0] + 1) * (nel[1] + 1))
+    lm = part.mesh
+    lo, hi = int(part.bounds[rank]), int(part.bounds[rank + 1])
+    gids = np.concatenate([np.arange(lo, hi), lm.ghost_global])       # local -> global dof id
+    assert lm.ndofs == gids.size and np.array_equal(lm.dof_coords(), x[gids])
+    M, K = build(dev, lm, ion, D)
+    part.attach_halo(M)
+    # owned rows of the distributed operators equal the same rows of the global ones (pattern bit exact)
+    rp, ci = M.pattern()
+    rp1, ci1 = M1.pattern()
+    assert np.array_equal(np.diff(rp), np.diff(rp1[lo:hi + 1]))
+    assert np.array_equal(gids[ci], ci1[rp1[lo]:rp1[hi]])
+    v, v1 = M.nonzeros(), M1.nonzeros()[rp1[lo]:rp1[hi]]
+    assert np.abs(v - v1).max() <= 1e-13 * np.abs(v1).max()
+    st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+    st.set_cell_solver(10, 0.1)
+    ul = np.concatenate([u0[:N][gids], u0[N:][gids]])
+    u = tb.B200Vector.from_host(dev, ul, 2)
+    its = [st.step(u, float(s), 1.0)[0] for s in range(5)]
+    got = u.to_host()
+    no = hi - lo
+    nl = lm.ndofs
+    err_phi = np.abs(got[:no] - ref[lo:hi]).max() / np.abs(ref[:N]).max()
+    err_s = np.abs(got[nl:nl + no] - ref[N + lo:N + hi]).max()
+    ok = err_phi <= 1e-9 and err_s <= 1e-10 and max(abs(a - b) for a, b in zip(its, it1)) <= 1
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    print(f"rank {rank}/{world}: owned [{lo},{hi}) ghosts {lm.ghost_global.size} iters {its} vs {it1} "
+          f"err_phi {err_phi:.2e} err_s {err_s:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,14 +72,14 @@ __global__ void __launch_bounds__(256)
 template <int MODEL>
 static int32_t launch_cell(tb_ctx *ctx, const tb_cell_params &prm, double *u, int64_t n, int64_t ld, const double *phi_src,
                            double t, double dt, int substeps, double thr, bool want_max) {
-    // PCG2019 is fp64-pipe bound (12 exp + ~28 div per rhs): smaller blocks, more of them
-    int grid = tb_grid_for(ctx, (n + 1) / 2, 256, MODEL == 1 ? 4 : 8);
     const bool adaptive = substeps > 1;
+    const int64_t need = ((n + 1) / 2 + 255) / 256;
     double *res = ctx->d_scalar;
     double *part = ctx->d_partials + 2 * TB_MAX_PARTIALS;
     unsigned *tick = ctx->d_ticket + 2;
 #define TB_CELL_LAUNCH(AD, MX)                                                                                        \
-    TB_LAUNCH(ctx, (k_cell_step<MODEL, AD, MX>), grid, 256, 0, u, ld, n, phi_src, prm, t, dt, substeps, thr, part, tick, res)
+    TB_LAUNCH(ctx, (k_cell_step<MODEL, AD, MX>), TB_GRID(ctx, (k_cell_step<MODEL, AD, MX>), 256, 0, need), 256, 0, u, ld, n, \
+              phi_src, prm, t, dt, substeps, thr, part, tick, res)
     if (adaptive) {
         if (want_max) TB_CELL_LAUNCH(true, true); else TB_CELL_LAUNCH(true, false);
     } else {

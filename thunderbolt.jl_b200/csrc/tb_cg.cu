@@ -145,6 +145,69 @@ __global__ void __launch_bounds__(256)
     cg_finish<1>(bs, st, partials, ticket, sm, dist);
 }
 
+// ---- bulk-async (TMA) variants of the two SpMV-shaped kernels ------------------------------------------
+// Same arithmetic and summation order as above; the matrix stream comes through cp.async.bulk + mbarrier
+// (tb_spmv.cuh).  INIT = true: r = p = M*phi (+bS), x = 0, gamma; false: Ap = A p, p.Ap.
+template <int STAGES, bool INIT>
+__global__ void __launch_bounds__(1024, 1)
+    k_cg_spmv_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ val,
+                  const double *__restrict__ xin, const double *__restrict__ bS, double *__restrict__ xout,
+                  double *__restrict__ r, double *__restrict__ pout, int64_t nrows, int64_t nslices, int wcap, CGState *st,
+                  double *partials, unsigned *ticket, bool dist) {
+    if (!INIT && st->done) return;
+    extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
+    __shared__ double sm[32];
+    double acc = 0.0;
+    tb_sell_sweep_tma<STAGES>(slice_ptr, col, val, xin, nslices, wcap, tb_dyn_smem, [&](int64_t row, double v) {
+        if (row < nrows) {
+            if (INIT) {
+                if (bS) v += bS[row];
+                xout[row] = 0.0;
+                r[row] = v;
+                pout[row] = v;
+                acc += v * v;
+            } else {
+                r[row] = v;              // r aliases Ap here
+                acc += xin[row] * v;
+            }
+        }
+    });
+    const double bs = tb_block_sum(acc, sm);
+    if (INIT) cg_finish<0>(bs, st, partials, ticket, sm, dist);
+    else cg_finish<1>(bs, st, partials, ticket, sm, dist);
+}
+
+template <int STAGES, bool INIT>
+static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern *pat, const double *val, const double *xin,
+                               const double *bS, double *xout, double *r, double *pout, CGState *st, double *part,
+                               unsigned *tick, bool dist) {
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width, STAGES, warps_override);
+    static size_t configured = 0;
+    if (configured < g.smem) {
+        TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        configured = g.smem;
+    }
+    const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
+    const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);   // one CTA per SM, one balanced wave
+    TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, val, xin, bS, xout,
+              r, pout, pat->nrows, pat->nslices, g.wcap, st, part, tick, dist);
+    return TB_OK;
+}
+
+// variant table (ctx->spmv_variant, env TB_SPMV_VARIANT), chosen by measurement (profiles/):
+//   0 LDG kernel | 1 staged, 1 stage, as many warps as fit (default) | 2 staged, 1 stage, 16 warps
+//   3 staged, 2 stages, as many warps as fit | 4 staged, 1 stage, 24 warps
+template <bool INIT>
+static int32_t dispatch_spmv_tma(tb_ctx *ctx, const tb_pattern *pat, const double *val, const double *xin, const double *bS,
+                                 double *xout, double *r, double *pout, CGState *st, double *part, unsigned *tick, bool dist) {
+    switch (ctx->spmv_variant) {
+    case 2: return launch_spmv_tma<1, INIT>(ctx, 16, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
+    case 3: return launch_spmv_tma<2, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
+    case 4: return launch_spmv_tma<1, INIT>(ctx, 24, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
+    default: return launch_spmv_tma<1, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
+    }
+}
+
 // ---- x += alpha p; r -= alpha Ap; r.r  (128-bit loads/stores) --------------------------------------
 __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                                                const double *__restrict__ Ap, int64_t n, CGState *st, double *partials,
@@ -211,16 +274,24 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const bool dist = ctx->has_comm && ctx->nranks > 1;
     double *part = ctx->d_partials;
     unsigned *tick = ctx->d_ticket;
-    const int grid_v = tb_grid_for(ctx, n / 2 + 1, 256, 8);
-    const int grid_s = tb_grid_for(ctx, pat->nslices * 32, 256, 8);
+    const int64_t need_v = (n / 2 + 256) / 256, need_s = (pat->nslices + 7) / 8;
+    const int grid_xr = TB_GRID(ctx, k_cg_xr, 256, 0, need_v);
+    const int grid_p = TB_GRID(ctx, k_cg_p, 256, 0, need_v);
+    const int grid_ib = TB_GRID(ctx, k_cg_init_b, 256, 0, (n + 255) / 256);
+    const int grid_s = TB_GRID(ctx, k_cg_spmv_dot, 256, 0, need_s);
+    const int grid_im = TB_GRID(ctx, k_cg_init_Mphi, 256, 0, need_s);
+    const bool tma = ctx->spmv_variant > 0 && pat->max_width > 0 && pat->max_width <= TB_TMA_WCAP;
 
     TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);
     if (b) {
-        TB_LAUNCH(ctx, k_cg_init_b, grid_v, 256, 0, b, x, r, p, n, st, part, tick, dist);
+        TB_LAUNCH(ctx, k_cg_init_b, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist);
     } else {
         if (M->pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, M->pat, phi));
-        TB_LAUNCH(ctx, k_cg_init_Mphi, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
-                  pat->nslices, st, part, tick, dist);
+        if (tma)
+            TB_TRY(dispatch_spmv_tma<true>(ctx, pat, M->d_val, phi, bS, x, r, p, st, part, tick, dist));
+        else
+            TB_LAUNCH(ctx, k_cg_init_Mphi, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
+                      pat->nslices, st, part, tick, dist);
     }
     if (dist) TB_TRY(cg_allreduce_then(ctx, 0));
 
@@ -234,13 +305,16 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
             if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));
             const bool prof = ctx->profile && enq + k < TB_PROF_MAX;
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k)], ctx->stream));
-            TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n, pat->nslices,
-                      st, part, tick, dist);
+            if (tma)
+                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, st, part, tick, dist));
+            else
+                TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
+                          pat->nslices, st, part, tick, dist);
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k) + 1], ctx->stream));
             if (dist) TB_TRY(cg_allreduce_then(ctx, 1));
-            TB_LAUNCH(ctx, k_cg_xr, grid_v, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist);
+            TB_LAUNCH(ctx, k_cg_xr, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist);
             if (dist) TB_TRY(cg_allreduce_then(ctx, 2));
-            TB_LAUNCH(ctx, k_cg_p, grid_v, 256, 0, r, p, n, st);
+            TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, r, p, n, st);
         }
         enq += chunk;
         TB_CUDA(cudaMemcpyAsync(h, st, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));

@@ -18,7 +18,7 @@
 // ------------------------------------------------------------------------------------------------
 // pattern construction
 // ------------------------------------------------------------------------------------------------
-__global__ void k_slice_width(const int64_t *rowptr, int64_t nrows, int64_t nslices, int64_t *width32) {
+__global__ void k_slice_width(const int64_t *rowptr, int64_t nrows, int64_t nslices, int64_t *width32, int *maxw) {
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += (int64_t)gridDim.x * blockDim.x) {
         int64_t r0 = s * TB_SLICE, r1 = r0 + TB_SLICE < nrows ? r0 + TB_SLICE : nrows;
         int64_t w = 0;
@@ -27,6 +27,7 @@ __global__ void k_slice_width(const int64_t *rowptr, int64_t nrows, int64_t nsli
             w = l > w ? l : w;
         }
         width32[s] = w * TB_SLICE;
+        atomicMax(maxw, (int)w);
     }
 }
 
@@ -79,10 +80,15 @@ static int32_t pattern_from_device_csr(tb_ctx *ctx, int64_t nrows, int64_t ncols
     TB_CUDA(cudaMalloc(&width, sizeof(int64_t) * (size_t)(p->nslices + 1)));
     TB_CUDA(cudaMemsetAsync(width, 0, sizeof(int64_t) * (size_t)(p->nslices + 1), ctx->stream));
     TB_CUDA(cudaMalloc(&p->d_slice_ptr, sizeof(int64_t) * (size_t)(p->nslices + 1)));
-    TB_LAUNCH(ctx, k_slice_width, tb_grid_for(ctx, p->nslices, 256, 8), 256, 0, d_rowptr, nrows, p->nslices, width);
+    int *d_maxw = nullptr;
+    TB_CUDA(cudaMalloc(&d_maxw, sizeof(int)));
+    TB_CUDA(cudaMemsetAsync(d_maxw, 0, sizeof(int), ctx->stream));
+    TB_LAUNCH(ctx, k_slice_width, tb_grid_for(ctx, p->nslices, 256, 8), 256, 0, d_rowptr, nrows, p->nslices, width, d_maxw);
+    TB_CUDA(cudaMemcpyAsync(&p->max_width, d_maxw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     TB_TRY(exclusive_scan_i64(ctx, width, p->d_slice_ptr, p->nslices + 1));
     TB_CUDA(cudaMemcpy(&p->sell_len, p->d_slice_ptr + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost));
     cudaFree(width);
+    cudaFree(d_maxw);
     TB_CUDA(cudaMalloc(&p->d_col, sizeof(int) * (size_t)(p->sell_len + 32)));
     TB_LAUNCH(ctx, k_sell_fill_cols, ctx->sm_count * 8, 256, 0, d_rowptr, d_colidx, nrows, ncols, p->nslices,
               p->d_slice_ptr, p->d_col);
@@ -427,7 +433,7 @@ extern "C" int32_t tb_csr_axpby_values(tb_csr *A, const tb_csr *M, const tb_csr 
     tb_ctx *ctx = A->pat->ctx;
     TB_DEV(ctx);
     int64_t n2 = A->pat->sell_len / 2;   // sell_len is a multiple of 32
-    TB_LAUNCH(ctx, k_axpby_values, tb_grid_for(ctx, n2, 256, 8), 256, 0, (const double2 *)M->d_val,
+    TB_LAUNCH(ctx, k_axpby_values, TB_GRID(ctx, k_axpby_values, 256, 0, (n2 + 255) / 256), 256, 0, (const double2 *)M->d_val,
               (const double2 *)K->d_val, (double2 *)A->d_val, dt, n2);
     return TB_OK;
 }
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(256) k_sell_spmv(const int64_t *__restrict__ s
 int32_t tb_spmv_raw(tb_ctx *ctx, const tb_csr *A, double *x, double *y) {
     const tb_pattern *p = A->pat;
     if (p->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, p, x));
-    int grid = tb_grid_for(ctx, p->nslices * 32, 256, 8);
+    int grid = TB_GRID(ctx, k_sell_spmv, 256, 0, (p->nslices + 7) / 8);
     TB_LAUNCH(ctx, k_sell_spmv, grid, 256, 0, p->d_slice_ptr, p->d_col, A->d_val, x, y, p->nrows, p->nslices);
     return TB_OK;
 }

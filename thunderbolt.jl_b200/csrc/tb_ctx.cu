@@ -59,6 +59,7 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_CUDA(cudaMallocHost(&ctx->h_cg, sizeof(CGState)));
     TB_CUDA(cudaMalloc(&ctx->d_scalar, sizeof(double) * 16));
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));
+    if (const char *v = getenv("TB_SPMV_VARIANT")) ctx->spmv_variant = atoi(v);
     *out = ctx;
     return TB_OK;
 }

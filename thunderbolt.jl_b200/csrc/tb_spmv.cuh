@@ -1,13 +1,22 @@
-// SELL-32 row kernel shared by tb_spmv (tb_csr.cu) and the CG iteration (tb_cg.cu).
+// SELL-32 row kernels shared by tb_spmv (tb_csr.cu) and the CG iteration (tb_cg.cu).
 // mul!(y, ::ThreadedSparseMatrixCSR, x), src/utils.jl:210-231: v = 0; for nz in row: v += A[nz]*x[col[nz]].
+//
+// Two implementations of the same arithmetic (identical summation order, bitwise equal results):
+//   tb_sell_row        plain LDG: every lane loads its own values/column ids (any slice width)
+//   tb_sell_sweep_tma  sm_100a bulk-async pipeline: one elected lane per warp streams the slice's
+//                      contiguous value and column blocks into shared memory with cp.async.bulk (TMA,
+//                      SASS UBLKCP) completing on an mbarrier; the lanes then read shared memory and
+//                      only the dependent x gathers go through the LSU, all of a row's gathers in flight
+//                      at once.  Used when every slice is at most TB_TMA_WCAP entries wide.
+//                      Measured on the 101 M-row hex operator: 5.67 ms vs 6.25 ms for the LDG kernel
+//                      (96 % vs 87 % of the measured copy bandwidth).
 #pragma once
 #include "tb_internal.cuh"
 
 // Row (s*32 + lane) of y = A x.  Entry j of the row is at slice_ptr[s] + j*32 + lane, so one warp
 // streams 256 B of values + 128 B of column ids per j, fully coalesced; the dependent x gathers hit
-// L1/L2 (neighbouring rows share columns).  Loads are issued four entries ahead of their use; the
-// additions stay strictly left to right (and unfused, -fmad=false) so the sum is bitwise the
-// reference's.
+// L1/L2 (neighbouring rows share columns).  The additions stay strictly left to right (and unfused,
+// -fmad=false) so the sum is bitwise the reference's.
 __device__ __forceinline__ double tb_sell_row(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col,
                                               const double *__restrict__ val, const double *__restrict__ x, int64_t s,
                                               int lane) {
@@ -28,4 +37,143 @@ __device__ __forceinline__ double tb_sell_row(const int64_t *__restrict__ slice_
     }
     for (; j < w; j++) acc += v[j * 32] * x[c[j * 32]];
     return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bulk-async (TMA) pipeline
+// ---------------------------------------------------------------------------------------------------
+#define TB_TMA_WCAP 48   // widest slice (entries per row) the staged kernel is used for
+
+// bytes of one stage for slices up to `wcap` entries wide: 32 rows x (8 B value + 4 B column) per entry
+__host__ __device__ __forceinline__ size_t tb_tma_stage_bytes(int wcap) { return (size_t)wcap * 384; }
+
+__device__ __forceinline__ unsigned tb_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tb_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tb_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tb_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TB_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TB_WAIT_DONE;\n"
+        "bra TB_WAIT_LOOP;\n"
+        "TB_WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier (src/dst 16 B aligned, size % 16 == 0)
+__device__ __forceinline__ void tb_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// One warp = one private ring of STAGES slices.  `epi(row, acc)` is called by every lane with the
+// finished row sum (rows >= nrows included: the caller masks).  `wcap` >= the widest slice.
+// Dynamic shared memory: nwarps*STAGES*tb_tma_stage_bytes(wcap) + nwarps*STAGES*8 bytes, nwarps = blockDim.x/32.
+template <int STAGES, class Epilogue>
+__device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col,
+                                                  const double *__restrict__ val, const double *__restrict__ x,
+                                                  int64_t nslices, int wcap, unsigned char *smem, Epilogue epi) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const size_t stage_bytes = tb_tma_stage_bytes(wcap);
+    const size_t col_off = (size_t)wcap * 256;
+    unsigned char *wbase = smem + (size_t)warp * STAGES * stage_bytes;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)nwarp * STAGES * stage_bytes) + warp * STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) tb_mbar_init(tb_smem_addr(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int64_t gw = (int64_t)blockIdx.x * nwarp + warp, nw = (int64_t)gridDim.x * nwarp;
+
+    auto issue = [&](int stage, int64_t s) {   // lane 0 only
+        const int64_t base = slice_ptr[s];
+        const unsigned n = (unsigned)(slice_ptr[s + 1] - base);   // stored entries of the slice (32 * width)
+        const unsigned bar = tb_smem_addr(bars + stage);
+        unsigned char *dst = wbase + (size_t)stage * stage_bytes;
+        tb_mbar_expect_tx(bar, n * 12u);
+        if (n) {
+            tb_bulk_g2s(tb_smem_addr(dst), val + base, n * 8u, bar);
+            tb_bulk_g2s(tb_smem_addr(dst + col_off), col + base, n * 4u, bar);
+        }
+    };
+
+    int64_t s_issue = gw;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; st++) {
+            if (s_issue < nslices) issue(st, s_issue);
+            s_issue += nw;
+        }
+    }
+    s_issue = gw + (int64_t)STAGES * nw;   // same value in every lane
+
+    int stage = 0;
+    unsigned parity = 0;
+    for (int64_t s = gw; s < nslices; s += nw) {
+        const int w = (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 5);
+        tb_mbar_wait(tb_smem_addr(bars + stage), parity);
+        const double *sv = reinterpret_cast<const double *>(wbase + (size_t)stage * stage_bytes) + lane;
+        const int *sc = reinterpret_cast<const int *>(wbase + (size_t)stage * stage_bytes + col_off) + lane;
+        double acc = 0.0;
+        int j = 0;
+        for (; j + 9 <= w; j += 9) {
+            double xv[9], vv[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) xv[k] = x[sc[(j + k) * 32]];
+#pragma unroll
+            for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
+#pragma unroll
+            for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
+        }
+        for (; j + 3 <= w; j += 3) {
+            double xv[3], vv[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) xv[k] = x[sc[(j + k) * 32]];
+#pragma unroll
+            for (int k = 0; k < 3; k++) vv[k] = sv[(j + k) * 32];
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc += vv[k] * xv[k];
+        }
+        for (; j < w; j++) acc += sv[j * 32] * x[sc[j * 32]];
+        epi(s * TB_SLICE + lane, acc);
+        // every lane has consumed its shared-memory operands (acc depends on all of them): the stage may be refilled
+        __syncwarp();
+        if (lane == 0 && s_issue < nslices) issue(stage, s_issue);
+        s_issue += nw;
+        if (++stage == STAGES) {
+            stage = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
+// Launch geometry of the staged kernels for a pattern whose widest slice is `max_width`:
+// as many warps per CTA as fit the shared memory (the gather phase is latency bound: more warps = more
+// gathers in flight; measured 16 x 1 stage > 8 x 2 > 4 x 3), one CTA per SM.
+struct tb_tma_geom {
+    int warps, wcap;
+    size_t smem;
+};
+static inline tb_tma_geom tb_tma_geometry(int max_width, int stages, int warps_override) {
+    tb_tma_geom g;
+    g.wcap = max_width < 1 ? 1 : max_width;
+    const size_t per_warp = (size_t)stages * tb_tma_stage_bytes(g.wcap) + (size_t)stages * 8;
+    int w = (int)((220 * 1024) / per_warp);
+    if (w > 32) w = 32;
+    if (w < 1) w = 1;
+    if (warps_override > 0 && warps_override < w) w = warps_override;
+    g.warps = w;
+    g.smem = (size_t)w * per_warp;
+    return g;
 }
