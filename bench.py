@@ -198,9 +198,19 @@ def run_b200(args):
     achieved = spmv_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None
     k_mean = float(np.mean(iters))
     step_bytes = (2 * ns * 8 + bytes_per_row(nnz, rows_local) * (1 + k_mean) + 72.0 * k_mean) * rows_local
-    roofline = {"bound": "hbm", "kernel": "k_cg_spmv_dot (SELL-32 SpMV fused with p.Ap)", "achieved": achieved,
+    # bytes the kernel really streams: stored values + the (losslessly compressed) column stream + x, y, p
+    stored, col_bytes, max_w = M.storage()
+    stored_bytes = stored * 8.0 + col_bytes + 24.0 * rows_local
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic.json"
+    if tfile.exists() and world == 1 and not args.grid:
+        traffic = json.loads(tfile.read_text()).get(args.workload, {}).get("spmv_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_cg_spmv_tma<1,false,true> (SELL-32 SpMV, TMA-staged, fused p.Ap)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "bytes_per_launch": spmv_bytes, "avg_launch_ms": avg_spmv_ms, "launches_timed": spmv_n,
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum+write.sum, profiles/traffic.json" if traffic else None,
+                "bytes_per_launch": spmv_bytes, "stored_bytes_per_launch": stored_bytes,
+                "stored_achieved_gbs": stored_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None,
+                "avg_launch_ms": avg_spmv_ms, "launches_timed": spmv_n,
                 "spmv_share_of_step": spmv_ms / ms if ms else None,
                 "step_bytes_per_dof": step_bytes / rows_local,
                 "step_achieved_gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 * 1.0,

@@ -160,6 +160,10 @@ int32_t tb_csr_create_from_mesh(tb_ctx *ctx, const tb_mesh *mesh, tb_csr **out);
 int32_t tb_csr_create_like(const tb_csr *pattern_of, tb_csr **out);
 int32_t tb_csr_destroy(tb_csr *a);
 int32_t tb_csr_sizes(const tb_csr *a, int64_t *nrows, int64_t *ncols, int64_t *nnz);
+/* HBM footprint of the operator's streams: stored (padded) entries, bytes of the column stream the SpMV
+ * actually reads (lossless compression: one offset per slot where col = row + off for a whole slice),
+ * widest slice.  Used by bench.py to report real bytes next to the algorithmic ones. */
+int32_t tb_csr_storage(const tb_csr *a, int64_t *stored_entries, int64_t *column_stream_bytes, int32_t *max_width);
 int32_t tb_csr_download_pattern(const tb_csr *a, int64_t *rowptr, int64_t *colidx, int32_t index_base);
 int32_t tb_csr_values_download(const tb_csr *a, double *vals); /* nonzeros(A), CSR order */
 int32_t tb_csr_values_upload(tb_csr *a, const double *vals);

@@ -35,17 +35,19 @@ def main():
     lengths = tuple(0.25 * n for n in nel)
     D = np.diag([0.0295, 0.0131, 0.0131])
     ion = tb.FHNModel()
+    dev1 = tb.B200Device(local)      # a second context WITHOUT a communicator for the single-GPU reference solve
     full = tb.generate_mesh(tb.Hexahedron, nel, (0, 0, 0), lengths, device=dev)
+    full1 = tb.generate_mesh(tb.Hexahedron, nel, (0, 0, 0), lengths, device=dev1)
     N = full.ndofs
     x = full.dof_coords()
     rng = np.random.default_rng(0)
     u0 = np.concatenate([np.where(x[:, 0] <= 0.5 * lengths[0], 1.0, 0.0) + 0.01 * rng.standard_normal(N),
                          np.where(x[:, 1] >= 0.5 * lengths[1], 0.1, 0.0)])
     # --- reference: the whole problem on this rank's GPU alone -------------------------------------
-    M1, K1 = build(dev, full, ion, D)
-    st1 = tb.MonodomainStepper(dev, M1, K1, ion.model_id, ion.params())
+    M1, K1 = build(dev1, full1, ion, D)
+    st1 = tb.MonodomainStepper(dev1, M1, K1, ion.model_id, ion.params())
     st1.set_cell_solver(10, 0.1)
-    u1 = tb.B200Vector.from_host(dev, u0, 2)
+    u1 = tb.B200Vector.from_host(dev1, u0, 2)
     it1 = [st1.step(u1, float(s), 1.0)[0] for s in range(5)]
     ref = u1.to_host()
     # --- partitioned ---------------------------------------------------------------------------------
@@ -60,8 +62,11 @@ def main():
     rp, ci = M.pattern()
     rp1, ci1 = M1.pattern()
     assert np.array_equal(np.diff(rp), np.diff(rp1[lo:hi + 1]))
-    assert np.array_equal(gids[ci], ci1[rp1[lo]:rp1[hi]])
-    v, v1 = M.nonzeros(), M1.nonzeros()[rp1[lo]:rp1[hi]]
+    # local columns are sorted by LOCAL id (owned first, ghosts after), so map to global ids and re-sort per row
+    rows = np.repeat(np.arange(hi - lo), np.diff(rp))
+    order = np.lexsort((gids[ci], rows))
+    assert np.array_equal(gids[ci][order], ci1[rp1[lo]:rp1[hi]])
+    v, v1 = M.nonzeros()[order], M1.nonzeros()[rp1[lo]:rp1[hi]]
     assert np.abs(v - v1).max() <= 1e-13 * np.abs(v1).max()
     st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
     st.set_cell_solver(10, 0.1)

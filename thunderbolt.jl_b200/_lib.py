@@ -100,6 +100,7 @@ _SIGNATURES = {
     "tb_csr_create_like": [_vp, _pp],
     "tb_csr_destroy": [_vp],
     "tb_csr_sizes": [_vp, _pi64, _pi64, _pi64],
+    "tb_csr_storage": [_vp, _pi64, _pi64, _pi32],
     "tb_csr_download_pattern": [_vp, _i64p, _i64p, C.c_int32],
     "tb_csr_values_download": [_vp, _f64p],
     "tb_csr_values_upload": [_vp, _f64p],

@@ -242,6 +242,12 @@ class B200CSRMatrix:
         L.call("tb_csr_create_like", self.h, C.byref(h))
         return B200CSRMatrix(self.dev, h)
 
+    def storage(self):
+        """(stored entries incl. padding, bytes of the column stream the SpMV reads, widest slice)"""
+        se, cb, mw = C.c_int64(), C.c_int64(), C.c_int32()
+        L.call("tb_csr_storage", self.h, C.byref(se), C.byref(cb), C.byref(mw))
+        return se.value, cb.value, mw.value
+
     def pattern(self, index_base=0):
         rowptr = np.empty(self.nrows + 1, dtype=np.int64)
         colidx = np.empty(self.nnz, dtype=np.int64)

@@ -148,17 +148,18 @@ __global__ void __launch_bounds__(256)
 // ---- bulk-async (TMA) variants of the two SpMV-shaped kernels ------------------------------------------
 // Same arithmetic and summation order as above; the matrix stream comes through cp.async.bulk + mbarrier
 // (tb_spmv.cuh).  INIT = true: r = p = M*phi (+bS), x = 0, gamma; false: Ap = A p, p.Ap.
-template <int STAGES, bool INIT>
+template <int STAGES, bool INIT, bool CC>
 __global__ void __launch_bounds__(1024, 1)
-    k_cg_spmv_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ val,
-                  const double *__restrict__ xin, const double *__restrict__ bS, double *__restrict__ xout,
-                  double *__restrict__ r, double *__restrict__ pout, int64_t nrows, int64_t nslices, int wcap, CGState *st,
-                  double *partials, unsigned *ticket, bool dist) {
+    k_cg_spmv_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
+                  const double *__restrict__ val, const double *__restrict__ xin, const double *__restrict__ bS,
+                  double *__restrict__ xout, double *__restrict__ r, double *__restrict__ pout, int64_t nrows,
+                  int64_t nslices, unsigned val_bytes, unsigned col_bytes, CGState *st, double *partials, unsigned *ticket,
+                  bool dist) {
     if (!INIT && st->done) return;
     extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
     __shared__ double sm[32];
     double acc = 0.0;
-    tb_sell_sweep_tma<STAGES>(slice_ptr, col, val, xin, nslices, wcap, tb_dyn_smem, [&](int64_t row, double v) {
+    tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, [&](int64_t row, double v) {
         if (row < nrows) {
             if (INIT) {
                 if (bS) v += bS[row];
@@ -181,16 +182,27 @@ template <int STAGES, bool INIT>
 static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern *pat, const double *val, const double *xin,
                                const double *bS, double *xout, double *r, double *pout, CGState *st, double *part,
                                unsigned *tick, bool dist) {
-    const tb_tma_geom g = tb_tma_geometry(pat->max_width, STAGES, warps_override);
-    static size_t configured = 0;
-    if (configured < g.smem) {
-        TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        configured = g.smem;
-    }
+    const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width, cc ? pat->max_ccol_ints : 32 * pat->max_width, STAGES, warps_override);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);   // one CTA per SM, one balanced wave
-    TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, val, xin, bS, xout,
-              r, pout, pat->nrows, pat->nslices, g.wcap, st, part, tick, dist);
+    if (cc) {
+        static size_t configured = 0;
+        if (configured < g.smem) {
+            TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+            configured = g.smem;
+        }
+        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_ccol,
+                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist);
+    } else {
+        static size_t configured = 0;
+        if (configured < g.smem) {
+            TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+            configured = g.smem;
+        }
+        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, nullptr,
+                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist);
+    }
     return TB_OK;
 }
 

@@ -60,6 +60,7 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_CUDA(cudaMalloc(&ctx->d_scalar, sizeof(double) * 16));
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));
     if (const char *v = getenv("TB_SPMV_VARIANT")) ctx->spmv_variant = atoi(v);
+    if (const char *v = getenv("TB_SPMV_COMPRESS")) ctx->spmv_compress = atoi(v);
     *out = ctx;
     return TB_OK;
 }

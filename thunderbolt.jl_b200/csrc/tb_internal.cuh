@@ -99,6 +99,7 @@ struct tb_ctx {
     size_t flush_bytes = 0;
     int assembly_mode = 0;
     int spmv_variant = 1;             // 0: LDG kernel, 1..: bulk-async (TMA) staged kernel configurations (env TB_SPMV_VARIANT)
+    int spmv_compress = 1;            // use the compressed column stream in the staged kernels (env TB_SPMV_COMPRESS)
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
     // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
     bool profile = false;
@@ -171,6 +172,11 @@ struct tb_pattern {
     int64_t *d_rowptr = nullptr;  // nrows+1 (CSR row pointers, 0-based)
     int64_t *d_slice_ptr = nullptr; // nslices+1 offsets into col/val, multiples of 32
     int *d_col = nullptr;         // sell_len column ids (padding: a valid column, value 0)
+    // compressed column stream (tb_csr.cu: one int32 offset per slot when col = row + off for all lanes)
+    int *d_ccol = nullptr;
+    int64_t *d_cptr = nullptr;    // nslices+1 offsets into d_ccol, in ints, multiples of 4
+    int64_t ccol_len = 0;
+    int max_ccol_ints = 0;        // largest per-slice stream (sizes the shared-memory stage)
     int refcount = 1;
     tb_halo halo;
     // element colouring cache (assembly mode 1)

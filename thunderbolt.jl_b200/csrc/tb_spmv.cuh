@@ -4,14 +4,16 @@
 // Two implementations of the same arithmetic (identical summation order, bitwise equal results):
 //   tb_sell_row        plain LDG: every lane loads its own values/column ids (any slice width)
 //   tb_sell_sweep_tma  sm_100a bulk-async pipeline: one elected lane per warp streams the slice's
-//                      contiguous value and column blocks into shared memory with cp.async.bulk (TMA,
-//                      SASS UBLKCP) completing on an mbarrier; the lanes then read shared memory and
-//                      only the dependent x gathers go through the LSU, all of a row's gathers in flight
-//                      at once.  Used when every slice is at most TB_TMA_WCAP entries wide.
-//                      Measured on the 101 M-row hex operator: 5.67 ms vs 6.25 ms for the LDG kernel
-//                      (96 % vs 87 % of the measured copy bandwidth).
+//                      contiguous value block and its (compressed) column stream into shared memory with
+//                      cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier; the lanes then read
+//                      shared memory and only the x gathers go through the LSU, all of a row's gathers
+//                      in flight at once.  Used when every slice is at most TB_TMA_WCAP entries wide.
+//                      Measured on the 101 M-row hex operator (uncompressed columns): 5.3 ms vs 6.25 ms
+//                      for the LDG kernel (1.02 vs 0.87 of the measured copy bandwidth).
 #pragma once
 #include "tb_internal.cuh"
+
+#define TB_CCOL_EXPLICIT INT32_MIN   // header value of a slot whose 32 column ids are stored explicitly
 
 // Row (s*32 + lane) of y = A x.  Entry j of the row is at slice_ptr[s] + j*32 + lane, so one warp
 // streams 256 B of values + 128 B of column ids per j, fully coalesced; the dependent x gathers hit
@@ -44,9 +46,6 @@ __device__ __forceinline__ double tb_sell_row(const int64_t *__restrict__ slice_
 // ---------------------------------------------------------------------------------------------------
 #define TB_TMA_WCAP 48   // widest slice (entries per row) the staged kernel is used for
 
-// bytes of one stage for slices up to `wcap` entries wide: 32 rows x (8 B value + 4 B column) per entry
-__host__ __device__ __forceinline__ size_t tb_tma_stage_bytes(int wcap) { return (size_t)wcap * 384; }
-
 __device__ __forceinline__ unsigned tb_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void tb_mbar_init(unsigned bar, unsigned count) {
@@ -75,16 +74,42 @@ __device__ __forceinline__ void tb_bulk_g2s(unsigned dst, const void *src, unsig
                  : "memory");
 }
 
+// Launch geometry of the staged kernels: as many warps per CTA as fit the shared memory (the gather
+// phase is latency bound: more warps = more gathers in flight; measured 21 x 1 stage > 16 x 1 > 8 x 2 >
+// 4 x 3), one CTA per SM.
+struct tb_tma_geom {
+    int warps;
+    unsigned val_bytes;    // bytes reserved per stage for the value block
+    unsigned col_bytes;    // bytes reserved per stage for the column stream
+    size_t smem;
+};
+// col_ints: largest per-slice column stream in ints (compressed), or 32*max_width (uncompressed)
+static inline tb_tma_geom tb_tma_geometry(int max_width, int col_ints, int stages, int warps_override) {
+    tb_tma_geom g;
+    const int w = max_width < 1 ? 1 : max_width;
+    g.val_bytes = (unsigned)w * 256u;
+    g.col_bytes = (unsigned)((col_ints + 3) & ~3) * 4u;
+    const size_t per_warp = (size_t)stages * (g.val_bytes + g.col_bytes) + (size_t)stages * 8;
+    int n = (int)((220 * 1024) / per_warp);
+    if (n > 32) n = 32;
+    if (n < 1) n = 1;
+    if (warps_override > 0 && warps_override < n) n = warps_override;
+    g.warps = n;
+    g.smem = (size_t)n * per_warp;
+    return g;
+}
+
 // One warp = one private ring of STAGES slices.  `epi(row, acc)` is called by every lane with the
-// finished row sum (rows >= nrows included: the caller masks).  `wcap` >= the widest slice.
-// Dynamic shared memory: nwarps*STAGES*tb_tma_stage_bytes(wcap) + nwarps*STAGES*8 bytes, nwarps = blockDim.x/32.
-template <int STAGES, class Epilogue>
-__device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col,
-                                                  const double *__restrict__ val, const double *__restrict__ x,
-                                                  int64_t nslices, int wcap, unsigned char *smem, Epilogue epi) {
+// finished row sum (rows >= nrows included: the caller masks).
+// CC = false: cstream = SELL column ids, cptr unused.  CC = true: cstream/cptr = compressed column stream.
+// Dynamic shared memory: nwarps*STAGES*(val_bytes+col_bytes) + nwarps*STAGES*8 bytes.
+template <int STAGES, bool CC, class Epilogue>
+__device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ slice_ptr, const double *__restrict__ val,
+                                                  const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
+                                                  const double *__restrict__ x, int64_t nslices, unsigned val_bytes,
+                                                  unsigned col_bytes, unsigned char *smem, Epilogue epi) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const size_t stage_bytes = tb_tma_stage_bytes(wcap);
-    const size_t col_off = (size_t)wcap * 256;
+    const size_t stage_bytes = (size_t)val_bytes + col_bytes;
     unsigned char *wbase = smem + (size_t)warp * STAGES * stage_bytes;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)nwarp * STAGES * stage_bytes) + warp * STAGES;
     if (lane == 0) {
@@ -101,10 +126,20 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         const unsigned n = (unsigned)(slice_ptr[s + 1] - base);   // stored entries of the slice (32 * width)
         const unsigned bar = tb_smem_addr(bars + stage);
         unsigned char *dst = wbase + (size_t)stage * stage_bytes;
-        tb_mbar_expect_tx(bar, n * 12u);
-        if (n) {
-            tb_bulk_g2s(tb_smem_addr(dst), val + base, n * 8u, bar);
-            tb_bulk_g2s(tb_smem_addr(dst + col_off), col + base, n * 4u, bar);
+        if (CC) {
+            const int64_t cb = cptr[s];
+            const unsigned cn = (unsigned)(cptr[s + 1] - cb);      // ints, multiple of 4
+            tb_mbar_expect_tx(bar, n * 8u + cn * 4u);
+            if (n) {
+                tb_bulk_g2s(tb_smem_addr(dst), val + base, n * 8u, bar);
+                tb_bulk_g2s(tb_smem_addr(dst + val_bytes), cstream + cb, cn * 4u, bar);
+            }
+        } else {
+            tb_mbar_expect_tx(bar, n * 12u);
+            if (n) {
+                tb_bulk_g2s(tb_smem_addr(dst), val + base, n * 8u, bar);
+                tb_bulk_g2s(tb_smem_addr(dst + val_bytes), cstream + base, n * 4u, bar);
+            }
         }
     };
 
@@ -122,30 +157,49 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
     unsigned parity = 0;
     for (int64_t s = gw; s < nslices; s += nw) {
         const int w = (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 5);
+        const int row = (int)(s * TB_SLICE) + lane;
         tb_mbar_wait(tb_smem_addr(bars + stage), parity);
         const double *sv = reinterpret_cast<const double *>(wbase + (size_t)stage * stage_bytes) + lane;
-        const int *sc = reinterpret_cast<const int *>(wbase + (size_t)stage * stage_bytes + col_off) + lane;
+        const int *sc = reinterpret_cast<const int *>(wbase + (size_t)stage * stage_bytes + val_bytes);
         double acc = 0.0;
-        int j = 0;
-        for (; j + 9 <= w; j += 9) {
-            double xv[9], vv[9];
+        if (CC) {
+            // header: one int per slot (uniform offset or EXPLICIT); explicit blocks follow the padded header
+            const int *sexp = sc + ((w + 3) & ~3) + lane;
+            int e = 0, j = 0;
+            for (; j + 9 <= w; j += 9) {
+                double xv[9], vv[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) xv[k] = x[sc[(j + k) * 32]];
+                for (int k = 0; k < 9; k++) {
+                    const int h = sc[j + k];                                  // broadcast read
+                    int c = row + h;
+                    if (h == TB_CCOL_EXPLICIT) c = sexp[(e++) * 32];          // warp-uniform branch
+                    xv[k] = x[c];
+                }
 #pragma unroll
-            for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
+                for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
 #pragma unroll
-            for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
+                for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
+            }
+            for (; j < w; j++) {
+                const int h = sc[j];
+                int c = row + h;
+                if (h == TB_CCOL_EXPLICIT) c = sexp[(e++) * 32];
+                acc += sv[j * 32] * x[c];
+            }
+        } else {
+            const int *scl = sc + lane;
+            int j = 0;
+            for (; j + 9 <= w; j += 9) {
+                double xv[9], vv[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) xv[k] = x[scl[(j + k) * 32]];
+#pragma unroll
+                for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
+#pragma unroll
+                for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
+            }
+            for (; j < w; j++) acc += sv[j * 32] * x[scl[j * 32]];
         }
-        for (; j + 3 <= w; j += 3) {
-            double xv[3], vv[3];
-#pragma unroll
-            for (int k = 0; k < 3; k++) xv[k] = x[sc[(j + k) * 32]];
-#pragma unroll
-            for (int k = 0; k < 3; k++) vv[k] = sv[(j + k) * 32];
-#pragma unroll
-            for (int k = 0; k < 3; k++) acc += vv[k] * xv[k];
-        }
-        for (; j < w; j++) acc += sv[j * 32] * x[sc[j * 32]];
         epi(s * TB_SLICE + lane, acc);
         // every lane has consumed its shared-memory operands (acc depends on all of them): the stage may be refilled
         __syncwarp();
@@ -156,24 +210,4 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             parity ^= 1u;
         }
     }
-}
-
-// Launch geometry of the staged kernels for a pattern whose widest slice is `max_width`:
-// as many warps per CTA as fit the shared memory (the gather phase is latency bound: more warps = more
-// gathers in flight; measured 16 x 1 stage > 8 x 2 > 4 x 3), one CTA per SM.
-struct tb_tma_geom {
-    int warps, wcap;
-    size_t smem;
-};
-static inline tb_tma_geom tb_tma_geometry(int max_width, int stages, int warps_override) {
-    tb_tma_geom g;
-    g.wcap = max_width < 1 ? 1 : max_width;
-    const size_t per_warp = (size_t)stages * tb_tma_stage_bytes(g.wcap) + (size_t)stages * 8;
-    int w = (int)((220 * 1024) / per_warp);
-    if (w > 32) w = 32;
-    if (w < 1) w = 1;
-    if (warps_override > 0 && warps_override < w) w = warps_override;
-    g.warps = w;
-    g.smem = (size_t)w * per_warp;
-    return g;
 }

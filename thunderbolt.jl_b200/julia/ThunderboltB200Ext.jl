@@ -1,0 +1,197 @@
+# ThunderboltB200Ext.jl -- the reference-side binding of libtbolt_b200.so.
+#
+# Replaces ext/CuThunderboltExt.jl (which is stale in v0.0.4, SURVEY 0-3) at exactly the dispatch points that
+# extension hooks (SURVEY 8b).  NOT EXECUTED in this repository's CI: there is no Julia toolchain in the build
+# image; the same C ABI is exercised through ctypes by thunderbolt.jl_b200/api.py and tests/.
+#
+# Load as a package extension of Thunderbolt (Project.toml: [weakdeps]/[extensions]) or `include` it after
+# `using Thunderbolt`.
+module ThunderboltB200Ext
+
+using Thunderbolt, LinearSolve, SciMLBase, LinearAlgebra, SparseArrays
+import Thunderbolt: create_system_vector, create_system_matrix, adapt_vector_type, setup_operator, update_operator!,
+    needs_update, _pointwise_step_outer_kernel!, PointwiseODEFunction, AbstractPointwiseSolverCache,
+    AdaptiveForwardEulerSubstepperCache, ForwardEulerCellSolverCache, BilinearMassIntegrator, BilinearDiffusionIntegrator,
+    LinearIntegrator, AnalyticalTransmembraneStimulationProtocol, ParametrizedFHNModel, ParametrizedPCG2019Model,
+    ConductivityToDiffusivityCoefficient, ConstantCoefficient, ElementAssemblyStrategy, AbstractGPUDevice, num_states
+import Ferrite
+
+const LIB = Ref{String}("libtbolt_b200.so")
+
+struct TBError <: Exception
+    status::Int32
+    msg::String
+end
+check(status::Int32) = status == 0 ? nothing : throw(TBError(status, unsafe_string(ccall((:tb_last_error, LIB[]), Cstring, ()))))
+macro tb(f, argtypes, args...)
+    esc(:(check(ccall(($(QuoteNode(f)), LIB[]), Int32, $argtypes, $(args...)))))
+end
+
+# ---- device (src/devices.jl:1-4) -------------------------------------------------------------------
+mutable struct B200Device <: AbstractGPUDevice
+    h::Ptr{Cvoid}
+    function B200Device(id::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        @tb tb_ctx_create (Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}) Int32(id) C_NULL r
+        finalizer(d -> ccall((:tb_ctx_destroy, LIB[]), Int32, (Ptr{Cvoid},), d.h), new(r[]))
+    end
+end
+const DEFAULT_DEVICE = Ref{Union{Nothing, B200Device}}(nothing)
+default_device() = something(DEFAULT_DEVICE[], (DEFAULT_DEVICE[] = B200Device(0)))
+
+# ---- vectors (src/solver/interface.jl:175-181, src/utils.jl:425-427) ---------------------------------
+mutable struct B200Vector{T} <: AbstractVector{T}
+    h::Ptr{Cvoid}
+    n::Int
+    ncols::Int
+    dev::B200Device
+end
+function B200Vector{Float64}(dev::B200Device, n::Integer, ncols::Integer = 1)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    @tb tb_vec_create (Ptr{Cvoid}, Int64, Int32, Ref{Ptr{Cvoid}}) dev.h n ncols r
+    finalizer(v -> ccall((:tb_vec_destroy, LIB[]), Int32, (Ptr{Cvoid},), v.h), B200Vector{Float64}(r[], n, ncols, dev))
+end
+Base.size(v::B200Vector) = (v.n * v.ncols,)
+function B200Vector(u::Vector{Float64}; nstates = 1, dev = default_device())
+    v = B200Vector{Float64}(dev, length(u) ÷ nstates, nstates)
+    @tb tb_vec_upload (Ptr{Cvoid}, Ptr{Float64}) v.h u
+    v
+end
+function Base.Array(v::B200Vector{Float64})
+    out = Vector{Float64}(undef, v.n * v.ncols)
+    @tb tb_vec_download (Ptr{Cvoid}, Ptr{Float64}) v.h out
+    out
+end
+create_system_vector(::Type{<:B200Vector{T}}, f::Thunderbolt.AbstractSemidiscreteFunction) where {T} =
+    B200Vector{T}(default_device(), Thunderbolt.solution_size(f))
+create_system_vector(::Type{<:B200Vector{T}}, dh::Ferrite.DofHandler) where {T} = B200Vector{T}(default_device(), Ferrite.ndofs(dh))
+adapt_vector_type(::Type{<:B200Vector}, v::Vector) = v   # coordinates stay on the host: FHN/PCG2019 ignore x (SURVEY a-5)
+
+# ---- mesh handle: what Ferrite hands the operators (fem.jl:180-182) ----------------------------------
+const CELLTYPE = Dict(Ferrite.Quadrilateral => 0, Ferrite.Hexahedron => 1, Ferrite.Triangle => 2, Ferrite.Tetrahedron => 3)
+mutable struct B200Mesh
+    h::Ptr{Cvoid}
+end
+function B200Mesh(dev::B200Device, dh::Ferrite.DofHandler)
+    grid = Ferrite.get_grid(dh)
+    CT = typeof(first(grid.cells))
+    nv = length(first(grid.cells).nodes)
+    conn = Int64[n for c in grid.cells for n in c.nodes]                       # 1-based node ids
+    coords = Float64[x for n in grid.nodes for x in n.x]
+    cdofs = Int64[d for c in 1:Ferrite.getncells(grid) for d in Ferrite.celldofs(dh, c)]
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    @tb tb_mesh_create (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Int64, Int32, Ref{Ptr{Cvoid}}) dev.h Int32(CELLTYPE[CT]) length(grid.cells) length(grid.nodes) conn coords cdofs Ferrite.ndofs(dh) Int32(1) r
+    finalizer(m -> ccall((:tb_mesh_destroy, LIB[]), Int32, (Ptr{Cvoid},), m.h), B200Mesh(r[]))
+end
+
+# ---- matrices (src/solver/interface.jl:159-173) --------------------------------------------------------
+mutable struct B200CSRMatrix{Tv, Ti} <: AbstractSparseMatrix{Tv, Ti}
+    h::Ptr{Cvoid}
+    n::Int
+    dev::B200Device
+end
+function create_system_matrix(::Type{<:B200CSRMatrix{Tv, Ti}}, dh::Ferrite.AbstractDofHandler) where {Tv, Ti}
+    dev = default_device()
+    # Ferrite's pattern, transposed to CSR exactly like the ThreadedSparseMatrixCSR method: bit-exact pattern parity
+    Acsc = convert(SparseMatrixCSC{Tv, Int64}, Ferrite.allocate_matrix(dh))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    n = size(Acsc, 1)
+    @tb tb_csr_create (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ref{Ptr{Cvoid}}) dev.h n n Acsc.colptr Acsc.rowval Int32(1) r
+    finalizer(A -> ccall((:tb_csr_destroy, LIB[]), Int32, (Ptr{Cvoid},), A.h), B200CSRMatrix{Tv, Ti}(r[], n, dev))
+end
+Base.size(A::B200CSRMatrix) = (A.n, A.n)
+function SparseArrays.nonzeros(A::B200CSRMatrix{Tv}) where {Tv}
+    nnz = Ref{Int64}(0)
+    @tb tb_csr_sizes (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Int64}) A.h C_NULL C_NULL nnz
+    v = Vector{Tv}(undef, nnz[])
+    @tb tb_csr_values_download (Ptr{Cvoid}, Ptr{Float64}) A.h v
+    v
+end
+LinearAlgebra.mul!(y::B200Vector, A::B200CSRMatrix, x::B200Vector) =
+    (@tb tb_spmv (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32) A.dev.h A.h x.h Int32(0) y.h Int32(0); y)
+# euler.jl:104-116
+Thunderbolt._implicit_euler_heat_solver_update_system_matrix!(A::B200CSRMatrix, M, K, Δt) =
+    @tb tb_csr_axpby_values (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64) A.h M.A.h K.A.h Float64(Δt)
+
+# ---- operators (src/solver/interface.jl:17-94; discretization/operator.jl:2-32) ---------------------------
+struct B200BilinearOperator{I}
+    A::B200CSRMatrix{Float64, Int32}
+    integrator::I
+    dh::Ferrite.DofHandler
+    mesh::B200Mesh
+end
+struct B200LinearOperator{I}
+    b::B200Vector{Float64}
+    integrator::I
+    dh::Ferrite.DofHandler
+    mesh::B200Mesh
+end
+const MESHES = IdDict{Any, B200Mesh}()
+mesh_of(dev, dh) = get!(() -> B200Mesh(dev, dh), MESHES, dh)
+
+function setup_operator(s::ElementAssemblyStrategy{<:B200Device}, i::Thunderbolt.AbstractBilinearIntegrator, solver::Thunderbolt.AbstractSolver, dh)
+    B200BilinearOperator(create_system_matrix(B200CSRMatrix{Float64, Int32}, dh), i, dh, mesh_of(s.device, dh))
+end
+function setup_operator(s::ElementAssemblyStrategy{<:B200Device}, i::LinearIntegrator, dh)
+    B200LinearOperator(B200Vector{Float64}(s.device, Ferrite.ndofs(dh)), i, dh, mesh_of(s.device, dh))
+end
+qorder(i) = Thunderbolt.getorder(i.qrc)
+
+function update_operator!(op::B200BilinearOperator{<:BilinearMassIntegrator}, t)
+    @tb tb_assemble_mass (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, Ptr{Cvoid}) op.A.dev.h op.mesh.h Int32(qorder(op.integrator)) Float64(op.integrator.ρ.val) op.A.h
+end
+function update_operator!(op::B200BilinearOperator{<:BilinearDiffusionIntegrator}, t)
+    D = op.integrator.D                                   # ConductivityToDiffusivityCoefficient(κ, Cₘ, χ)
+    κ = D.conductivity_tensor_coefficient.val
+    cmχ = D.capacitance_coefficient.val * D.χ_coefficient.val
+    data = κ isa Number ? Float64[κ] : Float64[κ[i, j] for i in 1:size(κ, 1) for j in 1:size(κ, 2)]
+    kind = κ isa Number ? 0 : 1                           # TB_D_SCALAR / TB_D_TENSOR; spectral: kind 2, see tbolt_b200.h
+    @tb tb_assemble_diffusion (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Float64, Ptr{Cvoid}) op.A.dev.h op.mesh.h Int32(qorder(op.integrator)) Int32(kind) data length(data) Float64(cmχ) op.A.h
+end
+# A Julia closure cannot cross the C ABI: evaluate f at the quadrature points on the host, ship the values.
+function update_operator!(op::B200LinearOperator, t)
+    proto = op.integrator.integrand::AnalyticalTransmembraneStimulationProtocol
+    fq = Thunderbolt.evaluate_at_quadrature_points(proto.f, op.dh, op.integrator.qrc, t)   # ncells × nq, helper to add
+    @tb tb_assemble_source_qp (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}, Int32) op.b.dev.h op.mesh.h Int32(qorder(op.integrator)) fq op.b.h Int32(0)
+end
+needs_update(op::B200LinearOperator, t) = any(iv -> iv[1] ≤ t ≤ iv[2], op.integrator.integrand.nonzero_intervals)
+LinearAlgebra.mul!(b::B200Vector, M::B200BilinearOperator, u::B200Vector) = mul!(b, M.A, u)
+Thunderbolt.add!(b::B200Vector, S::B200LinearOperator) =
+    @tb tb_vec_axpy (Ptr{Cvoid}, Int32, Float64, Ptr{Cvoid}, Int32) b.h Int32(0) 1.0 S.b.h Int32(0)
+
+# ---- linear solve (euler.jl:94,155-156) ----------------------------------------------------------------
+Base.@kwdef struct B200CG <: LinearSolve.SciMLLinearSolveAlgorithm
+    atol::Float64 = sqrt(eps(Float64))
+    rtol::Float64 = sqrt(eps(Float64))
+    maxiters::Int = 0            # 0 -> length(b), LinearSolve's default
+end
+mutable struct B200CGCache
+    iters::Int64
+    resid::Float64
+end
+LinearSolve.init_cacheval(::B200CG, A, b, u, Pl, Pr, maxiters, abstol, reltol, verbose, assumptions) = B200CGCache(0, 0.0)
+function SciMLBase.solve!(cache::LinearSolve.LinearCache, alg::B200CG; kwargs...)
+    A, b, u = cache.A::B200CSRMatrix, cache.b::B200Vector, cache.u::B200Vector
+    it, rn, conv = Ref{Int64}(0), Ref{Float64}(0.0), Ref{Int32}(0)
+    itmax = alg.maxiters == 0 ? length(b) : alg.maxiters
+    @tb tb_cg_solve (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Float64, Float64, Int64, Ref{Int64}, Ref{Float64}, Ref{Int32}) A.dev.h A.h b.h Int32(0) u.h Int32(0) alg.atol alg.rtol itmax it rn conv
+    cache.cacheval.iters, cache.cacheval.resid = it[], rn[]
+    # non-convergence is a retcode, not an exception: euler.jl:95-100 then returns false and the integrator rolls back
+    SciMLBase.build_linear_solution(alg, u, nothing, cache; retcode = conv[] == 1 ? ReturnCode.Success : ReturnCode.MaxIters, iters = it[])
+end
+
+# ---- cell sweep (partitioned_solver.jl:38-52; the method CuThunderboltExt.jl:111-124 had for CuVector) -----------
+model_id(::ParametrizedFHNModel) = Int32(0)
+model_id(::ParametrizedPCG2019Model) = Int32(1)
+params(m) = Float64[getfield(m, f) for f in fieldnames(typeof(m))]
+substeps(c::ForwardEulerCellSolverCache) = (Int32(1), 0.1)
+substeps(c::AdaptiveForwardEulerSubstepperCache) = (Int32(c.substeps), Float64(c.reaction_threshold))
+function _pointwise_step_outer_kernel!(f::PointwiseODEFunction, t::Real, Δt::Real, cache::AbstractPointwiseSolverCache, u::B200Vector)
+    p = params(f.ode)
+    ns, thr = substeps(cache)
+    φidx = Thunderbolt.transmembranepotential_index(f.ode) - 1
+    @tb tb_cell_step (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Cvoid}, Int32, Float64, Float64, Int32, Float64, Ptr{Float64}) u.dev.h model_id(f.ode) p Int32(length(p)) u.h Int32(φidx) Float64(t) Float64(Δt) ns thr C_NULL
+    return true
+end
+
+end # module
