@@ -39,8 +39,8 @@ int hm_element_matrix(int celltype, int qorder, int op, const double *X, double 
     double acc[36];
 #define RUN(NV, DIM)                                                                              \
     {                                                                                             \
-        if (op == 0) tb_element_mass<NV, DIM, 1>(&T, X, rho, acc);                                \
-        else tb_element_diffusion<NV, DIM, 1>(&T, X, kind, data, cmchi, cell, acc);               \
+        if (op == 0) tb_element_mass<NV, DIM, 1>(tb_view_of(&T), X, rho, acc);                                \
+        else tb_element_diffusion<NV, DIM, 1>(tb_view_of(&T), X, kind, data, cmchi, cell, acc);               \
         unpack<NV>(acc, out);                                                                     \
     }
     switch (celltype) {
@@ -58,10 +58,10 @@ int hm_element_source(int celltype, int qorder, const double *X, int kind, const
     tb_elem_tables T;
     if (tb_build_tables(celltype, qorder, &T)) return 1;
     switch (celltype) {
-    case 0: tb_element_source<4, 2, 1>(&T, X, kind, prm, t, fq, be); break;
-    case 1: tb_element_source<8, 3, 1>(&T, X, kind, prm, t, fq, be); break;
-    case 2: tb_element_source<3, 2, 1>(&T, X, kind, prm, t, fq, be); break;
-    default: tb_element_source<4, 3, 1>(&T, X, kind, prm, t, fq, be); break;
+    case 0: tb_element_source<4, 2, 1>(tb_view_of(&T), X, kind, prm, t, fq, be); break;
+    case 1: tb_element_source<8, 3, 1>(tb_view_of(&T), X, kind, prm, t, fq, be); break;
+    case 2: tb_element_source<3, 2, 1>(tb_view_of(&T), X, kind, prm, t, fq, be); break;
+    default: tb_element_source<4, 3, 1>(tb_view_of(&T), X, kind, prm, t, fq, be); break;
     }
     return 0;
 }

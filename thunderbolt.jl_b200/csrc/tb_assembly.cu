@@ -79,17 +79,19 @@ __device__ __forceinline__ void stage_tile(const int *__restrict__ conn, const i
 template <int NV, int DIM, int OP>
 __global__ void __launch_bounds__(AS_BLOCK)
     k_assemble_bilinear(const int *__restrict__ conn, const int *__restrict__ celldofs, const double *__restrict__ coords,
-                        int64_t ncells, const tb_elem_tables *__restrict__ gT, double rho, int kind,
+                        int64_t ncells, const tb_elem_tables *__restrict__ gT, int nq, double rho, int kind,
                         const double *__restrict__ ddata, double cmchi, SellView S) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tb_elem_tables *sT = reinterpret_cast<tb_elem_tables *>(smem_raw);
-    double *sX = reinterpret_cast<double *>(smem_raw + sizeof(tb_elem_tables));
+    // shared memory: the nq used rows of the quadrature/shape tables, then the coordinate tile, then the dof tile
+    double *sW = reinterpret_cast<double *>(smem_raw);
+    double *sN = sW + nq;
+    double *sdN = sN + nq * NV;
+    double *sX = sdN + nq * NV * DIM;
     int *sDof = reinterpret_cast<int *>(sX + NV * DIM * AS_BLOCK);
-    {
-        const int *src = reinterpret_cast<const int *>(gT);
-        int *dst = reinterpret_cast<int *>(sT);
-        for (int i = threadIdx.x; i < (int)(sizeof(tb_elem_tables) / sizeof(int)); i += AS_BLOCK) dst[i] = src[i];
-    }
+    for (int i = threadIdx.x; i < nq; i += AS_BLOCK) sW[i] = gT->w[i];
+    for (int i = threadIdx.x; i < nq * NV; i += AS_BLOCK) sN[i] = gT->N[i];
+    for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
+    const tb_tables_view sT{nq, sW, sN, sdN};
     const int64_t ntiles = (ncells + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = tile * AS_BLOCK;
@@ -120,19 +122,21 @@ __global__ void __launch_bounds__(AS_BLOCK)
 template <int NV, int DIM>
 __global__ void __launch_bounds__(AS_BLOCK)
     k_assemble_source(const int *__restrict__ conn, const int *__restrict__ celldofs, const double *__restrict__ coords,
-                      int64_t ncells, const tb_elem_tables *__restrict__ gT, int kind, const double *__restrict__ prm,
+                      int64_t ncells, const tb_elem_tables *__restrict__ gT, int nq, int kind, const double *__restrict__ prm,
                       double t, const double *__restrict__ fq, double *__restrict__ b, int64_t nrows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tb_elem_tables *sT = reinterpret_cast<tb_elem_tables *>(smem_raw);
-    double *sX = reinterpret_cast<double *>(smem_raw + sizeof(tb_elem_tables));
+    // shared memory: the nq used rows of the quadrature/shape tables, then the coordinate tile, then the dof tile
+    double *sW = reinterpret_cast<double *>(smem_raw);
+    double *sN = sW + nq;
+    double *sdN = sN + nq * NV;
+    double *sX = sdN + nq * NV * DIM;
     int *sDof = reinterpret_cast<int *>(sX + NV * DIM * AS_BLOCK);
+    for (int i = threadIdx.x; i < nq; i += AS_BLOCK) sW[i] = gT->w[i];
+    for (int i = threadIdx.x; i < nq * NV; i += AS_BLOCK) sN[i] = gT->N[i];
+    for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
+    const tb_tables_view sT{nq, sW, sN, sdN};
     __shared__ double sprm[8];
-    {
-        const int *src = reinterpret_cast<const int *>(gT);
-        int *dst = reinterpret_cast<int *>(sT);
-        for (int i = threadIdx.x; i < (int)(sizeof(tb_elem_tables) / sizeof(int)); i += AS_BLOCK) dst[i] = src[i];
-        if (threadIdx.x < 8) sprm[threadIdx.x] = prm ? prm[threadIdx.x] : 0.0;
-    }
+    if (threadIdx.x < 8) sprm[threadIdx.x] = prm ? prm[threadIdx.x] : 0.0;
     const int64_t ntiles = (ncells + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = tile * AS_BLOCK;
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
         const int64_t e = e0 + threadIdx.x;
         if (e < ncells) {
             double be[NV];
-            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * sT->nq : nullptr, be);
+            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * nq : nullptr, be);
 #pragma unroll
             for (int j = 0; j < NV; j++) {
                 const int d = sDof[threadIdx.x * NV + j];
@@ -152,8 +156,8 @@ __global__ void __launch_bounds__(AS_BLOCK)
     }
 }
 
-static size_t assembly_smem(int nv, int dim) {
-    return sizeof(tb_elem_tables) + sizeof(double) * nv * dim * AS_BLOCK + sizeof(int) * nv * AS_BLOCK;
+static size_t assembly_smem(int nv, int dim, int nq) {
+    return sizeof(double) * nq * (1 + nv + nv * dim) + sizeof(double) * nv * dim * AS_BLOCK + sizeof(int) * nv * AS_BLOCK;
 }
 
 static int32_t upload_tables(tb_ctx *ctx, int celltype, int qorder, tb_elem_tables **d_T, int *nq) {
@@ -168,14 +172,17 @@ static int32_t upload_tables(tb_ctx *ctx, int celltype, int qorder, tb_elem_tabl
 }
 
 template <int NV, int DIM, int OP>
-static int32_t launch_bilinear(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, double rho, int kind,
+static int32_t launch_bilinear(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, double rho, int kind,
                                const double *d_data, double cmchi, const SellView &S) {
-    const size_t smem = assembly_smem(NV, DIM);
+    const size_t smem = assembly_smem(NV, DIM, nq);
     TB_CUDA(cudaFuncSetAttribute(k_assemble_bilinear<NV, DIM, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (m->ncells + AS_BLOCK - 1) / AS_BLOCK;
-    int grid = (int)(ntiles < (int64_t)ctx->sm_count * 4 ? ntiles : (int64_t)ctx->sm_count * 4);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_bilinear<NV, DIM, OP>, AS_BLOCK, smem);
+    if (per_sm < 1) per_sm = 1;
+    int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
     TB_LAUNCH(ctx, (k_assemble_bilinear<NV, DIM, OP>), grid, AS_BLOCK, smem, m->d_conn, m->d_celldofs, m->d_coords,
-              m->ncells, d_T, rho, kind, d_data, cmchi, S);
+              m->ncells, d_T, nq, rho, kind, d_data, cmchi, S);
     return TB_OK;
 }
 
@@ -188,7 +195,8 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     TB_REQUIRE(ctx->assembly_mode == 0, "assemble: colouring mode is not implemented yet (use mode 0, atomics)");
     TB_DEV(ctx);
     tb_elem_tables *d_T = nullptr;
-    TB_TRY(upload_tables(ctx, mesh->celltype, qorder, &d_T, nullptr));
+    int nq = 0;
+    TB_TRY(upload_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
     double *d_data = nullptr;
     if (op == 1) {
         const int64_t need = kind == TB_D_SCALAR ? 1 : kind == TB_D_TENSOR ? mesh->dim * mesh->dim
@@ -205,8 +213,8 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     SellView S{A->pat->d_rowptr, A->pat->d_slice_ptr, A->pat->d_col, A->d_val, A->pat->nrows};
     int32_t st = TB_OK;
 #define DISPATCH(NV, DIM)                                                                                   \
-    st = op == 0 ? launch_bilinear<NV, DIM, 0>(ctx, mesh, d_T, rho, kind, d_data, cmchi, S)                \
-                 : launch_bilinear<NV, DIM, 1>(ctx, mesh, d_T, rho, kind, d_data, cmchi, S)
+    st = op == 0 ? launch_bilinear<NV, DIM, 0>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, S)            \
+                 : launch_bilinear<NV, DIM, 1>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, S)
     switch (mesh->celltype) {
     case TB_QUAD4: DISPATCH(4, 2); break;
     case TB_HEX8: DISPATCH(8, 3); break;
@@ -232,14 +240,14 @@ extern "C" int32_t tb_assemble_diffusion(tb_ctx *ctx, const tb_mesh *mesh, int32
 }
 
 template <int NV, int DIM>
-static int32_t launch_source(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int kind, const double *d_prm,
+static int32_t launch_source(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, int kind, const double *d_prm,
                              double t, const double *d_fq, double *b) {
-    const size_t smem = assembly_smem(NV, DIM);
+    const size_t smem = assembly_smem(NV, DIM, nq);
     TB_CUDA(cudaFuncSetAttribute(k_assemble_source<NV, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (m->ncells + AS_BLOCK - 1) / AS_BLOCK;
     int grid = (int)(ntiles < (int64_t)ctx->sm_count * 4 ? ntiles : (int64_t)ctx->sm_count * 4);
     TB_LAUNCH(ctx, (k_assemble_source<NV, DIM>), grid, AS_BLOCK, smem, m->d_conn, m->d_celldofs, m->d_coords, m->ncells,
-              d_T, kind, d_prm, t, d_fq, b, m->ndofs_owned);
+              d_T, nq, kind, d_prm, t, d_fq, b, m->ndofs_owned);
     return TB_OK;
 }
 
@@ -268,10 +276,10 @@ static int32_t assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int
     int32_t st = TB_OK;
     if (fq || kind != TB_SRC_NONE) {
         switch (mesh->celltype) {
-        case TB_QUAD4: st = launch_source<4, 2>(ctx, mesh, d_T, kind, d_prm, t, d_fq, bp); break;
-        case TB_HEX8: st = launch_source<8, 3>(ctx, mesh, d_T, kind, d_prm, t, d_fq, bp); break;
-        case TB_TRI3: st = launch_source<3, 2>(ctx, mesh, d_T, kind, d_prm, t, d_fq, bp); break;
-        default: st = launch_source<4, 3>(ctx, mesh, d_T, kind, d_prm, t, d_fq, bp); break;
+        case TB_QUAD4: st = launch_source<4, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+        case TB_HEX8: st = launch_source<8, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+        case TB_TRI3: st = launch_source<3, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+        default: st = launch_source<4, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
         }
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);

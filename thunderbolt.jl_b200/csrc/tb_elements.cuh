@@ -25,6 +25,13 @@ struct tb_elem_tables {
     double xi[TB_MAXQ * 3];       // reference points (for tb_quadrature)
 };
 
+// what the element kernels read: the first nq entries of the tables (a kernel stages just these in smem)
+struct tb_tables_view {
+    int nq;
+    const double *w, *N, *dN;
+};
+static inline tb_tables_view tb_view_of(const tb_elem_tables *T) { return tb_tables_view{T->nq, T->w, T->N, T->dN}; }
+
 // ---- host-side table construction --------------------------------------------------------------
 static inline int tb_gauss_1d(int order, double *p, double *w) {
     switch (order) {
@@ -231,12 +238,12 @@ TB_HD void tb_eval_D(int kind, const double *data, double cmchi, int64_t cell, c
 
 // ---- element matrices (packed upper triangle, NV*(NV+1)/2 entries) -----------------------------------
 template <int NV, int DIM, int XS>
-TB_HD void tb_element_mass(const tb_elem_tables *T, const double *X, double rho, double *acc) {
+TB_HD void tb_element_mass(const tb_tables_view T, const double *X, double rho, double *acc) {
 #pragma unroll
     for (int i = 0; i < NV * (NV + 1) / 2; i++) acc[i] = 0.0;
-    for (int q = 0; q < T->nq; q++) {
-        const double *Nq = T->N + q * NV;
-        const double dO = tb_map_qp<NV, DIM, XS, false>(X, T->dN + q * NV * DIM, nullptr) * T->w[q];
+    for (int q = 0; q < T.nq; q++) {
+        const double *Nq = T.N + q * NV;
+        const double dO = tb_map_qp<NV, DIM, XS, false>(X, T.dN + q * NV * DIM, nullptr) * T.w[q];
 #pragma unroll
         for (int i = 0; i < NV; i++)
 #pragma unroll
@@ -245,14 +252,14 @@ TB_HD void tb_element_mass(const tb_elem_tables *T, const double *X, double rho,
 }
 
 template <int NV, int DIM, int XS>
-TB_HD void tb_element_diffusion(const tb_elem_tables *T, const double *X, int kind, const double *data, double cmchi,
+TB_HD void tb_element_diffusion(const tb_tables_view T, const double *X, int kind, const double *data, double cmchi,
                                 int64_t cell, double *acc) {
 #pragma unroll
     for (int i = 0; i < NV * (NV + 1) / 2; i++) acc[i] = 0.0;
-    for (int q = 0; q < T->nq; q++) {
+    for (int q = 0; q < T.nq; q++) {
         double G[NV * DIM], D[DIM * DIM];
-        const double dO = tb_map_qp<NV, DIM, XS, true>(X, T->dN + q * NV * DIM, G) * T->w[q];
-        tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T->N + q * NV, D);
+        const double dO = tb_map_qp<NV, DIM, XS, true>(X, T.dN + q * NV * DIM, G) * T.w[q];
+        tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             if (kind == 0) {
@@ -305,13 +312,13 @@ template <int DIM> TB_HD double tb_source_eval(int kind, const double *prm, cons
 
 // fq != nullptr: host-evaluated f at this cell's quadrature points
 template <int NV, int DIM, int XS>
-TB_HD void tb_element_source(const tb_elem_tables *T, const double *X, int kind, const double *prm, double t,
+TB_HD void tb_element_source(const tb_tables_view T, const double *X, int kind, const double *prm, double t,
                              const double *fq, double *be) {
 #pragma unroll
     for (int j = 0; j < NV; j++) be[j] = 0.0;
-    for (int q = 0; q < T->nq; q++) {
-        const double *Nq = T->N + q * NV;
-        const double dO = tb_map_qp<NV, DIM, XS, false>(X, T->dN + q * NV * DIM, nullptr) * T->w[q];
+    for (int q = 0; q < T.nq; q++) {
+        const double *Nq = T.N + q * NV;
+        const double dO = tb_map_qp<NV, DIM, XS, false>(X, T.dN + q * NV * DIM, nullptr) * T.w[q];
         double fx;
         if (fq) {
             fx = fq[q];

@@ -164,8 +164,22 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         double acc = 0.0;
         if (CC) {
             // header: one int per slot (uniform offset or EXPLICIT); explicit blocks follow the padded header
-            const int *sexp = sc + ((w + 3) & ~3) + lane;
+            const int hdr_ints = (w + 3) & ~3;
+            const int *sexp = sc + hdr_ints + lane;
             int e = 0, j = 0;
+            if ((int)(cptr[s + 1] - cptr[s]) == hdr_ints) {
+                // fast path (most slices of a structured mesh): every slot is a uniform offset
+                for (; j + 9 <= w; j += 9) {
+                    double xv[9], vv[9];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) xv[k] = x[row + sc[j + k]];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
+                }
+                for (; j < w; j++) acc += sv[j * 32] * x[row + sc[j]];
+            }
             for (; j + 9 <= w; j += 9) {
                 double xv[9], vv[9];
 #pragma unroll
