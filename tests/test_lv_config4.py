@@ -91,17 +91,25 @@ def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
     model = tb.MonodomainModel(tb.ConstantCoefficient(1.0), tb.ConstantCoefficient(1.0), kappa, proto, tb.PCG2019(), "φₘ", "s")
     odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(model), tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), mesh)
     u0 = tb.create_initial_condition(odeform)
-    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 0.5)),
-                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(), tb.ForwardEulerCellSolver())), dt=0.01)
+    def make(cg):
+        return tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 0.5)),
+                       tb.LieTrotterGodunov((tb.BackwardEulerSolver(inner_solver=cg), tb.ForwardEulerCellSolver())), dt=0.01)
+    integ = make(tb.B200CG())
     # oracle with the same inputs
     data = np.concatenate([[k1, kr, kr], np.ascontiguousarray(fsn).reshape(tets.shape[0], 4, 9).ravel()])
     Mo, Ko = O.assemble_mass(mo, 2), O.assemble_diffusion(mo, 2, O.D_SPECTRAL, data)
     hc = integ.caches[0]
     assert np.array_equal(hc.M.A.pattern()[1], mo.pattern()[1])                    # pattern: bit exact
     assert np.allclose(hc.K.A.nonzeros(), Ko, rtol=0, atol=1e-13 * np.abs(Ko).max())
+    N = mo.ndofs
+
+    # (1) LinearSolve's default tolerances (sqrt(eps)).  On this mesh the CG residual history is sensitive to
+    # the summation order of the dot products at the 10 % level by iteration 39 (measured: sequential 1.683e-7,
+    # pairwise 1.604e-7, exactly rounded 1.436e-7 against a stopping threshold of 1.674e-7), so the stop can
+    # legitimately fall one iteration earlier or later than the oracle's: the rule is +-1 iteration, and phi may
+    # then differ by the CG stopping error cond(A)*sqrt(eps), not by 1e-10.
     orc = O.MonodomainOracle(mo, O.PCG2019, O.default_params(O.PCG2019), Mo, Ko)
     uo = u0.copy()
-    N = mo.ndofs
     t, dt = 0.0, 0.01
     for step in range(50):
         orc.bS = O.assemble_source(mo, 2, O.SRC_ENDO, [0.0, 2.0, 0.5, 0.25], t + dt)
@@ -109,9 +117,23 @@ def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
         assert tb.step_(integ) and convo
         assert abs(integ.cg_iterations[-1] - ito) <= 1
         t += dt
-        if step == 0:
-            h = integ.u.to_host()
-            assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-10
     h = integ.u.to_host()
-    assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-8
+    assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-6
     assert h[:N].max() > -84.0                                                     # the stimulus has started to depolarise
+
+    # (2) the 1e-10-after-one-step rule, with the linear solve converged below it on both sides
+    tight = dict(atol=1e-15, rtol=1e-14)
+    integ2 = make(tb.B200CG(**tight))
+    orc2 = O.MonodomainOracle(mo, O.PCG2019, O.default_params(O.PCG2019), Mo, Ko, **tight)
+    uo = u0.copy()
+    t = 0.0
+    for step in range(20):
+        orc2.bS = O.assemble_source(mo, 2, O.SRC_ENDO, [0.0, 2.0, 0.5, 0.25], t + dt)
+        ito, rno, convo = orc2.step(uo, t, dt)
+        assert tb.step_(integ2) and convo
+        t += dt
+        if step == 0:
+            h = integ2.u.to_host()
+            assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-10
+    h = integ2.u.to_host()
+    assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-9
