@@ -193,8 +193,16 @@ int32_t tb_assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, int
 /* general closure path: fq[cell*nq + q] = f(x_q, t) evaluated by the host */
 int32_t tb_assemble_source_qp(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, const double *fq, tb_vec *b,
                               int32_t bcol);
-/* deterministic variant of the scatter: 0 = fp64 atomics (default), 1 = greedy element colouring */
+/* Assembly strategy (FerriteOperators' strategies: sequential / per-colour / per-element, SURVEY a-10):
+ *   2 (default)  per-element results + ordered row gather: element matrices (vectors) go to a scratch buffer,
+ *                then every matrix row sums its contributions in ascending element order -- deterministic and
+ *                bitwise equal to the reference's sequential CPU assembly; rows are processed in chunks so the
+ *                scratch stays under the budget below.  Falls back to 0 if a chunk's cell range cannot fit.
+ *   0            fp64 atomic scatter (order of additions not deterministic, values equal to rounding).
+ * tb_assembly_info reports the requested mode, the one the LAST assembly call really ran and its chunk count. */
 int32_t tb_assembly_set_mode(tb_ctx *ctx, int32_t mode);
+int32_t tb_assembly_info(tb_ctx *ctx, int32_t *mode_requested, int32_t *mode_last_used, int32_t *chunks_last);
+int32_t tb_assembly_set_scratch_budget(tb_ctx *ctx, int64_t bytes);
 
 /* ---- linear solve -----------------------------------------------------------------------------
  * LinearSolve.solve!(cache) with KrylovJL_CG (euler.jl:10,94,155-156): unpreconditioned CG from

@@ -70,6 +70,7 @@ def hostmath():
     L.hm_cell_node_step.restype = C.c_double
     L.hm_tables.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), f64, f64, f64, f64]
     L.hm_element_matrix.argtypes = [C.c_int, C.c_int, C.c_int, f64, C.c_double, C.c_int, f64, C.c_double, C.c_int64, f64]
+    L.hm_element_diffusion_full.argtypes = [C.c_int, C.c_int, f64, C.c_int, f64, C.c_double, C.c_int64, f64]
     L.hm_element_source.argtypes = [C.c_int, C.c_int, f64, C.c_int, f64, C.c_double, C.c_void_p, f64]
     return L
 

@@ -53,6 +53,20 @@ int hm_element_matrix(int celltype, int qorder, int op, const double *X, double 
     return 0;
 }
 
+// full (non-symmetrised) diffusion matrix of the gather assembly: must be BITWISE the oracle's
+int hm_element_diffusion_full(int celltype, int qorder, const double *X, int kind, const double *data, double cmchi,
+                              int64_t cell, double *out) {
+    tb_elem_tables T;
+    if (tb_build_tables(celltype, qorder, &T)) return 1;
+    switch (celltype) {
+    case 0: tb_element_diffusion_full<4, 2, 1>(tb_view_of(&T), X, kind, data, cmchi, cell, out); break;
+    case 1: tb_element_diffusion_full<8, 3, 1>(tb_view_of(&T), X, kind, data, cmchi, cell, out); break;
+    case 2: tb_element_diffusion_full<3, 2, 1>(tb_view_of(&T), X, kind, data, cmchi, cell, out); break;
+    default: tb_element_diffusion_full<4, 3, 1>(tb_view_of(&T), X, kind, data, cmchi, cell, out); break;
+    }
+    return 0;
+}
+
 int hm_element_source(int celltype, int qorder, const double *X, int kind, const double *prm, double t, const double *fq,
                       double *be) {
     tb_elem_tables T;

@@ -72,6 +72,27 @@ def test_element_kernels(oracle, hostmath, name):
     assert np.allclose(be, O.element_source(ct, 2, X, 0, np.zeros(8), 0.0, fq=fq), rtol=1e-14, atol=1e-18)
 
 
+@pytest.mark.parametrize("name", list(CT))
+def test_full_element_matrices_bitwise(oracle, hostmath, name):
+    """What the deterministic gather assembly stores per element: mass (symmetric by construction) and the
+    full diffusion matrix, bit for bit the oracle's."""
+    O, ct = oracle, CT[name]
+    X = _cell(O, ct)
+    nv, dim = O.cell_nv(ct), O.cell_dim(ct)
+    out = np.zeros((nv, nv))
+    hostmath.hm_element_matrix(ct, 2, 0, X.ravel(), 1.3, 0, np.zeros(1), 1.0, 0, out.reshape(-1))
+    assert np.array_equal(out, O.element_mass(ct, 2, X, 1.3))
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((dim, dim))
+    D = A @ A.T + np.eye(dim)
+    cases = [(0, np.array([0.37]), 0), (1, D.ravel(), 0)]
+    if dim == 3:
+        cases.append((2, np.concatenate([[0.3, 0.1, 0.05], rng.standard_normal((3, nv, 9)).ravel()]), 2))
+    for kind, data, cell in cases:
+        hostmath.hm_element_diffusion_full(ct, 2, X.ravel(), kind, np.ascontiguousarray(data), 2.0, cell, out.reshape(-1))
+        assert np.array_equal(out, O.element_diffusion(ct, 2, X, kind, data, cmchi=2.0, cell=cell))
+
+
 def test_distorted_hex_fixture(oracle, hostmath):
     """test/test_coefficients.jl:239-279 coordinates through the product's mapping."""
     O = oracle

@@ -86,13 +86,16 @@ def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
                                               tb.FieldCoefficient(fsn[:, :, 2]))
     kappa = tb.SpectralTensorCoefficient(micro, tb.ConstantCoefficient((k1, kr, kr)))
     proto = tb.AnalyticalTransmembraneStimulationProtocol(
-        tb.AnalyticalCoefficient(tb.UniformEndocardialActivation(transmural_depth=0.0, tmax=2.0), tb.CartesianCoordinateSystem()),
+        tb.AnalyticalCoefficient(tb.UniformEndocardialActivation(transmural_depth=0.0, tmax=0.2, amplitude=0.3), tb.CartesianCoordinateSystem()),
         [(-np.inf, np.inf)])
     model = tb.MonodomainModel(tb.ConstantCoefficient(1.0), tb.ConstantCoefficient(1.0), kappa, proto, tb.PCG2019(), "φₘ", "s")
     odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(model), tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), mesh)
     u0 = tb.create_initial_condition(odeform)
+    # the reference adds the source vector WITHOUT a dt factor (euler.jl:85-91), so the tutorial's amplitude would drive
+    # phi to +150 mV within 40 steps of 0.01 and overflow the h gate; 0.3 for 0.2 ms gives a physiological upstroke
+    SRC = [0.0, 0.2, 0.3, 0.25]
     def make(cg):
-        return tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 0.5)),
+        return tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 2.0)),
                        tb.LieTrotterGodunov((tb.BackwardEulerSolver(inner_solver=cg), tb.ForwardEulerCellSolver())), dt=0.01)
     integ = make(tb.B200CG())
     # oracle with the same inputs
@@ -111,15 +114,21 @@ def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
     orc = O.MonodomainOracle(mo, O.PCG2019, O.default_params(O.PCG2019), Mo, Ko)
     uo = u0.copy()
     t, dt = 0.0, 0.01
-    for step in range(50):
-        orc.bS = O.assemble_source(mo, 2, O.SRC_ENDO, [0.0, 2.0, 0.5, 0.25], t + dt)
+    act_g, act_o = np.full(N, -1), np.full(N, -1)
+    for step in range(100):
+        orc.bS = O.assemble_source(mo, 2, O.SRC_ENDO, SRC, t + dt)
         ito, rno, convo = orc.step(uo, t, dt)
         assert tb.step_(integ) and convo
         assert abs(integ.cg_iterations[-1] - ito) <= 1
         t += dt
+        if step % 5 == 4 or step > 40:
+            h = integ.u.to_host()
+            act_g[(act_g < 0) & (h[:N] >= 0.0)] = step
+            act_o[(act_o < 0) & (uo[:N] >= 0.0)] = step
     h = integ.u.to_host()
     assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-6
-    assert h[:N].max() > -84.0                                                     # the stimulus has started to depolarise
+    assert h[:N].max() > 20.0 and (act_o >= 0).sum() > N // 4                      # a real upstroke happened
+    assert np.array_equal(act_g, act_o)                                            # activation steps identical
 
     # (2) the 1e-10-after-one-step rule, with the linear solve converged below it on both sides
     tight = dict(atol=1e-15, rtol=1e-14)
@@ -128,7 +137,7 @@ def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
     uo = u0.copy()
     t = 0.0
     for step in range(20):
-        orc2.bS = O.assemble_source(mo, 2, O.SRC_ENDO, [0.0, 2.0, 0.5, 0.25], t + dt)
+        orc2.bS = O.assemble_source(mo, 2, O.SRC_ENDO, SRC, t + dt)
         ito, rno, convo = orc2.step(uo, t, dt)
         assert tb.step_(integ2) and convo
         t += dt

@@ -114,6 +114,8 @@ _SIGNATURES = {
     "tb_assemble_source": [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_double, _vp, C.c_int32],
     "tb_assemble_source_qp": [_vp, _vp, C.c_int32, _f64p, _vp, C.c_int32],
     "tb_assembly_set_mode": [_vp, C.c_int32],
+    "tb_assembly_info": [_vp, _pi32, _pi32, _pi32],
+    "tb_assembly_set_scratch_budget": [_vp, C.c_int64],
     "tb_cg_solve": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                      _pf64],

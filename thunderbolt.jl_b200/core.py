@@ -62,6 +62,19 @@ class B200Device:
         L.call("tb_profile_get", self.h, C.byref(ms), C.byref(n))
         return ms.value, n.value
 
+    # ---- assembly strategy ---------------------------------------------------------------------------
+    def assembly_set_mode(self, mode: int):
+        """2 = per-element results + ordered gather (deterministic, default), 0 = fp64 atomic scatter."""
+        L.call("tb_assembly_set_mode", self.h, int(mode))
+
+    def assembly_info(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        L.call("tb_assembly_info", self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"mode": a.value, "last_mode": b.value, "last_chunks": c.value}
+
+    def assembly_set_scratch_budget(self, nbytes: int):
+        L.call("tb_assembly_set_scratch_budget", self.h, int(nbytes))
+
     # ---- multi-GPU --------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -2,7 +2,24 @@
 // Replaces update_operator!(op, t) of FerriteOperators' element loop as driven by
 // src/solver/time/euler.jl:143-153,173-175 and src/solver/interface.jl:66-94.
 //
-// Kernel shape (one element per thread, 128 elements per block iteration):
+// Two strategies (tb_assembly_set_mode / env TB_ASSEMBLY_MODE):
+//   mode 2 (default) "element assembly + ordered gather" -- the B200 take on the reference's
+//     ElementAssemblyStrategy (per-element results, then a reduction):
+//       phase 1  k_element_matrices / k_element_vectors: one element per thread, full element matrix
+//                (vector) written to a scratch buffer EA[cell][i][j] (EAb[cell][j]), no atomics;
+//       phase 2  k_gather_rows / k_gather_vec: one matrix row per lane (one SELL slice per warp); the
+//                row walks its dof -> (cell, local index) adjacency in ASCENDING cell order, adds row
+//                `a` of each adjacent element matrix into a shared-memory image of the row and stores
+//                the slice once, fully coalesced.  Every entry is the sum of its element contributions
+//                in the reference's sequential element order, starting from 0.0: the assembled values
+//                are BITWISE those of the CPU path, run to run and across GPU counts.
+//     Rows are processed in chunks so the scratch stays under ctx->ea_budget_bytes (default 8 GB; a
+//     chunk covers the contiguous cell range its rows touch, so a locality-preserving numbering wastes
+//     nothing); if some chunk's cell range cannot fit, the call falls back to mode 0 and says so
+//     (tb_assembly_info).
+//   mode 0 "atomic scatter": element matrix in registers, RED.ADD.F64 into the pattern.
+//
+// Mode-0 kernel shape (one element per thread, 128 elements per block iteration):
 //   1. the block copies the quadrature/shape tables into shared memory once;
 //   2. it reads 128 elements' connectivity + celldofs coalesced, and gathers their vertex coordinates
 //      with 128*nv independent loads into a transposed shared-memory tile X[c][e] (bank-conflict free
@@ -156,6 +173,365 @@ __global__ void __launch_bounds__(AS_BLOCK)
     }
 }
 
+
+// =====================================================================================================
+// mode 2: element matrices + ordered row gather
+// =====================================================================================================
+__global__ void k_adjg_count(const int *__restrict__ celldofs, int64_t npos, int nrows, int *count) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (int64_t)gridDim.x * blockDim.x) {
+        const int d = celldofs[p];
+        if (d < nrows) atomicAdd(&count[d], 1);
+    }
+}
+__global__ void k_adjg_widen(const int *__restrict__ src, int64_t *__restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_adjg_fill(const int *__restrict__ celldofs, int64_t npos, int nrows, const int64_t *__restrict__ adjptr,
+                            int *cursor, unsigned *__restrict__ adj) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npos; p += (int64_t)gridDim.x * blockDim.x) {
+        const int d = celldofs[p];
+        if (d < nrows) adj[adjptr[d] + atomicAdd(&cursor[d], 1)] = (unsigned)p;
+    }
+}
+// the fill order above is arbitrary (atomics); sorting each short list makes the adjacency -- and with it the
+// summation order of the gather -- deterministic and equal to the reference's element order
+__global__ void k_adjg_sort(int nrows, const int64_t *__restrict__ adjptr, unsigned *__restrict__ adj) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        unsigned *a = adj + adjptr[r];
+        const int n = (int)(adjptr[r + 1] - adjptr[r]);
+        for (int i = 1; i < n; i++) {
+            const unsigned v = a[i];
+            int k = i - 1;
+            while (k >= 0 && a[k] > v) {
+                a[k + 1] = a[k];
+                k--;
+            }
+            a[k + 1] = v;
+        }
+    }
+}
+
+static int32_t mesh_ensure_adjacency(tb_ctx *ctx, const tb_mesh *m) {
+    if (m->d_adjptr) return TB_OK;
+    const int nrows = (int)m->ndofs_owned;
+    const int64_t npos = m->ncells * m->nv;
+    TB_REQUIRE(npos < ((int64_t)1 << 32), "assembly: mesh has %lld (cell, vertex) pairs, the adjacency holds at most 2^32",
+               (long long)npos);
+    const int grid = ctx->sm_count * 8;
+    int *count = nullptr;
+    int64_t *count64 = nullptr, *adjptr = nullptr;
+    unsigned *adj = nullptr;
+    TB_CUDA(cudaMalloc(&count, sizeof(int) * (size_t)(nrows + 1)));
+    TB_CUDA(cudaMalloc(&count64, sizeof(int64_t) * (size_t)(nrows + 1)));
+    TB_CUDA(cudaMalloc(&adjptr, sizeof(int64_t) * (size_t)(nrows + 1)));
+    TB_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(nrows + 1), ctx->stream));
+    TB_LAUNCH(ctx, k_adjg_count, grid, 256, 0, m->d_celldofs, npos, nrows, count);
+    TB_LAUNCH(ctx, k_adjg_widen, grid, 256, 0, count, count64, (int64_t)nrows + 1);
+    TB_TRY(tb_exclusive_scan_i64(ctx, count64, adjptr, (int64_t)nrows + 1));
+    int64_t nadj = 0;
+    TB_CUDA(cudaMemcpy(&nadj, adjptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    TB_CUDA(cudaMalloc(&adj, sizeof(unsigned) * (size_t)(nadj + 1)));
+    TB_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(nrows + 1), ctx->stream));
+    TB_LAUNCH(ctx, k_adjg_fill, grid, 256, 0, m->d_celldofs, npos, nrows, adjptr, count, adj);
+    TB_LAUNCH(ctx, k_adjg_sort, tb_grid_for(ctx, nrows, 128, 16), 128, 0, nrows, adjptr, adj);
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(count);
+    cudaFree(count64);
+    m->d_adjptr = adjptr;
+    m->d_adj = adj;
+    m->nadj = nadj;
+    return TB_OK;
+}
+
+// per 32-row slice: smallest and largest adjacent cell (lists are sorted: first entry = smallest, last = largest)
+__global__ void k_slice_cell_range(int nrows, int64_t nslices, const int64_t *__restrict__ adjptr,
+                                   const unsigned *__restrict__ adj, int nv, int *__restrict__ smin, int *__restrict__ smax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += nw) {
+        const int64_t r = s * TB_SLICE + lane;
+        int mn = INT32_MAX, mx = -1;
+        if (r < nrows) {
+            const int64_t a = adjptr[r], b = adjptr[r + 1];
+            if (b > a) {
+                mn = (int)(adj[a] / (unsigned)nv);
+                mx = (int)(adj[b - 1] / (unsigned)nv);
+            }
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0) {
+            smin[s] = mn;
+            smax[s] = mx;
+        }
+    }
+}
+
+typedef tb_mesh::GatherPlan GatherPlan;
+
+// Largest row chunk whose contiguous cell range fits `budget_cells` (host arithmetic on the cached per-slice
+// ranges); plan.ok = false if even a single slice does not fit.  which: 0 matrices, 1 vectors.
+static int32_t plan_gather(tb_ctx *ctx, const tb_mesh *m, int64_t budget_cells, int which, const GatherPlan **out) {
+    GatherPlan &plan = m->plan[which];
+    *out = &plan;
+    if (plan.budget_cells == budget_cells) return TB_OK;
+    const int64_t nrows = m->ndofs_owned;
+    const int64_t nslices = (nrows + TB_SLICE - 1) / TB_SLICE;
+    if ((int64_t)m->slice_cmin.size() != nslices) {
+        int *d = nullptr;
+        TB_CUDA(cudaMalloc(&d, sizeof(int) * 2 * (size_t)(nslices + 1)));
+        TB_LAUNCH(ctx, k_slice_cell_range, tb_grid_for(ctx, nslices * 32, 256, 8), 256, 0, (int)nrows, nslices, m->d_adjptr,
+                  m->d_adj, m->nv, d, d + nslices);
+        m->slice_cmin.resize((size_t)nslices);
+        m->slice_cmax.resize((size_t)nslices);
+        TB_CUDA(cudaMemcpyAsync(m->slice_cmin.data(), d, sizeof(int) * (size_t)nslices, cudaMemcpyDeviceToHost, ctx->stream));
+        TB_CUDA(cudaMemcpyAsync(m->slice_cmax.data(), d + nslices, sizeof(int) * (size_t)nslices, cudaMemcpyDeviceToHost, ctx->stream));
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d);
+    }
+    plan = GatherPlan();
+    plan.budget_cells = budget_cells;
+    if (budget_cells < 1 || nslices == 0) return TB_OK;
+    const double cells_per_row = (double)m->ncells / (double)(nrows > 0 ? nrows : 1);
+    int64_t spc = (int64_t)((double)budget_cells / (cells_per_row > 1e-9 ? cells_per_row : 1e-9) * 0.9) / TB_SLICE;   // slices per chunk
+    if (spc > nslices) spc = nslices;
+    if (spc < 1) spc = 1;
+    for (;;) {
+        const int64_t nch = (nslices + spc - 1) / spc;
+        std::vector<int> cmin((size_t)nch, INT32_MAX), cmax((size_t)nch, -1);
+        int64_t worst = 0;
+        for (int64_t ch = 0; ch < nch; ch++) {
+            int mn = INT32_MAX, mx = -1;
+            const int64_t s1 = (ch + 1) * spc < nslices ? (ch + 1) * spc : nslices;
+            for (int64_t s = ch * spc; s < s1; s++) {
+                if (m->slice_cmin[(size_t)s] < mn) mn = m->slice_cmin[(size_t)s];
+                if (m->slice_cmax[(size_t)s] > mx) mx = m->slice_cmax[(size_t)s];
+            }
+            cmin[(size_t)ch] = mn;
+            cmax[(size_t)ch] = mx;
+            if (mx >= mn && (int64_t)mx - mn + 1 > worst) worst = (int64_t)mx - mn + 1;
+        }
+        if (worst <= budget_cells) {
+            plan.ok = true;
+            plan.rows_per_chunk = spc * TB_SLICE;
+            plan.cmin.swap(cmin);
+            plan.cmax.swap(cmax);
+            plan.max_cells = worst;
+            return TB_OK;
+        }
+        if (spc == 1) return TB_OK;
+        spc = (spc + 1) / 2;
+    }
+}
+
+// ---- phase 1: element matrices / vectors into the scratch buffer ------------------------------------------
+template <int NV, int DIM, int OP>
+__global__ void __launch_bounds__(AS_BLOCK)
+    k_element_matrices(const int *__restrict__ conn, const double *__restrict__ coords, int64_t c0, int64_t c1,
+                       const tb_elem_tables *__restrict__ gT, int nq, double rho, int kind, const double *__restrict__ ddata,
+                       double cmchi, double *__restrict__ EA) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sW = reinterpret_cast<double *>(smem_raw);
+    double *sN = sW + nq;
+    double *sdN = sN + nq * NV;
+    double *sX = sdN + nq * NV * DIM;
+    for (int i = threadIdx.x; i < nq; i += AS_BLOCK) sW[i] = gT->w[i];
+    for (int i = threadIdx.x; i < nq * NV; i += AS_BLOCK) sN[i] = gT->N[i];
+    for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
+    const tb_tables_view sT{nq, sW, sN, sdN};
+    const int64_t ncl = c1 - c0;
+    const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = c0 + tile * AS_BLOCK;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < AS_BLOCK * NV; idx += AS_BLOCK) {
+            const int e = idx / NV, a = idx - e * NV;
+            if (e0 + e < c1) {
+                const int64_t node = conn[e0 * NV + idx];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) sX[(a * DIM + d) * AS_BLOCK + e] = coords[node * DIM + d];
+            }
+        }
+        __syncthreads();
+        const int64_t e = e0 + threadIdx.x;
+        if (e < c1) {
+            double *out = EA + (e - c0) * (NV * NV);
+            if (OP == 0) {
+                double acc[NV * (NV + 1) / 2];
+                tb_element_mass<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, rho, acc);
+#pragma unroll
+                for (int i = 0; i < NV; i++)
+#pragma unroll
+                    for (int j = 0; j < NV; j++) out[i * NV + j] = i <= j ? acc[tb_sym<NV>(i, j)] : acc[tb_sym<NV>(j, i)];
+            } else {
+                double Ke[NV * NV];
+                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, ddata, cmchi, e, Ke);
+#pragma unroll
+                for (int i = 0; i < NV * NV; i++) out[i] = Ke[i];
+            }
+        }
+    }
+}
+
+template <int NV, int DIM>
+__global__ void __launch_bounds__(AS_BLOCK)
+    k_element_vectors(const int *__restrict__ conn, const double *__restrict__ coords, int64_t c0, int64_t c1,
+                      const tb_elem_tables *__restrict__ gT, int nq, int kind, const double *__restrict__ prm, double t,
+                      const double *__restrict__ fq, double *__restrict__ EAb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sW = reinterpret_cast<double *>(smem_raw);
+    double *sN = sW + nq;
+    double *sdN = sN + nq * NV;
+    double *sX = sdN + nq * NV * DIM;
+    for (int i = threadIdx.x; i < nq; i += AS_BLOCK) sW[i] = gT->w[i];
+    for (int i = threadIdx.x; i < nq * NV; i += AS_BLOCK) sN[i] = gT->N[i];
+    for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
+    const tb_tables_view sT{nq, sW, sN, sdN};
+    __shared__ double sprm[8];
+    if (threadIdx.x < 8) sprm[threadIdx.x] = prm ? prm[threadIdx.x] : 0.0;
+    const int64_t ncl = c1 - c0;
+    const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = c0 + tile * AS_BLOCK;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < AS_BLOCK * NV; idx += AS_BLOCK) {
+            const int e = idx / NV, a = idx - e * NV;
+            if (e0 + e < c1) {
+                const int64_t node = conn[e0 * NV + idx];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) sX[(a * DIM + d) * AS_BLOCK + e] = coords[node * DIM + d];
+            }
+        }
+        __syncthreads();
+        const int64_t e = e0 + threadIdx.x;
+        if (e < c1) {
+            double be[NV];
+            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * nq : nullptr, be);
+#pragma unroll
+            for (int j = 0; j < NV; j++) EAb[(e - c0) * NV + j] = be[j];
+        }
+    }
+}
+
+// ---- phase 2: ordered gather ---------------------------------------------------------------------------------
+// One warp per SELL slice, one row per lane.  sacc[j*32 + lane] is the shared-memory image of entry j of the
+// lane's row (bank-conflict free); the lane walks its adjacency in ascending (cell, a) order and adds row a of
+// EA[cell] at the positions of the cell's dofs (binary search in the row's sorted columns, which the 32 lanes
+// read from the same 128 B lines).  The slice is then stored once, 256 B per entry slot.
+template <int NV>
+__global__ void __launch_bounds__(256)
+    k_gather_rows(const int64_t *__restrict__ adjptr, const unsigned *__restrict__ adj, const int *__restrict__ celldofs,
+                  const double *__restrict__ EA, int64_t c0, SellView S, int64_t slice0, int64_t slice1, int maxw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    double *acc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * maxw * TB_SLICE + lane;
+    for (int64_t s = slice0 + (int64_t)blockIdx.x * nwb + warp; s < slice1; s += (int64_t)gridDim.x * nwb) {
+        const int64_t base = S.slice_ptr[s];
+        const int w = (int)((S.slice_ptr[s + 1] - base) >> 5);
+        for (int j = 0; j < w; j++) acc[j * TB_SLICE] = 0.0;
+        const int64_t r = s * TB_SLICE + lane;
+        if (r < S.nrows) {
+            const int len = (int)(S.rowptr[r + 1] - S.rowptr[r]);
+            const int *cols = S.col + base + lane;
+            const int64_t q1 = adjptr[r + 1];
+            for (int64_t q = adjptr[r]; q < q1; q++) {
+                const unsigned p = adj[q];
+                const unsigned c = p / (unsigned)NV;
+                const int a = (int)(p - c * (unsigned)NV);
+                const int *cd = celldofs + (int64_t)c * NV;
+                const double *ke = EA + ((int64_t)c - c0) * (NV * NV) + a * NV;
+                int dof[NV];
+                double kv[NV];
+                if constexpr (NV % 4 == 0) {
+#pragma unroll
+                    for (int b = 0; b < NV; b += 4) {
+                        const int4 d4 = *reinterpret_cast<const int4 *>(cd + b);
+                        dof[b] = d4.x; dof[b + 1] = d4.y; dof[b + 2] = d4.z; dof[b + 3] = d4.w;
+                    }
+#pragma unroll
+                    for (int b = 0; b < NV; b += 2) {
+                        const double2 k2 = *reinterpret_cast<const double2 *>(ke + b);
+                        kv[b] = k2.x; kv[b + 1] = k2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < NV; b++) {
+                        dof[b] = cd[b];
+                        kv[b] = ke[b];
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < NV; b++) {
+                    int lo = 0, hi = len;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (cols[mid * TB_SLICE] < dof[b]) lo = mid + 1; else hi = mid;
+                    }
+                    acc[lo * TB_SLICE] += kv[b];
+                }
+            }
+        }
+        double *dst = S.val + base + lane;
+        for (int j = 0; j < w; j++) dst[(int64_t)j * TB_SLICE] = acc[j * TB_SLICE];
+    }
+}
+
+// b[r] = sum over the row's adjacency (ascending cell order) of EAb[cell][a]
+__global__ void __launch_bounds__(256) k_gather_vec(const int64_t *__restrict__ adjptr, const unsigned *__restrict__ adj,
+                                                    const double *__restrict__ EAb, int64_t p0, double *__restrict__ b,
+                                                    int64_t r0, int64_t r1) {
+    for (int64_t r = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += (int64_t)gridDim.x * blockDim.x) {
+        double sum = 0.0;
+        const int64_t q1 = adjptr[r + 1];
+        for (int64_t q = adjptr[r]; q < q1; q++) sum += EAb[(int64_t)adj[q] - p0];
+        b[r] = sum;
+    }
+}
+
+static size_t element_smem(int nv, int dim, int nq) {
+    return sizeof(double) * nq * (1 + nv + nv * dim) + sizeof(double) * nv * dim * AS_BLOCK;
+}
+
+template <int NV, int DIM, int OP>
+static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, double rho, int kind,
+                                 const double *d_data, double cmchi, const tb_pattern *pat, const SellView &S,
+                                 const GatherPlan &plan, double *EA) {
+    const size_t smem1 = element_smem(NV, DIM, nq);
+    TB_CUDA(cudaFuncSetAttribute(k_element_matrices<NV, DIM, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_matrices<NV, DIM, OP>, AS_BLOCK, smem1);
+    if (per_sm < 1) per_sm = 1;
+    const int maxw = pat->max_width < 1 ? 1 : pat->max_width;
+    int warps = (int)((96 * 1024) / ((size_t)maxw * TB_SLICE * sizeof(double)));
+    warps = warps > 8 ? 8 : warps < 1 ? 1 : warps;
+    const size_t smem2 = (size_t)warps * maxw * TB_SLICE * sizeof(double);
+    TB_CUDA(cudaFuncSetAttribute(k_gather_rows<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int per_sm2 = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_gather_rows<NV>, warps * 32, smem2);
+    if (per_sm2 < 1) per_sm2 = 1;
+    const int nch = (int)plan.cmin.size();
+    for (int ch = 0; ch < nch; ch++) {
+        const int64_t r0 = (int64_t)ch * plan.rows_per_chunk;
+        const int64_t r1 = r0 + plan.rows_per_chunk < pat->nrows ? r0 + plan.rows_per_chunk : pat->nrows;
+        const int64_t s0 = r0 / TB_SLICE, s1 = (r1 + TB_SLICE - 1) / TB_SLICE;
+        int64_t c0 = 0;
+        if (plan.cmax[ch] >= plan.cmin[ch]) {
+            c0 = plan.cmin[ch];
+            const int64_t c1 = (int64_t)plan.cmax[ch] + 1;
+            const int64_t ntiles = (c1 - c0 + AS_BLOCK - 1) / AS_BLOCK;
+            const int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
+            TB_LAUNCH(ctx, (k_element_matrices<NV, DIM, OP>), grid, AS_BLOCK, smem1, m->d_conn, m->d_coords, c0, c1, d_T, nq,
+                      rho, kind, d_data, cmchi, EA);
+        }
+        const int64_t need = (s1 - s0 + warps - 1) / warps;
+        const int grid2 = (int)(need < (int64_t)ctx->sm_count * per_sm2 ? need : (int64_t)ctx->sm_count * per_sm2);
+        if (grid2 > 0)
+            TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, warps * 32, smem2, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, S, s0, s1,
+                      maxw);
+    }
+    return TB_OK;
+}
+
 static size_t assembly_smem(int nv, int dim, int nq) {
     return sizeof(double) * nq * (1 + nv + nv * dim) + sizeof(double) * nv * dim * AS_BLOCK + sizeof(int) * nv * AS_BLOCK;
 }
@@ -192,7 +568,6 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     TB_REQUIRE(A->pat->nrows == mesh->ndofs_owned && A->pat->ncols == mesh->ndofs,
                "assemble: operator is %lld x %lld but the mesh has %lld owned / %lld total dofs", (long long)A->pat->nrows,
                (long long)A->pat->ncols, (long long)mesh->ndofs_owned, (long long)mesh->ndofs);
-    TB_REQUIRE(ctx->assembly_mode == 0, "assemble: colouring mode is not implemented yet (use mode 0, atomics)");
     TB_DEV(ctx);
     tb_elem_tables *d_T = nullptr;
     int nq = 0;
@@ -209,9 +584,61 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         TB_CUDA(cudaMalloc(&d_data, sizeof(double) * (size_t)ndata));
         TB_CUDA(cudaMemcpyAsync(d_data, data, sizeof(double) * (size_t)ndata, cudaMemcpyHostToDevice, ctx->stream));
     }
-    TB_CUDA(cudaMemsetAsync(A->d_val, 0, sizeof(double) * (size_t)A->pat->sell_len, ctx->stream));
     SellView S{A->pat->d_rowptr, A->pat->d_slice_ptr, A->pat->d_col, A->d_val, A->pat->nrows};
     int32_t st = TB_OK;
+    // ---- mode 2: element matrices + ordered gather, when the scratch fits ----
+    bool gathered = false;
+    if (ctx->assembly_mode == 2 && A->pat->max_width <= TB_MAXROW) {
+        const GatherPlan *planp = nullptr;
+        bool ok = false;
+        double *EA = nullptr;
+        st = mesh_ensure_adjacency(ctx, mesh);
+        if (st == TB_OK) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            size_t budget = ctx->ea_budget_bytes;
+            if (budget > free_b / 2) budget = free_b / 2;
+            const int64_t per_cell = (int64_t)mesh->nv * mesh->nv * (int64_t)sizeof(double);
+            st = plan_gather(ctx, mesh, (int64_t)(budget / (size_t)per_cell), 0, &planp);
+            ok = st == TB_OK && planp->ok;
+            if (ok) {
+                const size_t bytes = (size_t)(planp->max_cells > 0 ? planp->max_cells : 1) * (size_t)per_cell;
+                if (cudaMalloc(&EA, bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                }
+            }
+        }
+        if (st == TB_OK && ok) {
+            const GatherPlan &plan = *planp;
+#define DISPATCH_G(NV, DIM)                                                                                         \
+    st = op == 0 ? gather_bilinear_t<NV, DIM, 0>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, A->pat, S, plan, EA) \
+                 : gather_bilinear_t<NV, DIM, 1>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, A->pat, S, plan, EA)
+            switch (mesh->celltype) {
+            case TB_QUAD4: DISPATCH_G(4, 2); break;
+            case TB_HEX8: DISPATCH_G(8, 3); break;
+            case TB_TRI3: DISPATCH_G(3, 2); break;
+            default: DISPATCH_G(4, 3); break;
+            }
+#undef DISPATCH_G
+            gathered = true;
+            ctx->assembly_last_mode = 2;
+            ctx->assembly_last_chunks = (int)plan.cmin.size();
+        }
+        if (gathered || st != TB_OK) {
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(EA);
+            cudaFree(d_T);
+            cudaFree(d_data);
+            if (st != TB_OK) return st;
+            if (e != cudaSuccess) return tb_fail(TB_ERR_CUDA, "assemble (gather): kernel failed: %s", cudaGetErrorString(e));
+            return TB_OK;
+        }
+    }
+    // ---- mode 0: atomic scatter ----
+    ctx->assembly_last_mode = 0;
+    ctx->assembly_last_chunks = 0;
+    TB_CUDA(cudaMemsetAsync(A->d_val, 0, sizeof(double) * (size_t)A->pat->sell_len, ctx->stream));
 #define DISPATCH(NV, DIM)                                                                                   \
     st = op == 0 ? launch_bilinear<NV, DIM, 0>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, S)            \
                  : launch_bilinear<NV, DIM, 1>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, S)
@@ -251,6 +678,18 @@ static int32_t launch_source(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables
     return TB_OK;
 }
 
+template <int NV, int DIM>
+static int32_t launch_element_vectors(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, int kind,
+                                      const double *d_prm, double t, const double *d_fq, int64_t c0, int64_t c1, double *EAb) {
+    const size_t smem = element_smem(NV, DIM, nq);
+    TB_CUDA(cudaFuncSetAttribute(k_element_vectors<NV, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (c1 - c0 + AS_BLOCK - 1) / AS_BLOCK;
+    const int grid = (int)(ntiles < (int64_t)ctx->sm_count * 4 ? ntiles : (int64_t)ctx->sm_count * 4);
+    TB_LAUNCH(ctx, (k_element_vectors<NV, DIM>), grid, AS_BLOCK, smem, m->d_conn, m->d_coords, c0, c1, d_T, nq, kind, d_prm, t,
+              d_fq, EAb);
+    return TB_OK;
+}
+
 static int32_t assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int kind, const double *prm, int nprm,
                                double t, const double *fq, tb_vec *b, int bcol) {
     TB_REQUIRE(ctx && mesh && b, "tb_assemble_source: NULL argument");
@@ -272,14 +711,73 @@ static int32_t assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int
         TB_CUDA(cudaMemcpyAsync(d_fq, fq, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     double *bp = b->d + (size_t)bcol * b->ld;
-    TB_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * (size_t)b->n, ctx->stream));
     int32_t st = TB_OK;
-    if (fq || kind != TB_SRC_NONE) {
-        switch (mesh->celltype) {
-        case TB_QUAD4: st = launch_source<4, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
-        case TB_HEX8: st = launch_source<8, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
-        case TB_TRI3: st = launch_source<3, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
-        default: st = launch_source<4, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+    bool gathered = false;
+    if (ctx->assembly_mode == 2 && (fq || kind != TB_SRC_NONE)) {
+        // ordered gather: element vectors into the cached scratch, then b[r] = sum over the row's adjacency
+        const GatherPlan *planp = nullptr;
+        bool ok = false;
+        st = mesh_ensure_adjacency(ctx, mesh);
+        if (st == TB_OK) {
+            size_t budget = ctx->ea_budget_bytes < ((size_t)2 << 30) ? ctx->ea_budget_bytes : ((size_t)2 << 30);
+            const int64_t per_cell = (int64_t)mesh->nv * (int64_t)sizeof(double);
+            st = plan_gather(ctx, mesh, (int64_t)(budget / (size_t)per_cell), 1, &planp);
+            ok = st == TB_OK && planp->ok;
+            if (ok) {
+                const size_t bytes = (size_t)(planp->max_cells > 0 ? planp->max_cells : 1) * (size_t)per_cell;
+                if (ctx->ea_bytes < bytes) {
+                    cudaFree(ctx->d_ea);
+                    ctx->d_ea = nullptr;
+                    ctx->ea_bytes = 0;
+                    if (cudaMalloc(&ctx->d_ea, bytes) == cudaSuccess) ctx->ea_bytes = bytes;
+                    else {
+                        cudaGetLastError();
+                        ok = false;
+                    }
+                }
+            }
+        }
+        if (st == TB_OK && ok) {
+            const GatherPlan &plan = *planp;
+            double *EAb = static_cast<double *>(ctx->d_ea);
+            const int nch = (int)plan.cmin.size();
+            const int64_t nrows = mesh->ndofs_owned;
+            for (int ch = 0; ch < nch && st == TB_OK; ch++) {
+                const int64_t r0 = (int64_t)ch * plan.rows_per_chunk;
+                const int64_t r1 = r0 + plan.rows_per_chunk < nrows ? r0 + plan.rows_per_chunk : nrows;
+                int64_t c0 = 0;
+                if (plan.cmax[ch] >= plan.cmin[ch]) {
+                    c0 = plan.cmin[ch];
+                    const int64_t c1 = (int64_t)plan.cmax[ch] + 1;
+                    switch (mesh->celltype) {
+                    case TB_QUAD4: st = launch_element_vectors<4, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, c0, c1, EAb); break;
+                    case TB_HEX8: st = launch_element_vectors<8, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, c0, c1, EAb); break;
+                    case TB_TRI3: st = launch_element_vectors<3, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, c0, c1, EAb); break;
+                    default: st = launch_element_vectors<4, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, c0, c1, EAb); break;
+                    }
+                }
+                if (st == TB_OK && r1 > r0)
+                    TB_LAUNCH(ctx, k_gather_vec, tb_grid_for(ctx, r1 - r0, 256, 8), 256, 0, mesh->d_adjptr, mesh->d_adj, EAb,
+                              c0 * mesh->nv, bp, r0, r1);
+            }
+            // rows past the owned block (ghost slots of a partitioned vector) stay zero like in mode 0
+            if (b->n > nrows) TB_CUDA(cudaMemsetAsync(bp + nrows, 0, sizeof(double) * (size_t)(b->n - nrows), ctx->stream));
+            gathered = true;
+            ctx->assembly_last_mode = 2;
+            ctx->assembly_last_chunks = nch;
+        }
+    }
+    if (!gathered && st == TB_OK) {
+        ctx->assembly_last_mode = 0;
+        ctx->assembly_last_chunks = 0;
+        TB_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * (size_t)b->n, ctx->stream));
+        if (fq || kind != TB_SRC_NONE) {
+            switch (mesh->celltype) {
+            case TB_QUAD4: st = launch_source<4, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+            case TB_HEX8: st = launch_source<8, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+            case TB_TRI3: st = launch_source<3, 2>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+            default: st = launch_source<4, 3>(ctx, mesh, d_T, nq, kind, d_prm, t, d_fq, bp); break;
+            }
         }
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -52,7 +52,7 @@ __global__ void k_sell_fill_cols(const int64_t *rowptr, const int *colidx, int64
     }
 }
 
-static int32_t exclusive_scan_i64(tb_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
+int32_t tb_exclusive_scan_i64(tb_ctx *ctx, const int64_t *in, int64_t *out, int64_t n) {
     size_t tmp_bytes = 0;
     TB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, ctx->stream));
     void *tmp = nullptr;
@@ -132,7 +132,7 @@ static int32_t build_ccol(tb_ctx *ctx, tb_pattern *p) {
     const int grid = ctx->sm_count * 8;
     TB_LAUNCH(ctx, (k_ccol_build<false>), grid, 256, 0, p->d_rowptr, p->nrows, p->ncols, p->nslices, p->d_slice_ptr, p->d_col,
               cnt, nullptr, nullptr, d_max);
-    TB_TRY(exclusive_scan_i64(ctx, cnt, p->d_cptr, p->nslices + 1));
+    TB_TRY(tb_exclusive_scan_i64(ctx, cnt, p->d_cptr, p->nslices + 1));
     TB_CUDA(cudaMemcpy(&p->ccol_len, p->d_cptr + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost));
     TB_CUDA(cudaMemcpy(&p->max_ccol_ints, d_max, sizeof(int), cudaMemcpyDeviceToHost));
     TB_CUDA(cudaMalloc(&p->d_ccol, sizeof(int) * (size_t)(p->ccol_len + 32)));
@@ -165,7 +165,7 @@ static int32_t pattern_from_device_csr(tb_ctx *ctx, int64_t nrows, int64_t ncols
     TB_CUDA(cudaMemsetAsync(d_maxw, 0, sizeof(int), ctx->stream));
     TB_LAUNCH(ctx, k_slice_width, tb_grid_for(ctx, p->nslices, 256, 8), 256, 0, d_rowptr, nrows, p->nslices, width, d_maxw);
     TB_CUDA(cudaMemcpyAsync(&p->max_width, d_maxw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    TB_TRY(exclusive_scan_i64(ctx, width, p->d_slice_ptr, p->nslices + 1));
+    TB_TRY(tb_exclusive_scan_i64(ctx, width, p->d_slice_ptr, p->nslices + 1));
     TB_CUDA(cudaMemcpy(&p->sell_len, p->d_slice_ptr + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost));
     cudaFree(width);
     cudaFree(d_maxw);
@@ -348,7 +348,7 @@ extern "C" int32_t tb_csr_create_from_mesh(tb_ctx *ctx, const tb_mesh *mesh, tb_
     TB_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(nrows + 1), ctx->stream));
     TB_LAUNCH(ctx, k_adj_count, grid, 256, 0, mesh->d_celldofs, npos, nrows, count);
     TB_LAUNCH(ctx, k_i32_to_i64_c, grid, 256, 0, count, count64, (int64_t)nrows + 1);
-    TB_TRY(exclusive_scan_i64(ctx, count64, adjptr, (int64_t)nrows + 1));
+    TB_TRY(tb_exclusive_scan_i64(ctx, count64, adjptr, (int64_t)nrows + 1));
     int64_t nadj = 0;
     TB_CUDA(cudaMemcpy(&nadj, adjptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
     TB_CUDA(cudaMalloc(&adj, sizeof(int) * (size_t)(nadj + 1)));
@@ -360,7 +360,7 @@ extern "C" int32_t tb_csr_create_from_mesh(tb_ctx *ctx, const tb_mesh *mesh, tb_
     TB_CUDA(cudaMemsetAsync(rowlen, 0, sizeof(int64_t) * (size_t)(nrows + 1), ctx->stream));
     TB_LAUNCH(ctx, k_row_len, tb_grid_for(ctx, nrows, 128, 16), 128, 0, nrows, adjptr, adj, mesh->d_celldofs, mesh->nv,
               rowlen, d_err);
-    TB_TRY(exclusive_scan_i64(ctx, rowlen, d_rowptr, (int64_t)nrows + 1));
+    TB_TRY(tb_exclusive_scan_i64(ctx, rowlen, d_rowptr, (int64_t)nrows + 1));
     int64_t nnz = 0;
     int err = 0;
     TB_CUDA(cudaMemcpy(&nnz, d_rowptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));

@@ -61,6 +61,8 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));
     if (const char *v = getenv("TB_SPMV_VARIANT")) ctx->spmv_variant = atoi(v);
     if (const char *v = getenv("TB_SPMV_COMPRESS")) ctx->spmv_compress = atoi(v);
+    if (const char *v = getenv("TB_ASSEMBLY_MODE")) ctx->assembly_mode = atoi(v) == 0 ? 0 : 2;
+    if (const char *v = getenv("TB_EA_BUDGET_MB")) ctx->ea_budget_bytes = (size_t)(atof(v) * 1048576.0);
     *out = ctx;
     return TB_OK;
 }
@@ -78,6 +80,7 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_scalar);
     cudaFreeHost(ctx->h_scalar);
     cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_ea);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * TB_PROF_MAX; i++)
@@ -291,7 +294,21 @@ extern "C" int32_t tb_profile_get(tb_ctx *ctx, double *spmv_ms_total, int64_t *s
 
 extern "C" int32_t tb_assembly_set_mode(tb_ctx *ctx, int32_t mode) {
     TB_REQUIRE(ctx, "tb_assembly_set_mode: ctx is NULL");
-    TB_REQUIRE(mode == 0 || mode == 1, "tb_assembly_set_mode: mode must be 0 (atomics) or 1 (colouring)");
+    TB_REQUIRE(mode == 0 || mode == 2, "tb_assembly_set_mode: mode must be 0 (atomic scatter) or 2 (ordered gather)");
     ctx->assembly_mode = mode;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_assembly_info(tb_ctx *ctx, int32_t *mode_requested, int32_t *mode_last_used, int32_t *chunks_last) {
+    TB_REQUIRE(ctx, "tb_assembly_info: ctx is NULL");
+    if (mode_requested) *mode_requested = ctx->assembly_mode;
+    if (mode_last_used) *mode_last_used = ctx->assembly_last_mode;
+    if (chunks_last) *chunks_last = ctx->assembly_last_chunks;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_assembly_set_scratch_budget(tb_ctx *ctx, int64_t bytes) {
+    TB_REQUIRE(ctx && bytes >= 0, "tb_assembly_set_scratch_budget: bad argument");
+    ctx->ea_budget_bytes = (size_t)bytes;
     return TB_OK;
 }

@@ -292,6 +292,49 @@ TB_HD void tb_element_diffusion(const tb_tables_view T, const double *X, int kin
     }
 }
 
+// Full NV x NV diffusion matrix, every (i, j) pair evaluated on its own exactly as the reference's double
+// loop does (diffusion.jl:40-47: Ke[i,j] -= ((gradNj . D) . gradNi) dOmega); Ke is NOT bitwise symmetric in
+// floating point, and the gather assembly (tb_assembly.cu) reproduces the CPU path bit for bit with this.
+template <int NV, int DIM, int XS>
+TB_HD void tb_element_diffusion_full(const tb_tables_view T, const double *X, int kind, const double *data, double cmchi,
+                                     int64_t cell, double *Ke) {
+#pragma unroll
+    for (int i = 0; i < NV * NV; i++) Ke[i] = 0.0;
+    for (int q = 0; q < T.nq; q++) {
+        double G[NV * DIM], D[DIM * DIM];
+        const double dO = tb_map_qp<NV, DIM, XS, true>(X, T.dN + q * NV * DIM, G) * T.w[q];
+        tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            if (kind == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) s += G[j * DIM + d] * G[i * DIM + d];
+                    Ke[i * NV + j] -= (s * D[0]) * dO;
+                }
+            } else {
+                double gD[DIM];
+#pragma unroll
+                for (int l = 0; l < DIM; l++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) s += G[j * DIM + k] * D[k * DIM + l];
+                    gD[l] = s;
+                }
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < DIM; l++) s += gD[l] * G[i * DIM + l];
+                    Ke[i * NV + j] -= s * dO;
+                }
+            }
+        }
+    }
+}
+
 // ---- built-in stimulus families (see tbolt_b200.h TB_SRC_*) --------------------------------------------
 template <int DIM> TB_HD double tb_source_eval(int kind, const double *prm, const double *x, double t) {
     double n2 = 0.0, mx = -INFINITY;

@@ -97,7 +97,12 @@ struct tb_ctx {
     double *h_scalar = nullptr;       // pinned
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
-    int assembly_mode = 0;
+    int assembly_mode = 2;            // 0: fp64-atomic scatter, 2: element matrices + ordered row gather (deterministic; env TB_ASSEMBLY_MODE)
+    int assembly_last_mode = -1;      // what the last assembly call really ran (2 falls back to 0 when the scratch cannot fit)
+    int assembly_last_chunks = 0;
+    size_t ea_budget_bytes = (size_t)8 << 30;   // scratch for element matrices per chunk (env TB_EA_BUDGET_MB)
+    void *d_ea = nullptr;             // cached scratch of the vector (per-step source) assembly
+    size_t ea_bytes = 0;
     int spmv_variant = 1;             // 0: LDG kernel, 1..: bulk-async (TMA) staged kernel configurations (env TB_SPMV_VARIANT)
     int spmv_compress = 1;            // use the compressed column stream in the staged kernels (env TB_SPMV_COMPRESS)
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
@@ -151,6 +156,21 @@ struct tb_mesh {
     int64_t *d_ghost_global = nullptr;
     int64_t nghost = 0;
     int64_t dof_lo = 0;         // global id of local dof 0
+    // dof -> (cell, local index) adjacency of the owned dofs, built on first use by the gather assembly
+    // (tb_assembly.cu): entry = cell*nv + a, each list sorted ascending = the reference's element order
+    mutable int64_t *d_adjptr = nullptr;   // ndofs_owned + 1
+    mutable unsigned *d_adj = nullptr;
+    mutable int64_t nadj = 0;
+    // per 32-row slice: smallest / largest adjacent cell (host copy), and the chunk plans derived from it
+    mutable std::vector<int> slice_cmin, slice_cmax;
+    struct GatherPlan {
+        int64_t budget_cells = -1;     // the budget this plan was made for
+        bool ok = false;
+        int64_t rows_per_chunk = 0;    // multiple of 32
+        std::vector<int> cmin, cmax;   // per chunk, inclusive; cmin > cmax: no cells
+        int64_t max_cells = 0;
+    };
+    mutable GatherPlan plan[2];        // [0] matrices, [1] vectors
 };
 
 struct tb_halo {
@@ -277,4 +297,5 @@ int32_t tb_spmv_raw(tb_ctx *ctx, const tb_csr *A, double *x, double *y);
 int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int nparams, double *u, int64_t n, int64_t ld,
                          int phi_idx, const double *phi_src, double t, double dt, int substeps, double thr,
                          double *max_dphi);
+int32_t tb_exclusive_scan_i64(tb_ctx *ctx, const int64_t *in, int64_t *out, int64_t n);
 int tb_grid_for(tb_ctx *ctx, int64_t work_items, int block, int blocks_per_sm);

@@ -190,6 +190,8 @@ extern "C" int32_t tb_mesh_destroy(tb_mesh *m) {
     cudaFree(m->d_coords);
     cudaFree(m->d_node2dof);
     cudaFree(m->d_ghost_global);
+    cudaFree(m->d_adjptr);
+    cudaFree(m->d_adj);
     delete m;
     return TB_OK;
 }
