@@ -138,8 +138,12 @@ def run_b200(args):
     tb.core.assemble_mass(dev, mesh, M, 2, 1.0)
     D = np.diag(W["kappa"][:dim])
     tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_TENSOR, D, 1.0)
+    peer_path = False
     if world > 1:
         part.attach_halo(M)
+        peer_path = bool(part.peer)
+    asm_info = dev.assembly_info()
+    dev.assembly_release_scratch()
     st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
     st.set_cg(SQRT_EPS, SQRT_EPS, None)
     st.set_cell_solver(W["substeps"], 0.1)
@@ -250,7 +254,12 @@ def run_b200(args):
                        "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "iters_per_step_mean": k_mean,
                               "iters_min": int(min(iters)), "iters_max": int(max(iters)), "all_converged": bool(conv_all)},
                        "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
-                       "parallelism": "single GPU" if world == 1 else f"dof-ownership z-slabs x{world}, NCCL halo + allreduce",
+                       "parallelism": "single GPU" if world == 1 else
+                       (f"dof-ownership z-slabs x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
+                        f"(CUDA IPC windows), NCCL for the per-step phi halo" if peer_path else
+                        f"dof-ownership z-slabs x{world}, NCCL halo + allreduce"),
+                       "assembly": {2: "element matrices + ordered gather (deterministic)", 0: "fp64 atomic scatter"}.get(
+                           asm_info["last_mode"], str(asm_info["last_mode"])) + f", {asm_info['last_chunks']} chunk(s)",
                        "l2": "working set (matrix + vectors) is far larger than the 126 MB L2, no flush needed"
                              if nnz * 12 > 4e8 else "working set fits L2: tb_l2_flush not applied between steps (steady-state regime)",
                        "setup_s": t_setup},

@@ -179,6 +179,19 @@ int32_t tb_spmv(tb_ctx *ctx, const tb_csr *A, const tb_vec *x, int32_t xcol, tb_
 int32_t tb_csr_set_halo(tb_csr *A, int32_t nneigh, const int32_t *neigh_ranks, const int64_t *send_ptr,
                         const int64_t *send_rows, const int64_t *recv_ptr);
 
+/* NVLink peer-memory path between the one-process-per-GPU ranks of ONE box (optional; NCCL is the fallback):
+ * every rank exports a TB_PEER_BLOB_BYTES blob (CUDA IPC handles of its mailbox window and its CG work vectors,
+ * sized for operators with up to `ncols` columns), the host ships all blobs to all ranks, tb_peer_attach maps
+ * them.  From then on the CG kernels finish their dot products by storing partial sums into every rank's window
+ * (summed in rank order: identical bits everywhere) and, once tb_csr_set_halo_peer told them where each
+ * neighbour keeps our ghost entries (offset inside the neighbour's vector, and which of its halo flags is ours),
+ * push the boundary of the direction vector straight into the neighbours' ghost blocks before each SpMV. */
+#define TB_PEER_BLOB_BYTES 160
+int32_t tb_peer_export(tb_ctx *ctx, int64_t ncols, void *blob_out);
+int32_t tb_peer_attach(tb_ctx *ctx, const void *blobs, int32_t nranks);
+int32_t tb_peer_enabled(tb_ctx *ctx, int32_t *on);
+int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const int32_t *dst_slot);
+
 /* ---- assembly ---------------------------------------------------------------------------------
  * update_operator!(op, t) of the FerriteOperators element loop (called at euler.jl:173-175) with the
  * element kernels of src/modeling/core/mass.jl:28-43, diffusion.jl:28-50,
@@ -203,6 +216,8 @@ int32_t tb_assemble_source_qp(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, 
 int32_t tb_assembly_set_mode(tb_ctx *ctx, int32_t mode);
 int32_t tb_assembly_info(tb_ctx *ctx, int32_t *mode_requested, int32_t *mode_last_used, int32_t *chunks_last);
 int32_t tb_assembly_set_scratch_budget(tb_ctx *ctx, int64_t bytes);
+/* the element scratch is cached on the context between assembly calls; this frees it (e.g. after setup) */
+int32_t tb_assembly_release_scratch(tb_ctx *ctx);
 
 /* ---- linear solve -----------------------------------------------------------------------------
  * LinearSolve.solve!(cache) with KrylovJL_CG (euler.jl:10,94,155-156): unpreconditioned CG from

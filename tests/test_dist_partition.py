@@ -90,3 +90,29 @@ def test_bounds_without_plane():
     assert b[0] == 0 and b[-1] == 1001 and np.all(np.diff(b) > 0)
     b = tbd.dof_bounds(100, 3, plane=7)       # not divisible: falls back to an even split
     assert b[-1] == 100
+
+
+def test_peer_targets_point_into_the_neighbours_ghost_blocks():
+    """Host logic of the NVLink peer path: our boundary entries must land, inside the neighbour's vector, exactly
+    where the neighbour's halo plan expects the entries it receives from us (owned block first, then ghosts in
+    neighbour order), and the flag slot is our position in the neighbour's list."""
+    sys.path.insert(0, str(ROOT))
+    import oracle as O
+    from thunderbolt_jl_b200 import dist as tbd
+    m = O.generate_grid(O.HEX8, (3, 3, 11), (0, 0, 0), (1, 1, 1))
+    world = 4
+    bounds = tbd.dof_bounds(m.ndofs, world, plane=16)
+    ghosts = [tbd.ghosts_of(m.celldofs, int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
+    plans = [tbd.build_halo_plan(r, bounds, ghosts[r], ghosts) for r in range(world)]
+    nrows = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+    # a global vector; every rank's local image = owned block + ghost block
+    x = np.arange(m.ndofs, dtype=np.float64) * 1.5
+    local = [np.concatenate([x[bounds[r]:bounds[r + 1]], np.full(ghosts[r].size, np.nan)]) for r in range(world)]
+    for r in range(world):
+        off, slot = tbd.peer_targets(r, plans[r], plans, nrows)
+        for i, q in enumerate(plans[r].neigh_ranks):
+            rows = plans[r].send_rows[plans[r].send_ptr[i]:plans[r].send_ptr[i + 1]]
+            assert plans[int(q)].neigh_ranks[slot[i]] == r
+            local[int(q)][off[i]:off[i] + rows.size] = local[r][rows]          # what k_halo_push stores
+    for r in range(world):
+        assert np.array_equal(local[r][nrows[r]:], x[ghosts[r]])                # every ghost received its owner's value

@@ -24,6 +24,7 @@ STATUS_NAMES = {0: "TB_OK", 1: "TB_ERR_INVALID", 2: "TB_ERR_CUDA", 3: "TB_ERR_NO
 QUAD4, HEX8, TRI3, TET4 = 0, 1, 2, 3
 FHN, PCG2019 = 0, 1
 D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
+PEER_BLOB_BYTES = 160
 SRC_NONE, SRC_BOX, SRC_BALL, SRC_COSEXP, SRC_NORMT, SRC_ENDO = 0, 1, 2, 3, 4, 5
 
 
@@ -108,6 +109,10 @@ _SIGNATURES = {
     "tb_csr_axpby_values": [_vp, _vp, _vp, C.c_double],
     "tb_spmv": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32],
     "tb_csr_set_halo": [_vp, C.c_int32, _vp, _vp, _vp, _vp],
+    "tb_peer_export": [_vp, C.c_int64, _vp],
+    "tb_peer_attach": [_vp, _vp, C.c_int32],
+    "tb_peer_enabled": [_vp, _pi32],
+    "tb_csr_set_halo_peer": [_vp, _vp, _vp],
     "tb_quadrature": [C.c_int32, C.c_int32, _pi32, _vp, _vp],
     "tb_assemble_mass": [_vp, _vp, C.c_int32, C.c_double, _vp],
     "tb_assemble_diffusion": [_vp, _vp, C.c_int32, C.c_int32, _f64p, C.c_int64, C.c_double, _vp],
@@ -116,6 +121,7 @@ _SIGNATURES = {
     "tb_assembly_set_mode": [_vp, C.c_int32],
     "tb_assembly_info": [_vp, _pi32, _pi32, _pi32],
     "tb_assembly_set_scratch_budget": [_vp, C.c_int64],
+    "tb_assembly_release_scratch": [_vp],
     "tb_cg_solve": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                      _pf64],

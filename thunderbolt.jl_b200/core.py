@@ -75,6 +75,9 @@ class B200Device:
     def assembly_set_scratch_budget(self, nbytes: int):
         L.call("tb_assembly_set_scratch_budget", self.h, int(nbytes))
 
+    def assembly_release_scratch(self):
+        L.call("tb_assembly_release_scratch", self.h)
+
     # ---- multi-GPU --------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -89,6 +92,21 @@ class B200Device:
 
     def barrier(self):
         L.call("tb_comm_barrier", self.h)
+
+    # NVLink peer-memory path (tb_dist.cu): export this rank's window + CG work vectors, attach everybody's
+    def peer_export(self, ncols: int) -> bytes:
+        buf = C.create_string_buffer(L.PEER_BLOB_BYTES)
+        L.call("tb_peer_export", self.h, int(ncols), buf)
+        return buf.raw
+
+    def peer_attach(self, blobs: bytes, nranks: int):
+        buf = C.create_string_buffer(blobs, len(blobs))
+        L.call("tb_peer_attach", self.h, buf, int(nranks))
+
+    def peer_enabled(self) -> bool:
+        on = C.c_int32()
+        L.call("tb_peer_enabled", self.h, C.byref(on))
+        return bool(on.value)
 
     def allreduce_max(self, v: float) -> float:
         x = C.c_double(v)
@@ -295,6 +313,11 @@ class B200CSRMatrix:
         sr = np.ascontiguousarray(send_rows, dtype=np.int64)
         rp = np.ascontiguousarray(recv_ptr, dtype=np.int64)
         L.call("tb_csr_set_halo", self.h, int(nr.size), L.ptr(nr), L.ptr(sp), L.ptr(sr), L.ptr(rp))
+
+    def set_halo_peer(self, dst_off, dst_slot):
+        do = np.ascontiguousarray(dst_off, dtype=np.int64)
+        ds = np.ascontiguousarray(dst_slot, dtype=np.int32)
+        L.call("tb_csr_set_halo_peer", self.h, L.ptr(do), L.ptr(ds))
 
     def free(self):
         if getattr(self, "h", None):

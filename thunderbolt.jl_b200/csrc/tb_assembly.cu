@@ -325,20 +325,27 @@ static int32_t plan_gather(tb_ctx *ctx, const tb_mesh *m, int64_t budget_cells, 
 }
 
 // ---- phase 1: element matrices / vectors into the scratch buffer ------------------------------------------
+// Each thread integrates one element matrix in registers; the warp then transposes its 32 matrices through a
+// padded shared-memory tile so that EA is written with fully coalesced 256 B stores (a thread writing its own
+// 8*NV*NV bytes would touch 32 different lines per store instruction).
+#define EA_PAD 33
 template <int NV, int DIM, int OP>
 __global__ void __launch_bounds__(AS_BLOCK)
     k_element_matrices(const int *__restrict__ conn, const double *__restrict__ coords, int64_t c0, int64_t c1,
                        const tb_elem_tables *__restrict__ gT, int nq, double rho, int kind, const double *__restrict__ ddata,
                        double cmchi, double *__restrict__ EA) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NE = NV * NV;
     double *sW = reinterpret_cast<double *>(smem_raw);
     double *sN = sW + nq;
     double *sdN = sN + nq * NV;
     double *sX = sdN + nq * NV * DIM;
+    double *sT = sX + NV * DIM * AS_BLOCK + (threadIdx.x >> 5) * (NE * EA_PAD);   // this warp's transpose tile
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < nq; i += AS_BLOCK) sW[i] = gT->w[i];
     for (int i = threadIdx.x; i < nq * NV; i += AS_BLOCK) sN[i] = gT->N[i];
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
-    const tb_tables_view sT{nq, sW, sN, sdN};
+    const tb_tables_view sT_tab{nq, sW, sN, sdN};
     const int64_t ncl = c1 - c0;
     const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -355,21 +362,31 @@ __global__ void __launch_bounds__(AS_BLOCK)
         __syncthreads();
         const int64_t e = e0 + threadIdx.x;
         if (e < c1) {
-            double *out = EA + (e - c0) * (NV * NV);
             if (OP == 0) {
                 double acc[NV * (NV + 1) / 2];
-                tb_element_mass<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, rho, acc);
+                tb_element_mass<NV, DIM, AS_BLOCK>(sT_tab, sX + threadIdx.x, rho, acc);
 #pragma unroll
                 for (int i = 0; i < NV; i++)
 #pragma unroll
-                    for (int j = 0; j < NV; j++) out[i * NV + j] = i <= j ? acc[tb_sym<NV>(i, j)] : acc[tb_sym<NV>(j, i)];
+                    for (int j = 0; j < NV; j++)
+                        sT[(i * NV + j) * EA_PAD + lane] = i <= j ? acc[tb_sym<NV>(i, j)] : acc[tb_sym<NV>(j, i)];
             } else {
-                double Ke[NV * NV];
-                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, ddata, cmchi, e, Ke);
+                double Ke[NE];
+                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT_tab, sX + threadIdx.x, kind, ddata, cmchi, e, Ke);
 #pragma unroll
-                for (int i = 0; i < NV * NV; i++) out[i] = Ke[i];
+                for (int i = 0; i < NE; i++) sT[i * EA_PAD + lane] = Ke[i];
             }
         }
+        __syncwarp();
+        // the warp's elements are EA[(ew0 - c0) .. +32) * NE, one contiguous run of 32*NE doubles
+        const int64_t ew0 = e0 + (threadIdx.x & ~31);
+        const int nvalid = (int)(c1 - ew0 < 32 ? (c1 - ew0 > 0 ? c1 - ew0 : 0) : 32);
+        double *out = EA + (ew0 - c0) * NE;
+        for (int k = lane; k < nvalid * NE; k += 32) {
+            const int el = k / NE, i = k - el * NE;
+            out[k] = sT[i * EA_PAD + el];
+        }
+        __syncwarp();
     }
 }
 
@@ -418,57 +435,78 @@ __global__ void __launch_bounds__(AS_BLOCK)
 // lane's row (bank-conflict free); the lane walks its adjacency in ascending (cell, a) order and adds row a of
 // EA[cell] at the positions of the cell's dofs (binary search in the row's sorted columns, which the 32 lanes
 // read from the same 128 B lines).  The slice is then stored once, 256 B per entry slot.
+template <int NV> struct GatherCell {
+    int dof[NV];
+    double kv[NV];
+};
+template <int NV>
+__device__ __forceinline__ void gather_load(GatherCell<NV> &g, unsigned p, const int *__restrict__ celldofs,
+                                            const double *__restrict__ EA, int64_t c0) {
+    const unsigned c = p / (unsigned)NV;
+    const int a = (int)(p - c * (unsigned)NV);
+    const int *cd = celldofs + (int64_t)c * NV;
+    const double *ke = EA + ((int64_t)c - c0) * (NV * NV) + a * NV;
+    if constexpr (NV % 4 == 0) {
+#pragma unroll
+        for (int b = 0; b < NV; b += 4) {
+            const int4 d4 = *reinterpret_cast<const int4 *>(cd + b);
+            g.dof[b] = d4.x; g.dof[b + 1] = d4.y; g.dof[b + 2] = d4.z; g.dof[b + 3] = d4.w;
+        }
+#pragma unroll
+        for (int b = 0; b < NV; b += 2) {
+            const double2 k2 = *reinterpret_cast<const double2 *>(ke + b);
+            g.kv[b] = k2.x; g.kv[b + 1] = k2.y;
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < NV; b++) {
+            g.dof[b] = cd[b];
+            g.kv[b] = ke[b];
+        }
+    }
+}
+
+// top_step = largest power of two <= maxw.  The NV lower-bound searches of one cell run in lock step (uniform
+// trip count, no divergence), probing the slice's column ids staged in shared memory; the next cell's dof ids and
+// matrix row are in flight while the current one is searched.
 template <int NV>
 __global__ void __launch_bounds__(256)
     k_gather_rows(const int64_t *__restrict__ adjptr, const unsigned *__restrict__ adj, const int *__restrict__ celldofs,
-                  const double *__restrict__ EA, int64_t c0, SellView S, int64_t slice0, int64_t slice1, int maxw) {
+                  const double *__restrict__ EA, int64_t c0, SellView S, int64_t slice0, int64_t slice1, int maxw, int top_step) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     double *acc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * maxw * TB_SLICE + lane;
+    int *scol = reinterpret_cast<int *>(smem_raw + (size_t)nwb * maxw * TB_SLICE * sizeof(double)) + (size_t)warp * maxw * TB_SLICE + lane;
     for (int64_t s = slice0 + (int64_t)blockIdx.x * nwb + warp; s < slice1; s += (int64_t)gridDim.x * nwb) {
         const int64_t base = S.slice_ptr[s];
         const int w = (int)((S.slice_ptr[s + 1] - base) >> 5);
-        for (int j = 0; j < w; j++) acc[j * TB_SLICE] = 0.0;
+        const int *gcol = S.col + base + lane;
+        for (int j = 0; j < w; j++) {
+            acc[j * TB_SLICE] = 0.0;
+            scol[j * TB_SLICE] = gcol[(int64_t)j * TB_SLICE];
+        }
         const int64_t r = s * TB_SLICE + lane;
         if (r < S.nrows) {
             const int len = (int)(S.rowptr[r + 1] - S.rowptr[r]);
-            const int *cols = S.col + base + lane;
+            int64_t q = adjptr[r];
             const int64_t q1 = adjptr[r + 1];
-            for (int64_t q = adjptr[r]; q < q1; q++) {
-                const unsigned p = adj[q];
-                const unsigned c = p / (unsigned)NV;
-                const int a = (int)(p - c * (unsigned)NV);
-                const int *cd = celldofs + (int64_t)c * NV;
-                const double *ke = EA + ((int64_t)c - c0) * (NV * NV) + a * NV;
-                int dof[NV];
-                double kv[NV];
-                if constexpr (NV % 4 == 0) {
+            GatherCell<NV> cur, nxt;
+            if (q < q1) gather_load<NV>(nxt, adj[q], celldofs, EA, c0);
+            for (; q < q1; q++) {
+                cur = nxt;
+                if (q + 1 < q1) gather_load<NV>(nxt, adj[q + 1], celldofs, EA, c0);
+                int lo[NV];
 #pragma unroll
-                    for (int b = 0; b < NV; b += 4) {
-                        const int4 d4 = *reinterpret_cast<const int4 *>(cd + b);
-                        dof[b] = d4.x; dof[b + 1] = d4.y; dof[b + 2] = d4.z; dof[b + 3] = d4.w;
-                    }
-#pragma unroll
-                    for (int b = 0; b < NV; b += 2) {
-                        const double2 k2 = *reinterpret_cast<const double2 *>(ke + b);
-                        kv[b] = k2.x; kv[b + 1] = k2.y;
-                    }
-                } else {
+                for (int b = 0; b < NV; b++) lo[b] = 0;
+                for (int step = top_step; step > 0; step >>= 1) {
 #pragma unroll
                     for (int b = 0; b < NV; b++) {
-                        dof[b] = cd[b];
-                        kv[b] = ke[b];
+                        const int t = lo[b] + step;
+                        if (t <= len && scol[(t - 1) * TB_SLICE] < cur.dof[b]) lo[b] = t;
                     }
                 }
 #pragma unroll
-                for (int b = 0; b < NV; b++) {
-                    int lo = 0, hi = len;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (cols[mid * TB_SLICE] < dof[b]) lo = mid + 1; else hi = mid;
-                    }
-                    acc[lo * TB_SLICE] += kv[b];
-                }
+                for (int b = 0; b < NV; b++) acc[lo[b] * TB_SLICE] += cur.kv[b];
             }
         }
         double *dst = S.val + base + lane;
@@ -491,20 +529,26 @@ __global__ void __launch_bounds__(256) k_gather_vec(const int64_t *__restrict__ 
 static size_t element_smem(int nv, int dim, int nq) {
     return sizeof(double) * nq * (1 + nv + nv * dim) + sizeof(double) * nv * dim * AS_BLOCK;
 }
+static size_t element_matrix_smem(int nv, int dim, int nq) {
+    return element_smem(nv, dim, nq) + sizeof(double) * (size_t)(AS_BLOCK / 32) * nv * nv * EA_PAD;
+}
 
 template <int NV, int DIM, int OP>
 static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, double rho, int kind,
                                  const double *d_data, double cmchi, const tb_pattern *pat, const SellView &S,
                                  const GatherPlan &plan, double *EA) {
-    const size_t smem1 = element_smem(NV, DIM, nq);
+    const size_t smem1 = element_matrix_smem(NV, DIM, nq);
     TB_CUDA(cudaFuncSetAttribute(k_element_matrices<NV, DIM, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_matrices<NV, DIM, OP>, AS_BLOCK, smem1);
     if (per_sm < 1) per_sm = 1;
     const int maxw = pat->max_width < 1 ? 1 : pat->max_width;
-    int warps = (int)((96 * 1024) / ((size_t)maxw * TB_SLICE * sizeof(double)));
+    const size_t per_warp = (size_t)maxw * TB_SLICE * (sizeof(double) + sizeof(int));
+    int warps = (int)((100 * 1024) / per_warp);
     warps = warps > 8 ? 8 : warps < 1 ? 1 : warps;
-    const size_t smem2 = (size_t)warps * maxw * TB_SLICE * sizeof(double);
+    const size_t smem2 = (size_t)warps * per_warp;
+    int top_step = 1;
+    while (top_step * 2 <= maxw) top_step *= 2;
     TB_CUDA(cudaFuncSetAttribute(k_gather_rows<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     int per_sm2 = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_gather_rows<NV>, warps * 32, smem2);
@@ -527,7 +571,7 @@ static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_ta
         const int grid2 = (int)(need < (int64_t)ctx->sm_count * per_sm2 ? need : (int64_t)ctx->sm_count * per_sm2);
         if (grid2 > 0)
             TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, warps * 32, smem2, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, S, s0, s1,
-                      maxw);
+                      maxw, top_step);
     }
     return TB_OK;
 }
@@ -602,11 +646,20 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
             st = plan_gather(ctx, mesh, (int64_t)(budget / (size_t)per_cell), 0, &planp);
             ok = st == TB_OK && planp->ok;
             if (ok) {
+                // the scratch is cached on the context (cudaMalloc/cudaFree of GBs costs 10-80 ms per call, measured);
+                // tb_assembly_release_scratch gives it back
                 const size_t bytes = (size_t)(planp->max_cells > 0 ? planp->max_cells : 1) * (size_t)per_cell;
-                if (cudaMalloc(&EA, bytes) != cudaSuccess) {
-                    cudaGetLastError();
-                    ok = false;
+                if (ctx->ea_bytes < bytes) {
+                    cudaFree(ctx->d_ea);
+                    ctx->d_ea = nullptr;
+                    ctx->ea_bytes = 0;
+                    if (cudaMalloc(&ctx->d_ea, bytes) == cudaSuccess) ctx->ea_bytes = bytes;
+                    else {
+                        cudaGetLastError();
+                        ok = false;
+                    }
                 }
+                EA = static_cast<double *>(ctx->d_ea);
             }
         }
         if (st == TB_OK && ok) {
@@ -627,7 +680,6 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         }
         if (gathered || st != TB_OK) {
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
-            cudaFree(EA);
             cudaFree(d_T);
             cudaFree(d_data);
             if (st != TB_OK) return st;
@@ -799,4 +851,14 @@ extern "C" int32_t tb_assemble_source_qp(tb_ctx *ctx, const tb_mesh *mesh, int32
                                          int32_t bcol) {
     TB_REQUIRE(fq, "tb_assemble_source_qp: fq is NULL");
     return assemble_source(ctx, mesh, qorder, 0, nullptr, 0, 0.0, fq, b, bcol);
+}
+
+extern "C" int32_t tb_assembly_release_scratch(tb_ctx *ctx) {
+    TB_REQUIRE(ctx, "tb_assembly_release_scratch: ctx is NULL");
+    TB_DEV(ctx);
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_ea);
+    ctx->d_ea = nullptr;
+    ctx->ea_bytes = 0;
+    return TB_OK;
 }

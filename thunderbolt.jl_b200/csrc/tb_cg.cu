@@ -48,11 +48,14 @@ __device__ __forceinline__ void cg_after_rr(CGState *st, double gnext) {
 }
 
 // which: 0 init, 1 pAp, 2 rr.  Used on the multi-GPU path after the NCCL all-reduce of st->local[0].
-__global__ void k_cg_scalar(CGState *st, int which) {
+// With a peer window (ar.wins != nullptr) this one thread IS the all-reduce: it waits for every rank's partial of this
+// epoch and adds them in rank order, so all ranks advance with bitwise identical scalars.
+__global__ void k_cg_scalar(CGState *st, int which, const tb_ar_args ar) {
     if (which != 0 && st->done) return;
-    if (which == 0) cg_after_init(st, st->local[0]);
-    else if (which == 1) cg_after_pAp(st, st->local[0]);
-    else cg_after_rr(st, st->local[0]);
+    const double total = ar.wins ? tb_ar_collect(ar) : st->local[0];
+    if (which == 0) cg_after_init(st, total);
+    else if (which == 1) cg_after_pAp(st, total);
+    else cg_after_rr(st, total);
 }
 
 __global__ void k_cg_set_tol(CGState *st, double atol, double rtol, long long itmax) {
@@ -68,10 +71,11 @@ __global__ void k_cg_set_tol(CGState *st, double atol, double rtol, long long it
 // multi GPU -> leave the rank-local sum for the all-reduce
 template <int WHICH>
 __device__ __forceinline__ void cg_finish(double block_value, CGState *st, double *partials, unsigned *ticket, double *sm,
-                                          bool dist) {
+                                          bool dist, const tb_ar_args &ar) {
     double total;
     if (tb_grid_sum(block_value, partials, ticket, sm, &total) && threadIdx.x == 0) {
-        if (dist) st->local[0] = total;
+        if (dist && ar.wins) tb_ar_publish(ar, total);
+        else if (dist) st->local[0] = total;
         else if (WHICH == 0) cg_after_init(st, total);
         else if (WHICH == 1) cg_after_pAp(st, total);
         else cg_after_rr(st, total);
@@ -81,7 +85,7 @@ __device__ __forceinline__ void cg_finish(double block_value, CGState *st, doubl
 // ---- init from a given right-hand side: x = 0, r = p = b, gamma = b.b ------------------------------
 __global__ void __launch_bounds__(256) k_cg_init_b(const double *__restrict__ b, double *__restrict__ x,
                                                    double *__restrict__ r, double *__restrict__ p, int64_t n, CGState *st,
-                                                   double *partials, unsigned *ticket, bool dist) {
+                                                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar) {
     __shared__ double sm[32];
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) k_cg_init_b(const double *__restrict__ b,
         acc += v * v;
     }
     const double bs = tb_block_sum(acc, sm);
-    cg_finish<0>(bs, st, partials, ticket, sm, dist);
+    cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 // ---- init fused with the backward-Euler right-hand side: r = p = M*phi (+ bS), x = 0 ----------------
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(256)
     k_cg_init_Mphi(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ Mval,
                    const double *__restrict__ phi, const double *__restrict__ bS, double *__restrict__ x,
                    double *__restrict__ r, double *__restrict__ p, int64_t nrows, int64_t nslices, CGState *st,
-                   double *partials, unsigned *ticket, bool dist) {
+                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar) {
     __shared__ double sm[32];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -119,15 +123,16 @@ __global__ void __launch_bounds__(256)
         }
     }
     const double bs = tb_block_sum(acc, sm);
-    cg_finish<0>(bs, st, partials, ticket, sm, dist);
+    cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 // ---- Ap = A p, p.Ap -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k_cg_spmv_dot(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ val,
                   const double *__restrict__ p, double *__restrict__ Ap, int64_t nrows, int64_t nslices, CGState *st,
-                  double *partials, unsigned *ticket, bool dist) {
+                  double *partials, unsigned *ticket, bool dist, const tb_ar_args ar, const tb_hwait_args hw) {
     if (st->done) return;
+    tb_halo_wait(hw);
     __shared__ double sm[32];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256)
         }
     }
     const double bs = tb_block_sum(acc, sm);
-    cg_finish<1>(bs, st, partials, ticket, sm, dist);
+    cg_finish<1>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 // ---- bulk-async (TMA) variants of the two SpMV-shaped kernels ------------------------------------------
@@ -154,8 +159,9 @@ __global__ void __launch_bounds__(1024, 1)
                   const double *__restrict__ val, const double *__restrict__ xin, const double *__restrict__ bS,
                   double *__restrict__ xout, double *__restrict__ r, double *__restrict__ pout, int64_t nrows,
                   int64_t nslices, unsigned val_bytes, unsigned col_bytes, CGState *st, double *partials, unsigned *ticket,
-                  bool dist) {
+                  bool dist, const tb_ar_args ar, const tb_hwait_args hw) {
     if (!INIT && st->done) return;
+    tb_halo_wait(hw);
     extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
     __shared__ double sm[32];
     double acc = 0.0;
@@ -174,14 +180,14 @@ __global__ void __launch_bounds__(1024, 1)
         }
     });
     const double bs = tb_block_sum(acc, sm);
-    if (INIT) cg_finish<0>(bs, st, partials, ticket, sm, dist);
-    else cg_finish<1>(bs, st, partials, ticket, sm, dist);
+    if (INIT) cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
+    else cg_finish<1>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 template <int STAGES, bool INIT>
 static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern *pat, const double *val, const double *xin,
                                const double *bS, double *xout, double *r, double *pout, CGState *st, double *part,
-                               unsigned *tick, bool dist) {
+                               unsigned *tick, bool dist, const tb_ar_args &ar, const tb_hwait_args &hw) {
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
     const tb_tma_geom g = tb_tma_geometry(pat->max_width, cc ? pat->max_ccol_ints : 32 * pat->max_width, STAGES, warps_override);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
@@ -193,7 +199,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             configured = g.smem;
         }
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_ccol,
-                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist);
+                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw);
     } else {
         static size_t configured = 0;
         if (configured < g.smem) {
@@ -201,7 +207,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             configured = g.smem;
         }
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, nullptr,
-                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist);
+                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw);
     }
     return TB_OK;
 }
@@ -211,19 +217,20 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
 //   3 staged, 2 stages, as many warps as fit | 4 staged, 1 stage, 24 warps
 template <bool INIT>
 static int32_t dispatch_spmv_tma(tb_ctx *ctx, const tb_pattern *pat, const double *val, const double *xin, const double *bS,
-                                 double *xout, double *r, double *pout, CGState *st, double *part, unsigned *tick, bool dist) {
+                                 double *xout, double *r, double *pout, CGState *st, double *part, unsigned *tick, bool dist,
+                                 const tb_ar_args &ar, const tb_hwait_args &hw) {
     switch (ctx->spmv_variant) {
-    case 2: return launch_spmv_tma<1, INIT>(ctx, 16, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
-    case 3: return launch_spmv_tma<2, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
-    case 4: return launch_spmv_tma<1, INIT>(ctx, 24, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
-    default: return launch_spmv_tma<1, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist);
+    case 2: return launch_spmv_tma<1, INIT>(ctx, 16, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
+    case 3: return launch_spmv_tma<2, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
+    case 4: return launch_spmv_tma<1, INIT>(ctx, 24, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
+    default: return launch_spmv_tma<1, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
     }
 }
 
 // ---- x += alpha p; r -= alpha Ap; r.r  (128-bit loads/stores) --------------------------------------
 __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                                                const double *__restrict__ Ap, int64_t n, CGState *st, double *partials,
-                                               unsigned *ticket, bool dist) {
+                                               unsigned *ticket, bool dist, const tb_ar_args ar) {
     if (st->done) return;
     __shared__ double sm[32];
     const double alpha = st->alpha;
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
         acc += rn * rn;
     }
     const double bs = tb_block_sum(acc, sm);
-    cg_finish<2>(bs, st, partials, ticket, sm, dist);
+    cg_finish<2>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 // ---- p = r + beta p ---------------------------------------------------------------------------------
@@ -268,9 +275,27 @@ __global__ void __launch_bounds__(256) k_cg_p(const double *__restrict__ r, doub
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
 }
 
-static int32_t cg_allreduce_then(tb_ctx *ctx, int which) {
-    TB_NCCL(ncclAllReduce(ctx->d_cg->local, ctx->d_cg->local, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
-    TB_LAUNCH(ctx, k_cg_scalar, 1, 1, 0, ctx->d_cg, which);
+// next all-reduce epoch on the window path (all ranks call this in the same order), or the NCCL marker
+static tb_ar_args cg_next_ar(tb_ctx *ctx, bool peer) {
+    tb_ar_args a;
+    a.wins = nullptr;
+    a.rank = ctx->rank;
+    a.nranks = ctx->nranks;
+    a.slot = 0;
+    a.epoch = 0;
+    if (peer) {
+        a.wins = ctx->peer.d_peer_win;
+        a.epoch = ++ctx->peer.ar_epoch;
+        a.slot = (int)(a.epoch % TB_AR_SLOTS);
+    }
+    return a;
+}
+
+// finish a distributed dot product: window path = one single-thread kernel that collects; NCCL path = all-reduce + scalar kernel
+static int32_t cg_allreduce_then(tb_ctx *ctx, int which, const tb_ar_args &ar) {
+    if (!ar.wins)
+        TB_NCCL(ncclAllReduce(ctx->d_cg->local, ctx->d_cg->local, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    TB_LAUNCH(ctx, k_cg_scalar, 1, 1, 0, ctx->d_cg, which, ar);
     return TB_OK;
 }
 
@@ -284,6 +309,9 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
     CGState *st = ctx->d_cg;
     const bool dist = ctx->has_comm && ctx->nranks > 1;
+    // peer-memory path: dot products through the windows; halo of p by direct stores when the plan has peer targets
+    const bool peer_ar = dist && ctx->peer.on;
+    const bool peer_halo = peer_ar && pat->halo.nneigh > 0 && pat->halo.peer_ready;
     double *part = ctx->d_partials;
     unsigned *tick = ctx->d_ticket;
     const int64_t need_v = (n / 2 + 256) / 256, need_s = (pat->nslices + 7) / 8;
@@ -293,19 +321,23 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const int grid_s = TB_GRID(ctx, k_cg_spmv_dot, 256, 0, need_s);
     const int grid_im = TB_GRID(ctx, k_cg_init_Mphi, 256, 0, need_s);
     const bool tma = ctx->spmv_variant > 0 && pat->max_width > 0 && pat->max_width <= TB_TMA_WCAP;
+    const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
 
     TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);
-    if (b) {
-        TB_LAUNCH(ctx, k_cg_init_b, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist);
-    } else {
-        if (M->pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, M->pat, phi));
-        if (tma)
-            TB_TRY(dispatch_spmv_tma<true>(ctx, pat, M->d_val, phi, bS, x, r, p, st, part, tick, dist));
-        else
-            TB_LAUNCH(ctx, k_cg_init_Mphi, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
-                      pat->nslices, st, part, tick, dist);
+    {
+        const tb_ar_args ar = cg_next_ar(ctx, peer_ar);
+        if (b) {
+            TB_LAUNCH(ctx, k_cg_init_b, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist, ar);
+        } else {
+            if (M->pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, M->pat, phi));   // phi lives in the caller's vector: NCCL
+            if (tma)
+                TB_TRY(dispatch_spmv_tma<true>(ctx, pat, M->d_val, phi, bS, x, r, p, st, part, tick, dist, ar, nowait));
+            else
+                TB_LAUNCH(ctx, k_cg_init_Mphi, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
+                          pat->nslices, st, part, tick, dist, ar);
+        }
+        if (dist) TB_TRY(cg_allreduce_then(ctx, 0, ar));
     }
-    if (dist) TB_TRY(cg_allreduce_then(ctx, 0));
 
     int64_t enq = 0;
     int64_t chunk = ctx->last_cg_iters + 1;
@@ -314,18 +346,22 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     for (;;) {
         if (chunk > itmax - enq) chunk = itmax - enq;
         for (int64_t k = 0; k < chunk; k++) {
-            if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));
+            tb_hwait_args hw = nowait;
+            if (peer_halo) TB_TRY(tb_halo_push(ctx, pat, p, st, &hw));
+            else if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));
             const bool prof = ctx->profile && enq + k < TB_PROF_MAX;
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k)], ctx->stream));
+            const tb_ar_args ar1 = cg_next_ar(ctx, peer_ar);
             if (tma)
-                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, st, part, tick, dist));
+                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, st, part, tick, dist, ar1, hw));
             else
                 TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
-                          pat->nslices, st, part, tick, dist);
+                          pat->nslices, st, part, tick, dist, ar1, hw);
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k) + 1], ctx->stream));
-            if (dist) TB_TRY(cg_allreduce_then(ctx, 1));
-            TB_LAUNCH(ctx, k_cg_xr, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist);
-            if (dist) TB_TRY(cg_allreduce_then(ctx, 2));
+            if (dist) TB_TRY(cg_allreduce_then(ctx, 1, ar1));
+            const tb_ar_args ar2 = cg_next_ar(ctx, peer_ar);
+            TB_LAUNCH(ctx, k_cg_xr, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2);
+            if (dist) TB_TRY(cg_allreduce_then(ctx, 2, ar2));
             TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, r, p, n, st);
         }
         enq += chunk;
@@ -335,6 +371,11 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
         chunk = 4;
     }
     ctx->last_cg_iters = h->iter;
+    if (peer_ar) {
+        unsigned long long err = 0;
+        TB_CUDA(cudaMemcpy(&err, &ctx->peer.win->err, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) return tb_fail(TB_ERR_COMM, "CG: a wait on a peer rank's data timed out (peer dead or out of step)");
+    }
     if (ctx->profile) {
         // only launches that did work: iteration k ran its SpMV iff k < iter (later ones saw done = 1)
         const int64_t nreal = h->iter < TB_PROF_MAX ? h->iter : TB_PROF_MAX;

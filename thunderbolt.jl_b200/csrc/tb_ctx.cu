@@ -71,6 +71,7 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     if (!ctx) return TB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    tb_peer_release(ctx);
     if (ctx->has_comm) ncclCommDestroy(ctx->comm);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_ticket);
@@ -147,6 +148,9 @@ extern "C" int32_t tb_l2_flush(tb_ctx *ctx) {
 int32_t tb_ctx_ensure_cgwork(tb_ctx *ctx, int64_t n) {
     int64_t ld = tb_round_up(n, 32);
     if (ld <= ctx->cgwork_ld && ctx->d_cgwork) return TB_OK;
+    if (ctx->peer.win)
+        return tb_fail(TB_ERR_INVALID, "CG work vectors of %lld rows are mapped by the peer ranks (tb_peer_export); an operator with %lld "
+                       "columns cannot be solved on this context", (long long)ctx->cgwork_ld, (long long)n);
     if (ctx->d_cgwork) {
         TB_CUDA(cudaStreamSynchronize(ctx->stream));
         TB_CUDA(cudaFree(ctx->d_cgwork));

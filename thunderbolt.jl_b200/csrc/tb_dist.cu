@@ -104,3 +104,151 @@ int32_t tb_halo_exchange(tb_ctx *ctx, const tb_pattern *pat, double *x) {
     TB_NCCL(ncclGroupEnd());
     return TB_OK;
 }
+
+// =====================================================================================================
+// Peer-memory path (NVLink stores between the ranks of one box), see tb_internal.cuh "tb_peer_window".
+// =====================================================================================================
+struct tb_peer_blob {   // what every rank publishes to the others (TB_PEER_BLOB_BYTES)
+    cudaIpcMemHandle_t win;      // 64 B
+    cudaIpcMemHandle_t cgwork;   // 64 B
+    int64_t cgwork_ld;
+    int64_t reserved[3];
+};
+static_assert(sizeof(tb_peer_blob) == TB_PEER_BLOB_BYTES, "tb_peer_blob layout");
+
+extern "C" int32_t tb_peer_export(tb_ctx *ctx, int64_t ncols, void *blob_out) {
+    TB_REQUIRE(ctx && blob_out && ncols > 0, "tb_peer_export: bad argument");
+    TB_REQUIRE(ctx->has_comm && ctx->nranks > 1 && ctx->nranks <= TB_MAX_RANKS, "tb_peer_export: needs a communicator of 2..%d ranks", TB_MAX_RANKS);
+    TB_REQUIRE(!ctx->peer.on && !ctx->peer.win, "tb_peer_export: already exported");
+    TB_DEV(ctx);
+    TB_TRY(tb_ctx_ensure_cgwork(ctx, ncols));
+    TB_CUDA(cudaMalloc(&ctx->peer.win, sizeof(tb_peer_window)));
+    TB_CUDA(cudaMemset(ctx->peer.win, 0, sizeof(tb_peer_window)));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    tb_peer_blob b;
+    memset(&b, 0, sizeof(b));
+    TB_CUDA(cudaIpcGetMemHandle(&b.win, ctx->peer.win));
+    TB_CUDA(cudaIpcGetMemHandle(&b.cgwork, ctx->d_cgwork));
+    b.cgwork_ld = ctx->cgwork_ld;
+    memcpy(blob_out, &b, sizeof(b));
+    return TB_OK;
+}
+
+extern "C" int32_t tb_peer_attach(tb_ctx *ctx, const void *blobs, int32_t nranks) {
+    TB_REQUIRE(ctx && blobs, "tb_peer_attach: NULL argument");
+    TB_REQUIRE(ctx->peer.win && !ctx->peer.on, "tb_peer_attach: call tb_peer_export first (once)");
+    TB_REQUIRE(nranks == ctx->nranks, "tb_peer_attach: %d blobs for %d ranks", nranks, ctx->nranks);
+    TB_DEV(ctx);
+    const tb_peer_blob *b = static_cast<const tb_peer_blob *>(blobs);
+    tb_peer &P = ctx->peer;
+    for (int q = 0; q < nranks; q++) {
+        if (q == ctx->rank) {
+            P.peer_win[q] = P.win;
+            P.peer_cgwork[q] = ctx->d_cgwork;
+        } else {
+            void *w = nullptr, *c = nullptr;
+            TB_CUDA(cudaIpcOpenMemHandle(&w, b[q].win, cudaIpcMemLazyEnablePeerAccess));
+            TB_CUDA(cudaIpcOpenMemHandle(&c, b[q].cgwork, cudaIpcMemLazyEnablePeerAccess));
+            P.peer_win[q] = static_cast<tb_peer_window *>(w);
+            P.peer_cgwork[q] = static_cast<double *>(c);
+        }
+        P.peer_ld[q] = b[q].cgwork_ld;
+    }
+    TB_CUDA(cudaMalloc(&P.d_peer_win, sizeof(tb_peer_window *) * TB_MAX_RANKS));
+    TB_CUDA(cudaMemcpy(P.d_peer_win, P.peer_win, sizeof(tb_peer_window *) * TB_MAX_RANKS, cudaMemcpyHostToDevice));
+    P.on = true;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_peer_enabled(tb_ctx *ctx, int32_t *on) {
+    TB_REQUIRE(ctx && on, "tb_peer_enabled: NULL argument");
+    *on = ctx->peer.on ? 1 : 0;
+    return TB_OK;
+}
+
+// must run on every rank before the context goes away (peers may still hold mappings of our memory)
+int32_t tb_peer_release(tb_ctx *ctx) {
+    tb_peer &P = ctx->peer;
+    for (int q = 0; q < TB_MAX_RANKS; q++) {
+        if (P.on && q != ctx->rank && q < ctx->nranks) {
+            if (P.peer_win[q]) cudaIpcCloseMemHandle(P.peer_win[q]);
+            if (P.peer_cgwork[q]) cudaIpcCloseMemHandle(P.peer_cgwork[q]);
+        }
+        P.peer_win[q] = nullptr;
+        P.peer_cgwork[q] = nullptr;
+    }
+    cudaFree(P.d_peer_win);
+    cudaFree(P.win);
+    P = tb_peer();
+    return TB_OK;
+}
+
+extern "C" int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const int32_t *dst_slot) {
+    TB_REQUIRE(A && dst_off && dst_slot, "tb_csr_set_halo_peer: NULL argument");
+    tb_halo &h = A->pat->halo;
+    tb_ctx *ctx = A->pat->ctx;
+    TB_REQUIRE(ctx->peer.on, "tb_csr_set_halo_peer: peers are not attached");
+    TB_REQUIRE(h.nneigh > 0 && h.nneigh <= TB_MAX_RANKS, "tb_csr_set_halo_peer: set the halo plan first");
+    TB_REQUIRE(A->pat->ncols <= ctx->cgwork_ld, "tb_csr_set_halo_peer: operator has more columns than the exported work vectors");
+    h.dst_off.assign(dst_off, dst_off + h.nneigh);
+    h.dst_slot.assign(dst_slot, dst_slot + h.nneigh);
+    for (int i = 0; i < h.nneigh; i++) {
+        const int64_t ns = h.send_ptr[i + 1] - h.send_ptr[i];
+        TB_REQUIRE(h.dst_slot[i] >= 0 && h.dst_slot[i] < TB_MAX_RANKS, "tb_csr_set_halo_peer: bad flag slot");
+        TB_REQUIRE(h.dst_off[i] >= 0 && h.dst_off[i] + ns <= ctx->peer.peer_ld[h.ranks[i]],
+                   "tb_csr_set_halo_peer: destination range outside the neighbour's work vector");
+    }
+    h.peer_ready = true;
+    return TB_OK;
+}
+
+struct HaloPush {
+    int n;
+    long long begin[TB_MAX_RANKS + 1];
+    double *dst[TB_MAX_RANKS];
+    unsigned long long *flag[TB_MAX_RANKS];
+};
+
+// dst_k[i - begin_k] = p[rows[i]] for every neighbour k, then (last block) raise the neighbours' flags
+__global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ p, const int *__restrict__ rows, const HaloPush hp,
+                                                   unsigned long long epoch, unsigned *ticket, const CGState *st) {
+    if (st && st->done) return;
+    const long long n = hp.begin[hp.n];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (i >= hp.begin[k + 1]) k++;
+        hp.dst[k][i - hp.begin[k]] = p[rows[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            for (int k = 0; k < hp.n; k++) *(volatile unsigned long long *)hp.flag[k] = epoch;
+        }
+    }
+}
+
+// Pushes the boundary entries of p (the CG direction vector inside ctx->d_cgwork) into the neighbours' ghost blocks.
+// wait_out: what the following SpMV on this rank has to wait for.
+int32_t tb_halo_push(tb_ctx *ctx, const tb_pattern *pat, const double *p, const CGState *st, tb_hwait_args *wait_out) {
+    const tb_halo &h = pat->halo;
+    tb_peer &P = ctx->peer;
+    const unsigned long long epoch = ++P.halo_epoch;
+    HaloPush hp;
+    hp.n = h.nneigh;
+    for (int i = 0; i < h.nneigh; i++) {
+        const int q = h.ranks[i];
+        hp.begin[i] = h.send_ptr[i];
+        hp.dst[i] = P.peer_cgwork[q] + P.peer_ld[q] + h.dst_off[i];       // p is the second work vector
+        hp.flag[i] = &P.peer_win[q]->hflag[h.dst_slot[i]];
+    }
+    hp.begin[h.nneigh] = h.nsend;
+    TB_LAUNCH(ctx, k_halo_push, tb_grid_for(ctx, h.nsend, 256, 4), 256, 0, p, h.d_send_rows, hp, epoch, ctx->d_ticket + 4, st);
+    wait_out->hflag = P.win->hflag;
+    wait_out->n = h.nneigh;
+    wait_out->epoch = epoch;
+    wait_out->err = &P.win->err;
+    return TB_OK;
+}

@@ -76,6 +76,46 @@ int32_t tb_fail(int32_t code, const char *fmt, ...);
         return (int)(n__ < cap__ ? n__ : cap__);                                                    \
     }())
 
+// ---- peer-memory (NVLink) communication between the one-process-per-GPU ranks of a box ----------------
+// Every rank owns one tb_peer_window in its HBM and maps the windows (and CG work vectors) of all other
+// ranks through CUDA IPC.  Kernels then communicate with plain stores over NVLink:
+//   * dot products: the last block of a reducing kernel stores its rank-local sum into slot [e % SLOTS][rank]
+//     of EVERY rank's window, fences, then stores the epoch e into the matching flag; the consumer (one
+//     thread) waits for all flags of epoch e and adds the values in rank order -- identical bits on all ranks;
+//   * halo: the owner stores its boundary entries of p straight into the neighbour's ghost block of p and then
+//     raises hflag[slot] = epoch in the neighbour's window; the neighbour's SpMV waits for it at kernel start.
+#define TB_MAX_RANKS 16
+#define TB_AR_SLOTS 8
+struct tb_peer_window {
+    double val[TB_AR_SLOTS][TB_MAX_RANKS];
+    unsigned long long flag[TB_AR_SLOTS][TB_MAX_RANKS];
+    unsigned long long hflag[TB_MAX_RANKS];
+    unsigned long long err;          // set by a waiter that timed out
+    unsigned long long pad[15];
+};
+struct tb_peer {
+    bool on = false;
+    tb_peer_window *win = nullptr;                     // this rank's window
+    tb_peer_window *peer_win[TB_MAX_RANKS] = {};       // windows of all ranks as seen from this GPU
+    double *peer_cgwork[TB_MAX_RANKS] = {};            // base of every rank's CG work vectors (r | p | Ap)
+    int64_t peer_ld[TB_MAX_RANKS] = {};
+    tb_peer_window **d_peer_win = nullptr;             // device copy of peer_win
+    unsigned long long ar_epoch = 0, halo_epoch = 0;
+};
+// what a reducing / consuming kernel needs to take part in the window all-reduce (wins == nullptr: NCCL path)
+struct tb_ar_args {
+    tb_peer_window *const *wins;
+    int rank, nranks, slot;
+    unsigned long long epoch;
+};
+// halo wait of an SpMV kernel (n == 0: nothing to wait for)
+struct tb_hwait_args {
+    const unsigned long long *hflag;
+    int n;
+    unsigned long long epoch;
+    unsigned long long *err;
+};
+
 struct tb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -115,6 +155,7 @@ struct tb_ctx {
     bool has_comm = false;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    tb_peer peer;
 };
 
 // device-resident scalars of a CG solve; mirrors the locals of Krylov.jl's cg!
@@ -180,6 +221,11 @@ struct tb_halo {
     int *d_send_rows = nullptr;   // concatenated local row ids to pack
     double *d_sendbuf = nullptr;
     int64_t nsend = 0, nrecv = 0;
+    // peer-memory push (tb_csr_set_halo_peer): where each neighbour wants our entries inside ITS p vector,
+    // and which of its halo flags is ours
+    bool peer_ready = false;
+    std::vector<int64_t> dst_off;
+    std::vector<int> dst_slot;
 };
 
 // sparsity pattern shared by M, K and A (sliced ELL image of the reference's CSR pattern)
@@ -290,6 +336,54 @@ __device__ __forceinline__ bool tb_grid_sum(double block_value /* valid in threa
 int32_t tb_pattern_release(tb_pattern *p);
 int32_t tb_ctx_ensure_cgwork(tb_ctx *ctx, int64_t n);
 int32_t tb_halo_exchange(tb_ctx *ctx, const tb_pattern *pat, double *x);
+int32_t tb_peer_release(tb_ctx *ctx);
+int32_t tb_halo_push(tb_ctx *ctx, const tb_pattern *pat, const double *p, const struct CGState *st, tb_hwait_args *wait_out);
+
+// ---- device side of the window protocol -------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long tb_ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long tb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= epoch; gives up after 20 s (a dead peer must not hang the GPU) and records it in *err
+__device__ __forceinline__ void tb_wait_flag(const unsigned long long *flag, unsigned long long epoch, unsigned long long *err) {
+    if (tb_ld_acquire_sys(flag) >= epoch) return;
+    const unsigned long long t0 = tb_globaltimer();
+    while (tb_ld_acquire_sys(flag) < epoch) {
+        if (tb_globaltimer() - t0 > 20000000000ull) {
+            if (err) *err = 1;
+            return;
+        }
+    }
+}
+// one thread: publish this rank's partial sum to every rank's window
+__device__ __forceinline__ void tb_ar_publish(const tb_ar_args &a, double v) {
+    for (int q = 0; q < a.nranks; q++) a.wins[q]->val[a.slot][a.rank] = v;
+    __threadfence_system();
+    for (int q = 0; q < a.nranks; q++) *(volatile unsigned long long *)&a.wins[q]->flag[a.slot][a.rank] = a.epoch;
+}
+// one thread: wait for all ranks' partials of this epoch and add them in rank order
+__device__ __forceinline__ double tb_ar_collect(const tb_ar_args &a) {
+    tb_peer_window *w = a.wins[a.rank];
+    double s = 0.0;
+    for (int q = 0; q < a.nranks; q++) {
+        tb_wait_flag(&w->flag[a.slot][q], a.epoch, &w->err);
+        s += *(volatile double *)&w->val[a.slot][q];
+    }
+    return s;
+}
+// kernel prologue of an SpMV that reads ghost entries pushed by the neighbours
+__device__ __forceinline__ void tb_halo_wait(const tb_hwait_args &h) {
+    if (h.n > 0) {
+        if ((int)threadIdx.x < h.n) tb_wait_flag(h.hflag + threadIdx.x, h.epoch, h.err);
+        __syncthreads();
+    }
+}
 int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                        int32_t *converged);

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import numpy as np
 
 from .core import B200CSRMatrix, B200Device, DeviceMesh
@@ -78,6 +80,18 @@ def init_comm(dev: B200Device, dist) -> None:
     dev.comm_init(rank, world, box[0])
 
 
+def peer_targets(rank: int, plan: HaloPlan, all_plans: list, all_nrows: list):
+    """For each of our neighbours q: where our boundary entries go inside q's vector (q's owned block, then q's
+    ghost block in q's neighbour order) and which of q's halo flags is ours.  Pure host logic."""
+    dst_off, dst_slot = [], []
+    for q in plan.neigh_ranks:
+        pq = all_plans[int(q)]
+        idx = int(np.flatnonzero(np.asarray(pq.neigh_ranks) == rank)[0])
+        dst_off.append(int(all_nrows[int(q)]) + int(pq.recv_ptr[idx]))
+        dst_slot.append(idx)
+    return np.array(dst_off, dtype=np.int64), np.array(dst_slot, dtype=np.int32)
+
+
 @dataclass
 class Partition:
     mesh: DeviceMesh          # local cells, owned dofs first then ghosts
@@ -85,11 +99,48 @@ class Partition:
     plan: HaloPlan
     rank: int
     nranks: int
+    dist: object = None
+    peer: bool = False        # True once the NVLink peer-memory path is active
 
-    def attach_halo(self, A: B200CSRMatrix):
-        """M, K and A share one pattern object, so attaching to one attaches to all."""
+    def attach_halo(self, A: B200CSRMatrix, p2p: bool | None = None):
+        """M, K and A share one pattern object, so attaching to one attaches to all.
+
+        p2p (default: env TB_P2P != "0"): map every rank's CG work vectors and mailbox window into every other rank
+        (CUDA IPC) so that the halo of p and the dot-product reductions are plain NVLink stores issued by the
+        kernels themselves; NCCL stays for everything else.  Falls back to NCCL if the mapping fails."""
         p = self.plan
         A.set_halo(p.neigh_ranks, p.send_ptr, p.send_rows, p.recv_ptr)
+        if p2p is None:
+            p2p = os.environ.get("TB_P2P", "1") != "0"
+        if not p2p or self.dist is None or self.nranks < 2:
+            return
+        dev, dist = A.dev, self.dist
+        ok = True
+        try:
+            if not dev.peer_enabled():
+                blob = dev.peer_export(A.ncols)
+            else:
+                blob = None
+        except Exception as e:                      # noqa: BLE001 - any failure means "no IPC here"
+            print(f"[tb dist] rank {self.rank}: peer export failed ({e}); staying on NCCL", flush=True)
+            blob, ok = None, False
+        gathered = [None] * self.nranks
+        dist.all_gather_object(gathered, (ok, blob, p, int(self.mesh.ndofs_owned)))
+        if not all(g[0] for g in gathered):
+            return
+        if blob is not None:
+            try:
+                dev.peer_attach(b"".join(g[1] for g in gathered), self.nranks)
+            except Exception as e:                  # noqa: BLE001
+                print(f"[tb dist] rank {self.rank}: peer attach failed ({e}); staying on NCCL", flush=True)
+                ok = False
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            raise RuntimeError("peer attach succeeded on some ranks only; set TB_P2P=0")
+        off, slot = peer_targets(self.rank, p, [g[2] for g in gathered], [g[3] for g in gathered])
+        A.set_halo_peer(off, slot)
+        self.peer = True
 
 
 def partition_mesh(dev: B200Device, mesh: DeviceMesh, dist, plane: int | None = None) -> Partition:
@@ -100,4 +151,4 @@ def partition_mesh(dev: B200Device, mesh: DeviceMesh, dist, plane: int | None = 
     gathered = [None] * world
     dist.all_gather_object(gathered, local.ghost_global)
     plan = build_halo_plan(rank, bounds, local.ghost_global, gathered)
-    return Partition(local, bounds, plan, rank, world)
+    return Partition(local, bounds, plan, rank, world, dist)
