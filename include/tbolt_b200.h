@@ -251,6 +251,10 @@ int32_t tb_monodomain_set_source(tb_monodomain *md, const tb_vec *bS, int32_t co
 int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                            int32_t *converged);
 /* `nsteps` steps back to back with one host round trip at the end (iters = total, converged = all) */
+/* the same step, also returning the reaction tangent R = max_i du[i, phi_m] left by the cell sweep's last rhs
+ * evaluation, maximum over all ranks: the input of ReactionTangentController (src/solver/time/rtc.jl:51-78,121-133) */
+int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
+                              int32_t *converged, double *reaction_tangent);
 int32_t tb_monodomain_run(tb_monodomain *md, tb_vec *u, double t0, double dt, int64_t nsteps, int64_t *iters_total,
                           int32_t *all_converged);
 /* end-to-end variant on HOST buffers: uploads u_in, steps, downloads into u_out (may alias u_in) */

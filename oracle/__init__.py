@@ -298,6 +298,15 @@ def cell_step(model, prm, u, n, t, dt, substeps=1, threshold=0.1, phi_idx=0, ld=
     return du
 
 
+def rtc_next_dt(R, sigma_s, sigma_c, dt_bounds):
+    """ReactionTangentController's step_accept_controller! (src/solver/time/rtc.jl:121-133): the next step length
+    is sigma(R); sigma_s = Inf makes it a step function with R == sigma_c on the dt_max side."""
+    lo, hi = dt_bounds
+    if np.isinf(sigma_s):
+        return lo if R > sigma_c else hi
+    return (1 - 1 / (1 + np.exp((sigma_c - R) * sigma_s))) * (hi - lo) + lo
+
+
 class MonodomainOracle:
     """Holds M, K, A = M - dt K and steps LTG(BackwardEuler, cell solver) like the reference."""
 
@@ -330,3 +339,8 @@ class MonodomainOracle:
                                 self.itmax, int(self.threaded_blas1), self.work, C.byref(rn), C.byref(conv))
         self.iters.append(int(it))
         return int(it), rn.value, bool(conv.value)
+
+    def reaction_tangent(self):
+        """get_reaction_tangent (rtc.jl:51-78): maximum (not maximum(abs)) of the phi_m column of the cell solver's
+        du left by the last step."""
+        return float(self.du[self.phi_idx * self.n:(self.phi_idx + 1) * self.n].max())

@@ -597,6 +597,27 @@ class LieTrotterGodunov:
     inner_algs: tuple
 
 
+@dataclass
+class ReactionTangentController:
+    """rtc.jl:23-40: LieTrotterGodunov whose next step length is sigma(R_max), R_max = max_i dphi_m/dt of the cell
+    sweep (rtc.jl:51-78).  A heuristic map: no error estimator, a step is rejected only when an inner solve fails."""
+    inner_algs: object
+    σ_s: float
+    σ_c: float
+    Δt_bounds: tuple
+
+    def __post_init__(self):
+        if isinstance(self.inner_algs, LieTrotterGodunov):          # rtc.jl:37-38
+            self.inner_algs = self.inner_algs.inner_algs
+
+    def next_dt(self, R: float) -> float:
+        """step_accept_controller!, rtc.jl:121-133"""
+        lo, hi = self.Δt_bounds
+        if math.isinf(self.σ_s):
+            return lo if R > self.σ_c else hi
+        return (1 - 1 / (1 + math.exp((self.σ_c - R) * self.σ_s))) * (hi - lo) + lo
+
+
 class ReturnCode(enum.Enum):
     Default = 0
     Success = 1
@@ -672,7 +693,7 @@ def _isapprox(a, b):
     return a == b or abs(a - b) <= SQRT_EPS * max(abs(a), abs(b))
 
 
-def perform_step_(f, cache, t, Δt) -> bool:
+def perform_step_(f, cache, t, Δt, want_tangent=False) -> bool:
     """perform_step!(f, cache, t, Δt) -> Bool for the two (function, solver) pairs on the path."""
     if isinstance(cache, BackwardEulerSolverCache):
         dev = cache.dev
@@ -691,7 +712,10 @@ def perform_step_(f, cache, t, Δt) -> bool:
         cache.resid.append(rn)
         return conv
     ion = f.ode
-    core.cell_step(cache.uₙ.dev, ion.model_id, ion.params(), cache.uₙ, t, Δt, cache.substeps, cache.threshold)
+    R = core.cell_step(cache.uₙ.dev, ion.model_id, ion.params(), cache.uₙ, t, Δt, cache.substeps, cache.threshold,
+                       want_max=want_tangent)
+    if want_tangent:
+        cache.R = R                                   # max over the dumat column of phi_m (rtc.jl:64-67)
     return True
 
 
@@ -714,6 +738,9 @@ class ThunderboltTimeIntegrator:
         self.sol = Solution()
         self.maxiters = maxiters
         self.iter = 0
+        self.controller = alg if isinstance(alg, ReactionTangentController) else None
+        self.R = 0.0                                  # ReactionTangentControllerCache.R (rtc.jl:85-88)
+        self.dts = []                                 # accepted step lengths
         f = prob.f
         dev = self._device_of(f)
         self.dev = dev
@@ -755,6 +782,10 @@ class ThunderboltTimeIntegrator:
         return default_device()
 
     @property
+    def dtcache(self):
+        return self.dt
+
+    @property
     def cg_iterations(self):
         hc = self.caches[0]
         return hc.iters if isinstance(hc, BackwardEulerSolverCache) else []
@@ -777,18 +808,26 @@ class ThunderboltTimeIntegrator:
             if needs_update(src, t + dt):
                 update_operator_(src, t + dt)
             self.fused.set_source(None if isinstance(src, LinearNullOperator) else src.b)
-            it, rn, ok = self.fused.step(self.u, t, dt)
+            if self.controller is not None:
+                it, rn, ok, self.R = self.fused.step_rt(self.u, t, dt)
+            else:
+                it, rn, ok = self.fused.step(self.u, t, dt)
             hc.iters.append(it)
             hc.resid.append(rn)
         else:
             for f, cache in zip(self._functions(), self.caches):     # children in tuple order: heat, then cells
-                if not perform_step_(f, cache, t, dt):
+                if not perform_step_(f, cache, t, dt, want_tangent=self.controller is not None):
                     ok = False
                     break
+            if self.controller is not None and ok:
+                self.R = self.dev.allreduce_max(self.caches[-1].R)
         self.iter += 1
         if ok:
             self.stats.naccept += 1
             self.t = t + dt
+            self.dts.append(dt)
+            if self.controller is not None:           # stepsize_controller! + step_accept_controller!, rtc.jl:103-133
+                self.dt = self.controller.next_dt(self.R)
         else:
             self.stats.nreject += 1
             for c in range(self.u.ncols):

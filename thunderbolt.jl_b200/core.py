@@ -403,6 +403,12 @@ class MonodomainStepper:
         L.call("tb_monodomain_step", self.h, u.h, float(t), float(dt), C.byref(it), C.byref(rn), C.byref(cv))
         return it.value, rn.value, bool(cv.value)
 
+    def step_rt(self, u: B200Vector, t, dt):
+        """step + reaction tangent R (rtc.jl:51-78)"""
+        it, rn, cv, R = C.c_int64(), C.c_double(), C.c_int32(), C.c_double()
+        L.call("tb_monodomain_step_rt", self.h, u.h, float(t), float(dt), C.byref(it), C.byref(rn), C.byref(cv), C.byref(R))
+        return it.value, rn.value, bool(cv.value), R.value
+
     def run(self, u: B200Vector, t0, dt, nsteps):
         it, cv = C.c_int64(), C.c_int32()
         L.call("tb_monodomain_run", self.h, u.h, float(t0), float(dt), int(nsteps), C.byref(it), C.byref(cv))

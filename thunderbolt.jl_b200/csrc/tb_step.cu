@@ -115,8 +115,25 @@ static bool approx_equal(double a, double b) {
     return a == b || fabs(a - b) <= rt * fmax(fabs(a), fabs(b));
 }
 
+static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
+                                    int32_t *converged, double *max_dphi);
+
 extern "C" int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                                       int32_t *converged) {
+    return monodomain_step_impl(md, u, t, dt, iters, rnorm, converged, nullptr);
+}
+
+// Same step, additionally returning the reaction tangent R = max_i du[i, phi] of the cell sweep's last rhs
+// evaluation (over ALL ranks), which is what ReactionTangentController reads from cache.dumat (rtc.jl:51-78).
+extern "C" int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
+                                         int32_t *converged, double *reaction_tangent) {
+    TB_REQUIRE(reaction_tangent, "tb_monodomain_step_rt: reaction_tangent is NULL");
+    TB_TRY(monodomain_step_impl(md, u, t, dt, iters, rnorm, converged, reaction_tangent));
+    return tb_comm_allreduce_max(md->ctx, reaction_tangent);
+}
+
+static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
+                                    int32_t *converged, double *max_dphi) {
     TB_REQUIRE(md && u, "tb_monodomain_step: NULL argument");
     tb_ctx *ctx = md->ctx;
     const tb_pattern *pat = md->M->pat;
@@ -142,7 +159,7 @@ extern "C" int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, do
     // reaction step on the owned points, phi taken from the CG solution (the reference copies x into the
     // u view even when the solve failed; the caller then rolls back, type.jl:510-532)
     TB_TRY(tb_cell_step_raw(ctx, md->model, md->params, md->nparams, u->d, pat->nrows, u->ld, md->phi_idx, md->x->d, t, dt,
-                            md->substeps, md->threshold, nullptr));
+                            md->substeps, md->threshold, max_dphi));
     if (md->timing) {
         TB_CUDA(cudaEventRecord(md->ev[2], ctx->stream));
         TB_CUDA(cudaEventSynchronize(md->ev[2]));
