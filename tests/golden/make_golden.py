@@ -58,6 +58,39 @@ def c1_small():
     np.savez_compressed(HERE / "c1_small.npz", **out)
 
 
+def c1_full():
+    """config 1 at FULL size (ep01_spiral-wave.jl:30-65,113-141): 256x256 quads, FHN, dt = 1, 1000 steps, default
+    sqrt(eps) tolerances.  Stored: phi_m after step 1 and after step 1000, CG iteration counts of all steps, and the
+    activation step of every dof (threshold 0.5) -- the three things the parity rule is stated on."""
+    n = 256
+    m = O.generate_grid(O.QUAD4, (n, n), (0.0, 0.0), (2.5, 2.5))
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, [4.5e-5, 0, 0, 2.0e-5])
+    x = m.dof_coords
+    N = m.ndofs
+    u = np.zeros(2 * N)
+    u[:N] = np.where((x[:, 0] <= 1.25) & (x[:, 1] <= 1.25), 1.0, 0.0)
+    u[N:] = np.where(x[:, 1] >= 1.25, 0.1, 0.0)
+    orc = O.MonodomainOracle(m, O.FHN, O.default_params(O.FHN), M, K, substeps=1)
+    v = u.copy()
+    act = np.full(N, -1, dtype=np.int16)
+    below = v[:N] < 0.5
+    out = {}
+    for step in range(1000):
+        it, rn, conv = orc.step(v, float(step), 1.0)
+        assert conv
+        hit = (v[:N] >= 0.5) & below & (act < 0)
+        act[hit] = step + 1
+        below |= v[:N] < 0.5
+        if step == 0:
+            out["phi1"] = v[:N].astype(np.float64).copy()
+    out["phi1000"] = v[:N].copy()
+    out["s1000"] = v[N:].copy()
+    out["iters"] = np.array(orc.iters, dtype=np.int16)
+    out["act"] = act
+    np.savez_compressed(HERE / "c1_full.npz", **out)
+
+
 def c2_small():
     """config 2 (conduction-velocity-benchmark.jl) on 16x16x4 hexes, h = 0.25: PCG2019, corner stimulus."""
     m = O.generate_grid(O.HEX8, (16, 16, 4), (0, 0, 0), (4.0, 4.0, 1.0))
@@ -88,6 +121,11 @@ def c2_small():
         out[f"act_{name}"] = activation_steps(np.array(hist), 0.0)
     np.savez_compressed(HERE / "c2_small.npz", **out)
 
+
+if __name__ == "__main__" and "--c1-full" in sys.argv:
+    c1_full()
+    print("wrote", HERE / "c1_full.npz")
+    sys.exit(0)
 
 if __name__ == "__main__":
     c1_small()

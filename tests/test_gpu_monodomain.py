@@ -66,6 +66,38 @@ def test_c1_small_against_golden(tb, dev, variant, cell):
     assert integ.stats.naccept == 200 and integ.stats.nreject == 0
 
 
+def test_c1_full_size_1000_steps_against_golden(tb, dev):
+    """BASELINE config 1 at its FULL size and length (256x256 quads, 1000 steps of dt = 1, ep01_spiral-wave.jl): the three
+    north_star rules -- 1e-10 after one step, 1e-6 after 1000 steps, CG iterations +-1, activation steps identical."""
+    g = np.load(GOLD / "c1_full.npz")
+    mesh = tb.generate_mesh(tb.Quadrilateral, (256, 256), (0.0, 0.0), (2.5, 2.5), device=dev)
+    odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(_c1_model(tb, (4.5e-5, 2.0e-5))),
+                                tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), mesh)
+    u0 = tb.create_initial_condition(odeform)
+    tb.setvariable_(u0, odeform, "φₘ", lambda x: 1.0 if (x[0] <= 1.25 and x[1] <= 1.25) else 0.0)
+    tb.setvariable_(u0, odeform, "s", lambda x: 0.1 if x[1] >= 1.25 else 0.0)
+    N = mesh.ndofs
+    assert N == 66049
+    stepper = tb.LieTrotterGodunov((tb.BackwardEulerSolver(), tb.ForwardEulerCellSolver()))
+    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0, (0.0, 1000.0)), stepper, dt=1.0)
+    act = np.full(N, -1, dtype=np.int16)
+    below = u0[:N] < 0.5
+    for step in range(1000):
+        assert tb.step_(integ)
+        phi = integ.u.column(0)
+        hit = (phi >= 0.5) & below & (act < 0)
+        act[hit] = step + 1
+        below |= phi < 0.5
+        if step == 0:
+            assert rel_linf(phi, g["phi1"]) <= 1e-10
+    u = integ.u.to_host()
+    assert rel_linf(u[:N], g["phi1000"]) <= 1e-6 and rel_linf(u[N:], g["s1000"]) <= 1e-6
+    it = np.array(integ.cg_iterations)
+    assert it.shape == g["iters"].shape and np.abs(it - g["iters"]).max() <= 1
+    assert np.array_equal(act, g["act"])
+    assert (act > 0).sum() > N // 2                                      # the spiral wave really swept the domain
+
+
 @pytest.mark.parametrize("variant,sub", [("fe", 1), ("adaptive", 10)])
 def test_c2_small_against_golden(tb, dev, variant, sub):
     """config 2 (PCG2019 + corner stimulus with a time window) through the raw C-ABI objects, 300 steps."""

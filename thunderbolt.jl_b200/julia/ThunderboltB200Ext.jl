@@ -190,8 +190,41 @@ function _pointwise_step_outer_kernel!(f::PointwiseODEFunction, t::Real, Δt::Re
     p = params(f.ode)
     ns, thr = substeps(cache)
     φidx = Thunderbolt.transmembranepotential_index(f.ode) - 1
-    @tb tb_cell_step (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Cvoid}, Int32, Float64, Float64, Int32, Float64, Ptr{Float64}) u.dev.h model_id(f.ode) p Int32(length(p)) u.h Int32(φidx) Float64(t) Float64(Δt) ns thr C_NULL
+    # The reaction tangent R = maximum(dumat[:, φₘidx]) that ReactionTangentController reads (src/solver/time/rtc.jl:51-78)
+    # is reduced inside the sweep and kept on the cache instead of a dumat that never exists on the device.
+    R = Ref{Float64}(0.0)
+    @tb tb_cell_step (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Cvoid}, Int32, Float64, Float64, Int32, Float64, Ptr{Float64}) u.dev.h model_id(f.ode) p Int32(length(p)) u.h Int32(φidx) Float64(t) Float64(Δt) ns thr R
+    REACTION_TANGENT[objectid(cache)] = R[]
     return true
 end
+
+# ---- ReactionTangentController (src/solver/time/rtc.jl:51-78) ------------------------------------------------
+# get_reaction_tangent walks the sub-integrators and takes maximum(cache.dumat[:, φₘidx]); for a B200Vector-typed
+# pointwise cache the value was already reduced on the device by the sweep above.
+const REACTION_TANGENT = Dict{UInt, Float64}()
+reaction_tangent(cache::AbstractPointwiseSolverCache) = get(REACTION_TANGENT, objectid(cache), 0.0)
+# upstream change (one method, rtc.jl:64-67):
+#   R = max(R, subintegrator.cache.uₙ isa B200Vector ? reaction_tangent(subintegrator.cache) :
+#                                                       maximum(@view subintegrator.cache.dumat[:, φₘidx]))
+
+# ---- assembly strategy knobs ------------------------------------------------------------------------------------
+# 2 = per-element results + ordered row gather (default: deterministic, bitwise the sequential CPU assembly),
+# 0 = fp64 atomic scatter.  FerriteOperators' ElementAssemblyStrategy maps to 2.
+set_assembly_mode!(dev::B200Device, mode::Integer) = @tb tb_assembly_set_mode (Ptr{Cvoid}, Int32) dev.h Int32(mode)
+release_assembly_scratch!(dev::B200Device) = @tb tb_assembly_release_scratch (Ptr{Cvoid},) dev.h
+
+# ---- multi-GPU (one Julia process per GPU, e.g. under MPI.jl; the reference itself is shared-memory only) -----------
+# comm_init! joins the NCCL communicator; peer_attach! additionally maps every rank's mailbox window and CG work
+# vectors through CUDA IPC so that the CG kernels exchange halos and dot products with plain NVLink stores.
+function comm_init!(dev::B200Device, rank::Integer, nranks::Integer, unique_id::Vector{UInt8})
+    @tb tb_ctx_comm_init (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}) dev.h Int32(rank) Int32(nranks) unique_id
+end
+function peer_export(dev::B200Device, ncols::Integer)
+    blob = zeros(UInt8, 160)                       # TB_PEER_BLOB_BYTES
+    @tb tb_peer_export (Ptr{Cvoid}, Int64, Ptr{UInt8}) dev.h Int64(ncols) blob
+    blob
+end
+peer_attach!(dev::B200Device, blobs::Vector{UInt8}, nranks::Integer) =
+    @tb tb_peer_attach (Ptr{Cvoid}, Ptr{UInt8}, Int32) dev.h blobs Int32(nranks)
 
 end # module
