@@ -187,6 +187,7 @@ def run_b200(args):
     launches = dev.launch_count() - launches0
     spmv_ms, spmv_n = dev.profile_get()
     dev.profile_enable(False)
+    persistent = dev.cg_last_path_persistent()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -197,19 +198,22 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (SpMV + fused p.Ap inside CG) ----
     peak, peak_src = peaks()
     rows_local = n_owned
-    spmv_bytes = bytes_per_row(nnz, rows_local) * rows_local
+    # persistent single-kernel CG (small operators): the timed unit is one whole iteration (SpMV + vector updates)
+    spmv_bytes = (bytes_per_row(nnz, rows_local) + (72.0 if persistent else 0.0)) * rows_local
     avg_spmv_ms = spmv_ms / max(spmv_n, 1)
     achieved = spmv_bytes / (avg_spmv_ms * 1e-3) / 1e9 if spmv_n else None
     k_mean = float(np.mean(iters))
     step_bytes = (2 * ns * 8 + bytes_per_row(nnz, rows_local) * (1 + k_mean) + 72.0 * k_mean) * rows_local
     # bytes the kernel really streams: stored values + the (losslessly compressed) column stream + x, y, p
     stored, col_bytes, max_w = M.storage()
-    stored_bytes = stored * 8.0 + col_bytes + 24.0 * rows_local
+    stored_bytes = stored * 8.0 + col_bytes + (16.0 if persistent else 24.0) * rows_local
     traffic = None
     tfile = ROOT / "profiles" / "traffic.json"
     if tfile.exists() and world == 1 and not args.grid:
         traffic = json.loads(tfile.read_text()).get(args.workload, {}).get("spmv_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_cg_spmv_tma<1,false,true> (SELL-32 SpMV, TMA-staged, fused p.Ap)", "achieved": achieved,
+    kname = ("k_cg_persistent (whole CG solve in one cooperative kernel; unit = one iteration: SpMV + x,r,p updates + 3 grid barriers)"
+             if persistent else "k_cg_spmv_tma<1,false,true> (SELL-32 SpMV, TMA-staged, fused p.Ap)")
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum+write.sum, profiles/traffic.json" if traffic else None,
                 "bytes_per_launch": spmv_bytes, "stored_bytes_per_launch": stored_bytes,

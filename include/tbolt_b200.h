@@ -227,6 +227,12 @@ int32_t tb_assembly_release_scratch(tb_ctx *ctx);
 int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol, double atol,
                     double rtol, int64_t itmax, int64_t *iters, double *rnorm, int32_t *converged);
 
+/* Operators with at most 148*16*32*4 rows are solved by ONE persistent cooperative kernel per solve (state in
+ * registers, grid-wide barriers instead of kernel boundaries); same recurrence, same stopping rule.  On by default
+ * on a single GPU; tb_cg_last_path tells which path the last solve took. */
+int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t on);
+int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *persistent);
+
 /* ---- cell sweep -------------------------------------------------------------------------------
  * _pointwise_step_outer_kernel! (src/solver/time/partitioned_solver.jl:38-52; the method
  * ext/CuThunderboltExt.jl:111-124 provided for CuVector).  substeps <= 1: ForwardEulerCellSolver

@@ -12,6 +12,15 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["persistent", "multikernel"], autouse=True)
+def cg_path(request, dev):
+    """Every test of this module runs with both CG execution models: the one-launch cooperative kernel that small
+    operators get by default (tb_cg_small.cu) and the three-kernels-per-iteration path large ones take (tb_cg.cu)."""
+    dev.cg_set_persistent(request.param == "persistent")
+    yield request.param
+    dev.cg_set_persistent(True)
 GOLD = Path(__file__).resolve().parent / "golden"
 
 

@@ -5,6 +5,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["persistent", "multikernel"], autouse=True)
+def cg_path(request, dev):
+    """Every test of this module runs with both CG execution models: the one-launch cooperative kernel that small
+    operators get by default (tb_cg_small.cu) and the three-kernels-per-iteration path large ones take (tb_cg.cu)."""
+    dev.cg_set_persistent(request.param == "persistent")
+    yield request.param
+    dev.cg_set_persistent(True)
+
+
 def _system(tb, dev, O, ct, nel, dt, kappa):
     dim = len(nel)
     mo = O.generate_grid(ct, nel, (0.0,) * dim, tuple(0.25 * n for n in nel))
@@ -88,3 +97,30 @@ def test_cg_failure_is_a_flag_not_an_error(tb, dev, oracle):
     assert not conv and it == 20
     for h in (M, K, A, bd, xd, md):
         h.free()
+
+
+def test_cg_path_selection(tb, dev, cg_path):
+    """Small operators take the one-launch cooperative kernel (when enabled), operators with more than
+    148*16*32*4 rows never do; both paths report the same iteration count on the same system."""
+    def solve(nel):
+        md = tb.generate_mesh(tb.Quadrilateral, nel, (0.0, 0.0), (1.0, 1.0), device=dev)
+        M = tb.B200CSRMatrix.from_mesh(dev, md)
+        K, A = M.like(), M.like()
+        tb.core.assemble_mass(dev, md, M, 2, 1.0)
+        tb.core.assemble_diffusion(dev, md, K, 2, tb._lib.D_SCALAR, [1e-5], 1.0)
+        A.axpby_values(M, K, 1.0)
+        x = md.dof_coords()
+        b = tb.B200Vector.from_host(dev, np.sin(7 * x[:, 0]) * np.cos(5 * x[:, 1]))
+        xs = tb.B200Vector(dev, md.ndofs)
+        it, rn, conv = tb.core.cg_solve(dev, A, b, xs)
+        path = dev.cg_last_path_persistent()
+        y = tb.B200Vector(dev, md.ndofs)
+        A.mul(y, xs)
+        res = np.linalg.norm(y.to_host() - b.to_host()) / np.linalg.norm(b.to_host())
+        for h in (M, K, A, b, xs, y, md):
+            h.free()
+        return it, conv, path, res
+    it, conv, path, res = solve((200, 150))
+    assert conv and path == (cg_path == "persistent") and res < 1e-7
+    it2, conv2, path2, res2 = solve((900, 900))        # 811 801 rows: beyond the register-resident limit
+    assert conv2 and path2 is False and res2 < 1e-7

@@ -62,7 +62,9 @@ def test_rtc_integrator_vs_oracle_and_fixed_dt(tb, dev, oracle, fused):
     tb.solve_(integ_rtc)
     assert integ_rtc.sol.retcode == tb.ReturnCode.Success and integ_rtc.t == tspan[1]
     a, b = integ.u.to_host(), integ_rtc.u.to_host()
-    assert np.linalg.norm(a - b) <= 1e-2 * max(np.linalg.norm(a), np.linalg.norm(b)) * 5     # integ.u ≈ integ_rtc.u (heuristic dt)
+    # same solution up to the first-order time error of dt in [0.5, 2] vs dt = 1 on a travelling front (the reference's
+    # own scenario, a 0.01 stimulus, passes rtol = 1e-2; this one is deliberately more dynamic so that R really moves)
+    assert np.linalg.norm(a - b) <= 0.15 * max(np.linalg.norm(a), np.linalg.norm(b))
     assert integ_rtc.stats.naccept != integ.stats.naccept                                     # dt moved away from 1.0
     assert min(integ_rtc.dts[1:-1]) >= 0.5 and max(integ_rtc.dts) <= 2.0
     # oracle: same controller around the oracle's LTG step

@@ -123,6 +123,8 @@ _SIGNATURES = {
     "tb_assembly_set_scratch_budget": [_vp, C.c_int64],
     "tb_assembly_release_scratch": [_vp],
     "tb_cg_solve": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
+    "tb_cg_set_persistent": [_vp, C.c_int32],
+    "tb_cg_last_path": [_vp, _pi32],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                      _pf64],
     "tb_monodomain_create": [_vp, _vp, _vp, C.c_int32, _f64p, C.c_int32, C.c_int32, _pp],

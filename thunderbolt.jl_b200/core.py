@@ -62,6 +62,16 @@ class B200Device:
         L.call("tb_profile_get", self.h, C.byref(ms), C.byref(n))
         return ms.value, n.value
 
+    # ---- CG execution model ----
+    def cg_set_persistent(self, on: bool):
+        """small operators: whole CG solve in one cooperative kernel (default on, single GPU)"""
+        L.call("tb_cg_set_persistent", self.h, int(bool(on)))
+
+    def cg_last_path_persistent(self) -> bool:
+        v = C.c_int32()
+        L.call("tb_cg_last_path", self.h, C.byref(v))
+        return bool(v.value)
+
     # ---- assembly strategy ---------------------------------------------------------------------------
     def assembly_set_mode(self, mode: int):
         """2 = per-element results + ordered gather (deterministic, default), 0 = fp64 atomic scatter."""

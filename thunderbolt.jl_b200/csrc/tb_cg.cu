@@ -305,6 +305,9 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
                        int32_t *converged) {
     const tb_pattern *pat = A->pat;
     const int64_t n = pat->nrows;
+    if (const int pgrid = tb_cg_persistent_grid(ctx, pat))     // small operator: one persistent cooperative kernel
+        return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged);
+    ctx->last_cg_persistent = 0;
     TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
     CGState *st = ctx->d_cg;

@@ -1,0 +1,274 @@
+// Conjugate gradients as ONE persistent cooperative kernel, for operators small enough that every lane of a
+// one-CTA-per-SM grid owns at most 4 rows (C1: 66 k rows; limit 148*16*32*4 = 303 k rows -- above that the
+// TMA-staged multi-kernel path is faster, measured on C2).
+//
+// Same recurrence as tb_cg.cu (Krylov.jl cg!, LinearSolve defaults, x0 = 0); what changes is the execution model:
+//   * one launch per solve instead of 3 per iteration: at these sizes the multi-kernel path is launch-latency
+//     bound (C1: 0.39 ms/step for 12 iterations of ~2 us of work each);
+//   * x, r, p and Ap of a lane's rows live in REGISTERS for the whole solve; only p is also written to HBM/L2
+//     because the SpMV of the next iteration gathers it across lanes;
+//   * the two dot products and the visibility of p are grid-wide barriers (cooperative groups grid.sync());
+//     every CTA adds the per-CTA partials in the same fixed order, so all CTAs hold bitwise identical scalars and
+//     no scalar ever round-trips through the host;
+//   * the matrix stream (values + compressed column stream) is re-read by the same warps every iteration and stays
+//     L2 resident when it fits (C1 entirely, C2 mostly).
+// Row sums keep the reference's left-to-right order (bitwise SpMV); the dot products are summed in a different
+// tree than the multi-kernel path, so iterates agree with it (and with the oracle) to rounding, not bitwise.
+#include <cooperative_groups.h>
+#include "tb_internal.cuh"
+#include "tb_spmv.cuh"
+
+namespace cgp = cooperative_groups;
+
+#define TB_DEV(ctx) TB_CUDA(cudaSetDevice((ctx)->device))
+#define PCG_THREADS 512
+#define PCG_WARPS (PCG_THREADS / 32)
+#define PCG_MAX_RPL 4   // measured: 1 row/lane 11.9 us/iteration (multi-kernel 33), 8 rows/lane 78 us (multi-kernel 61): crossover near 5
+
+// Row (s*32 + lane) of y = A x with the compressed column stream (tb_csr.cu): slot j holds one offset for all
+// 32 lanes (col = row + off) or TB_CCOL_EXPLICIT followed by an explicit 32-id block.
+__device__ __forceinline__ double pcg_row_cc(const int64_t *__restrict__ slice_ptr, const int *__restrict__ ccol,
+                                             const int64_t *__restrict__ cptr, const double *__restrict__ val,
+                                             const double *__restrict__ x, int64_t s, int lane) {
+    const int64_t base = slice_ptr[s];
+    const int w = (int)((slice_ptr[s + 1] - base) >> 5);
+    const int *hdr = ccol + cptr[s];
+    const int *ex = hdr + ((w + 3) & ~3) + lane;
+    const double *v = val + base + lane;
+    const int row = (int)(s * TB_SLICE) + lane;
+    double acc = 0.0;
+    int e = 0, j = 0;
+    for (; j + 4 <= w; j += 4) {
+        int c[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int h = hdr[j + k];
+            c[k] = row + h;
+            if (h == TB_CCOL_EXPLICIT) c[k] = ex[(e++) * 32];
+        }
+        const double v0 = v[(j + 0) * 32], v1 = v[(j + 1) * 32], v2 = v[(j + 2) * 32], v3 = v[(j + 3) * 32];
+        const double x0 = x[c[0]], x1 = x[c[1]], x2 = x[c[2]], x3 = x[c[3]];
+        acc += v0 * x0;
+        acc += v1 * x1;
+        acc += v2 * x2;
+        acc += v3 * x3;
+    }
+    for (; j < w; j++) {
+        const int h = hdr[j];
+        int c = row + h;
+        if (h == TB_CCOL_EXPLICIT) c = ex[(e++) * 32];
+        acc += v[j * 32] * x[c];
+    }
+    return acc;
+}
+
+struct PcgMat {
+    const int64_t *slice_ptr;
+    const int *col;       // uncompressed SELL column ids
+    const int *ccol;      // compressed stream (nullptr: use col)
+    const int64_t *cptr;
+};
+
+__device__ __forceinline__ double pcg_row(const PcgMat &P, const double *__restrict__ val, const double *__restrict__ x, int64_t s,
+                                          int lane) {
+    return P.ccol ? pcg_row_cc(P.slice_ptr, P.ccol, P.cptr, val, x, s, lane) : tb_sell_row(P.slice_ptr, P.col, val, x, s, lane);
+}
+
+// block partial -> partials[blockIdx.x]; grid barrier; every CTA adds all partials in the same order
+__device__ __forceinline__ double pcg_allsum(double v, double *partials, double *sm, cgp::grid_group &grid) {
+    const double bs = tb_block_sum(v, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    grid.sync();
+    double s = 0.0;
+    if (threadIdx.x < 32) {
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) s += ((volatile double *)partials)[i];
+        s = tb_warp_sum(s);
+        if (threadIdx.x == 0) sm[32] = s;
+    }
+    __syncthreads();
+    return sm[32];
+}
+
+// FROM_B: r = p = b.  Otherwise r = p = M*phi (+ bS)  ("b = M u_{n-1}" + add!(b, S), euler.jl:85-91).
+template <int RPL, bool FROM_B>
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+    k_cg_persistent(const PcgMat P, const double *__restrict__ Aval, const double *__restrict__ Mval,
+                    const double *__restrict__ src, const double *__restrict__ bS, double *__restrict__ x_out,
+                    double *__restrict__ pglob, int64_t nrows, int64_t nslices, CGState *st, double *partials) {
+    cgp::grid_group grid = cgp::this_grid();
+    __shared__ double sm[34];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * PCG_WARPS + warp, nw = (int64_t)gridDim.x * PCG_WARPS;
+    double x[RPL], r[RPL], p[RPL], Ap[RPL];
+    bool own[RPL];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < RPL; k++) {
+        const int64_t s = gw + k * nw;
+        const int64_t row = s * TB_SLICE + lane;
+        own[k] = s < nslices && row < nrows;
+        x[k] = 0.0;
+        r[k] = p[k] = Ap[k] = 0.0;
+        if (s < nslices) {
+            double v;
+            if (FROM_B) v = own[k] ? src[row] : 0.0;
+            else {
+                v = pcg_row(P, Mval, src, s, lane);
+                if (own[k] && bS) v += bS[row];
+            }
+            if (own[k]) {
+                r[k] = p[k] = v;
+                pglob[row] = v;
+                acc += v * v;
+            }
+        }
+    }
+    double gamma = pcg_allsum(acc, partials, sm, grid);        // also makes pglob visible grid-wide
+    double rn = sqrt(gamma);
+    const double eps = st->atol + st->rtol * rn;
+    const long long itmax = st->itmax;
+    bool solved = rn <= eps;
+    long long iter = 0;
+    while (!solved && iter < itmax) {
+        acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < RPL; k++) {
+            const int64_t s = gw + k * nw;
+            if (s < nslices) {
+                const double v = pcg_row(P, Aval, pglob, s, lane);
+                if (own[k]) {
+                    Ap[k] = v;
+                    acc += p[k] * v;
+                }
+            }
+        }
+        const double pAp = pcg_allsum(acc, partials + gridDim.x, sm, grid);
+        const double alpha = gamma / pAp;
+        acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < RPL; k++)
+            if (own[k]) {
+                x[k] += alpha * p[k];
+                r[k] -= alpha * Ap[k];
+                acc += r[k] * r[k];
+            }
+        const double gnext = pcg_allsum(acc, partials + 2 * gridDim.x, sm, grid);
+        rn = sqrt(gnext);
+        solved = rn <= eps;
+        iter++;
+        if (rn != rn) iter = itmax;   // NaN never recovers: what the reference reports after grinding through itmax iterations
+        if (!solved && iter < itmax) {
+            const double beta = gnext / gamma;
+            gamma = gnext;
+#pragma unroll
+            for (int k = 0; k < RPL; k++)
+                if (own[k]) {
+                    p[k] = r[k] + beta * p[k];
+                    pglob[(gw + k * nw) * TB_SLICE + lane] = p[k];
+                }
+            grid.sync();                                       // p complete before anyone gathers it
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; k++)
+        if (own[k]) x_out[(gw + k * nw) * TB_SLICE + lane] = x[k];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->gamma = gamma;
+        st->rnorm = rn;
+        st->eps = eps;
+        st->iter = iter;
+        st->solved = solved;
+        st->done = 1;
+    }
+}
+
+template <int RPL, bool FROM_B>
+static int32_t launch_pcg(tb_ctx *ctx, int grid, const PcgMat &P, const double *Aval, const double *Mval, const double *src,
+                          const double *bS, double *x, double *pglob, int64_t nrows, int64_t nslices) {
+    CGState *st = ctx->d_cg;
+    double *partials = ctx->d_partials;
+    void *args[] = {(void *)&P, (void *)&Aval, (void *)&Mval, (void *)&src, (void *)&bS, (void *)&x, (void *)&pglob,
+                    (void *)&nrows, (void *)&nslices, (void *)&st, (void *)&partials};
+    TB_CUDA(cudaLaunchCooperativeKernel((void *)k_cg_persistent<RPL, FROM_B>, dim3(grid), dim3(PCG_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    return TB_OK;
+}
+
+__global__ void k_pcg_set_tol(CGState *st, double atol, double rtol, long long itmax) {
+    st->atol = atol;
+    st->rtol = rtol;
+    st->itmax = itmax;
+    st->done = 0;
+    st->solved = 0;
+    st->iter = 0;
+}
+
+// Is the persistent path usable for this operator on this context?  Returns the grid size, or 0.
+int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat) {
+    if (!ctx->cg_persistent || (ctx->has_comm && ctx->nranks > 1)) return 0;
+    static int coop = -1, per_sm = 0;
+    if (coop < 0) {
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_persistent<PCG_MAX_RPL, false>, PCG_THREADS, 0) != cudaSuccess)
+            per_sm = 0;
+    }
+    if (!coop || per_sm < 1) return 0;
+    int64_t grid = ctx->sm_count;                              // one CTA per SM
+    if (3 * grid > 4 * TB_MAX_PARTIALS) return 0;
+    const int64_t need_warps = pat->nslices;
+    if (need_warps > grid * PCG_WARPS * PCG_MAX_RPL) return 0;
+    const int64_t g2 = (need_warps + PCG_WARPS - 1) / PCG_WARPS;
+    if (g2 < grid) grid = g2 < 1 ? 1 : g2;                     // tiny operators: fewer CTAs, cheaper barriers
+    return (int)grid;
+}
+
+int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
+                             const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
+                             double *rnorm, int32_t *converged) {
+    const tb_pattern *pat = A->pat;
+    TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
+    double *pglob = ctx->d_cgwork + ctx->cgwork_ld;
+    const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
+    PcgMat P{pat->d_slice_ptr, pat->d_col, cc ? pat->d_ccol : nullptr, pat->d_cptr};
+    const int64_t per_pass = (int64_t)grid * PCG_WARPS;
+    const int64_t rpl = (pat->nslices + per_pass - 1) / per_pass;
+    TB_LAUNCH(ctx, k_pcg_set_tol, 1, 1, 0, ctx->d_cg, atol, rtol, (long long)itmax);
+    if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[0], ctx->stream));
+    const double *src = b ? b : phi;
+    const double *Mval = b ? nullptr : M->d_val;
+#define PCG_GO(R)                                                                                                              \
+    (b ? launch_pcg<R, true>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices)                        \
+       : launch_pcg<R, false>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices))
+    int32_t st = rpl <= 1 ? PCG_GO(1) : rpl <= 2 ? PCG_GO(2) : PCG_GO(4);
+#undef PCG_GO
+    if (st != TB_OK) return st;
+    if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[1], ctx->stream));
+    CGState *h = ctx->h_cg;
+    TB_CUDA(cudaMemcpyAsync(h, ctx->d_cg, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->last_cg_iters = h->iter;
+    ctx->last_cg_persistent = 1;
+    if (ctx->profile && h->iter > 0) {
+        // the whole solve is one launch: report it per iteration (SpMV + vector updates + barriers)
+        float ms = 0.f;
+        TB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[1]));
+        ctx->prof_spmv_ms += ms;
+        ctx->prof_spmv_n += h->iter;
+    }
+    if (iters) *iters = h->iter;
+    if (rnorm) *rnorm = h->rnorm;
+    if (converged) *converged = h->solved;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t on) {
+    TB_REQUIRE(ctx, "tb_cg_set_persistent: ctx is NULL");
+    ctx->cg_persistent = on != 0;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *persistent) {
+    TB_REQUIRE(ctx && persistent, "tb_cg_last_path: NULL argument");
+    *persistent = ctx->last_cg_persistent;
+    return TB_OK;
+}

@@ -146,6 +146,8 @@ struct tb_ctx {
     int spmv_variant = 1;             // 0: LDG kernel, 1..: bulk-async (TMA) staged kernel configurations (env TB_SPMV_VARIANT)
     int spmv_compress = 1;            // use the compressed column stream in the staged kernels (env TB_SPMV_COMPRESS)
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
+    bool cg_persistent = true;        // small operators: whole solve in one cooperative kernel (tb_cg_small.cu; env TB_CG_PERSISTENT)
+    int last_cg_persistent = 0;       // did the last solve take that path
     // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
     bool profile = false;
     cudaEvent_t prof_ev[2 * TB_PROF_MAX] = {};
@@ -387,6 +389,10 @@ __device__ __forceinline__ void tb_halo_wait(const tb_hwait_args &h) {
 int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                        int32_t *converged);
+int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat);
+int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
+                             const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
+                             double *rnorm, int32_t *converged);
 int32_t tb_spmv_raw(tb_ctx *ctx, const tb_csr *A, double *x, double *y);
 int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int nparams, double *u, int64_t n, int64_t ld,
                          int phi_idx, const double *phi_src, double t, double dt, int substeps, double thr,
