@@ -256,16 +256,23 @@ int32_t tb_monodomain_set_source(tb_monodomain *md, const tb_vec *bS, int32_t co
 /* after the system matrix is formed K's values may be released to save HBM when dt is fixed */
 int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                            int32_t *converged);
-/* `nsteps` steps back to back with one host round trip at the end (iters = total, converged = all) */
 /* the same step, also returning the reaction tangent R = max_i du[i, phi_m] left by the cell sweep's last rhs
  * evaluation, maximum over all ranks: the input of ReactionTangentController (src/solver/time/rtc.jl:51-78,121-133) */
 int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                               int32_t *converged, double *reaction_tangent);
+/* `nsteps` steps back to back with one host round trip at the end (iters = total, converged = all) */
 int32_t tb_monodomain_run(tb_monodomain *md, tb_vec *u, double t0, double dt, int64_t nsteps, int64_t *iters_total,
                           int32_t *all_converged);
 /* end-to-end variant on HOST buffers: uploads u_in, steps, downloads into u_out (may alias u_in) */
 int32_t tb_monodomain_step_host(tb_monodomain *md, tb_vec *u_dev, const double *u_in, double *u_out, double t, double dt,
                                 int64_t *iters, double *rnorm, int32_t *converged);
+/* `nsteps` steps with the state living in HOST memory between steps (what a host-side integrator that owns `u` sees):
+ * step n reads buf[n & 1] and writes buf[(n+1) & 1]; layout of a buffer = tb_vec_download's (column c at c*n).  Every
+ * step uploads the whole state and downloads the whole result, but the transfers are pipelined on two copy streams:
+ * the download of step n's phi (in chunks) runs full duplex with the upload of step n+1's phi, and the other state
+ * columns travel while CG runs (the diffusion solve only needs phi).  Pinned buffers are required for the overlap. */
+int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u_dev, double *buf0, double *buf1, double t0, double dt,
+                               int64_t nsteps, int64_t *iters_total, int32_t *all_converged);
 /* per-section CUDA-event timings of the last step, ms: [0] "b = M u", [1] "inner solve",
  * [2] "reaction solve" (the reference's TimerOutputs labels, euler.jl:85,94; partitioned_solver.jl:20) */
 int32_t tb_monodomain_section_ms(tb_monodomain *md, double *ms3);

@@ -229,6 +229,23 @@ def test_random_inputs_one_step_vs_oracle(tb, dev, oracle):
     out = np.empty_like(u)
     it2, rn2, conv2 = st.step_host(ud, u, out, 0.0, 0.5)
     assert (it2, conv2) == (it, conv) and np.array_equal(out, h)
+    # pipelined multi-step variant with the state in (pinned) host memory between steps == device-resident stepping
+    import torch
+    for nsteps in (1, 4, 5):
+        ud.upload(u)
+        tot, t = 0, 0.0
+        for _ in range(nsteps):
+            i_, _r, c_ = st.step(ud, t, 0.5)
+            tot += i_
+            t += 0.5
+        want = ud.to_host()
+        b0 = torch.empty(u.size, dtype=torch.float64, pin_memory=True).numpy()
+        b1 = torch.empty(u.size, dtype=torch.float64, pin_memory=True).numpy()
+        b0[:] = u
+        b1[:] = np.nan
+        tot2, conv3 = st.run_host(ud, b0, b1, 0.0, 0.5, nsteps)
+        res = b1 if nsteps % 2 else b0
+        assert conv3 and tot2 == tot and np.array_equal(res, want) and np.array_equal(ud.to_host(), want)
     for x in (st, ud, bS, M, K, md):
         x.free()
 

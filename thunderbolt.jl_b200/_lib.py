@@ -135,6 +135,7 @@ _SIGNATURES = {
     "tb_monodomain_step": [_vp, _vp, C.c_double, C.c_double, _pi64, _pf64, _pi32],
     "tb_monodomain_step_rt": [_vp, _vp, C.c_double, C.c_double, _pi64, _pf64, _pi32, _pf64],
     "tb_monodomain_run": [_vp, _vp, C.c_double, C.c_double, C.c_int64, _pi64, _pi32],
+    "tb_monodomain_run_host": [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int64, _pi64, _pi32],
     "tb_monodomain_step_host": [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _pi64, _pf64, _pi32],
     "tb_monodomain_section_ms": [_vp, _pf64],
     "tb_monodomain_enable_timing": [_vp, C.c_int32],

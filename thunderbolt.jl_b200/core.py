@@ -424,6 +424,13 @@ class MonodomainStepper:
         L.call("tb_monodomain_run", self.h, u.h, float(t0), float(dt), int(nsteps), C.byref(it), C.byref(cv))
         return it.value, bool(cv.value)
 
+    def run_host(self, u_dev: B200Vector, buf0: np.ndarray, buf1: np.ndarray, t0, dt, nsteps):
+        """nsteps steps with the state in host memory between steps (step n: buf[n&1] -> buf[(n+1)&1]), transfers pipelined."""
+        it, cv = C.c_int64(), C.c_int32()
+        L.call("tb_monodomain_run_host", self.h, u_dev.h, L.ptr(buf0), L.ptr(buf1), float(t0), float(dt), int(nsteps),
+               C.byref(it), C.byref(cv))
+        return it.value, bool(cv.value)
+
     def step_host(self, u_dev: B200Vector, u_in: np.ndarray, u_out: np.ndarray, t, dt):
         it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()
         L.call("tb_monodomain_step_host", self.h, u_dev.h, L.ptr(u_in), L.ptr(u_out), float(t), float(dt), C.byref(it),

@@ -274,6 +274,9 @@ struct tb_monodomain {
     bool timing;
     cudaEvent_t ev[4];
     double section_ms[3];
+    // tb_monodomain_run_host: copy streams and events (created on first use)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_phi = nullptr, e_s = nullptr, e_done = nullptr, o_s = nullptr, e_chunk[16] = {};
 };
 
 static inline int64_t tb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

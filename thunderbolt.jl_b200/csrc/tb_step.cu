@@ -68,6 +68,12 @@ extern "C" int32_t tb_monodomain_destroy(tb_monodomain *md) {
     tb_csr_destroy(md->A);
     tb_vec_destroy(md->x);
     for (int i = 0; i < 4; i++) cudaEventDestroy(md->ev[i]);
+    if (md->s_in) cudaStreamDestroy(md->s_in);
+    if (md->s_out) cudaStreamDestroy(md->s_out);
+    for (cudaEvent_t e : {md->e_phi, md->e_s, md->e_done, md->o_s})
+        if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 16; i++)
+        if (md->e_chunk[i]) cudaEventDestroy(md->e_chunk[i]);
     delete md;
     return TB_OK;
 }
@@ -116,7 +122,7 @@ static bool approx_equal(double a, double b) {
 }
 
 static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
-                                    int32_t *converged, double *max_dphi);
+                                    int32_t *converged, double *max_dphi, cudaEvent_t before_cells = nullptr);
 
 extern "C" int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                                       int32_t *converged) {
@@ -133,7 +139,7 @@ extern "C" int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t,
 }
 
 static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
-                                    int32_t *converged, double *max_dphi) {
+                                    int32_t *converged, double *max_dphi, cudaEvent_t before_cells) {
     TB_REQUIRE(md && u, "tb_monodomain_step: NULL argument");
     tb_ctx *ctx = md->ctx;
     const tb_pattern *pat = md->M->pat;
@@ -156,6 +162,7 @@ static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, doub
     int32_t conv = 0;
     TB_TRY(tb_cg_run_impl(ctx, md->A, nullptr, md->M, phi, bS, md->x->d, md->atol, md->rtol, md->itmax, &it, &rn, &conv));
     if (md->timing) TB_CUDA(cudaEventRecord(md->ev[1], ctx->stream));
+    if (before_cells) TB_CUDA(cudaStreamWaitEvent(ctx->stream, before_cells, 0));   // run_host: the non-phi columns are still in flight
     // reaction step on the owned points, phi taken from the CG solution (the reference copies x into the
     // u view even when the solve failed; the caller then rolls back, type.jl:510-532)
     TB_TRY(tb_cell_step_raw(ctx, md->model, md->params, md->nparams, u->d, pat->nrows, u->ld, md->phi_idx, md->x->d, t, dt,
@@ -209,5 +216,76 @@ extern "C" int32_t tb_monodomain_step_host(tb_monodomain *md, tb_vec *u_dev, con
     TB_CUDA(cudaMemcpy2DAsync(u_out, sizeof(double) * u_dev->n, u_dev->d, sizeof(double) * u_dev->ld,
                               sizeof(double) * u_dev->n, u_dev->ncols, cudaMemcpyDeviceToHost, ctx->stream));
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
+}
+
+#define RH_CHUNKS 8
+extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *buf0, double *buf1, double t0, double dt,
+                                          int64_t nsteps, int64_t *iters_total, int32_t *all_converged) {
+    TB_REQUIRE(md && u && buf0 && buf1 && nsteps >= 0, "tb_monodomain_run_host: bad argument");
+    TB_REQUIRE(buf0 != buf1, "tb_monodomain_run_host: the two host buffers must be distinct");
+    tb_ctx *ctx = md->ctx;
+    TB_DEV(ctx);
+    if (!md->s_in) {
+        TB_CUDA(cudaStreamCreateWithFlags(&md->s_in, cudaStreamNonBlocking));
+        TB_CUDA(cudaStreamCreateWithFlags(&md->s_out, cudaStreamNonBlocking));
+        for (cudaEvent_t *e : {&md->e_phi, &md->e_s, &md->e_done, &md->o_s}) TB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (int i = 0; i < RH_CHUNKS; i++) TB_CUDA(cudaEventCreateWithFlags(&md->e_chunk[i], cudaEventDisableTiming));
+    }
+    const int64_t n = u->n, ld = u->ld;
+    const int nc = u->ncols, phic = md->phi_idx;
+    const int64_t csz = tb_round_up((n + RH_CHUNKS - 1) / RH_CHUNKS, 32);
+    double *buf[2] = {buf0, buf1};
+    int64_t total = 0;
+    int32_t all = 1;
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // step 0: nothing to wait for
+    TB_CUDA(cudaMemcpyAsync(u->d + (size_t)phic * ld, buf[0] + (size_t)phic * n, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, md->s_in));
+    TB_CUDA(cudaEventRecord(md->e_phi, md->s_in));
+    for (int c = 0; c < nc; c++)
+        if (c != phic)
+            TB_CUDA(cudaMemcpyAsync(u->d + (size_t)c * ld, buf[0] + (size_t)c * n, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, md->s_in));
+    TB_CUDA(cudaEventRecord(md->e_s, md->s_in));
+    for (int64_t s = 0; s < nsteps; s++) {
+        double *out = buf[(s + 1) & 1];
+        int64_t it = 0;
+        int32_t conv = 0;
+        TB_CUDA(cudaStreamWaitEvent(ctx->stream, md->e_phi, 0));
+        TB_TRY(monodomain_step_impl(md, u, t0, dt, &it, nullptr, &conv, nullptr, md->e_s));
+        TB_CUDA(cudaEventRecord(md->e_done, ctx->stream));
+        t0 += dt;
+        total += it;
+        all &= conv;
+        const bool more = s + 1 < nsteps;
+        // download of this step's result; the upload of the next step's input chases it chunk by chunk (full duplex)
+        TB_CUDA(cudaStreamWaitEvent(md->s_out, md->e_done, 0));
+        for (int k = 0; k < RH_CHUNKS; k++) {
+            const int64_t o = k * csz, len = o + csz <= n ? csz : n - o;
+            if (len <= 0) break;
+            TB_CUDA(cudaMemcpyAsync(out + (size_t)phic * n + o, u->d + (size_t)phic * ld + o, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, md->s_out));
+            TB_CUDA(cudaEventRecord(md->e_chunk[k], md->s_out));
+            if (more) {
+                TB_CUDA(cudaStreamWaitEvent(md->s_in, md->e_chunk[k], 0));
+                TB_CUDA(cudaMemcpyAsync(u->d + (size_t)phic * ld + o, out + (size_t)phic * n + o, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, md->s_in));
+            }
+        }
+        if (more) TB_CUDA(cudaEventRecord(md->e_phi, md->s_in));
+        for (int c = 0; c < nc; c++)
+            if (c != phic)
+                TB_CUDA(cudaMemcpyAsync(out + (size_t)c * n, u->d + (size_t)c * ld, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, md->s_out));
+        TB_CUDA(cudaEventRecord(md->o_s, md->s_out));
+        if (more) {
+            TB_CUDA(cudaStreamWaitEvent(md->s_in, md->o_s, 0));
+            for (int c = 0; c < nc; c++)
+                if (c != phic)
+                    TB_CUDA(cudaMemcpyAsync(u->d + (size_t)c * ld, out + (size_t)c * n, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, md->s_in));
+            TB_CUDA(cudaEventRecord(md->e_s, md->s_in));
+        }
+    }
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(md->s_out));
+    TB_CUDA(cudaStreamSynchronize(md->s_in));
+    if (iters_total) *iters_total = total;
+    if (all_converged) *all_converged = all;
     return TB_OK;
 }
