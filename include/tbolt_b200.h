@@ -227,6 +227,15 @@ int32_t tb_assembly_release_scratch(tb_ctx *ctx);
 int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol, double atol,
                     double rtol, int64_t itmax, int64_t *iters, double *rnorm, int32_t *converged);
 
+/* Preconditioned variant: LinearSolve.KrylovJL_CG(precs = ..., ldiv = false) as in bak/examples-gpu/spiral-wave.jl:95-105
+ * and the tip at ep01_spiral-wave.jl:129-131.  z = M r with M the stored inverse of the preconditioner, gamma = r.z,
+ * stop on sqrt(r.z) <= atol + rtol*sqrt(r0.z0), p = z + beta p (Krylov.jl cg!).  TB_PRECOND_JACOBI: M = diag(A)^-1
+ * (KrylovPreconditioners' BlockJacobi with blocks of one row), rebuilt from the operator at every solve. */
+#define TB_PRECOND_NONE 0
+#define TB_PRECOND_JACOBI 1
+int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol, int32_t precond,
+                       double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm, int32_t *converged);
+
 /* Operators with at most 148*16*32*4 rows are solved by ONE persistent cooperative kernel per solve (state in
  * registers, grid-wide barriers instead of kernel boundaries); same recurrence, same stopping rule.  On by default
  * on a single GPU; tb_cg_last_path tells which path the last solve took. */
@@ -250,6 +259,7 @@ int32_t tb_monodomain_create(tb_ctx *ctx, const tb_csr *M, const tb_csr *K, int3
                              int32_t nparams, int32_t phi_idx, tb_monodomain **out);
 int32_t tb_monodomain_destroy(tb_monodomain *md);
 int32_t tb_monodomain_set_cg(tb_monodomain *md, double atol, double rtol, int64_t itmax);
+int32_t tb_monodomain_set_preconditioner(tb_monodomain *md, int32_t precond);   /* TB_PRECOND_* for the inner CG */
 int32_t tb_monodomain_set_cell_solver(tb_monodomain *md, int32_t substeps, double reaction_threshold);
 /* bS (nullable): the source operator's vector, added to b as is (euler.jl:88-91).  Borrowed. */
 int32_t tb_monodomain_set_source(tb_monodomain *md, const tb_vec *bS, int32_t col);

@@ -74,6 +74,9 @@ def lib():
         L.orc_cg.argtypes = [C.c_int64, _i64p, _i64p, _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_int64,
                              C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.orc_cg.restype = C.c_int64
+        L.orc_pcg_jacobi.argtypes = [C.c_int64, _i64p, _i64p, _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_int64,
+                                     _f64p, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+        L.orc_pcg_jacobi.restype = C.c_int64
         L.orc_cell_nstates.argtypes = [C.c_int]
         L.orc_cell_nstates.restype = C.c_int
         L.orc_fhn_default_params.argtypes = [_f64p]
@@ -257,6 +260,17 @@ def cg(rowptr, colidx, vals, b, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, thread
     return x, int(it), rn.value, bool(conv.value)
 
 
+def pcg_jacobi(rowptr, colidx, vals, b, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None):
+    """KrylovJL_CG with a Jacobi preconditioner (precs, ldiv = false): stops on sqrt(r.z) <= atol + rtol*sqrt(r0.z0)."""
+    n = rowptr.size - 1
+    itmax = n if itmax is None else itmax
+    x, work, dinv = np.empty(n), np.empty(4 * n), np.empty(n)
+    rn, conv = C.c_double(), C.c_int32()
+    it = lib().orc_pcg_jacobi(n, rowptr, colidx, np.ascontiguousarray(vals, dtype=np.float64),
+                              np.ascontiguousarray(b, dtype=np.float64), x, atol, rtol, itmax, dinv, work, C.byref(rn), C.byref(conv))
+    return x, int(it), rn.value, bool(conv.value)
+
+
 def cell_nstates(model):
     return lib().orc_cell_nstates(model)
 
@@ -311,7 +325,7 @@ class MonodomainOracle:
     """Holds M, K, A = M - dt K and steps LTG(BackwardEuler, cell solver) like the reference."""
 
     def __init__(self, mesh: Mesh, model, prm, Mvals, Kvals, phi_idx=0, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None,
-                 substeps=1, threshold=0.1, threaded_blas1=False):
+                 substeps=1, threshold=0.1, threaded_blas1=False, precond=None):
         self.mesh, self.model, self.prm = mesh, model, _ddata(prm)
         self.rowptr, self.colidx = mesh.pattern()
         self.M, self.K = Mvals, Kvals
@@ -321,6 +335,7 @@ class MonodomainOracle:
         self.itmax = self.n if itmax is None else itmax
         self.substeps, self.threshold = substeps, threshold
         self.threaded_blas1 = threaded_blas1
+        self.precond = precond        # None or "jacobi" (KrylovJL_CG(precs = ...))
         self.dt_last = 0.0
         self.A = None
         self.bS = None  # last assembled source vector (stays added once assembled, euler.jl:88-91)
@@ -332,6 +347,17 @@ class MonodomainOracle:
         if self.A is None or not np.isclose(dt, self.dt_last, rtol=np.sqrt(np.finfo(float).eps), atol=0):
             self.A = axpby_values(self.M, self.K, dt)
             self.dt_last = dt
+        if self.precond == "jacobi":
+            # same LTG step composed from the exported pieces: b = M phi (+ bS); PCG; cell sweep (euler.jl:71-101)
+            n, pi = self.n, self.phi_idx
+            b = spmv(self.rowptr, self.colidx, self.M, u[pi * n:(pi + 1) * n])
+            if self.bS is not None:
+                b += self.bS
+            x, it, rnv, cv = pcg_jacobi(self.rowptr, self.colidx, self.A, b, self.atol, self.rtol, self.itmax)
+            u[pi * n:(pi + 1) * n] = x
+            lib().orc_cell_step(self.model, self.prm, u, self.du, n, n, t, dt, self.substeps, self.threshold, pi)
+            self.iters.append(int(it))
+            return int(it), rnv, bool(cv)
         rn, conv = C.c_double(), C.c_int32()
         it = lib().orc_ltg_step(self.n, self.rowptr, self.colidx, self.A, self.M,
                                 None if self.bS is None else self.bS.ctypes.data, self.model, self.prm, u, self.du,

@@ -618,6 +618,50 @@ int64_t orc_cg(int64_t n, const int64_t *rowptr, const int64_t *colidx, const do
     return iter;
 }
 
+/* Preconditioned CG as LinearSolve.KrylovJL_CG(precs = ..., ldiv = false) runs it (Krylov.jl 0.10.9 cg!, the usage
+ * shown in bak/examples-gpu/spiral-wave.jl:95-105 and recommended at ep01_spiral-wave.jl:129-131): z = M r with M the
+ * stored INVERSE of the preconditioner, gamma = r.z, the stopping test is on sqrt(r.z) (the M-norm of the residual),
+ * p = z + beta p.  Here M = diag(A)^-1 (Jacobi = KrylovPreconditioners' BlockJacobi with blocks of one row).
+ * dinv: n doubles, 1/a_ii.  work: 4n doubles. */
+int64_t orc_pcg_jacobi(int64_t n, const int64_t *rowptr, const int64_t *colidx, const double *vals, const double *b,
+                       double *x, double atol, double rtol, int64_t itmax, double *dinv, double *work, double *rnorm,
+                       int32_t *converged) {
+    double *r = work, *p = work + n, *Ap = work + 2 * n, *z = work + 3 * n;
+    for (int64_t i = 0; i < n; i++) {
+        dinv[i] = 0.0;
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++)
+            if (colidx[k] == i) dinv[i] = 1.0 / vals[k];
+    }
+    for (int64_t i = 0; i < n; i++) { x[i] = 0.0; r[i] = b[i]; z[i] = dinv[i] * r[i]; p[i] = z[i]; }
+    double gamma = dot_serial(n, r, z);
+    double rn = sqrt(gamma);
+    double eps = atol + rtol * rn;
+    int solved = rn <= eps;
+    int64_t iter = 0;
+    int tired = iter >= itmax;
+    while (!(solved || tired)) {
+        orc_spmv(n, rowptr, colidx, vals, p, Ap);
+        double pAp = dot_serial(n, p, Ap);
+        double alpha = gamma / pAp;
+        for (int64_t i = 0; i < n; i++) x[i] += alpha * p[i];
+        for (int64_t i = 0; i < n; i++) r[i] -= alpha * Ap[i];
+        for (int64_t i = 0; i < n; i++) z[i] = dinv[i] * r[i];
+        double gnext = dot_serial(n, r, z);
+        rn = sqrt(gnext);
+        solved = rn <= eps;
+        if (!solved) {
+            double beta = gnext / gamma;
+            gamma = gnext;
+            for (int64_t i = 0; i < n; i++) p[i] = z[i] + beta * p[i];
+        }
+        iter++;
+        tired = iter >= itmax;
+    }
+    *rnorm = rn;
+    *converged = solved;
+    return iter;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Cell models.  prm arrays hold the struct fields in declaration order.
  * FHN      src/modeling/cells/fhn.jl:6-34       prm = a,b,c,d,e,f

@@ -146,3 +146,46 @@ def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
             assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-10
     h = integ2.u.to_host()
     assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-9
+
+
+@pytest.mark.gpu
+def test_config4_jacobi_preconditioned_cg(tb, dev, oracle):
+    """SURVEY 8f-2 on the mesh it is meant for (ep01_spiral-wave.jl:129-131: "on non-trivial geometries it is highly
+    recommended to use a preconditioner"): the LV's element sizes vary by an order of magnitude, Jacobi cuts the CG
+    iterations, and the preconditioned integrator follows the oracle's."""
+    O = oracle
+    lv, nodes, hexes, wedges, prm, tets = _lv(16, 3, 8)
+    fsn = lv.odb25lt_fibres(prm, tets)
+    k1, kr = 0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24)
+    mo = O.Mesh(O.TET4, tets, nodes)
+    mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+    micro = tb.OrthotropicMicrostructureModel(tb.FieldCoefficient(fsn[:, :, 0]), tb.FieldCoefficient(fsn[:, :, 1]),
+                                              tb.FieldCoefficient(fsn[:, :, 2]))
+    kappa = tb.SpectralTensorCoefficient(micro, tb.ConstantCoefficient((k1, kr, kr)))
+    SRC = [0.0, 0.2, 0.3, 0.25]
+    proto = tb.AnalyticalTransmembraneStimulationProtocol(
+        tb.AnalyticalCoefficient(tb.UniformEndocardialActivation(transmural_depth=0.0, tmax=0.2, amplitude=0.3), tb.CartesianCoordinateSystem()),
+        [(-np.inf, np.inf)])
+    model = tb.MonodomainModel(tb.ConstantCoefficient(1.0), tb.ConstantCoefficient(1.0), kappa, proto, tb.PCG2019(), "φₘ", "s")
+    odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(model), tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), mesh)
+    u0 = tb.create_initial_condition(odeform)
+    data = np.concatenate([[k1, kr, kr], np.ascontiguousarray(fsn).reshape(tets.shape[0], 4, 9).ravel()])
+    Mo, Ko = O.assemble_mass(mo, 2), O.assemble_diffusion(mo, 2, O.D_SPECTRAL, data)
+    N = mo.ndofs
+    tight = dict(atol=1e-15, rtol=1e-14)
+    cg = tb.B200CG(precs=tb.JacobiPreconditioner(), **tight)
+    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 2.0)),
+                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(inner_solver=cg), tb.ForwardEulerCellSolver())), dt=0.01)
+    orc = O.MonodomainOracle(mo, O.PCG2019, O.default_params(O.PCG2019), Mo, Ko, precond="jacobi", **tight)
+    plain = O.MonodomainOracle(mo, O.PCG2019, O.default_params(O.PCG2019), Mo, Ko, **tight)
+    uo, up, t, dt = u0.copy(), u0.copy(), 0.0, 0.01
+    for step in range(20):
+        orc.bS = plain.bS = O.assemble_source(mo, 2, O.SRC_ENDO, SRC, t + dt)
+        ito, rno, convo = orc.step(uo, t, dt)
+        plain.step(up, t, dt)
+        assert tb.step_(integ) and convo and abs(integ.cg_iterations[-1] - ito) <= 1
+        t += dt
+    h = integ.u.to_host()
+    assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-9
+    assert np.abs(uo[:N] - up[:N]).max() / np.abs(up[:N]).max() <= 1e-9          # same solution as unpreconditioned CG
+    assert np.mean(orc.iters) < 0.8 * np.mean(plain.iters)                       # and markedly fewer iterations

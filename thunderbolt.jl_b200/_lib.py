@@ -25,6 +25,7 @@ QUAD4, HEX8, TRI3, TET4 = 0, 1, 2, 3
 FHN, PCG2019 = 0, 1
 D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
 PEER_BLOB_BYTES = 160
+PRECOND_NONE, PRECOND_JACOBI = 0, 1
 SRC_NONE, SRC_BOX, SRC_BALL, SRC_COSEXP, SRC_NORMT, SRC_ENDO = 0, 1, 2, 3, 4, 5
 
 
@@ -123,6 +124,8 @@ _SIGNATURES = {
     "tb_assembly_set_scratch_budget": [_vp, C.c_int64],
     "tb_assembly_release_scratch": [_vp],
     "tb_cg_solve": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
+    "tb_cg_solve_pc": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
+    "tb_monodomain_set_preconditioner": [_vp, C.c_int32],
     "tb_cg_set_persistent": [_vp, C.c_int32],
     "tb_cg_last_path": [_vp, _pi32],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,

@@ -561,6 +561,17 @@ class B200CG:
     atol: float = SQRT_EPS
     rtol: float = SQRT_EPS
     maxiters: int | None = None
+    precs: object = None          # None, or JacobiPreconditioner() (LinearSolve's `precs`, used with ldiv = false)
+
+    @property
+    def precond(self) -> int:
+        return L.PRECOND_JACOBI if isinstance(self.precs, JacobiPreconditioner) else L.PRECOND_NONE
+
+
+@dataclass
+class JacobiPreconditioner:
+    """M = diag(A)^-1, rebuilt from the operator at every solve; stands where the reference's examples put
+    KrylovPreconditioners.BlockJacobiPreconditioner (bak/examples-gpu/spiral-wave.jl:95-105) with one-row blocks."""
 
 
 KrylovJL_CG = B200CG
@@ -707,7 +718,8 @@ def perform_step_(f, cache, t, Δt, want_tangent=False) -> bool:
         if not isinstance(cache.source_term, LinearNullOperator):    # add!(b, S) is unconditional, euler.jl:88-91
             _add(dev, cache.b, cache.source_term.b)
         s = cache.solver.inner_solver
-        it, rn, conv = core.cg_solve(dev, cache.A, cache.b, cache.uₙ, s.atol, s.rtol, s.maxiters, xcol=cache.ucol)
+        it, rn, conv = core.cg_solve(dev, cache.A, cache.b, cache.uₙ, s.atol, s.rtol, s.maxiters, xcol=cache.ucol,
+                                     precond=s.precond)
         cache.iters.append(it)
         cache.resid.append(rn)
         return conv
@@ -759,6 +771,7 @@ class ThunderboltTimeIntegrator:
                 st = core.MonodomainStepper(dev, hc.M.A, hc.K.A, odefun.ode.model_id, odefun.ode.params(), φcol)
                 s = heat_alg.inner_solver
                 st.set_cg(s.atol, s.rtol, s.maxiters)
+                st.set_preconditioner(s.precond)
                 st.set_cell_solver(cc.substeps, cc.threshold)
                 self.fused = st
         elif isinstance(f, AffineODEFunction):

@@ -364,11 +364,11 @@ def assemble_source_qp(dev, mesh, b: B200Vector, qorder, fq, col=0):
 
 
 def cg_solve(dev, A: B200CSRMatrix, b: B200Vector, x: B200Vector, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, bcol=0,
-             xcol=0):
+             xcol=0, precond=L.PRECOND_NONE):
     it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()
     itmax = A.nrows if itmax is None else itmax
-    L.call("tb_cg_solve", dev.h, A.h, b.h, int(bcol), x.h, int(xcol), float(atol), float(rtol), int(itmax), C.byref(it),
-           C.byref(rn), C.byref(cv))
+    L.call("tb_cg_solve_pc", dev.h, A.h, b.h, int(bcol), x.h, int(xcol), int(precond), float(atol), float(rtol), int(itmax),
+           C.byref(it), C.byref(rn), C.byref(cv))
     return it.value, rn.value, bool(cv.value)
 
 
@@ -392,6 +392,9 @@ class MonodomainStepper:
 
     def set_cg(self, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None):
         L.call("tb_monodomain_set_cg", self.h, float(atol), float(rtol), int(self.M.nrows if itmax is None else itmax))
+
+    def set_preconditioner(self, precond=L.PRECOND_NONE):
+        L.call("tb_monodomain_set_preconditioner", self.h, int(precond))
 
     def set_cell_solver(self, substeps=1, threshold=0.1):
         L.call("tb_monodomain_set_cell_solver", self.h, int(substeps), float(threshold))

@@ -85,15 +85,17 @@ __device__ __forceinline__ void cg_finish(double block_value, CGState *st, doubl
 // ---- init from a given right-hand side: x = 0, r = p = b, gamma = b.b ------------------------------
 __global__ void __launch_bounds__(256) k_cg_init_b(const double *__restrict__ b, double *__restrict__ x,
                                                    double *__restrict__ r, double *__restrict__ p, int64_t n, CGState *st,
-                                                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar) {
+                                                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar,
+                                                   const double *__restrict__ dinv) {
     __shared__ double sm[32];
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double v = b[i];
+        const double z = dinv ? dinv[i] * v : v;      // z = M r (Jacobi), p = z, gamma = r.z
         x[i] = 0.0;
         r[i] = v;
-        p[i] = v;
-        acc += v * v;
+        p[i] = z;
+        acc += v * z;
     }
     const double bs = tb_block_sum(acc, sm);
     cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256)
     k_cg_init_Mphi(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ Mval,
                    const double *__restrict__ phi, const double *__restrict__ bS, double *__restrict__ x,
                    double *__restrict__ r, double *__restrict__ p, int64_t nrows, int64_t nslices, CGState *st,
-                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar) {
+                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar, const double *__restrict__ dinv) {
     __shared__ double sm[32];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -116,10 +118,11 @@ __global__ void __launch_bounds__(256)
         const int64_t row = s * TB_SLICE + lane;
         if (row < nrows) {
             if (bS) v += bS[row];
+            const double z = dinv ? dinv[row] * v : v;
             x[row] = 0.0;
             r[row] = v;
-            p[row] = v;
-            acc += v * v;
+            p[row] = z;
+            acc += v * z;
         }
     }
     const double bs = tb_block_sum(acc, sm);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(1024, 1)
                   const double *__restrict__ val, const double *__restrict__ xin, const double *__restrict__ bS,
                   double *__restrict__ xout, double *__restrict__ r, double *__restrict__ pout, int64_t nrows,
                   int64_t nslices, unsigned val_bytes, unsigned col_bytes, CGState *st, double *partials, unsigned *ticket,
-                  bool dist, const tb_ar_args ar, const tb_hwait_args hw) {
+                  bool dist, const tb_ar_args ar, const tb_hwait_args hw, const double *__restrict__ dinv) {
     if (!INIT && st->done) return;
     tb_halo_wait(hw);
     extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
@@ -169,10 +172,11 @@ __global__ void __launch_bounds__(1024, 1)
         if (row < nrows) {
             if (INIT) {
                 if (bS) v += bS[row];
+                const double z = dinv ? dinv[row] * v : v;
                 xout[row] = 0.0;
                 r[row] = v;
-                pout[row] = v;
-                acc += v * v;
+                pout[row] = z;
+                acc += v * z;
             } else {
                 r[row] = v;              // r aliases Ap here
                 acc += xin[row] * v;
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(1024, 1)
 template <int STAGES, bool INIT>
 static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern *pat, const double *val, const double *xin,
                                const double *bS, double *xout, double *r, double *pout, CGState *st, double *part,
-                               unsigned *tick, bool dist, const tb_ar_args &ar, const tb_hwait_args &hw) {
+                               unsigned *tick, bool dist, const tb_ar_args &ar, const tb_hwait_args &hw, const double *dinv) {
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
     const tb_tma_geom g = tb_tma_geometry(pat->max_width, cc ? pat->max_ccol_ints : 32 * pat->max_width, STAGES, warps_override);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
@@ -199,7 +203,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             configured = g.smem;
         }
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_ccol,
-                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw);
+                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv);
     } else {
         static size_t configured = 0;
         if (configured < g.smem) {
@@ -207,7 +211,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             configured = g.smem;
         }
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, nullptr,
-                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw);
+                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv);
     }
     return TB_OK;
 }
@@ -218,19 +222,20 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
 template <bool INIT>
 static int32_t dispatch_spmv_tma(tb_ctx *ctx, const tb_pattern *pat, const double *val, const double *xin, const double *bS,
                                  double *xout, double *r, double *pout, CGState *st, double *part, unsigned *tick, bool dist,
-                                 const tb_ar_args &ar, const tb_hwait_args &hw) {
+                                 const tb_ar_args &ar, const tb_hwait_args &hw, const double *dinv) {
     switch (ctx->spmv_variant) {
-    case 2: return launch_spmv_tma<1, INIT>(ctx, 16, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
-    case 3: return launch_spmv_tma<2, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
-    case 4: return launch_spmv_tma<1, INIT>(ctx, 24, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
-    default: return launch_spmv_tma<1, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw);
+    case 2: return launch_spmv_tma<1, INIT>(ctx, 16, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw, dinv);
+    case 3: return launch_spmv_tma<2, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw, dinv);
+    case 4: return launch_spmv_tma<1, INIT>(ctx, 24, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw, dinv);
+    default: return launch_spmv_tma<1, INIT>(ctx, 0, pat, val, xin, bS, xout, r, pout, st, part, tick, dist, ar, hw, dinv);
     }
 }
 
 // ---- x += alpha p; r -= alpha Ap; r.r  (128-bit loads/stores) --------------------------------------
 __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                                                const double *__restrict__ Ap, int64_t n, CGState *st, double *partials,
-                                               unsigned *ticket, bool dist, const tb_ar_args ar) {
+                                               unsigned *ticket, bool dist, const tb_ar_args ar,
+                                               const double *__restrict__ dinv) {
     if (st->done) return;
     __shared__ double sm[32];
     const double alpha = st->alpha;
@@ -245,15 +250,21 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
         rv.y -= alpha * av.y;
         reinterpret_cast<double2 *>(x)[i] = xv;
         reinterpret_cast<double2 *>(r)[i] = rv;
-        acc += rv.x * rv.x;
-        acc += rv.y * rv.y;
+        if (dinv) {   // gamma' = r.z, z = M r
+            const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+            acc += rv.x * (dv.x * rv.x);
+            acc += rv.y * (dv.y * rv.y);
+        } else {
+            acc += rv.x * rv.x;
+            acc += rv.y * rv.y;
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = n - 1;
         const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * Ap[i];
         x[i] = xn;
         r[i] = rn;
-        acc += rn * rn;
+        acc += dinv ? rn * (dinv[i] * rn) : rn * rn;
     }
     const double bs = tb_block_sum(acc, sm);
     cg_finish<2>(bs, st, partials, ticket, sm, dist, ar);
@@ -261,18 +272,67 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
 
 // ---- p = r + beta p ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cg_p(const double *__restrict__ r, double *__restrict__ p, int64_t n,
-                                              const CGState *st) {
+                                              const CGState *st, const double *__restrict__ dinv) {
     if (st->done) return;
     const double beta = st->beta;
     const int64_t n2 = n >> 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
-        const double2 rv = reinterpret_cast<const double2 *>(r)[i];
+        double2 rv = reinterpret_cast<const double2 *>(r)[i];
+        if (dinv) {   // p = z + beta p
+            const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+            rv.x = dv.x * rv.x;
+            rv.y = dv.y * rv.y;
+        }
         double2 pv = reinterpret_cast<double2 *>(p)[i];
         pv.x = rv.x + beta * pv.x;
         pv.y = rv.y + beta * pv.y;
         reinterpret_cast<double2 *>(p)[i] = pv;
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = (dinv ? dinv[n - 1] * r[n - 1] : r[n - 1]) + beta * p[n - 1];
+}
+
+// ---- Jacobi preconditioner: dinv = 1 / diag(A) ------------------------------------------------------------------
+__global__ void k_diag_slot(const int64_t *__restrict__ rowptr, const int64_t *__restrict__ slice_ptr,
+                            const int *__restrict__ col, int64_t nrows, int *__restrict__ slot) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t base = slice_ptr[r >> 5] + (r & 31);
+        const int len = (int)(rowptr[r + 1] - rowptr[r]);
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (col[base + (int64_t)mid * TB_SLICE] < (int)r) lo = mid + 1; else hi = mid;
+        }
+        slot[r] = (lo < len && col[base + (int64_t)lo * TB_SLICE] == (int)r) ? lo : -1;
+    }
+}
+__global__ void k_dinv(const int64_t *__restrict__ slice_ptr, const int *__restrict__ slot, const double *__restrict__ val,
+                       int64_t nrows, int64_t len, double *__restrict__ dinv) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < len; r += (int64_t)gridDim.x * blockDim.x) {
+        double d = 0.0;
+        if (r < nrows && slot[r] >= 0) d = 1.0 / val[slice_ptr[r >> 5] + (r & 31) + (int64_t)slot[r] * TB_SLICE];
+        dinv[r] = d;
+    }
+}
+static int32_t cg_build_dinv(tb_ctx *ctx, const tb_csr *A, const double **out) {
+    tb_pattern *pat = A->pat;
+    if (!pat->d_diag_slot) {
+        TB_CUDA(cudaMalloc(&pat->d_diag_slot, sizeof(int) * (size_t)(pat->nrows + 1)));
+        TB_LAUNCH(ctx, k_diag_slot, tb_grid_for(ctx, pat->nrows, 256, 8), 256, 0, pat->d_rowptr, pat->d_slice_ptr, pat->d_col,
+                  pat->nrows, pat->d_diag_slot);
+    }
+    const int64_t len = tb_round_up(pat->nrows, 32);
+    if (ctx->dinv_len < len) {
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_dinv);
+        ctx->d_dinv = nullptr;
+        ctx->dinv_len = 0;
+        TB_CUDA(cudaMalloc(&ctx->d_dinv, sizeof(double) * (size_t)len));
+        ctx->dinv_len = len;
+    }
+    TB_LAUNCH(ctx, k_dinv, tb_grid_for(ctx, len, 256, 8), 256, 0, pat->d_slice_ptr, pat->d_diag_slot, A->d_val, pat->nrows, len,
+              ctx->d_dinv);
+    *out = ctx->d_dinv;
+    return TB_OK;
 }
 
 // next all-reduce epoch on the window path (all ranks call this in the same order), or the NCCL marker
@@ -302,11 +362,13 @@ static int32_t cg_allreduce_then(tb_ctx *ctx, int which, const tb_ar_args &ar) {
 // b != NULL: solve A x = b.  b == NULL: right-hand side is M*phi (+ bS), built inside the init kernel.
 int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
-                       int32_t *converged) {
+                       int32_t *converged, int precond) {
     const tb_pattern *pat = A->pat;
     const int64_t n = pat->nrows;
+    const double *dinv = nullptr;
+    if (precond == TB_PRECOND_JACOBI) TB_TRY(cg_build_dinv(ctx, A, &dinv));
     if (const int pgrid = tb_cg_persistent_grid(ctx, pat))     // small operator: one persistent cooperative kernel
-        return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged);
+        return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
     ctx->last_cg_persistent = 0;
     TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
@@ -330,14 +392,14 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     {
         const tb_ar_args ar = cg_next_ar(ctx, peer_ar);
         if (b) {
-            TB_LAUNCH(ctx, k_cg_init_b, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist, ar);
+            TB_LAUNCH(ctx, k_cg_init_b, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist, ar, dinv);
         } else {
             if (M->pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, M->pat, phi));   // phi lives in the caller's vector: NCCL
             if (tma)
-                TB_TRY(dispatch_spmv_tma<true>(ctx, pat, M->d_val, phi, bS, x, r, p, st, part, tick, dist, ar, nowait));
+                TB_TRY(dispatch_spmv_tma<true>(ctx, pat, M->d_val, phi, bS, x, r, p, st, part, tick, dist, ar, nowait, dinv));
             else
                 TB_LAUNCH(ctx, k_cg_init_Mphi, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
-                          pat->nslices, st, part, tick, dist, ar);
+                          pat->nslices, st, part, tick, dist, ar, dinv);
         }
         if (dist) TB_TRY(cg_allreduce_then(ctx, 0, ar));
     }
@@ -356,16 +418,16 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k)], ctx->stream));
             const tb_ar_args ar1 = cg_next_ar(ctx, peer_ar);
             if (tma)
-                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, st, part, tick, dist, ar1, hw));
+                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, st, part, tick, dist, ar1, hw, nullptr));
             else
                 TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
                           pat->nslices, st, part, tick, dist, ar1, hw);
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k) + 1], ctx->stream));
             if (dist) TB_TRY(cg_allreduce_then(ctx, 1, ar1));
             const tb_ar_args ar2 = cg_next_ar(ctx, peer_ar);
-            TB_LAUNCH(ctx, k_cg_xr, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2);
+            TB_LAUNCH(ctx, k_cg_xr, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, dinv);
             if (dist) TB_TRY(cg_allreduce_then(ctx, 2, ar2));
-            TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, r, p, n, st);
+            TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, r, p, n, st, dinv);
         }
         enq += chunk;
         TB_CUDA(cudaMemcpyAsync(h, st, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -395,14 +457,25 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     return TB_OK;
 }
 
+extern "C" int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol,
+                                  int32_t precond, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
+                                  int32_t *converged);
+
 extern "C" int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol,
                                double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                                int32_t *converged) {
+    return tb_cg_solve_pc(ctx, A, b, bcol, x, xcol, TB_PRECOND_NONE, atol, rtol, itmax, iters, rnorm, converged);
+}
+
+extern "C" int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol,
+                                  int32_t precond, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
+                                  int32_t *converged) {
     TB_REQUIRE(ctx && A && b && x, "tb_cg_solve: NULL argument");
+    TB_REQUIRE(precond == TB_PRECOND_NONE || precond == TB_PRECOND_JACOBI, "tb_cg_solve: unknown preconditioner %d", precond);
     TB_REQUIRE(bcol >= 0 && bcol < b->ncols && xcol >= 0 && xcol < x->ncols, "tb_cg_solve: column out of range");
     TB_REQUIRE(b->n >= A->pat->nrows && x->n >= A->pat->nrows, "tb_cg_solve: vector shorter than the operator");
     TB_REQUIRE(itmax >= 0, "tb_cg_solve: itmax must be >= 0");
     TB_DEV(ctx);
     return tb_cg_run_impl(ctx, A, b->d + (size_t)bcol * b->ld, nullptr, nullptr, nullptr, x->d + (size_t)xcol * x->ld, atol,
-                          rtol, itmax, iters, rnorm, converged);
+                          rtol, itmax, iters, rnorm, converged, precond);
 }

@@ -94,12 +94,13 @@ template <int RPL, bool FROM_B>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
     k_cg_persistent(const PcgMat P, const double *__restrict__ Aval, const double *__restrict__ Mval,
                     const double *__restrict__ src, const double *__restrict__ bS, double *__restrict__ x_out,
-                    double *__restrict__ pglob, int64_t nrows, int64_t nslices, CGState *st, double *partials) {
+                    double *__restrict__ pglob, int64_t nrows, int64_t nslices, CGState *st, double *partials,
+                    const double *__restrict__ dinv) {
     cgp::grid_group grid = cgp::this_grid();
     __shared__ double sm[34];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t gw = (int64_t)blockIdx.x * PCG_WARPS + warp, nw = (int64_t)gridDim.x * PCG_WARPS;
-    double x[RPL], r[RPL], p[RPL], Ap[RPL];
+    double x[RPL], r[RPL], p[RPL], Ap[RPL], di[RPL];   // di = 1/a_ii (Jacobi) or 1
     bool own[RPL];
     double acc = 0.0;
 #pragma unroll
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         own[k] = s < nslices && row < nrows;
         x[k] = 0.0;
         r[k] = p[k] = Ap[k] = 0.0;
+        di[k] = (dinv && own[k]) ? dinv[row] : 1.0;
         if (s < nslices) {
             double v;
             if (FROM_B) v = own[k] ? src[row] : 0.0;
@@ -117,9 +119,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
                 if (own[k] && bS) v += bS[row];
             }
             if (own[k]) {
-                r[k] = p[k] = v;
-                pglob[row] = v;
-                acc += v * v;
+                const double z = dinv ? di[k] * v : v;         // z = M r, p = z, gamma = r.z
+                r[k] = v;
+                p[k] = z;
+                pglob[row] = z;
+                acc += v * z;
             }
         }
     }
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
             if (own[k]) {
                 x[k] += alpha * p[k];
                 r[k] -= alpha * Ap[k];
-                acc += r[k] * r[k];
+                acc += dinv ? r[k] * (di[k] * r[k]) : r[k] * r[k];
             }
         const double gnext = pcg_allsum(acc, partials + 2 * gridDim.x, sm, grid);
         rn = sqrt(gnext);
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 #pragma unroll
             for (int k = 0; k < RPL; k++)
                 if (own[k]) {
-                    p[k] = r[k] + beta * p[k];
+                    p[k] = (dinv ? di[k] * r[k] : r[k]) + beta * p[k];
                     pglob[(gw + k * nw) * TB_SLICE + lane] = p[k];
                 }
             grid.sync();                                       // p complete before anyone gathers it
@@ -184,11 +188,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 
 template <int RPL, bool FROM_B>
 static int32_t launch_pcg(tb_ctx *ctx, int grid, const PcgMat &P, const double *Aval, const double *Mval, const double *src,
-                          const double *bS, double *x, double *pglob, int64_t nrows, int64_t nslices) {
+                          const double *bS, double *x, double *pglob, int64_t nrows, int64_t nslices, const double *dinv) {
     CGState *st = ctx->d_cg;
     double *partials = ctx->d_partials;
     void *args[] = {(void *)&P, (void *)&Aval, (void *)&Mval, (void *)&src, (void *)&bS, (void *)&x, (void *)&pglob,
-                    (void *)&nrows, (void *)&nslices, (void *)&st, (void *)&partials};
+                    (void *)&nrows, (void *)&nslices, (void *)&st, (void *)&partials, (void *)&dinv};
     TB_CUDA(cudaLaunchCooperativeKernel((void *)k_cg_persistent<RPL, FROM_B>, dim3(grid), dim3(PCG_THREADS), args, 0, ctx->stream));
     ctx->launches++;
     return TB_OK;
@@ -224,7 +228,7 @@ int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat) {
 
 int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
                              const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
-                             double *rnorm, int32_t *converged) {
+                             double *rnorm, int32_t *converged, const double *dinv) {
     const tb_pattern *pat = A->pat;
     TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
     double *pglob = ctx->d_cgwork + ctx->cgwork_ld;
@@ -237,8 +241,8 @@ int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const doubl
     const double *src = b ? b : phi;
     const double *Mval = b ? nullptr : M->d_val;
 #define PCG_GO(R)                                                                                                              \
-    (b ? launch_pcg<R, true>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices)                        \
-       : launch_pcg<R, false>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices))
+    (b ? launch_pcg<R, true>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices, dinv)                  \
+       : launch_pcg<R, false>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices, dinv))
     int32_t st = rpl <= 1 ? PCG_GO(1) : rpl <= 2 ? PCG_GO(2) : PCG_GO(4);
 #undef PCG_GO
     if (st != TB_OK) return st;

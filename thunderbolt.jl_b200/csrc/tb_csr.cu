@@ -184,6 +184,7 @@ int32_t tb_pattern_release(tb_pattern *p) {
     cudaFree(p->d_rowptr);
     cudaFree(p->d_slice_ptr);
     cudaFree(p->d_col);
+    cudaFree(p->d_diag_slot);
     cudaFree(p->halo.d_send_rows);
     cudaFree(p->halo.d_sendbuf);
     delete p;

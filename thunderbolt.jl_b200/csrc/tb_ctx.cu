@@ -82,6 +82,7 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_scalar);
     cudaFreeHost(ctx->h_scalar);
     cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_dinv);
     cudaFree(ctx->d_ea);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);

@@ -135,6 +135,8 @@ struct tb_ctx {
     struct CGState *h_cg = nullptr;   // pinned mirror
     double *d_scalar = nullptr;       // small device scratch (16 doubles)
     double *h_scalar = nullptr;       // pinned
+    double *d_dinv = nullptr;         // Jacobi preconditioner: 1/diag(A) of the operator being solved
+    int64_t dinv_len = 0;
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
     int assembly_mode = 2;            // 0: fp64-atomic scatter, 2: element matrices + ordered row gather (deterministic; env TB_ASSEMBLY_MODE)
@@ -246,6 +248,7 @@ struct tb_pattern {
     int64_t ccol_len = 0;
     int max_ccol_ints = 0;        // largest per-slice stream (sizes the shared-memory stage)
     int refcount = 1;
+    int *d_diag_slot = nullptr;   // per row: entry slot of the diagonal (-1: none); built on first use by the Jacobi preconditioner
     tb_halo halo;
     // element colouring cache (assembly mode 1)
 };
@@ -265,6 +268,7 @@ struct tb_monodomain {
     int phi_idx;
     double atol, rtol;
     int64_t itmax;
+    int precond = 0;
     int substeps;
     double threshold;
     const tb_vec *bS;
@@ -391,11 +395,11 @@ __device__ __forceinline__ void tb_halo_wait(const tb_hwait_args &h) {
 }
 int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
-                       int32_t *converged);
+                       int32_t *converged, int precond = 0);
 int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat);
 int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
                              const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
-                             double *rnorm, int32_t *converged);
+                             double *rnorm, int32_t *converged, const double *dinv);
 int32_t tb_spmv_raw(tb_ctx *ctx, const tb_csr *A, double *x, double *y);
 int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int nparams, double *u, int64_t n, int64_t ld,
                          int phi_idx, const double *phi_src, double t, double dt, int substeps, double thr,

@@ -12,10 +12,6 @@
 
 #define TB_DEV(ctx) TB_CUDA(cudaSetDevice((ctx)->device))
 
-int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
-                       double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
-                       int32_t *converged);
-
 extern "C" int32_t tb_monodomain_create(tb_ctx *ctx, const tb_csr *M, const tb_csr *K, int32_t model, const double *params,
                                         int32_t nparams, int32_t phi_idx, tb_monodomain **out) {
     TB_REQUIRE(ctx && M && K && params && out, "tb_monodomain_create: NULL argument");
@@ -84,6 +80,13 @@ extern "C" int32_t tb_monodomain_set_cg(tb_monodomain *md, double atol, double r
     md->atol = atol;
     md->rtol = rtol;
     md->itmax = itmax;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_monodomain_set_preconditioner(tb_monodomain *md, int32_t precond) {
+    TB_REQUIRE(md, "tb_monodomain_set_preconditioner: handle is NULL");
+    TB_REQUIRE(precond == TB_PRECOND_NONE || precond == TB_PRECOND_JACOBI, "tb_monodomain_set_preconditioner: unknown preconditioner %d", precond);
+    md->precond = precond;
     return TB_OK;
 }
 
@@ -160,7 +163,7 @@ static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, doub
     int64_t it = 0;
     double rn = 0.0;
     int32_t conv = 0;
-    TB_TRY(tb_cg_run_impl(ctx, md->A, nullptr, md->M, phi, bS, md->x->d, md->atol, md->rtol, md->itmax, &it, &rn, &conv));
+    TB_TRY(tb_cg_run_impl(ctx, md->A, nullptr, md->M, phi, bS, md->x->d, md->atol, md->rtol, md->itmax, &it, &rn, &conv, md->precond));
     if (md->timing) TB_CUDA(cudaEventRecord(md->ev[1], ctx->stream));
     if (before_cells) TB_CUDA(cudaStreamWaitEvent(ctx->stream, before_cells, 0));   // run_host: the non-phi columns are still in flight
     // reaction step on the owned points, phi taken from the CG solution (the reference copies x into the
