@@ -49,6 +49,7 @@ extern "C" {
  * src/modeling/cells/pcg2019.jl:4-48 (36 parameters in declaration order g_Na .. E_Ca) */
 #define TB_FHN 0
 #define TB_PCG2019 1
+#define TB_ALIEV_PANFILOV 2   /* src/modeling/cells/aliev-panfilov.jl:1-34: 6 parameters c_t,k,a,eps0,mu1,mu2; states (s, phi_m): phi_idx = 1 */
 
 /* diffusion coefficient kinds, D = kappa/(Cm*chi)  (src/modeling/core/coefficients.jl:152-162)
  *   SCALAR   data[0]                                   ConstantCoefficient(number)

@@ -25,7 +25,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_build" / "liboracle.so"
 
 QUAD4, HEX8, TRI3, TET4 = 0, 1, 2, 3
-FHN, PCG2019, TIMEPROBE = 0, 1, 99
+FHN, PCG2019, ALIEV_PANFILOV, TIMEPROBE = 0, 1, 2, 99
 D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
 SRC_NONE, SRC_BOX, SRC_BALL, SRC_COSEXP, SRC_NORMT, SRC_ENDO = 0, 1, 2, 3, 4, 5
 
@@ -81,6 +81,7 @@ def lib():
         L.orc_cell_nstates.restype = C.c_int
         L.orc_fhn_default_params.argtypes = [_f64p]
         L.orc_pcg2019_default_params.argtypes = [_f64p]
+        L.orc_aliev_panfilov_default_params.argtypes = [_f64p]
         L.orc_pcg2019_default_state.argtypes = [_f64p, _f64p]
         L.orc_cell_rhs.argtypes = [C.c_int, _f64p, _f64p, C.c_double, _f64p]
         L.orc_cell_step.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int64, C.c_int64, C.c_double, C.c_double,
@@ -282,6 +283,9 @@ def default_params(model):
     elif model == PCG2019:
         p = np.empty(36)
         lib().orc_pcg2019_default_params(p)
+    elif model == ALIEV_PANFILOV:
+        p = np.empty(6)
+        lib().orc_aliev_panfilov_default_params(p)
     else:
         p = np.zeros(1)
     return p
@@ -289,7 +293,7 @@ def default_params(model):
 
 def default_initial_state(model, prm=None):
     """default_initial_state (fhn.jl:19, pcg2019.jl:137-152)."""
-    if model == FHN:
+    if model in (FHN, ALIEV_PANFILOV):
         return np.zeros(2)
     if model == PCG2019:
         u0 = np.empty(7)

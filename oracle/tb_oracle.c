@@ -669,12 +669,16 @@ int64_t orc_pcg_jacobi(int64_t n, const int64_t *rowptr, const int64_t *colidx, 
  * ---------------------------------------------------------------------------------------- */
 #define ORC_FHN 0
 #define ORC_PCG2019 1
+#define ORC_ALIEV_PANFILOV 2 /* src/modeling/cells/aliev-panfilov.jl:1-34; states (s, phi_m) */
 #define ORC_TIMEPROBE 99 /* test/test_time_integrator.jl:275-280: du = 1 + sin(t) */
 
-int orc_cell_nstates(int model) { return model == ORC_FHN ? 2 : model == ORC_PCG2019 ? 7 : 1; }
+int orc_cell_nstates(int model) { return model == ORC_FHN || model == ORC_ALIEV_PANFILOV ? 2 : model == ORC_PCG2019 ? 7 : 1; }
 
 void orc_fhn_default_params(double *p) {
     p[0] = 0.1; p[1] = 0.5; p[2] = 1.0; p[3] = 0.0; p[4] = 0.01; p[5] = 1.0;
+}
+void orc_aliev_panfilov_default_params(double *p) { /* aliev-panfilov.jl:2-7 */
+    p[0] = 1.0 / 12.9; p[1] = 8.0; p[2] = 0.05; p[3] = 0.002; p[4] = 0.2; p[5] = 0.3;
 }
 void orc_pcg2019_default_params(double *p) {
     static const double d[36] = {12.0, -52.244, 6.5472, 0.12, -78.7, 5.93, 0.799163, 6.80738, /* I_Na */
@@ -707,6 +711,12 @@ void orc_cell_rhs(int model, const double *p, const double *u, double t, double 
         double phi = u[0], s = u[1];
         du[0] = p[5] * (phi * (1 - phi) * (phi - p[0]) - s);
         du[1] = p[4] * (p[1] * phi - p[2] * s - p[3]);
+    } else if (model == ORC_ALIEV_PANFILOV) { /* aliev-panfilov.jl:15-34: u = (s, phi) */
+        double ct = p[0], k = p[1], a = p[2], e0 = p[3], mu1 = p[4], mu2 = p[5];
+        double phi = u[1], s = u[0];
+        double eps = e0 + s * mu1 / (phi + mu2);
+        du[1] = ct * (k * phi * (phi - 1.0) * (phi - a) - phi * s);
+        du[0] = ct * eps * (-s - k * phi * (phi - a - 1.0));
     } else if (model == ORC_PCG2019) {
         const double C_m = 1.0;
         double phi = u[0], h = u[1], m = u[2], f = u[3], s = u[4], xs = u[5], xr = u[6];

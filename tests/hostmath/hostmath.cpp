@@ -15,7 +15,8 @@ extern "C" {
 double hm_cell_node_step(int model, int adaptive, const double *prm, double *u, double t, double dt, int substeps, double thr) {
     tb_cell_params P;
     std::memset(&P, 0, sizeof(P));
-    for (int i = 0; i < (model == 0 ? 6 : 36); i++) P.p[i] = prm[i];
+    for (int i = 0; i < (model == 1 ? 36 : 6); i++) P.p[i] = prm[i];
+    if (model == 2) return adaptive ? tb_cell_node_step<2, true>(P, u, t, dt, substeps, thr) : tb_cell_node_step<2, false>(P, u, t, dt, substeps, thr);
     if (model == 0) return adaptive ? tb_cell_node_step<0, true>(P, u, t, dt, substeps, thr) : tb_cell_node_step<0, false>(P, u, t, dt, substeps, thr);
     return adaptive ? tb_cell_node_step<1, true>(P, u, t, dt, substeps, thr) : tb_cell_node_step<1, false>(P, u, t, dt, substeps, thr);
 }

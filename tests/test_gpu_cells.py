@@ -28,6 +28,27 @@ def test_fhn_bitwise(tb, dev, oracle, n, sub):
     ud.free()
 
 
+@pytest.mark.parametrize("n", [1, 33, 4097])
+@pytest.mark.parametrize("sub", [1, 10])
+def test_aliev_panfilov_bitwise(tb, dev, oracle, n, sub):
+    """The one model with phi_m NOT in state 0 (aliev-panfilov.jl:13-14: state_symbols = (s, phi_m))."""
+    O = oracle
+    prm = O.default_params(O.ALIEV_PANFILOV)
+    rng = np.random.default_rng(5)
+    u = np.concatenate([rng.uniform(0.0, 2.5, n), rng.uniform(-0.1, 1.1, n)])      # column 0 = s, column 1 = phi
+    ud = tb.B200Vector.from_host(dev, u, 2)
+    t = 0.0
+    for step in range(3):
+        du = O.cell_step(O.ALIEV_PANFILOV, prm, u, n, t, 0.5, substeps=sub, threshold=0.1, phi_idx=1)
+        R = tb.core.cell_step(dev, tb._lib.ALIEV_PANFILOV, prm, ud, t, 0.5, substeps=sub, threshold=0.1, phi_idx=1, want_max=True)
+        assert R == du[n:].max()                                                   # reaction tangent on the phi column
+        t += 0.5
+    assert np.array_equal(ud.to_host(), u)
+    with pytest.raises(tb.TBError):
+        tb.core.cell_step(dev, tb._lib.ALIEV_PANFILOV, prm, ud, t, 0.5, phi_idx=0)
+    ud.free()
+
+
 def test_fhn_adaptive_branch_is_exercised(tb, dev, oracle):
     O = oracle
     prm = O.default_params(O.FHN)

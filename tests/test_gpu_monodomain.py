@@ -250,6 +250,40 @@ def test_random_inputs_one_step_vs_oracle(tb, dev, oracle):
         x.free()
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_aliev_panfilov_monodomain_vs_oracle(tb, dev, oracle, fused):
+    """Aliev-Panfilov through the reference-shaped API: phi_m is the SECOND state column, so the heat solve reads and
+    writes column 1 (heat_dofrange = N+1:2N, fem.jl:399-402) while the cell sweep owns both."""
+    O = oracle
+    nel = (24, 24)
+    mesh = tb.generate_mesh(tb.Quadrilateral, nel, (0.0, 0.0), (2.5, 2.5), device=dev)
+    ion = tb.AlievPanfilovModel()
+    assert tb.state_symbols(ion) == ("s", "φₘ") and tb.transmembranepotential_index(ion) == 2
+    model = tb.MonodomainModel(tb.ConstantCoefficient(1.0), tb.ConstantCoefficient(1.0),
+                               tb.ConstantCoefficient(tb.SymmetricTensor(2, (4.5e-3, 0, 2.0e-3))),
+                               tb.NoStimulationProtocol(), ion, "φₘ", "s")
+    odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(model), tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), mesh)
+    u0 = tb.create_initial_condition(odeform)
+    tb.setvariable_(u0, odeform, "φₘ", lambda x: 1.0 if (x[0] <= 1.25 and x[1] <= 1.25) else 0.0)
+    tb.setvariable_(u0, odeform, "s", lambda x: 0.5 if x[1] >= 1.25 else 0.0)
+    N = mesh.ndofs
+    assert u0[:N].max() == 0.5 and u0[N:].max() == 1.0                             # layout: s block, then phi block
+    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 60.0)),
+                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(), tb.AdaptiveForwardEulerSubstepper())), dt=0.5, fused=fused)
+    mo = O.generate_grid(O.QUAD4, nel, (0.0, 0.0), (2.5, 2.5))
+    orc = O.MonodomainOracle(mo, O.ALIEV_PANFILOV, O.default_params(O.ALIEV_PANFILOV), O.assemble_mass(mo, 2),
+                             O.assemble_diffusion(mo, 2, O.D_TENSOR, [4.5e-3, 0, 0, 2.0e-3]), phi_idx=1, substeps=10)
+    uo = u0.copy()
+    for step in range(120):
+        ito, rno, convo = orc.step(uo, 0.5 * step, 0.5)
+        assert tb.step_(integ) and convo and abs(integ.cg_iterations[-1] - ito) <= 1
+        if step == 0:
+            assert rel_linf(integ.u.to_host(), uo) <= 1e-10
+    h = integ.u.to_host()
+    assert rel_linf(h[N:], uo[N:]) <= 1e-6 and rel_linf(h[:N], uo[:N]) <= 1e-6
+    assert np.abs(uo - u0).max() > 0.1                                             # something happened
+
+
 def test_c2_full_size_properties(tb, dev):
     """BASELINE config 2 at FULL size (128x128x32, PCG2019): properties that need no oracle.
     Pure-Neumann diffusion conserves 1^T M phi; the CG residual really is below tolerance; resting

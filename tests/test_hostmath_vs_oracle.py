@@ -117,6 +117,27 @@ def test_fhn_node_step_bitwise(oracle, hostmath):
             assert np.array_equal(a, b)
 
 
+def test_aliev_panfilov_node_step_bitwise(oracle, hostmath):
+    """aliev-panfilov.jl:15-34, states (s, phi): rational in the state, so bitwise like FHN."""
+    O = oracle
+    prm = O.default_params(O.ALIEV_PANFILOV)
+    assert np.array_equal(prm, [1.0 / 12.9, 8.0, 0.05, 0.002, 0.2, 0.3])          # aliev-panfilov.jl:2-7
+    rng = np.random.default_rng(8)
+    for _ in range(200):
+        u = np.array([rng.uniform(0.0, 2.5), rng.uniform(-0.1, 1.1)])
+        for sub in (1, 10):
+            a, b = u.copy(), u.copy()
+            du = O.cell_step(O.ALIEV_PANFILOV, prm, a, 1, 0.3, 0.7, substeps=sub, threshold=0.1, phi_idx=1)
+            d = hostmath.hm_cell_node_step(2, int(sub > 1), prm, b, 0.3, 0.7, sub, 0.1)
+            assert np.array_equal(a, b) and d == du[1]
+    # closed form of one rhs evaluation
+    s_, phi = 0.4, 0.6
+    du = O.cell_rhs(O.ALIEV_PANFILOV, prm, [s_, phi])
+    ct, k, a_, e0, m1, m2 = prm
+    assert du[1] == ct * (k * phi * (phi - 1.0) * (phi - a_) - phi * s_)
+    assert du[0] == ct * (e0 + s_ * m1 / (phi + m2)) * (-s_ - k * phi * (phi - a_ - 1.0))
+
+
 def test_pcg2019_node_step(oracle, hostmath):
     O = oracle
     prm = O.default_params(O.PCG2019)

@@ -22,7 +22,7 @@ STATUS_NAMES = {0: "TB_OK", 1: "TB_ERR_INVALID", 2: "TB_ERR_CUDA", 3: "TB_ERR_NO
                 5: "TB_ERR_UNSUPPORTED"}
 
 QUAD4, HEX8, TRI3, TET4 = 0, 1, 2, 3
-FHN, PCG2019 = 0, 1
+FHN, PCG2019, ALIEV_PANFILOV = 0, 1, 2
 D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
 PEER_BLOB_BYTES = 160
 PRECOND_NONE, PRECOND_JACOBI = 0, 1

@@ -47,6 +47,25 @@ class ParametrizedFHNModel:
 
 FHNModel = ParametrizedFHNModel
 
+
+@dataclass
+class ParametrizedAlievPanfilovModel:
+    """src/modeling/cells/aliev-panfilov.jl:1-34.  The recovery variable comes first: state_symbols = (s, φₘ), so the
+    transmembrane potential is state 2 (1-based) -- the one model on the path with φₘ not in front."""
+    c_t: float = 1.0 / 12.9     # cₜ
+    k: float = 8.0
+    a: float = 0.05
+    eps0: float = 0.002         # ϵ₀
+    mu1: float = 0.2            # μ₁
+    mu2: float = 0.3            # μ₂
+    model_id = L.ALIEV_PANFILOV
+
+    def params(self):
+        return np.array([self.c_t, self.k, self.a, self.eps0, self.mu1, self.mu2])
+
+
+AlievPanfilovModel = ParametrizedAlievPanfilovModel
+
 _PCG_FIELDS = ("g_Na E_m k_m tau_m E_h k_h delta_h tau_h0 g_K1 E_z k_z g_to E_r k_r E_s k_s tau_s g_CaL E_d k_d E_f k_f "
                "tau_f g_Kr E_xr k_xr tau_xr E_y k_y g_Ks E_xs k_xs tau_xs E_Na E_K E_Ca").split()
 _PCG_DEFAULTS = (12.0, -52.244, 6.5472, 0.12, -78.7, 5.93, 0.799163, 6.80738, 0.73893, -91.9655, 12.4997, 0.1688, 14.3116,
@@ -74,21 +93,23 @@ PCG2019 = ParametrizedPCG2019Model
 
 
 def num_states(ion) -> int:
-    return 2 if ion.model_id == L.FHN else 7
+    return 7 if ion.model_id == L.PCG2019 else 2
 
 
 def state_symbols(ion):
+    if ion.model_id == L.ALIEV_PANFILOV:
+        return ("s", "φₘ")                                      # aliev-panfilov.jl:13-14
     return ("φₘ", "s") if ion.model_id == L.FHN else ("φₘ", "h", "m", "f", "s", "xs", "xr")
 
 
 def transmembranepotential_index(ion) -> int:
-    """1-based like the reference (electrophysiology.jl:107-153)."""
-    return 1
+    """1-based like the reference (electrophysiology.jl:107-153): position of :φₘ in state_symbols."""
+    return state_symbols(ion).index("φₘ") + 1
 
 
 def default_initial_state(ion) -> np.ndarray:
     """fhn.jl:19, pcg2019.jl:137-152"""
-    if ion.model_id == L.FHN:
+    if ion.model_id in (L.FHN, L.ALIEV_PANFILOV):
         return np.zeros(2)
     p = ion
 
@@ -428,9 +449,10 @@ def setvariable_(u0: np.ndarray, f: GenericSplitFunction, sym: str, fn: Callable
     heatfun, odefun = f.functions
     n = heatfun.dh.ndofs
     syms = state_symbols(odefun.ode)
-    names = {heatfun.mass_term.sym: 0}
-    names.update({s: i for i, s in enumerate(syms)})
-    names[odefun.state_symbol] = 1
+    φcol = transmembranepotential_index(odefun.ode) - 1
+    names = {s: i for i, s in enumerate(syms)}
+    names[heatfun.mass_term.sym] = φcol                          # the user's name for the transmembrane potential
+    names.setdefault(odefun.state_symbol, next(i for i in range(len(syms)) if i != φcol))   # ... and for the first internal state
     if sym not in names:
         raise KeyError(f"unknown solution variable {sym}")
     s = names[sym]
@@ -725,7 +747,7 @@ def perform_step_(f, cache, t, Δt, want_tangent=False) -> bool:
         return conv
     ion = f.ode
     R = core.cell_step(cache.uₙ.dev, ion.model_id, ion.params(), cache.uₙ, t, Δt, cache.substeps, cache.threshold,
-                       want_max=want_tangent)
+                       phi_idx=transmembranepotential_index(ion) - 1, want_max=want_tangent)
     if want_tangent:
         cache.R = R                                   # max over the dumat column of phi_m (rtc.jl:64-67)
     return True

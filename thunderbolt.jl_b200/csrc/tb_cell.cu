@@ -92,15 +92,17 @@ static int32_t launch_cell(tb_ctx *ctx, const tb_cell_params &prm, double *u, in
 int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int nparams, double *u, int64_t n, int64_t ld,
                          int phi_idx, const double *phi_src, double t, double dt, int substeps, double thr,
                          double *max_dphi) {
-    TB_REQUIRE(model == TB_FHN || model == TB_PCG2019, "tb_cell_step: unknown ionic model %d", model);
-    const int np = model == TB_FHN ? 6 : 36;
+    TB_REQUIRE(tb_model_known(model), "tb_cell_step: unknown ionic model %d", model);
+    const int np = tb_model_nparams(model);
     TB_REQUIRE(params && nparams == np, "tb_cell_step: model %d takes %d parameters, got %d", model, np, nparams);
-    TB_REQUIRE(phi_idx == 0, "tb_cell_step: FHN and PCG2019 keep the transmembrane potential in state 0");
+    TB_REQUIRE(phi_idx == tb_model_phi(model), "tb_cell_step: model %d keeps the transmembrane potential in state %d, not %d", model,
+               tb_model_phi(model), phi_idx);
     TB_REQUIRE((ld & 1) == 0, "tb_cell_step: column stride must be even");
     if (n == 0) return TB_OK;
     tb_cell_params prm;
     for (int i = 0; i < 36; i++) prm.p[i] = i < np ? params[i] : 0.0;
     if (model == TB_FHN) TB_TRY((launch_cell<0>(ctx, prm, u, n, ld, phi_src, t, dt, substeps, thr, max_dphi != nullptr)));
+    else if (model == TB_ALIEV_PANFILOV) TB_TRY((launch_cell<2>(ctx, prm, u, n, ld, phi_src, t, dt, substeps, thr, max_dphi != nullptr)));
     else TB_TRY((launch_cell<1>(ctx, prm, u, n, ld, phi_src, t, dt, substeps, thr, max_dphi != nullptr)));
     if (max_dphi) {
         TB_CUDA(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -114,7 +116,8 @@ extern "C" int32_t tb_cell_step(tb_ctx *ctx, int32_t model, const double *params
                                 int32_t phi_idx, double t, double dt, int32_t substeps, double reaction_threshold,
                                 double *max_dphi) {
     TB_REQUIRE(ctx && u, "tb_cell_step: NULL argument");
-    const int ns = model == TB_FHN ? 2 : 7;
+    TB_REQUIRE(tb_model_known(model), "tb_cell_step: unknown ionic model %d", model);
+    const int ns = tb_model_nstates(model);
     TB_REQUIRE(u->ncols == ns, "tb_cell_step: state vector has %d columns, model needs %d", u->ncols, ns);
     TB_DEV(ctx);
     return tb_cell_step_raw(ctx, model, params, nparams, u->d, u->n, u->ld, phi_idx, nullptr, t, dt, substeps,

@@ -2,6 +2,7 @@
 // check the arithmetic against the oracle without a GPU).
 //   FHN      src/modeling/cells/fhn.jl:6-34
 //   PCG2019  src/modeling/cells/pcg2019.jl:4-133
+//   Aliev-Panfilov  src/modeling/cells/aliev-panfilov.jl:1-34 (recovery variable FIRST: phi_m is state index 2 there, 1 here)
 // Operation order follows the reference expression by expression (m*m*m*h*h, sigmoid as
 // 1/(1+exp(sign*(phi-E)/k))); the library is compiled with -fmad=false because Julia does not
 // contract a*b+c, so FHN is bitwise the reference and PCG2019 differs only through exp's last ulp.
@@ -21,6 +22,7 @@ struct tb_cell_params {
 template <int MODEL> struct tb_cell_traits;
 template <> struct tb_cell_traits<0> { static constexpr int NS = 2; static constexpr int NP = 6; static constexpr int PHI = 0; };
 template <> struct tb_cell_traits<1> { static constexpr int NS = 7; static constexpr int NP = 36; static constexpr int PHI = 0; };
+template <> struct tb_cell_traits<2> { static constexpr int NS = 2; static constexpr int NP = 6; static constexpr int PHI = 1; };
 
 namespace tbpcg {
 enum { g_Na, E_m, k_m, tau_m, E_h, k_h, delta_h, tau_h0, g_K1, E_z, k_z, g_to, E_r, k_r, E_s, k_s, tau_s, g_CaL, E_d, k_d,
@@ -36,6 +38,15 @@ template <> TB_HD void tb_cell_rhs<0>(const tb_cell_params &prm, const double *u
     const double phi = u[0], s = u[1];
     du[0] = f * (phi * (1 - phi) * (phi - a) - s);
     du[1] = e * (b * phi - c * s - d);
+}
+
+// aliev-panfilov.jl:15-34; prm = c_t, k, a, eps0, mu1, mu2; u = (s, phi)
+template <> TB_HD void tb_cell_rhs<2>(const tb_cell_params &prm, const double *u, double t, double *du) {
+    const double ct = prm.p[0], k = prm.p[1], a = prm.p[2], e0 = prm.p[3], mu1 = prm.p[4], mu2 = prm.p[5];
+    const double phi = u[1], s = u[0];
+    const double eps = e0 + s * mu1 / (phi + mu2);
+    du[1] = ct * (k * phi * (phi - 1.0) * (phi - a) - phi * s);
+    du[0] = ct * eps * (-s - k * phi * (phi - a - 1.0));
 }
 
 template <> TB_HD void tb_cell_rhs<1>(const tb_cell_params &prm, const double *u, double t, double *du) {

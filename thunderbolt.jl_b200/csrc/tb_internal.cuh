@@ -283,6 +283,12 @@ struct tb_monodomain {
     cudaEvent_t e_phi = nullptr, e_s = nullptr, e_done = nullptr, o_s = nullptr, e_chunk[16] = {};
 };
 
+// ionic model tables (tb_cells.cuh traits, host side)
+static inline bool tb_model_known(int m) { return m == TB_FHN || m == TB_PCG2019 || m == TB_ALIEV_PANFILOV; }
+static inline int tb_model_nstates(int m) { return m == TB_PCG2019 ? 7 : 2; }
+static inline int tb_model_nparams(int m) { return m == TB_PCG2019 ? 36 : 6; }
+static inline int tb_model_phi(int m) { return m == TB_ALIEV_PANFILOV ? 1 : 0; }
+
 static inline int64_t tb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- device helpers -------------------------------------------------------------------------

@@ -16,9 +16,10 @@ extern "C" int32_t tb_monodomain_create(tb_ctx *ctx, const tb_csr *M, const tb_c
                                         int32_t nparams, int32_t phi_idx, tb_monodomain **out) {
     TB_REQUIRE(ctx && M && K && params && out, "tb_monodomain_create: NULL argument");
     TB_REQUIRE(M->pat == K->pat, "tb_monodomain_create: M and K must share one pattern");
-    TB_REQUIRE(model == TB_FHN || model == TB_PCG2019, "tb_monodomain_create: unknown ionic model %d", model);
-    TB_REQUIRE(nparams == (model == TB_FHN ? 6 : 36), "tb_monodomain_create: wrong parameter count %d", nparams);
-    TB_REQUIRE(phi_idx == 0, "tb_monodomain_create: FHN and PCG2019 keep the transmembrane potential in state 0");
+    TB_REQUIRE(tb_model_known(model), "tb_monodomain_create: unknown ionic model %d", model);
+    TB_REQUIRE(nparams == tb_model_nparams(model), "tb_monodomain_create: wrong parameter count %d", nparams);
+    TB_REQUIRE(phi_idx == tb_model_phi(model), "tb_monodomain_create: model %d keeps the transmembrane potential in state %d", model,
+               tb_model_phi(model));
     TB_DEV(ctx);
     *out = nullptr;
     tb_monodomain *md = new (std::nothrow) tb_monodomain();
@@ -146,7 +147,7 @@ static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, doub
     TB_REQUIRE(md && u, "tb_monodomain_step: NULL argument");
     tb_ctx *ctx = md->ctx;
     const tb_pattern *pat = md->M->pat;
-    const int ns = md->model == TB_FHN ? 2 : 7;
+    const int ns = tb_model_nstates(md->model);
     TB_REQUIRE(u->ncols == ns, "tb_monodomain_step: state vector has %d columns, model needs %d", u->ncols, ns);
     TB_REQUIRE(u->n >= pat->ncols, "tb_monodomain_step: state vector has %lld rows, operator needs %lld", (long long)u->n,
                (long long)pat->ncols);
