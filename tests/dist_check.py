@@ -58,6 +58,8 @@ def main():
     assert lm.ndofs == gids.size and np.array_equal(lm.dof_coords(), x[gids])
     M, K = build(dev, lm, ion, D)
     part.attach_halo(M)
+    if rank == 0:
+        print("peer path on" if part.peer else "peer path off (NCCL)", flush=True)
     # owned rows of the distributed operators equal the same rows of the global ones (pattern bit exact)
     rp, ci = M.pattern()
     rp1, ci1 = M1.pattern()
