@@ -220,6 +220,16 @@ int32_t tb_assembly_set_scratch_budget(tb_ctx *ctx, int64_t bytes);
 /* the element scratch is cached on the context between assembly calls; this frees it (e.g. after setup) */
 int32_t tb_assembly_release_scratch(tb_ctx *ctx);
 
+/* ---- ECG post-processing ---------------------------------------------------------------------------
+ * Plonsey1964ECGGaussCache (src/modeling/electrophysiology/ecg.jl:55-160): update_ecg!(cache, phi_m) followed by
+ * evaluate_ecg(cache, x, kappa_t) for `ne` electrodes, fused into one element sweep:
+ *   phi_e(x) = -1/(4 pi kappa_t) * sum_cells sum_q ((flux_q . (x_q - x)) / |x_q - x|^3) dOmega,
+ *   flux_q = sum_i (D(x_q) . gradN_i) phi_i,  D = the coefficient of the diffusion operator (kind/data/cm_chi as in
+ * tb_assemble_diffusion).  electrodes: ne x dim doubles; phi_e: ne doubles. */
+int32_t tb_ecg_plonsey(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, int32_t kind, const double *data, int64_t ndata,
+                       double cm_chi, const tb_vec *phi, int32_t phicol, const double *electrodes, int32_t ne, double kappa_t,
+                       double *phi_e);
+
 /* ---- linear solve -----------------------------------------------------------------------------
  * LinearSolve.solve!(cache) with KrylovJL_CG (euler.jl:10,94,155-156): unpreconditioned CG from
  * x0 = 0, stop when |r| <= atol + rtol*|r0|, at most itmax iterations.  Non-convergence is NOT an

@@ -69,6 +69,8 @@ def lib():
                                             C.c_int, _f64p, C.c_double, _i64p, _i64p, _f64p]
         L.orc_assemble_source.argtypes = [C.c_int, C.c_int, C.c_int64, _i64p, _f64p, _i64p, C.c_int, _f64p,
                                           C.c_double, C.c_void_p, C.c_int64, _f64p]
+        L.orc_ecg_plonsey.argtypes = [C.c_int, C.c_int, C.c_int64, _i64p, _f64p, _i64p, C.c_int, _f64p, C.c_double, _f64p,
+                                      C.c_int, _f64p, C.c_double, _f64p, _f64p]
         L.orc_spmv.argtypes = [C.c_int64, _i64p, _i64p, _f64p, _f64p, _f64p]
         L.orc_axpby_values.argtypes = [C.c_int64, _f64p, _f64p, C.c_double, _f64p]
         L.orc_cg.argtypes = [C.c_int64, _i64p, _i64p, _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_int64,
@@ -233,6 +235,18 @@ def assemble_source(mesh: Mesh, qorder, kind, prm, t, fq_all=None):
     lib().orc_assemble_source(mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs, kind,
                               _ddata(prm), t, None if fqp is None else fqp.ctypes.data, mesh.ndofs, b)
     return b
+
+
+def ecg_plonsey(mesh: Mesh, qorder, kind, data, phi, electrodes, kappa_t, cmchi=1.0):
+    """Plonsey1964ECGGaussCache: update_ecg!(cache, phi) then evaluate_ecg(cache, x, kappa_t) for every electrode x
+    (src/modeling/electrophysiology/ecg.jl:55-160)."""
+    el = np.ascontiguousarray(np.atleast_2d(np.asarray(electrodes, dtype=np.float64)))
+    nq = len(quadrature(mesh.celltype, qorder)[1])
+    flux = np.empty(mesh.ncells * nq * mesh.dim)
+    out = np.empty(el.shape[0])
+    lib().orc_ecg_plonsey(mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs, kind, _ddata(data),
+                          cmchi, np.ascontiguousarray(phi, dtype=np.float64), el.shape[0], el.reshape(-1), kappa_t, flux, out)
+    return out
 
 
 def spmv(rowptr, colidx, vals, x):

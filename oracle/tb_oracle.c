@@ -537,6 +537,66 @@ void orc_assemble_source(int ct, int qorder, int64_t ncells, const int64_t *conn
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Pseudo-ECG after Plonsey (1964) with the Gauss theorem applied, Plonsey1964ECGGaussCache
+ * (src/modeling/electrophysiology/ecg.jl:1-160):
+ *   update_ecg!    flux[cell][q] = sum_i (D(x_q) . gradN_i) * phi[dof_i]            (:14-38, no dOmega here)
+ *   evaluate_ecg   phi_e(x) = -1/(4 pi kappa_t) * sum_cells sum_q ((flux . (xq - x)) / |xq - x|^3) * dOmega  (:86-148)
+ * D is the coefficient of the diffusion operator the cache was built on.  flux: ncells*nq*dim doubles (scratch).
+ * ---------------------------------------------------------------------------------------- */
+void orc_ecg_plonsey(int ct, int qorder, int64_t ncells, const int64_t *conn, const double *coords, const int64_t *celldofs,
+                     int kind, const double *data, double cmchi, const double *phi, int ne, const double *electrodes,
+                     double kappa_t, double *flux, double *out) {
+    int nv = cell_nv(ct), dim = cell_dim(ct);
+    double pts[ORC_MAXQ * 3], w[ORC_MAXQ], N[ORC_MAXNV], dN[ORC_MAXNV * 3], G[ORC_MAXNV * 3], D[9], X[ORC_MAXNV * 3];
+    int nq = orc_quadrature(ct, qorder, pts, w);
+    /* update_ecg!: fill!(0) then compute_quadrature_fluxes! */
+    for (int64_t c = 0; c < ncells; c++) {
+        for (int a = 0; a < nv; a++)
+            for (int d = 0; d < dim; d++) X[a * dim + d] = coords[conn[c * nv + a] * dim + d];
+        for (int q = 0; q < nq; q++) {
+            double *f = flux + (c * nq + q) * dim;
+            for (int d = 0; d < dim; d++) f[d] = 0.0;
+            orc_shape(ct, pts + q * dim, N, dN);
+            map_qp(nv, dim, X, dN, G);
+            eval_D(kind, data, cmchi, dim, nv, c, N, D);
+            for (int i = 0; i < nv; i++) {
+                double ui = phi[celldofs[c * nv + i]];
+                for (int r = 0; r < dim; r++) {
+                    double s = 0;
+                    for (int k = 0; k < dim; k++) s += D[r * dim + k] * G[i * dim + k];
+                    f[r] += s * ui;
+                }
+            }
+        }
+    }
+    for (int e = 0; e < ne; e++) {
+        const double *xe = electrodes + e * dim;
+        double phie = 0.0;
+        for (int64_t c = 0; c < ncells; c++) {
+            for (int a = 0; a < nv; a++)
+                for (int d = 0; d < dim; d++) X[a * dim + d] = coords[conn[c * nv + a] * dim + d];
+            double local = 0.0;
+            for (int q = 0; q < nq; q++) {
+                orc_shape(ct, pts + q * dim, N, dN);
+                double dO = map_qp(nv, dim, X, dN, NULL) * w[q];
+                double dvec[3], n2 = 0, fd = 0;
+                const double *f = flux + (c * nq + q) * dim;
+                for (int d = 0; d < dim; d++) {
+                    double xq = 0;
+                    for (int a = 0; a < nv; a++) xq += N[a] * X[a * dim + d];
+                    dvec[d] = xq - xe[d];
+                }
+                for (int d = 0; d < dim; d++) { n2 += dvec[d] * dvec[d]; fd += f[d] * dvec[d]; }
+                double n = sqrt(n2);
+                local += fd / (n * n * n) * dO;
+            }
+            phie += local;
+        }
+        out[e] = -phie / (4 * M_PI * kappa_t);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * SpMV  y = A x  (src/utils.jl:210-231): threads over rows, sequential left-to-right row sum.
  * ---------------------------------------------------------------------------------------- */
 void orc_spmv(int64_t n, const int64_t *rowptr, const int64_t *colidx, const double *vals, const double *x, double *y) {

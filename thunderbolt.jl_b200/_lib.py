@@ -124,6 +124,8 @@ _SIGNATURES = {
     "tb_assembly_set_scratch_budget": [_vp, C.c_int64],
     "tb_assembly_release_scratch": [_vp],
     "tb_cg_solve": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
+    "tb_ecg_plonsey": [_vp, _vp, C.c_int32, C.c_int32, _f64p, C.c_int64, C.c_double, _vp, C.c_int32, _f64p, C.c_int32, C.c_double,
+                       _f64p],
     "tb_cg_solve_pc": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
     "tb_monodomain_set_preconditioner": [_vp, C.c_int32],
     "tb_cg_set_persistent": [_vp, C.c_int32],

@@ -524,6 +524,44 @@ def setup_operator(strategy, integrator, solver, dh: DeviceMesh, pattern_of: B20
     return BilinearOperator(integrator, dh, A)
 
 
+# ---------------------------------------------------------------------------------------------
+# ECG post-processing
+# ---------------------------------------------------------------------------------------------
+class Plonsey1964ECGGaussCache:
+    """src/modeling/electrophysiology/ecg.jl:55-75: built on the diffusion operator `op` (its integrator's D and
+    quadrature rule, its dof handler) and a transmembrane potential vector.  The reference stores kappa*grad(phi) at
+    every quadrature point between update_ecg! and evaluate_ecg; here the cache keeps a device copy of phi and the
+    flux is formed in registers inside the one element sweep evaluate_ecg launches (tb_ecg_plonsey)."""
+
+    def __init__(self, op: "BilinearOperator", φₘ):
+        if not isinstance(op.integrator, BilinearDiffusionIntegrator):
+            raise TypeError("Plonsey1964ECGGaussCache needs the diffusion operator")
+        self.op = op
+        self.φₘ = B200Vector(op.dh.dev, op.dh.ndofs, 1)
+        update_ecg_(self, φₘ)
+
+
+def update_ecg_(cache: Plonsey1964ECGGaussCache, φₘ, col: int = 0):
+    """update_ecg!(cache, φₘ), ecg.jl:150-158.  φₘ: host array of ndofs values, or a B200Vector (state column `col`)."""
+    if isinstance(φₘ, B200Vector):
+        cache.φₘ.copy_from(φₘ, scol=col, dcol=0)
+    else:
+        φ = np.ascontiguousarray(φₘ, dtype=np.float64).ravel()
+        if φ.size != cache.op.dh.ndofs:
+            raise ValueError("φₘ must have one value per dof")
+        cache.φₘ.upload(φ)
+
+
+def evaluate_ecg(cache: Plonsey1964ECGGaussCache, x, κₜ: float):
+    """evaluate_ecg(cache, x, κₜ), ecg.jl:86-148: x one point (returns a float) or a sequence of points (an array)."""
+    dh = cache.op.dh
+    kind, data, cmchi = _diffusion_data(cache.op.integrator.D, dh)
+    pts = np.asarray(x, dtype=np.float64)
+    single = pts.ndim == 1
+    out = core.ecg_plonsey(dh.dev, dh, cache.op.integrator.qrc.order, kind, data, cache.φₘ, np.atleast_2d(pts), κₜ, cmchi)
+    return float(out[0]) if single else out
+
+
 def needs_update(op, t) -> bool:
     """src/discretization/operator.jl:2-32: closed intervals."""
     if isinstance(op, LinearNullOperator):

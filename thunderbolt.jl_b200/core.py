@@ -363,6 +363,18 @@ def assemble_source_qp(dev, mesh, b: B200Vector, qorder, fq, col=0):
     L.call("tb_assemble_source_qp", dev.h, mesh.h, int(qorder), fq, b.h, int(col))
 
 
+def ecg_plonsey(dev, mesh, qorder, kind, data, phi: B200Vector, electrodes, kappa_t, cm_chi=1.0, phicol=0):
+    """update_ecg! + evaluate_ecg of Plonsey1964ECGGaussCache for all electrodes in one element sweep (ecg.jl:55-160)."""
+    data = np.ascontiguousarray(np.atleast_1d(np.asarray(data, dtype=np.float64)).ravel())
+    el = np.ascontiguousarray(np.atleast_2d(np.asarray(electrodes, dtype=np.float64)))
+    if el.shape[1] != mesh.dim:
+        raise ValueError(f"electrodes must have {mesh.dim} coordinates each")
+    out = np.empty(el.shape[0])
+    L.call("tb_ecg_plonsey", dev.h, mesh.h, int(qorder), int(kind), data, data.size, float(cm_chi), phi.h, int(phicol),
+           el.reshape(-1), el.shape[0], float(kappa_t), out)
+    return out
+
+
 def cg_solve(dev, A: B200CSRMatrix, b: B200Vector, x: B200Vector, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, bcol=0,
              xcol=0, precond=L.PRECOND_NONE):
     it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()
