@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -227,20 +227,29 @@ def run_b200(args):
     # ---- e2e: same steps through the host-buffer entry point: the state lives in PINNED HOST memory between steps; every
     # step uploads the whole state and downloads the whole result (tb_monodomain_run_host pipelines the copies) ----
     e2e = None
-    if world == 1:
+    if args.e2e_steps > 0:
         hin = torch.empty(ns * n_local, dtype=torch.float64, pin_memory=True)
         hout = torch.empty(ns * n_local, dtype=torch.float64, pin_memory=True)
         hin.numpy()[:] = u.to_host()
         ke = max(1, min(args.steps, args.e2e_steps))
         st.run_host(u, hin.numpy(), hout.numpy(), t, dt, 1)          # warm-up (creates the copy streams)
-        dev.sync()
+        barrier()
         t0 = time.perf_counter()
         st.run_host(u, hout.numpy(), hin.numpy(), t + dt, dt, ke)
         dev.sync()
         te = time.perf_counter() - t0
+        if world > 1:                                                 # max over ranks, like the device-timed value
+            tt = torch.tensor([te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
+            nb = torch.tensor([float(ns * n_local * 8)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+            bytes_step = int(nb.item())
+        else:
+            bytes_step = ns * n_local * 8
         t += (ke + 1) * dt
-        e2e = {"value": N_global * ke / te, "unit": "DoF*steps/s", "h2d_bytes_per_step": ns * n_local * 8,
-               "d2h_bytes_per_step": ns * n_local * 8, "steps": ke, "ms_per_step": te / ke * 1e3,
+        e2e = {"value": N_global * ke / te, "unit": "DoF*steps/s", "h2d_bytes_per_step": bytes_step,
+               "d2h_bytes_per_step": bytes_step, "steps": ke, "ms_per_step": te / ke * 1e3,
                "api": "tb_monodomain_run_host (C ABI): state in pinned host buffers between steps, full state H2D + D2H every "
                       "step, copies pipelined on two copy streams (phi download/upload full duplex in chunks, other columns under CG)"}
 
