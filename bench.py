@@ -187,7 +187,8 @@ def run_b200(args):
     launches = dev.launch_count() - launches0
     spmv_ms, spmv_n = dev.profile_get()
     dev.profile_enable(False)
-    persistent = dev.cg_last_path_persistent()
+    cg_path = dev.cg_last_path()
+    persistent = cg_path != 0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -206,12 +207,13 @@ def run_b200(args):
     step_bytes = (2 * ns * 8 + bytes_per_row(nnz, rows_local) * (1 + k_mean) + 72.0 * k_mean) * rows_local
     # bytes the kernel really streams: stored values + the (losslessly compressed) column stream + x, y, p
     stored, col_bytes, max_w = M.storage()
-    stored_bytes = stored * 8.0 + col_bytes + (16.0 if persistent else 24.0) * rows_local
+    stored_bytes = stored * 8.0 + col_bytes + ({0: 24.0, 1: 16.0, 2: 24.0 + 72.0}[cg_path]) * rows_local
     traffic = None
     tfile = ROOT / "profiles" / "traffic.json"
     if tfile.exists() and world == 1 and not args.grid:
         traffic = json.loads(tfile.read_text()).get(args.workload, {}).get("spmv_dram_bytes_per_launch")
-    kname = ("k_cg_persistent (whole CG solve in one cooperative kernel; unit = one iteration: SpMV + x,r,p updates + 3 grid barriers)"
+    kname = (("k_cg_persistent" if cg_path == 1 else "k_cg_persistent_tma") +
+             " (whole CG solve in one cooperative kernel; unit = one iteration: SpMV + x,r,p updates + 3 grid barriers)"
              if persistent else "k_cg_spmv_tma<1,false,true> (SELL-32 SpMV, TMA-staged, fused p.Ap)")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

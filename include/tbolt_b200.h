@@ -247,11 +247,16 @@ int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol,
 int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol, int32_t precond,
                        double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm, int32_t *converged);
 
-/* Operators with at most 148*16*32*4 rows are solved by ONE persistent cooperative kernel per solve (state in
- * registers, grid-wide barriers instead of kernel boundaries); same recurrence, same stopping rule.  On by default
- * on a single GPU; tb_cg_last_path tells which path the last solve took. */
-int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t on);
-int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *persistent);
+/* Single-GPU solves of small and mid-size operators run as ONE persistent cooperative kernel per solve (grid-wide
+ * barriers instead of kernel boundaries; same recurrence, same stopping rule):
+ *   path 1: <= 148*16*32*4 rows -- x, r, p, Ap of a lane's rows live in registers for the whole solve;
+ *   path 2: <= 4 M rows (env TB_CG_PERSISTENT_MAX_ROWS) -- vectors stay in L2-resident global memory, the SpMV is the
+ *           TMA-staged sweep of the large-operator path;
+ *   path 0: everything else (and every multi-GPU solve): three kernels per iteration, scalars polled by the host.
+ * mode 0 = never, 1 = auto (default), 2 = path 2 whenever it is eligible (lets the tests reach it on tiny systems).
+ * tb_cg_last_path reports the path of the last solve. */
+int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t mode);
+int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *path);
 
 /* ---- cell sweep -------------------------------------------------------------------------------
  * _pointwise_step_outer_kernel! (src/solver/time/partitioned_solver.jl:38-52; the method

@@ -14,13 +14,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["persistent", "multikernel"], autouse=True)
+@pytest.fixture(params=["persistent", "persistent_tma", "multikernel"], autouse=True)
 def cg_path(request, dev):
-    """Every test of this module runs with both CG execution models: the one-launch cooperative kernel that small
-    operators get by default (tb_cg_small.cu) and the three-kernels-per-iteration path large ones take (tb_cg.cu)."""
-    dev.cg_set_persistent(request.param == "persistent")
+    """Every test of this module runs with all three CG execution models: the one-launch cooperative kernels that small
+    (register-resident) and mid-size (TMA sweep) operators get by default (tb_cg_small.cu) and the
+    three-kernels-per-iteration path large and multi-GPU ones take (tb_cg.cu)."""
+    dev.cg_set_persistent({"persistent": 1, "persistent_tma": 2, "multikernel": 0}[request.param])
     yield request.param
-    dev.cg_set_persistent(True)
+    dev.cg_set_persistent(1)
 GOLD = Path(__file__).resolve().parent / "golden"
 
 

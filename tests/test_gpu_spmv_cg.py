@@ -5,13 +5,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["persistent", "multikernel"], autouse=True)
+@pytest.fixture(params=["persistent", "persistent_tma", "multikernel"], autouse=True)
 def cg_path(request, dev):
-    """Every test of this module runs with both CG execution models: the one-launch cooperative kernel that small
-    operators get by default (tb_cg_small.cu) and the three-kernels-per-iteration path large ones take (tb_cg.cu)."""
-    dev.cg_set_persistent(request.param == "persistent")
+    """Every test of this module runs with all three CG execution models: the one-launch cooperative kernels that small
+    (register-resident) and mid-size (TMA sweep) operators get by default (tb_cg_small.cu) and the
+    three-kernels-per-iteration path large and multi-GPU ones take (tb_cg.cu)."""
+    dev.cg_set_persistent({"persistent": 1, "persistent_tma": 2, "multikernel": 0}[request.param])
     yield request.param
-    dev.cg_set_persistent(True)
+    dev.cg_set_persistent(1)
 
 
 def _system(tb, dev, O, ct, nel, dt, kappa):
@@ -113,7 +114,7 @@ def test_cg_path_selection(tb, dev, cg_path):
         b = tb.B200Vector.from_host(dev, np.sin(7 * x[:, 0]) * np.cos(5 * x[:, 1]))
         xs = tb.B200Vector(dev, md.ndofs)
         it, rn, conv = tb.core.cg_solve(dev, A, b, xs)
-        path = dev.cg_last_path_persistent()
+        path = dev.cg_last_path()
         y = tb.B200Vector(dev, md.ndofs)
         A.mul(y, xs)
         res = np.linalg.norm(y.to_host() - b.to_host()) / np.linalg.norm(b.to_host())
@@ -121,9 +122,9 @@ def test_cg_path_selection(tb, dev, cg_path):
             h.free()
         return it, conv, path, res
     it, conv, path, res = solve((200, 150))
-    assert conv and path == (cg_path == "persistent") and res < 1e-7
-    it2, conv2, path2, res2 = solve((900, 900))        # 811 801 rows: beyond the register-resident limit
-    assert conv2 and path2 is False and res2 < 1e-7
+    assert conv and path == {"persistent": 1, "persistent_tma": 2, "multikernel": 0}[cg_path] and res < 1e-7
+    it2, conv2, path2, res2 = solve((900, 900))        # 811 801 rows: beyond the register-resident limit -> TMA kernel
+    assert conv2 and path2 == (0 if cg_path == "multikernel" else 2) and res2 < 1e-7
 
 
 @pytest.mark.parametrize("ct,nel,dt", [(0, (40, 40), 1.0), (1, (12, 10, 8), 0.5), (3, (6, 6, 6), 0.5)])
@@ -139,7 +140,7 @@ def test_jacobi_pcg_matches_oracle(tb, dev, oracle, ct, nel, dt, cg_path):
     for atol, rtol in ((O.SQRT_EPS, O.SQRT_EPS), (1e-12, 1e-12)):
         xo, ito, rno, convo = O.pcg_jacobi(rp, ci, Ao, b, atol, rtol)
         it, rn, conv = tb.core.cg_solve(dev, A, bd, xd, atol, rtol, precond=tb._lib.PRECOND_JACOBI)
-        assert dev.cg_last_path_persistent() == (cg_path == "persistent")
+        assert dev.cg_last_path() == {"persistent": 1, "persistent_tma": 2, "multikernel": 0}[cg_path]
         assert conv == convo and abs(it - ito) <= 1, (it, ito)
         if it == ito:
             assert rn == pytest.approx(rno, rel=1e-6)

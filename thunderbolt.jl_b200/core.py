@@ -63,14 +63,19 @@ class B200Device:
         return ms.value, n.value
 
     # ---- CG execution model ----
-    def cg_set_persistent(self, on: bool):
-        """small operators: whole CG solve in one cooperative kernel (default on, single GPU)"""
-        L.call("tb_cg_set_persistent", self.h, int(bool(on)))
+    def cg_set_persistent(self, mode):
+        """whole CG solve in one cooperative kernel: 0/False never, 1/True auto (default), 2 the TMA-staged variant
+        whenever eligible (single GPU only)"""
+        L.call("tb_cg_set_persistent", self.h, int(mode))
 
-    def cg_last_path_persistent(self) -> bool:
+    def cg_last_path(self) -> int:
+        """0 multi-kernel, 1 persistent with register-resident vectors, 2 persistent with the TMA sweep"""
         v = C.c_int32()
         L.call("tb_cg_last_path", self.h, C.byref(v))
-        return bool(v.value)
+        return v.value
+
+    def cg_last_path_persistent(self) -> bool:
+        return self.cg_last_path() != 0
 
     # ---- assembly strategy ---------------------------------------------------------------------------
     def assembly_set_mode(self, mode: int):

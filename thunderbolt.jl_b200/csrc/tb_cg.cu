@@ -367,8 +367,10 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const int64_t n = pat->nrows;
     const double *dinv = nullptr;
     if (precond == TB_PRECOND_JACOBI) TB_TRY(cg_build_dinv(ctx, A, &dinv));
-    if (const int pgrid = tb_cg_persistent_grid(ctx, pat))     // small operator: one persistent cooperative kernel
-        return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
+    int pgrid = 0;
+    const int pkind = tb_cg_persistent_kind(ctx, pat, &pgrid);   // small / mid-size operator: one persistent cooperative kernel
+    if (pkind == 1) return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
+    if (pkind == 2) return tb_cg_run_persistent_tma(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
     ctx->last_cg_persistent = 0;
     TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;

@@ -207,6 +207,223 @@ __global__ void k_pcg_set_tol(CGState *st, double atol, double rtol, long long i
     st->iter = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Mid-size operators (C2: 549 k rows): same idea, different residency.  The rows no longer fit the registers of one
+// wave of lanes, so x, r, p, Ap stay in global memory -- they are L2-resident at these sizes (4 vectors of 4.4 MB) --
+// and the SpMV is the bulk-async (TMA + mbarrier) sweep of tb_spmv.cuh, which is what makes the large-operator path
+// fast.  What is saved is everything BETWEEN the phases: three launches, three last-block reductions and their
+// scalar round trips per iteration (measured on C2: 36 + 13 + 6.5 us of kernels plus gaps = 61 us per iteration).
+// ---------------------------------------------------------------------------------------------------------------
+struct PcgTmaArgs {
+    const int64_t *slice_ptr;
+    const int *cstream;        // compressed column stream (CC) or SELL column ids
+    const int64_t *cptr;
+    unsigned val_bytes, col_bytes;
+};
+
+__device__ __forceinline__ double pcg_allsum_t(double v, double *partials, double *sm, cgp::grid_group &grid) {
+    const double bs = tb_block_sum(v, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    grid.sync();
+    double s = 0.0;
+    if (threadIdx.x < 32) {
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) s += ((volatile double *)partials)[i];
+        s = tb_warp_sum(s);
+        if (threadIdx.x == 0) sm[32] = s;
+    }
+    __syncthreads();
+    const double out = sm[32];
+    __syncthreads();
+    return out;
+}
+
+template <bool FROM_B, bool CC>
+__global__ void __launch_bounds__(1024, 1)
+    k_cg_persistent_tma(const PcgTmaArgs P, const double *__restrict__ Aval, const double *__restrict__ Mval,
+                        const double *__restrict__ src, const double *__restrict__ bS, double *__restrict__ x,
+                        double *__restrict__ r, double *__restrict__ p, double *__restrict__ Ap, int64_t nrows,
+                        int64_t nslices, CGState *st, double *partials, const double *__restrict__ dinv) {
+    cgp::grid_group grid = cgp::this_grid();
+    extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
+    __shared__ double sm[34];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    tb_tma_ring ring;
+    double acc = 0.0;
+    if (FROM_B) {
+        for (int64_t i = tid; i < nrows; i += nth) {
+            const double v = src[i];
+            const double z = dinv ? dinv[i] * v : v;
+            x[i] = 0.0;
+            r[i] = v;
+            p[i] = z;
+            acc += v * z;
+        }
+    } else {
+        tb_sell_sweep_tma<1, CC>(P.slice_ptr, Mval, P.cstream, P.cptr, src, nslices, P.val_bytes, P.col_bytes, tb_dyn_smem,
+                                 [&](int64_t row, double v) {
+                                     if (row < nrows) {
+                                         if (bS) v += bS[row];
+                                         const double z = dinv ? dinv[row] * v : v;
+                                         x[row] = 0.0;
+                                         r[row] = v;
+                                         p[row] = z;
+                                         acc += v * z;
+                                     }
+                                 }, &ring);
+    }
+    double gamma = pcg_allsum_t(acc, partials, sm, grid);          // also publishes p grid-wide
+    double rn = sqrt(gamma);
+    const double eps = st->atol + st->rtol * rn;
+    const long long itmax = st->itmax;
+    bool solved = rn <= eps;
+    long long iter = 0;
+    const int64_t n2 = nrows >> 1;
+    while (!solved && iter < itmax) {
+        acc = 0.0;
+        tb_sell_sweep_tma<1, CC>(P.slice_ptr, Aval, P.cstream, P.cptr, p, nslices, P.val_bytes, P.col_bytes, tb_dyn_smem,
+                                 [&](int64_t row, double v) {
+                                     if (row < nrows) {
+                                         Ap[row] = v;
+                                         acc += p[row] * v;
+                                     }
+                                 }, &ring);
+        const double pAp = pcg_allsum_t(acc, partials + gridDim.x, sm, grid);
+        const double alpha = gamma / pAp;
+        acc = 0.0;
+        for (int64_t i = tid; i < n2; i += nth) {
+            double2 xv = reinterpret_cast<double2 *>(x)[i], rv = reinterpret_cast<double2 *>(r)[i];
+            const double2 pv = reinterpret_cast<const double2 *>(p)[i], av = reinterpret_cast<const double2 *>(Ap)[i];
+            xv.x += alpha * pv.x;
+            xv.y += alpha * pv.y;
+            rv.x -= alpha * av.x;
+            rv.y -= alpha * av.y;
+            reinterpret_cast<double2 *>(x)[i] = xv;
+            reinterpret_cast<double2 *>(r)[i] = rv;
+            if (dinv) {
+                const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+                acc += rv.x * (dv.x * rv.x);
+                acc += rv.y * (dv.y * rv.y);
+            } else {
+                acc += rv.x * rv.x;
+                acc += rv.y * rv.y;
+            }
+        }
+        if ((nrows & 1) && tid == 0) {
+            const int64_t i = nrows - 1;
+            const double xn = x[i] + alpha * p[i], rr = r[i] - alpha * Ap[i];
+            x[i] = xn;
+            r[i] = rr;
+            acc += dinv ? rr * (dinv[i] * rr) : rr * rr;
+        }
+        const double gnext = pcg_allsum_t(acc, partials + 2 * gridDim.x, sm, grid);
+        rn = sqrt(gnext);
+        solved = rn <= eps;
+        iter++;
+        if (rn != rn) iter = itmax;
+        if (!solved && iter < itmax) {
+            const double beta = gnext / gamma;
+            gamma = gnext;
+            for (int64_t i = tid; i < n2; i += nth) {
+                double2 rv = reinterpret_cast<const double2 *>(r)[i];
+                if (dinv) {
+                    const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+                    rv.x = dv.x * rv.x;
+                    rv.y = dv.y * rv.y;
+                }
+                double2 pv = reinterpret_cast<double2 *>(p)[i];
+                pv.x = rv.x + beta * pv.x;
+                pv.y = rv.y + beta * pv.y;
+                reinterpret_cast<double2 *>(p)[i] = pv;
+            }
+            if ((nrows & 1) && tid == 0) p[nrows - 1] = (dinv ? dinv[nrows - 1] * r[nrows - 1] : r[nrows - 1]) + beta * p[nrows - 1];
+            grid.sync();
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->gamma = gamma;
+        st->rnorm = rn;
+        st->eps = eps;
+        st->iter = iter;
+        st->solved = solved;
+        st->done = 1;
+    }
+}
+
+template <bool FROM_B, bool CC>
+static int32_t launch_pcg_tma(tb_ctx *ctx, int grid, int threads, size_t smem, const PcgTmaArgs &P, const double *Aval,
+                              const double *Mval, const double *src, const double *bS, double *x, double *r, double *p, double *Ap,
+                              int64_t nrows, int64_t nslices, const double *dinv) {
+    static size_t configured = 0;
+    if (configured < smem) {
+        TB_CUDA(cudaFuncSetAttribute(k_cg_persistent_tma<FROM_B, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    CGState *st = ctx->d_cg;
+    double *partials = ctx->d_partials;
+    void *args[] = {(void *)&P, (void *)&Aval, (void *)&Mval, (void *)&src, (void *)&bS, (void *)&x, (void *)&r, (void *)&p,
+                    (void *)&Ap, (void *)&nrows, (void *)&nslices, (void *)&st, (void *)&partials, (void *)&dinv};
+    TB_CUDA(cudaLaunchCooperativeKernel((void *)k_cg_persistent_tma<FROM_B, CC>, dim3(grid), dim3(threads), args, smem, ctx->stream));
+    ctx->launches++;
+    return TB_OK;
+}
+
+// 0: not eligible; 1: register-resident kernel; 2: TMA-staged kernel with vectors in global memory
+int tb_cg_persistent_kind(tb_ctx *ctx, const tb_pattern *pat, int *grid_out) {
+    *grid_out = 0;
+    if (ctx->cg_persistent != 2)
+        if (const int g = tb_cg_persistent_grid(ctx, pat)) {
+            *grid_out = g;
+            return 1;
+        }
+    if (!ctx->cg_persistent || (ctx->has_comm && ctx->nranks > 1)) return 0;
+    if (!(ctx->spmv_variant > 0 && pat->max_width > 0 && pat->max_width <= TB_TMA_WCAP)) return 0;
+    if (pat->nrows > ctx->cg_persistent_max_rows) return 0;     // large operators: launch overhead is < 2 %, keep host-side polling
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (!coop || 3 * ctx->sm_count > 4 * TB_MAX_PARTIALS) return 0;
+    *grid_out = ctx->sm_count;
+    return 2;
+}
+
+int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
+                                 const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
+                                 double *rnorm, int32_t *converged, const double *dinv) {
+    const tb_pattern *pat = A->pat;
+    TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
+    double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
+    const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width, cc ? pat->max_ccol_ints : 32 * pat->max_width, 1, 0);
+    PcgTmaArgs P{pat->d_slice_ptr, cc ? pat->d_ccol : pat->d_col, pat->d_cptr, g.val_bytes, g.col_bytes};
+    const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
+    if (need < grid) grid = (int)(need < 1 ? 1 : need);
+    TB_LAUNCH(ctx, k_pcg_set_tol, 1, 1, 0, ctx->d_cg, atol, rtol, (long long)itmax);
+    if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[0], ctx->stream));
+    const double *src = b ? b : phi;
+    const double *Mval = b ? nullptr : M->d_val;
+    int32_t st;
+    if (b) st = cc ? launch_pcg_tma<true, true>(ctx, grid, g.warps * 32, g.smem, P, A->d_val, Mval, src, bS, x, r, p, Ap, pat->nrows, pat->nslices, dinv)
+                   : launch_pcg_tma<true, false>(ctx, grid, g.warps * 32, g.smem, P, A->d_val, Mval, src, bS, x, r, p, Ap, pat->nrows, pat->nslices, dinv);
+    else st = cc ? launch_pcg_tma<false, true>(ctx, grid, g.warps * 32, g.smem, P, A->d_val, Mval, src, bS, x, r, p, Ap, pat->nrows, pat->nslices, dinv)
+                 : launch_pcg_tma<false, false>(ctx, grid, g.warps * 32, g.smem, P, A->d_val, Mval, src, bS, x, r, p, Ap, pat->nrows, pat->nslices, dinv);
+    if (st != TB_OK) return st;
+    if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[1], ctx->stream));
+    CGState *h = ctx->h_cg;
+    TB_CUDA(cudaMemcpyAsync(h, ctx->d_cg, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->last_cg_iters = h->iter;
+    ctx->last_cg_persistent = 2;
+    if (ctx->profile && h->iter > 0) {
+        float ms = 0.f;
+        TB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[1]));
+        ctx->prof_spmv_ms += ms;
+        ctx->prof_spmv_n += h->iter;
+    }
+    if (iters) *iters = h->iter;
+    if (rnorm) *rnorm = h->rnorm;
+    if (converged) *converged = h->solved;
+    return TB_OK;
+}
+
 // Is the persistent path usable for this operator on this context?  Returns the grid size, or 0.
 int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat) {
     if (!ctx->cg_persistent || (ctx->has_comm && ctx->nranks > 1)) return 0;
@@ -265,9 +482,10 @@ int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const doubl
     return TB_OK;
 }
 
-extern "C" int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t on) {
+extern "C" int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t mode) {
     TB_REQUIRE(ctx, "tb_cg_set_persistent: ctx is NULL");
-    ctx->cg_persistent = on != 0;
+    TB_REQUIRE(mode >= 0 && mode <= 2, "tb_cg_set_persistent: mode must be 0 (off), 1 (auto) or 2 (TMA kernel whenever eligible)");
+    ctx->cg_persistent = mode;
     return TB_OK;
 }
 

@@ -61,7 +61,8 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));
     if (const char *v = getenv("TB_SPMV_VARIANT")) ctx->spmv_variant = atoi(v);
     if (const char *v = getenv("TB_SPMV_COMPRESS")) ctx->spmv_compress = atoi(v);
-    if (const char *v = getenv("TB_CG_PERSISTENT")) ctx->cg_persistent = atoi(v) != 0;
+    if (const char *v = getenv("TB_CG_PERSISTENT")) ctx->cg_persistent = atoi(v) < 0 ? 0 : atoi(v) > 2 ? 2 : atoi(v);
+    if (const char *v = getenv("TB_CG_PERSISTENT_MAX_ROWS")) ctx->cg_persistent_max_rows = atoll(v);
     if (const char *v = getenv("TB_ASSEMBLY_MODE")) ctx->assembly_mode = atoi(v) == 0 ? 0 : 2;
     if (const char *v = getenv("TB_EA_BUDGET_MB")) ctx->ea_budget_bytes = (size_t)(atof(v) * 1048576.0);
     *out = ctx;

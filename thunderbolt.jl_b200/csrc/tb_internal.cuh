@@ -148,8 +148,9 @@ struct tb_ctx {
     int spmv_variant = 1;             // 0: LDG kernel, 1..: bulk-async (TMA) staged kernel configurations (env TB_SPMV_VARIANT)
     int spmv_compress = 1;            // use the compressed column stream in the staged kernels (env TB_SPMV_COMPRESS)
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
-    bool cg_persistent = true;        // small operators: whole solve in one cooperative kernel (tb_cg_small.cu; env TB_CG_PERSISTENT)
-    int last_cg_persistent = 0;       // did the last solve take that path
+    int cg_persistent = 1;            // 0: never; 1: auto (small: register-resident kernel, mid-size: TMA kernel); 2: TMA kernel whenever eligible (tests); env TB_CG_PERSISTENT
+    int last_cg_persistent = 0;       // path of the last solve: 0 multi-kernel, 1 persistent (registers), 2 persistent (TMA sweep, vectors in L2)
+    int64_t cg_persistent_max_rows = 4000000;   // above this the multi-kernel path is used (env TB_CG_PERSISTENT_MAX_ROWS)
     // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
     bool profile = false;
     cudaEvent_t prof_ev[2 * TB_PROF_MAX] = {};
@@ -403,6 +404,10 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                        int32_t *converged, int precond = 0);
 int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat);
+int tb_cg_persistent_kind(tb_ctx *ctx, const tb_pattern *pat, int *grid_out);
+int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
+                                 const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
+                                 double *rnorm, int32_t *converged, const double *dinv);
 int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,
                              const double *bS, double *x, double atol, double rtol, int64_t itmax, int64_t *iters,
                              double *rnorm, int32_t *converged, const double *dinv);

@@ -103,21 +103,33 @@ static inline tb_tma_geom tb_tma_geometry(int max_width, int col_ints, int stage
 // finished row sum (rows >= nrows included: the caller masks).
 // CC = false: cstream = SELL column ids, cptr unused.  CC = true: cstream/cptr = compressed column stream.
 // Dynamic shared memory: nwarps*STAGES*(val_bytes+col_bytes) + nwarps*STAGES*8 bytes.
+// Ring state of one warp, carried across several sweeps of ONE kernel (persistent CG): the mbarriers are initialised
+// once (re-initialising a live mbarrier is undefined) and the phase parity simply keeps counting.
+struct tb_tma_ring {
+    int stage = 0;
+    unsigned parity = 0;
+    bool ready = false;
+};
+
 template <int STAGES, bool CC, class Epilogue>
 __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ slice_ptr, const double *__restrict__ val,
                                                   const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
                                                   const double *__restrict__ x, int64_t nslices, unsigned val_bytes,
-                                                  unsigned col_bytes, unsigned char *smem, Epilogue epi) {
+                                                  unsigned col_bytes, unsigned char *smem, Epilogue epi,
+                                                  tb_tma_ring *ring = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const size_t stage_bytes = (size_t)val_bytes + col_bytes;
     unsigned char *wbase = smem + (size_t)warp * STAGES * stage_bytes;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)nwarp * STAGES * stage_bytes) + warp * STAGES;
-    if (lane == 0) {
+    if (!ring || !ring->ready) {
+        if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; s++) tb_mbar_init(tb_smem_addr(bars + s), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int s = 0; s < STAGES; s++) tb_mbar_init(tb_smem_addr(bars + s), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (ring) ring->ready = true;
     }
-    __syncwarp();
 
     const int64_t gw = (int64_t)blockIdx.x * nwarp + warp, nw = (int64_t)gridDim.x * nwarp;
 
@@ -143,18 +155,21 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         }
     };
 
+    // a sweep always leaves every stage consumed, so the next one (same kernel, `ring`) starts filling at ring->stage
+    int stage = ring ? ring->stage : 0;
+    unsigned parity = ring ? ring->parity : 0;
     int64_t s_issue = gw;
     if (lane == 0) {
+        int st = stage;
 #pragma unroll
-        for (int st = 0; st < STAGES; st++) {
+        for (int k = 0; k < STAGES; k++) {
             if (s_issue < nslices) issue(st, s_issue);
             s_issue += nw;
+            if (++st == STAGES) st = 0;
         }
     }
     s_issue = gw + (int64_t)STAGES * nw;   // same value in every lane
 
-    int stage = 0;
-    unsigned parity = 0;
     for (int64_t s = gw; s < nslices; s += nw) {
         const int w = (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 5);
         const int row = (int)(s * TB_SLICE) + lane;
@@ -223,5 +238,9 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             stage = 0;
             parity ^= 1u;
         }
+    }
+    if (ring) {
+        ring->stage = stage;
+        ring->parity = parity;
     }
 }
