@@ -91,6 +91,33 @@ def c1_full():
     np.savez_compressed(HERE / "c1_full.npz", **out)
 
 
+def c2_full():
+    """config 2 at FULL size (128x128x32 hexes, h = 0.25, PCG2019, dt = 0.01; conduction-velocity-benchmark.jl:29-53) with
+    the corner stimulus, 40 steps of the adaptive substepper: phi_m sampled at every 61st dof after step 1 and step 40, all
+    CG iteration counts, and the number of dofs above -40 mV (the stimulated corner)."""
+    m = O.generate_grid(O.HEX8, (128, 128, 32), (0, 0, 0), (32.0, 32.0, 8.0))
+    k1 = 0.17 * 0.62 / (0.17 + 0.62)
+    kr = 0.019 * 0.24 / (0.019 + 0.24)
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag([k1, kr, kr]))
+    N = m.ndofs
+    u = np.repeat(O.default_initial_state(O.PCG2019), N)
+    orc = O.MonodomainOracle(m, O.PCG2019, O.default_params(O.PCG2019), M, K, substeps=10, threaded_blas1=False)
+    out, t, dt = {}, 0.0, 0.01
+    for step in range(40):
+        orc.bS = O.assemble_source(m, 2, O.SRC_BOX, [1.5, 2.0, 0.5], t + dt)
+        it, rn, conv = orc.step(u, t, dt)
+        assert conv
+        t += dt
+        if step == 0:
+            out["phi1"] = u[:N:61].copy()
+    out["phi40"] = u[:N:61].copy()
+    out["h40"] = u[N:2 * N:61].copy()
+    out["iters"] = np.array(orc.iters, dtype=np.int16)
+    out["n_above"] = np.array([(u[:N] > -84.0).sum()])
+    np.savez_compressed(HERE / "c2_full.npz", **out)
+
+
 def c2_small():
     """config 2 (conduction-velocity-benchmark.jl) on 16x16x4 hexes, h = 0.25: PCG2019, corner stimulus."""
     m = O.generate_grid(O.HEX8, (16, 16, 4), (0, 0, 0), (4.0, 4.0, 1.0))
@@ -121,6 +148,11 @@ def c2_small():
         out[f"act_{name}"] = activation_steps(np.array(hist), 0.0)
     np.savez_compressed(HERE / "c2_small.npz", **out)
 
+
+if __name__ == "__main__" and "--c2-full" in sys.argv:
+    c2_full()
+    print("wrote", HERE / "c2_full.npz")
+    sys.exit(0)
 
 if __name__ == "__main__" and "--c1-full" in sys.argv:
     c1_full()
