@@ -189,3 +189,53 @@ def test_config4_jacobi_preconditioned_cg(tb, dev, oracle):
     assert np.abs(h[:N] - uo[:N]).max() / np.abs(uo[:N]).max() <= 1e-9
     assert np.abs(uo[:N] - up[:N]).max() / np.abs(up[:N]).max() <= 1e-9          # same solution as unpreconditioned CG
     assert np.mean(orc.iters) < 0.8 * np.mean(plain.iters)                       # and markedly fewer iterations
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nc,nr,nl", [(64, 2, 6), (96, 3, 8)])
+@pytest.mark.parametrize("cg_mode", [0, 1, 2])
+def test_lv_high_valence_apex_rows(tb, dev, oracle, nc, nr, nl, cg_mode):
+    """Ragged input: the apex vertices of the LV touch every wedge of their ring, so their rows have 2*nc + 3 entries
+    (131 and 195 here) while the mean row has 12.  One slice is far wider than the shared-memory stage of the bulk-async
+    SpMV: it must take the LDG row kernel inside the same sweep, the device pattern builder must cope with the row, and
+    the gather assembly must size its row image per width class -- all still bit exact / within the CG rule."""
+    O = oracle
+    lv, nodes, hexes, wedges, prm, tets = _lv(nc, nr, nl)
+    mo = O.Mesh(O.TET4, tets, nodes)
+    mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+    M = tb.B200CSRMatrix.from_mesh(dev, mesh)                                     # device builder, rows up to TB_MAXROW = 512
+    rp, ci = M.pattern()
+    rpo, cio = mo.pattern()
+    assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+    stored, colbytes, maxw = M.storage()
+    assert maxw == np.diff(rpo).max() == 2 * nc + 3
+    K, A = M.like(), M.like()
+    fsn = lv.odb25lt_fibres(prm, tets)
+    data = np.concatenate([[0.1334, 0.0176, 0.0176], np.ascontiguousarray(fsn).reshape(tets.shape[0], 4, 9).ravel()])
+    tb.core.assemble_mass(dev, mesh, M, 2, 1.0)
+    assert dev.assembly_info()["last_mode"] == 2
+    tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_SPECTRAL, data, 1.0)
+    Mo, Ko = O.assemble_mass(mo, 2), O.assemble_diffusion(mo, 2, O.D_SPECTRAL, data)
+    assert np.array_equal(M.nonzeros(), Mo) and np.array_equal(K.nonzeros(), Ko)   # gather assembly: bitwise, wide slice included
+    A.axpby_values(M, K, 0.01)
+    Ao = O.axpby_values(Mo, Ko, 0.01)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(mo.ndofs)
+    xv, yv = tb.B200Vector.from_host(dev, x), tb.B200Vector(dev, mo.ndofs)
+    A.mul(yv, xv)
+    assert np.array_equal(yv.to_host(), O.spmv(rpo, cio, Ao, x))                   # SpMV: bitwise
+    b = O.spmv(rpo, cio, Mo, x)
+    bv = tb.B200Vector.from_host(dev, b)
+    dev.cg_set_persistent(cg_mode)
+    try:
+        tight = (1e-15, 1e-14)
+        for precond, ocg in ((tb._lib.PRECOND_NONE, O.cg), (tb._lib.PRECOND_JACOBI, O.pcg_jacobi)):
+            xo, ito, rno, convo = ocg(rpo, cio, Ao, b, *tight)
+            it, rn, conv = tb.core.cg_solve(dev, A, bv, yv, *tight, precond=precond)
+            assert dev.cg_last_path() == cg_mode
+            assert conv and convo and abs(it - ito) <= 2
+            assert np.abs(yv.to_host() - xo).max() <= 1e-9 * np.abs(xo).max()
+    finally:
+        dev.cg_set_persistent(1)
+    for h in (M, K, A, xv, yv, bv, mesh):
+        h.free()

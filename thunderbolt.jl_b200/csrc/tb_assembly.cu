@@ -472,7 +472,8 @@ __device__ __forceinline__ void gather_load(GatherCell<NV> &g, unsigned p, const
 template <int NV>
 __global__ void __launch_bounds__(256)
     k_gather_rows(const int64_t *__restrict__ adjptr, const unsigned *__restrict__ adj, const int *__restrict__ celldofs,
-                  const double *__restrict__ EA, int64_t c0, SellView S, int64_t slice0, int64_t slice1, int maxw, int top_step) {
+                  const double *__restrict__ EA, int64_t c0, SellView S, int64_t slice0, int64_t slice1, int maxw, int top_step,
+                  int wlo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     double *acc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * maxw * TB_SLICE + lane;
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(256)
     for (int64_t s = slice0 + (int64_t)blockIdx.x * nwb + warp; s < slice1; s += (int64_t)gridDim.x * nwb) {
         const int64_t base = S.slice_ptr[s];
         const int w = (int)((S.slice_ptr[s + 1] - base) >> 5);
+        if (w <= wlo || w > maxw) continue;      // this launch handles slices with wlo < width <= maxw (warp-uniform)
         const int *gcol = S.col + base + lane;
         for (int j = 0; j < w; j++) {
             acc[j * TB_SLICE] = 0.0;
@@ -542,17 +544,40 @@ static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_ta
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_matrices<NV, DIM, OP>, AS_BLOCK, smem1);
     if (per_sm < 1) per_sm = 1;
-    const int maxw = pat->max_width < 1 ? 1 : pat->max_width;
-    const size_t per_warp = (size_t)maxw * TB_SLICE * (sizeof(double) + sizeof(int));
-    int warps = (int)((100 * 1024) / per_warp);
-    warps = warps > 8 ? 8 : warps < 1 ? 1 : warps;
-    const size_t smem2 = (size_t)warps * per_warp;
-    int top_step = 1;
-    while (top_step * 2 <= maxw) top_step *= 2;
-    TB_CUDA(cudaFuncSetAttribute(k_gather_rows<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    int per_sm2 = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_gather_rows<NV>, warps * 32, smem2);
-    if (per_sm2 < 1) per_sm2 = 1;
+    // Two width classes: the bulk of the slices (<= TB_TMA_WCAP entries per row) and the few wide ones a high-valence
+    // vertex produces (LV apex: 2*nc + 3).  Sizing the shared-memory row image for the widest slice would leave one
+    // warp per CTA for the whole mesh, so each class gets its own launch geometry.
+    struct GatherGeom {
+        int maxw, wlo, warps, top_step, per_sm;
+        size_t smem;
+    } gg[2];
+    int ngeom = 0;
+    auto make_geom = [&](int maxw, int wlo) -> int32_t {
+        GatherGeom &G = gg[ngeom++];
+        G.maxw = maxw < 1 ? 1 : maxw;
+        G.wlo = wlo;
+        const size_t per_warp = (size_t)G.maxw * TB_SLICE * (sizeof(double) + sizeof(int));
+        int warps = (int)((100 * 1024) / per_warp);
+        G.warps = warps > 8 ? 8 : warps < 1 ? 1 : warps;
+        G.smem = (size_t)G.warps * per_warp;
+        G.top_step = 1;
+        while (G.top_step * 2 <= G.maxw) G.top_step *= 2;
+        G.per_sm = 1;
+        return TB_OK;
+    };
+    if (pat->n_wide > 0 && pat->max_width_tma > 0) {
+        make_geom(pat->max_width_tma, 0);
+        make_geom(pat->max_width, pat->max_width_tma);
+    } else {
+        make_geom(pat->max_width, 0);
+    }
+    size_t smem_max = 0;
+    for (int k = 0; k < ngeom; k++) smem_max = gg[k].smem > smem_max ? gg[k].smem : smem_max;
+    TB_CUDA(cudaFuncSetAttribute(k_gather_rows<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    for (int k = 0; k < ngeom; k++) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gg[k].per_sm, k_gather_rows<NV>, gg[k].warps * 32, gg[k].smem);
+        if (gg[k].per_sm < 1) gg[k].per_sm = 1;
+    }
     const int nch = (int)plan.cmin.size();
     for (int ch = 0; ch < nch; ch++) {
         const int64_t r0 = (int64_t)ch * plan.rows_per_chunk;
@@ -567,11 +592,14 @@ static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_ta
             TB_LAUNCH(ctx, (k_element_matrices<NV, DIM, OP>), grid, AS_BLOCK, smem1, m->d_conn, m->d_coords, c0, c1, d_T, nq,
                       rho, kind, d_data, cmchi, EA);
         }
-        const int64_t need = (s1 - s0 + warps - 1) / warps;
-        const int grid2 = (int)(need < (int64_t)ctx->sm_count * per_sm2 ? need : (int64_t)ctx->sm_count * per_sm2);
-        if (grid2 > 0)
-            TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, warps * 32, smem2, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, S, s0, s1,
-                      maxw, top_step);
+        for (int k = 0; k < ngeom; k++) {
+            const GatherGeom &G = gg[k];
+            const int64_t need = (s1 - s0 + G.warps - 1) / G.warps;
+            const int grid2 = (int)(need < (int64_t)ctx->sm_count * G.per_sm ? need : (int64_t)ctx->sm_count * G.per_sm);
+            if (grid2 > 0)
+                TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, G.warps * 32, G.smem, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, S, s0,
+                          s1, G.maxw, G.top_step, G.wlo);
+        }
     }
     return TB_OK;
 }
@@ -586,7 +614,9 @@ static int32_t upload_tables(tb_ctx *ctx, int celltype, int qorder, tb_elem_tabl
     if (tb_build_tables(celltype, qorder, &T))
         return tb_fail(TB_ERR_UNSUPPORTED, "assembly: quadrature order %d not available for cell type %d", qorder, celltype);
     TB_CUDA(cudaMalloc(d_T, sizeof(T)));
-    TB_CUDA(cudaMemcpy(*d_T, &T, sizeof(T), cudaMemcpyHostToDevice));
+    // stream-ordered: the context stream is non-blocking, a plain cudaMemcpy is not ordered against its kernels
+    TB_CUDA(cudaMemcpyAsync(*d_T, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (nq) *nq = T.nq;
     return TB_OK;
 }

@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(256)
 // (tb_spmv.cuh).  INIT = true: r = p = M*phi (+bS), x = 0, gamma; false: Ap = A p, p.Ap.
 template <int STAGES, bool INIT, bool CC>
 __global__ void __launch_bounds__(1024, 1)
-    k_cg_spmv_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
+    k_cg_spmv_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const int *__restrict__ cstream,
+                  const int64_t *__restrict__ cptr,
                   const double *__restrict__ val, const double *__restrict__ xin, const double *__restrict__ bS,
                   double *__restrict__ xout, double *__restrict__ r, double *__restrict__ pout, int64_t nrows,
                   int64_t nslices, unsigned val_bytes, unsigned col_bytes, CGState *st, double *partials, unsigned *ticket,
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(1024, 1)
     extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
     __shared__ double sm[32];
     double acc = 0.0;
-    tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, [&](int64_t row, double v) {
+    auto epi = [&](int64_t row, double v) {
         if (row < nrows) {
             if (INIT) {
                 if (bS) v += bS[row];
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(1024, 1)
                 acc += xin[row] * v;
             }
         }
-    });
+    };
+    tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, epi, nullptr, col);
     const double bs = tb_block_sum(acc, sm);
     if (INIT) cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
     else cg_finish<1>(bs, st, partials, ticket, sm, dist, ar);
@@ -193,7 +195,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
                                const double *bS, double *xout, double *r, double *pout, CGState *st, double *part,
                                unsigned *tick, bool dist, const tb_ar_args &ar, const tb_hwait_args &hw, const double *dinv) {
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
-    const tb_tma_geom g = tb_tma_geometry(pat->max_width, cc ? pat->max_ccol_ints : 32 * pat->max_width, STAGES, warps_override);
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? pat->max_ccol_ints : 32 * pat->max_width_tma, STAGES, warps_override);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);   // one CTA per SM, one balanced wave
     if (cc) {
@@ -202,7 +204,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
             configured = g.smem;
         }
-        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_ccol,
+        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_ccol,
                   pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv);
     } else {
         static size_t configured = 0;
@@ -210,7 +212,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
             configured = g.smem;
         }
-        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, nullptr,
+        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_col, nullptr,
                   val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv);
     }
     return TB_OK;
@@ -387,7 +389,7 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const int grid_ib = TB_GRID(ctx, k_cg_init_b, 256, 0, (n + 255) / 256);
     const int grid_s = TB_GRID(ctx, k_cg_spmv_dot, 256, 0, need_s);
     const int grid_im = TB_GRID(ctx, k_cg_init_Mphi, 256, 0, need_s);
-    const bool tma = ctx->spmv_variant > 0 && pat->max_width > 0 && pat->max_width <= TB_TMA_WCAP;
+    const bool tma = ctx->spmv_variant > 0 && pat->max_width_tma > 0;   // slices above TB_TMA_WCAP take the LDG row kernel inside the sweep
     const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
 
     TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);

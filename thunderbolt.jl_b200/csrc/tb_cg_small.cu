@@ -216,6 +216,7 @@ __global__ void k_pcg_set_tol(CGState *st, double atol, double rtol, long long i
 // ---------------------------------------------------------------------------------------------------------------
 struct PcgTmaArgs {
     const int64_t *slice_ptr;
+    const int *col;            // SELL column ids (wide slices, tb_spmv.cuh)
     const int *cstream;        // compressed column stream (CC) or SELL column ids
     const int64_t *cptr;
     unsigned val_bytes, col_bytes;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(1024, 1)
                                          p[row] = z;
                                          acc += v * z;
                                      }
-                                 }, &ring);
+                                 }, &ring, P.col);
     }
     double gamma = pcg_allsum_t(acc, partials, sm, grid);          // also publishes p grid-wide
     double rn = sqrt(gamma);
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(1024, 1)
                                          Ap[row] = v;
                                          acc += p[row] * v;
                                      }
-                                 }, &ring);
+                                 }, &ring, P.col);
         const double pAp = pcg_allsum_t(acc, partials + gridDim.x, sm, grid);
         const double alpha = gamma / pAp;
         acc = 0.0;
@@ -376,7 +377,7 @@ int tb_cg_persistent_kind(tb_ctx *ctx, const tb_pattern *pat, int *grid_out) {
             return 1;
         }
     if (!ctx->cg_persistent || (ctx->has_comm && ctx->nranks > 1)) return 0;
-    if (!(ctx->spmv_variant > 0 && pat->max_width > 0 && pat->max_width <= TB_TMA_WCAP)) return 0;
+    if (!(ctx->spmv_variant > 0 && pat->max_width_tma > 0)) return 0;
     if (pat->nrows > ctx->cg_persistent_max_rows) return 0;     // large operators: launch overhead is < 2 %, keep host-side polling
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
@@ -392,8 +393,8 @@ int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const d
     TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
-    const tb_tma_geom g = tb_tma_geometry(pat->max_width, cc ? pat->max_ccol_ints : 32 * pat->max_width, 1, 0);
-    PcgTmaArgs P{pat->d_slice_ptr, cc ? pat->d_ccol : pat->d_col, pat->d_cptr, g.val_bytes, g.col_bytes};
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? pat->max_ccol_ints : 32 * pat->max_width_tma, 1, 0);
+    PcgTmaArgs P{pat->d_slice_ptr, pat->d_col, cc ? pat->d_ccol : pat->d_col, pat->d_cptr, g.val_bytes, g.col_bytes};
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
     TB_LAUNCH(ctx, k_pcg_set_tol, 1, 1, 0, ctx->d_cg, atol, rtol, (long long)itmax);

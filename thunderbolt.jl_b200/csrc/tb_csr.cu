@@ -18,6 +18,7 @@
 // ------------------------------------------------------------------------------------------------
 // pattern construction
 // ------------------------------------------------------------------------------------------------
+// maxw[0] widest slice, maxw[1] widest slice not above TB_TMA_WCAP, maxw[2] number of slices above it
 __global__ void k_slice_width(const int64_t *rowptr, int64_t nrows, int64_t nslices, int64_t *width32, int *maxw) {
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += (int64_t)gridDim.x * blockDim.x) {
         int64_t r0 = s * TB_SLICE, r1 = r0 + TB_SLICE < nrows ? r0 + TB_SLICE : nrows;
@@ -28,6 +29,8 @@ __global__ void k_slice_width(const int64_t *rowptr, int64_t nrows, int64_t nsli
         }
         width32[s] = w * TB_SLICE;
         atomicMax(maxw, (int)w);
+        if (w <= TB_TMA_WCAP) atomicMax(maxw + 1, (int)w);
+        else atomicAdd(maxw + 2, 1);
     }
 }
 
@@ -116,7 +119,7 @@ __global__ void k_ccol_build(const int64_t *rowptr, int64_t nrows, int64_t ncols
         } else if (lane == 0) {
             const int ints = hdr_ints + nexp * 32;
             cnt[s] = ints;
-            atomicMax(max_ints, ints);
+            if (w <= TB_TMA_WCAP) atomicMax(max_ints, ints);   // wide slices are never staged (tb_spmv.cuh)
         }
     }
 }
@@ -161,10 +164,15 @@ static int32_t pattern_from_device_csr(tb_ctx *ctx, int64_t nrows, int64_t ncols
     TB_CUDA(cudaMemsetAsync(width, 0, sizeof(int64_t) * (size_t)(p->nslices + 1), ctx->stream));
     TB_CUDA(cudaMalloc(&p->d_slice_ptr, sizeof(int64_t) * (size_t)(p->nslices + 1)));
     int *d_maxw = nullptr;
-    TB_CUDA(cudaMalloc(&d_maxw, sizeof(int)));
-    TB_CUDA(cudaMemsetAsync(d_maxw, 0, sizeof(int), ctx->stream));
+    int h_maxw[3] = {0, 0, 0};
+    TB_CUDA(cudaMalloc(&d_maxw, sizeof(int) * 3));
+    TB_CUDA(cudaMemsetAsync(d_maxw, 0, sizeof(int) * 3, ctx->stream));
     TB_LAUNCH(ctx, k_slice_width, tb_grid_for(ctx, p->nslices, 256, 8), 256, 0, d_rowptr, nrows, p->nslices, width, d_maxw);
-    TB_CUDA(cudaMemcpyAsync(&p->max_width, d_maxw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(cudaMemcpyAsync(h_maxw, d_maxw, sizeof(int) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));   // the context stream is non-blocking: a plain cudaMemcpy would not wait for the kernel
+    p->max_width = h_maxw[0];
+    p->max_width_tma = h_maxw[1];
+    p->n_wide = h_maxw[2];
     TB_TRY(tb_exclusive_scan_i64(ctx, width, p->d_slice_ptr, p->nslices + 1));
     TB_CUDA(cudaMemcpy(&p->sell_len, p->d_slice_ptr + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost));
     cudaFree(width);

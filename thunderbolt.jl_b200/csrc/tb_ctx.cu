@@ -53,9 +53,9 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_CUDA(cudaEventCreate(&ctx->ev1));
     TB_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 4 * TB_MAX_PARTIALS));
     TB_CUDA(cudaMalloc(&ctx->d_ticket, sizeof(unsigned) * 8));
-    TB_CUDA(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned) * 8));
+    TB_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned) * 8, ctx->stream));
     TB_CUDA(cudaMalloc(&ctx->d_cg, sizeof(CGState)));
-    TB_CUDA(cudaMemset(ctx->d_cg, 0, sizeof(CGState)));
+    TB_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(CGState), ctx->stream));
     TB_CUDA(cudaMallocHost(&ctx->h_cg, sizeof(CGState)));
     TB_CUDA(cudaMalloc(&ctx->d_scalar, sizeof(double) * 16));
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));

@@ -80,7 +80,8 @@ extern "C" int32_t tb_csr_set_halo(tb_csr *A, int32_t nneigh, const int32_t *nei
     }
     TB_CUDA(cudaMalloc(&h.d_send_rows, sizeof(int) * (size_t)(h.nsend + 1)));
     TB_CUDA(cudaMalloc(&h.d_sendbuf, sizeof(double) * (size_t)(h.nsend + 1)));
-    TB_CUDA(cudaMemcpy(h.d_send_rows, rows.data(), sizeof(int) * (size_t)h.nsend, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpyAsync(h.d_send_rows, rows.data(), sizeof(int) * (size_t)h.nsend, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
     return TB_OK;
 }
 
@@ -123,7 +124,7 @@ extern "C" int32_t tb_peer_export(tb_ctx *ctx, int64_t ncols, void *blob_out) {
     TB_DEV(ctx);
     TB_TRY(tb_ctx_ensure_cgwork(ctx, ncols));
     TB_CUDA(cudaMalloc(&ctx->peer.win, sizeof(tb_peer_window)));
-    TB_CUDA(cudaMemset(ctx->peer.win, 0, sizeof(tb_peer_window)));
+    TB_CUDA(cudaMemsetAsync(ctx->peer.win, 0, sizeof(tb_peer_window), ctx->stream));
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
     tb_peer_blob b;
     memset(&b, 0, sizeof(b));
@@ -155,7 +156,8 @@ extern "C" int32_t tb_peer_attach(tb_ctx *ctx, const void *blobs, int32_t nranks
         P.peer_ld[q] = b[q].cgwork_ld;
     }
     TB_CUDA(cudaMalloc(&P.d_peer_win, sizeof(tb_peer_window *) * TB_MAX_RANKS));
-    TB_CUDA(cudaMemcpy(P.d_peer_win, P.peer_win, sizeof(tb_peer_window *) * TB_MAX_RANKS, cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpyAsync(P.d_peer_win, P.peer_win, sizeof(tb_peer_window *) * TB_MAX_RANKS, cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
     P.on = true;
     return TB_OK;
 }

@@ -15,7 +15,9 @@
 
 #define TB_SLICE 32            // SELL slice height = warp size
 #define TB_MAX_PARTIALS 4096   // upper bound on blocks of any reducing kernel
-#define TB_MAXROW 128          // max nonzeros per row the device pattern builder supports
+#define TB_MAXROW 512          // max nonzeros per row the device pattern builder supports (apex rows of an LV mesh reach 2*nc + 3)
+#define TB_TMA_WCAP 48         // widest slice (entries per row) that is staged through shared memory by the bulk-async SpMV;
+                               // wider slices (a handful of high-valence rows) take the LDG row kernel inside the same sweep
 #define TB_PROF_MAX 256        // SpMV launches per solve that the profiler brackets with events
 
 int32_t tb_fail(int32_t code, const char *fmt, ...);
@@ -240,6 +242,8 @@ struct tb_pattern {
     int64_t nslices;
     int64_t sell_len;             // padded number of stored entries
     int max_width = 0;            // widest slice (entries per row)
+    int max_width_tma = 0;        // widest slice among those <= TB_TMA_WCAP (sizes the staged kernel's shared-memory stage)
+    int64_t n_wide = 0;           // slices wider than TB_TMA_WCAP
     int64_t *d_rowptr = nullptr;  // nrows+1 (CSR row pointers, 0-based)
     int64_t *d_slice_ptr = nullptr; // nslices+1 offsets into col/val, multiples of 32
     int *d_col = nullptr;         // sell_len column ids (padding: a valid column, value 0)

@@ -7,7 +7,8 @@
 //                      contiguous value block and its (compressed) column stream into shared memory with
 //                      cp.async.bulk (TMA, SASS UBLKCP) completing on an mbarrier; the lanes then read
 //                      shared memory and only the x gathers go through the LSU, all of a row's gathers
-//                      in flight at once.  Used when every slice is at most TB_TMA_WCAP entries wide.
+//                      in flight at once.  Slices wider than TB_TMA_WCAP (a few high-valence rows of an
+//                      unstructured mesh) are not staged: the same warp runs tb_sell_row on them.
 //                      Measured on the 101 M-row hex operator (uncompressed columns): 5.3 ms vs 6.25 ms
 //                      for the LDG kernel (1.02 vs 0.87 of the measured copy bandwidth).
 #pragma once
@@ -44,7 +45,6 @@ __device__ __forceinline__ double tb_sell_row(const int64_t *__restrict__ slice_
 // ---------------------------------------------------------------------------------------------------
 // bulk-async (TMA) pipeline
 // ---------------------------------------------------------------------------------------------------
-#define TB_TMA_WCAP 48   // widest slice (entries per row) the staged kernel is used for
 
 __device__ __forceinline__ unsigned tb_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -116,7 +116,7 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
                                                   const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
                                                   const double *__restrict__ x, int64_t nslices, unsigned val_bytes,
                                                   unsigned col_bytes, unsigned char *smem, Epilogue epi,
-                                                  tb_tma_ring *ring = nullptr) {
+                                                  tb_tma_ring *ring = nullptr, const int *__restrict__ col = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const size_t stage_bytes = (size_t)val_bytes + col_bytes;
     unsigned char *wbase = smem + (size_t)warp * STAGES * stage_bytes;
@@ -138,6 +138,10 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         const unsigned n = (unsigned)(slice_ptr[s + 1] - base);   // stored entries of the slice (32 * width)
         const unsigned bar = tb_smem_addr(bars + stage);
         unsigned char *dst = wbase + (size_t)stage * stage_bytes;
+        if (n > TB_TMA_WCAP * 32u) {            // wide slice: nothing is staged, the phase completes at once
+            tb_mbar_expect_tx(bar, 0u);
+            return;
+        }
         if (CC) {
             const int64_t cb = cptr[s];
             const unsigned cn = (unsigned)(cptr[s + 1] - cb);      // ints, multiple of 4
@@ -177,7 +181,9 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         const double *sv = reinterpret_cast<const double *>(wbase + (size_t)stage * stage_bytes) + lane;
         const int *sc = reinterpret_cast<const int *>(wbase + (size_t)stage * stage_bytes + val_bytes);
         double acc = 0.0;
-        if (CC) {
+        if (w > TB_TMA_WCAP) {
+            acc = tb_sell_row(slice_ptr, CC ? col : cstream, val, x, s, lane);   // not staged (see `issue`)
+        } else if (CC) {
             // header: one int per slot (uniform offset or EXPLICIT); explicit blocks follow the padded header
             const int hdr_ints = (w + 3) & ~3;
             const int *sexp = sc + hdr_ints + lane;
