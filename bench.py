@@ -40,6 +40,10 @@ WORKLOADS = {
     "c2": dict(name="C2 3D hex slab 128x128x32 PCG2019 (BASELINE config 2)", celltype="hex", nel=(128, 128, 32), h=0.25,
                model="pcg2019", kappa=(0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24), 0.019 * 0.24 / (0.019 + 0.24)),
                dt=0.01, substeps=1),
+    "c4": dict(name="C4 idealized LV, tetrahedralised (240 x 24 x 160 rings -> 5.5 M tets), ODB25LT fibres, spectral tensor, "
+                    "PCG2019 (BASELINE config 4)", celltype="lv", nel=(240, 24, 160), h=0.0, model="pcg2019",
+               kappa=(0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24), 0.019 * 0.24 / (0.019 + 0.24)),
+               dt=0.01, substeps=10),
     "c1": dict(name="C1 2D quad 256x256 FHN spiral wave (BASELINE config 1)", celltype="quad", nel=(256, 256), h=2.5 / 256,
                model="fhn", kappa=(4.5e-5, 2.0e-5), dt=1.0, substeps=1),
 }
@@ -125,7 +129,21 @@ def run_b200(args):
     dim = len(nel)
     lengths = tuple(n * W["h"] for n in nel)
     t_setup = time.time()
-    mesh = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
+    lv_data = None
+    if W["celltype"] == "lv":
+        if world > 1:
+            raise SystemExit("workload c4 (unstructured LV) is single-GPU in this bench: its numbering has no plane structure to cut")
+        from thunderbolt_jl_b200 import lv
+        nodes, hexes, wedges, prm = lv.generate_ideal_lv_mesh(*nel)
+        tets = lv.tetrahedralize(nodes, hexes, wedges)
+        fsn = lv.odb25lt_fibres(prm, tets)
+        lv_data = np.concatenate([np.asarray(W["kappa"], dtype=np.float64), np.ascontiguousarray(fsn).reshape(-1)])
+        del fsn
+        mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+        dim = 3
+        lengths = tuple(float(v) for v in (nodes.max(axis=0) - nodes.min(axis=0)))
+    else:
+        mesh = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
     N_global = mesh.ndofs
     ion = tb.FHNModel() if W["model"] == "fhn" else tb.PCG2019()
     ns = tb.num_states(ion)
@@ -136,8 +154,11 @@ def run_b200(args):
     M = tb.B200CSRMatrix.from_mesh(dev, mesh)
     K = M.like()
     tb.core.assemble_mass(dev, mesh, M, 2, 1.0)
-    D = np.diag(W["kappa"][:dim])
-    tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_TENSOR, D, 1.0)
+    if lv_data is not None:
+        tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_SPECTRAL, lv_data, 1.0)
+        del lv_data
+    else:
+        tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_TENSOR, np.diag(W["kappa"][:dim]), 1.0)
     peer_path = False
     if world > 1:
         part.attach_halo(M)
@@ -146,11 +167,17 @@ def run_b200(args):
     dev.assembly_release_scratch()
     st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
     st.set_cg(SQRT_EPS, SQRT_EPS, None)
+    if args.precond == "jacobi":
+        st.set_preconditioner(tb._lib.PRECOND_JACOBI)
     st.set_cell_solver(W["substeps"], 0.1)
     x = mesh.dof_coords()
     n_local = mesh.ndofs                                    # owned + ghosts
     n_owned = mesh.ndofs_owned
-    u0 = initial_state(x, W["model"], lengths, tb)
+    if W["celltype"] == "lv":   # rest, apex region depolarised
+        u0 = np.repeat(tb.default_initial_state(tb.PCG2019()), mesh.ndofs)
+        u0[:mesh.ndofs] = np.where(x[:, 2] > x[:, 2].max() - 0.15 * lengths[2], 20.0, u0[:mesh.ndofs])
+    else:
+        u0 = initial_state(x, W["model"], lengths, tb)
     del x
     u = tb.B200Vector.from_host(dev, u0, ns)
     nnz = M.nnz
@@ -257,7 +284,7 @@ def run_b200(args):
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded z-slab of the same mesh ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and W["celltype"] != "lv":
         cpu = cpu_baseline(args, W, nel)
 
     if rank == 0:
@@ -267,7 +294,7 @@ def run_b200(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": W["name"] if not args.grid else f"{W['name']} [grid override {nel}]", "nel": list(nel),
                        "dofs": N_global, "nnz": int(nnz) if world == 1 else None, "cell_model": W["model"], "dt": dt,
-                       "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "iters_per_step_mean": k_mean,
+                       "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "preconditioner": args.precond, "iters_per_step_mean": k_mean,
                               "iters_min": int(min(iters)), "iters_max": int(max(iters)), "all_converged": bool(conv_all)},
                        "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
                        "parallelism": "single GPU" if world == 1 else
@@ -335,6 +362,9 @@ def run_reference(args):
     if rank != 0:
         return
     W = WORKLOADS[args.workload]
+    if W["celltype"] == "lv":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is implemented for the structured workloads (c1, c2, c5) only"}))
+        return
     nel = tuple(int(v) for v in args.grid.split(",")) if args.grid else W["nel"]
     import oracle as O
     dim = len(nel)
@@ -384,6 +414,7 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=2, help="z-layers of cells in the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precond", default="none", choices=["none", "jacobi"], help="inner CG preconditioner (SURVEY 8f-2)")
     args = ap.parse_args()
     if args.warmup < 3:
         print("note: the timing rules ask for >= 3 warm-up steps", file=sys.stderr)

@@ -232,7 +232,7 @@ def test_lv_high_valence_apex_rows(tb, dev, oracle, nc, nr, nl, cg_mode):
         for precond, ocg in ((tb._lib.PRECOND_NONE, O.cg), (tb._lib.PRECOND_JACOBI, O.pcg_jacobi)):
             xo, ito, rno, convo = ocg(rpo, cio, Ao, b, *tight)
             it, rn, conv = tb.core.cg_solve(dev, A, bv, yv, *tight, precond=precond)
-            assert dev.cg_last_path() == cg_mode
+            assert dev.cg_last_path() == (2 if cg_mode == 1 else cg_mode)     # rows bound to lanes (path 1) never take a wide slice
             assert conv and convo and abs(it - ito) <= 2
             assert np.abs(yv.to_host() - xo).max() <= 1e-9 * np.abs(xo).max()
     finally:

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(1024, 1)
                   const double *__restrict__ val, const double *__restrict__ xin, const double *__restrict__ bS,
                   double *__restrict__ xout, double *__restrict__ r, double *__restrict__ pout, int64_t nrows,
                   int64_t nslices, unsigned val_bytes, unsigned col_bytes, CGState *st, double *partials, unsigned *ticket,
-                  bool dist, const tb_ar_args ar, const tb_hwait_args hw, const double *__restrict__ dinv) {
+                  bool dist, const tb_ar_args ar, const tb_hwait_args hw, const double *__restrict__ dinv, const tb_wide_list wide) {
     if (!INIT && st->done) return;
     tb_halo_wait(hw);
     extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(1024, 1)
             }
         }
     };
-    tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, epi, nullptr, col);
+    tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, epi, nullptr, col, wide);
     const double bs = tb_block_sum(acc, sm);
     if (INIT) cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
     else cg_finish<1>(bs, st, partials, ticket, sm, dist, ar);
@@ -198,6 +198,9 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
     const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? pat->max_ccol_ints : 32 * pat->max_width_tma, STAGES, warps_override);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);   // one CTA per SM, one balanced wave
+    tb_wide_list wide;
+    wide.slices = pat->d_wide_slices;
+    wide.n = (int)pat->n_wide;
     if (cc) {
         static size_t configured = 0;
         if (configured < g.smem) {
@@ -205,7 +208,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             configured = g.smem;
         }
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_ccol,
-                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv);
+                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv, wide);
     } else {
         static size_t configured = 0;
         if (configured < g.smem) {
@@ -213,7 +216,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
             configured = g.smem;
         }
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_col, nullptr,
-                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv);
+                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv, wide);
     }
     return TB_OK;
 }

@@ -220,6 +220,7 @@ struct PcgTmaArgs {
     const int *cstream;        // compressed column stream (CC) or SELL column ids
     const int64_t *cptr;
     unsigned val_bytes, col_bytes;
+    tb_wide_list wide;
 };
 
 __device__ __forceinline__ double pcg_allsum_t(double v, double *partials, double *sm, cgp::grid_group &grid) {
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(1024, 1)
                                          p[row] = z;
                                          acc += v * z;
                                      }
-                                 }, &ring, P.col);
+                                 }, &ring, P.col, P.wide);
     }
     double gamma = pcg_allsum_t(acc, partials, sm, grid);          // also publishes p grid-wide
     double rn = sqrt(gamma);
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(1024, 1)
                                          Ap[row] = v;
                                          acc += p[row] * v;
                                      }
-                                 }, &ring, P.col);
+                                 }, &ring, P.col, P.wide);
         const double pAp = pcg_allsum_t(acc, partials + gridDim.x, sm, grid);
         const double alpha = gamma / pAp;
         acc = 0.0;
@@ -394,7 +395,9 @@ int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const d
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
     const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? pat->max_ccol_ints : 32 * pat->max_width_tma, 1, 0);
-    PcgTmaArgs P{pat->d_slice_ptr, pat->d_col, cc ? pat->d_ccol : pat->d_col, pat->d_cptr, g.val_bytes, g.col_bytes};
+    PcgTmaArgs P{pat->d_slice_ptr, pat->d_col, cc ? pat->d_ccol : pat->d_col, pat->d_cptr, g.val_bytes, g.col_bytes, tb_wide_list()};
+    P.wide.slices = pat->d_wide_slices;
+    P.wide.n = (int)pat->n_wide;
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
     TB_LAUNCH(ctx, k_pcg_set_tol, 1, 1, 0, ctx->d_cg, atol, rtol, (long long)itmax);
@@ -428,6 +431,7 @@ int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const d
 // Is the persistent path usable for this operator on this context?  Returns the grid size, or 0.
 int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat) {
     if (!ctx->cg_persistent || (ctx->has_comm && ctx->nranks > 1)) return 0;
+    if (pat->n_wide > 0) return 0;   // rows are bound to lanes here: a wide slice would be one warp's serial job (use the TMA kernel)
     static int coop = -1, per_sm = 0;
     if (coop < 0) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);

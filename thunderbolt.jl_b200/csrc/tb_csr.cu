@@ -9,6 +9,7 @@
 // 128 contiguous bytes of column ids per j, and each lane accumulates its row strictly left to right
 // -- the same summation order as the reference's row loop, so SpMV results are bitwise identical.
 // Padding entries carry value 0 and the row's own index as column.
+#include <algorithm>
 #include "tb_internal.cuh"
 #include "tb_spmv.cuh"
 #include <cub/cub.cuh>
@@ -32,6 +33,11 @@ __global__ void k_slice_width(const int64_t *rowptr, int64_t nrows, int64_t nsli
         if (w <= TB_TMA_WCAP) atomicMax(maxw + 1, (int)w);
         else atomicAdd(maxw + 2, 1);
     }
+}
+
+__global__ void k_collect_wide(const int64_t *slice_ptr, int64_t nslices, int64_t *out, int *count) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += (int64_t)gridDim.x * blockDim.x)
+        if (((slice_ptr[s + 1] - slice_ptr[s]) >> 5) > TB_TMA_WCAP) out[atomicAdd(count, 1)] = s;
 }
 
 // one warp per slice: copies CSR column ids into the slice, pads with the row index
@@ -176,6 +182,17 @@ static int32_t pattern_from_device_csr(tb_ctx *ctx, int64_t nrows, int64_t ncols
     TB_TRY(tb_exclusive_scan_i64(ctx, width, p->d_slice_ptr, p->nslices + 1));
     TB_CUDA(cudaMemcpy(&p->sell_len, p->d_slice_ptr + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost));
     cudaFree(width);
+    if (p->n_wide > 0) {   // ids of the wide slices, ascending (collected in arbitrary order, sorted on the host: there are few)
+        TB_CUDA(cudaMalloc(&p->d_wide_slices, sizeof(int64_t) * (size_t)p->n_wide));
+        TB_CUDA(cudaMemsetAsync(d_maxw, 0, sizeof(int), ctx->stream));
+        TB_LAUNCH(ctx, k_collect_wide, tb_grid_for(ctx, p->nslices, 256, 8), 256, 0, p->d_slice_ptr, p->nslices, p->d_wide_slices, d_maxw);
+        std::vector<int64_t> hw((size_t)p->n_wide);
+        TB_CUDA(cudaMemcpyAsync(hw.data(), p->d_wide_slices, sizeof(int64_t) * hw.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::sort(hw.begin(), hw.end());
+        TB_CUDA(cudaMemcpyAsync(p->d_wide_slices, hw.data(), sizeof(int64_t) * hw.size(), cudaMemcpyHostToDevice, ctx->stream));
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     cudaFree(d_maxw);
     TB_CUDA(cudaMalloc(&p->d_col, sizeof(int) * (size_t)(p->sell_len + 32)));
     TB_LAUNCH(ctx, k_sell_fill_cols, ctx->sm_count * 8, 256, 0, d_rowptr, d_colidx, nrows, ncols, p->nslices,
@@ -193,6 +210,7 @@ int32_t tb_pattern_release(tb_pattern *p) {
     cudaFree(p->d_slice_ptr);
     cudaFree(p->d_col);
     cudaFree(p->d_diag_slot);
+    cudaFree(p->d_wide_slices);
     cudaFree(p->halo.d_send_rows);
     cudaFree(p->halo.d_sendbuf);
     delete p;

@@ -244,6 +244,7 @@ struct tb_pattern {
     int max_width = 0;            // widest slice (entries per row)
     int max_width_tma = 0;        // widest slice among those <= TB_TMA_WCAP (sizes the staged kernel's shared-memory stage)
     int64_t n_wide = 0;           // slices wider than TB_TMA_WCAP
+    int64_t *d_wide_slices = nullptr;   // their ids, ascending (tb_spmv.cuh: tb_wide_list)
     int64_t *d_rowptr = nullptr;  // nrows+1 (CSR row pointers, 0-based)
     int64_t *d_slice_ptr = nullptr; // nslices+1 offsets into col/val, multiples of 32
     int *d_col = nullptr;         // sell_len column ids (padding: a valid column, value 0)

@@ -111,12 +111,22 @@ struct tb_tma_ring {
     bool ready = false;
 };
 
+// Slices wider than TB_TMA_WCAP (ids ascending).  A lane-per-row sweep over such a slice is one warp walking hundreds of
+// dependent gathers while the rest of the grid waits at the next barrier (LV, 483-wide apex slice: ~60 us of a 124 us
+// iteration).  With the list, every (wide slice, row) pair becomes ONE WARP's job instead: the lanes fetch 32 entries of
+// the row at once and the products are added in entry order through shuffles -- the same left-to-right sum, bit for bit.
+struct tb_wide_list {
+    const int64_t *slices = nullptr;
+    int n = 0;
+};
+
 template <int STAGES, bool CC, class Epilogue>
 __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ slice_ptr, const double *__restrict__ val,
                                                   const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
                                                   const double *__restrict__ x, int64_t nslices, unsigned val_bytes,
                                                   unsigned col_bytes, unsigned char *smem, Epilogue epi,
-                                                  tb_tma_ring *ring = nullptr, const int *__restrict__ col = nullptr) {
+                                                  tb_tma_ring *ring = nullptr, const int *__restrict__ col = nullptr,
+                                                  const tb_wide_list wide = tb_wide_list()) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const size_t stage_bytes = (size_t)val_bytes + col_bytes;
     unsigned char *wbase = smem + (size_t)warp * STAGES * stage_bytes;
@@ -174,6 +184,25 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
     }
     s_issue = gw + (int64_t)STAGES * nw;   // same value in every lane
 
+    // wide rows first (the first staged slices are already in flight): one warp per row
+    for (int64_t q = gw; q < (int64_t)wide.n * TB_SLICE; q += nw) {
+        const int64_t s = wide.slices[q >> 5];
+        const int rl = (int)(q & 31);
+        const int64_t base = slice_ptr[s];
+        const int w = (int)((slice_ptr[s + 1] - base) >> 5);
+        const int *c = (CC ? col : cstream) + base + rl;
+        const double *v = val + base + rl;
+        double acc = 0.0;
+        for (int j0 = 0; j0 < w; j0 += 32) {
+            const int j = j0 + lane;
+            double prod = 0.0;
+            if (j < w) prod = v[(int64_t)j * 32] * x[c[(int64_t)j * 32]];
+            const int m = w - j0 < 32 ? w - j0 : 32;
+            for (int k = 0; k < m; k++) acc += __shfl_sync(0xffffffffu, prod, k);
+        }
+        if (lane == 0) epi(s * TB_SLICE + rl, acc);
+    }
+
     for (int64_t s = gw; s < nslices; s += nw) {
         const int w = (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 5);
         const int row = (int)(s * TB_SLICE) + lane;
@@ -181,8 +210,9 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         const double *sv = reinterpret_cast<const double *>(wbase + (size_t)stage * stage_bytes) + lane;
         const int *sc = reinterpret_cast<const int *>(wbase + (size_t)stage * stage_bytes + val_bytes);
         double acc = 0.0;
+        const bool wide_done = w > TB_TMA_WCAP && wide.n > 0;   // handled row by row above
         if (w > TB_TMA_WCAP) {
-            acc = tb_sell_row(slice_ptr, CC ? col : cstream, val, x, s, lane);   // not staged (see `issue`)
+            if (!wide_done) acc = tb_sell_row(slice_ptr, CC ? col : cstream, val, x, s, lane);   // not staged (see `issue`)
         } else if (CC) {
             // header: one int per slot (uniform offset or EXPLICIT); explicit blocks follow the padded header
             const int hdr_ints = (w + 3) & ~3;
@@ -235,7 +265,7 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             }
             for (; j < w; j++) acc += sv[j * 32] * x[scl[j * 32]];
         }
-        epi(s * TB_SLICE + lane, acc);
+        if (!wide_done) epi(s * TB_SLICE + lane, acc);
         // every lane has consumed its shared-memory operands (acc depends on all of them): the stage may be refilled
         __syncwarp();
         if (lane == 0 && s_issue < nslices) issue(stage, s_issue);
