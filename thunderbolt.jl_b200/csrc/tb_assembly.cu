@@ -36,8 +36,6 @@
 #define TB_DEV(ctx) TB_CUDA(cudaSetDevice((ctx)->device))
 #define AS_BLOCK 128
 
-static int nv_of(int ct) { return ct == TB_QUAD4 ? 4 : ct == TB_HEX8 ? 8 : ct == TB_TRI3 ? 3 : 4; }
-
 extern "C" int32_t tb_quadrature(int32_t celltype, int32_t qorder, int32_t *nq, double *pts, double *weights) {
     TB_REQUIRE(nq, "tb_quadrature: nq is NULL");
     TB_REQUIRE(celltype >= TB_QUAD4 && celltype <= TB_TET4, "tb_quadrature: unknown cell type %d", celltype);
