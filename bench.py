@@ -148,7 +148,8 @@ def run_b200(args):
     ion = tb.FHNModel() if W["model"] == "fhn" else tb.PCG2019()
     ns = tb.num_states(ion)
     if world > 1:
-        part = tbd.partition_mesh(dev, mesh, dist, plane=(nel[0] + 1) * (nel[1] + 1) if dim == 3 else nel[0] + 1)
+        plane = (nel[0] + 1) * (nel[1] + 1) if dim == 3 else nel[0] + 1
+        part = tbd.partition_mesh(dev, mesh, dist, plane=plane if args.cut == "planes" else None)
         mesh.free()
         mesh = part.mesh
     M = tb.B200CSRMatrix.from_mesh(dev, mesh)
@@ -300,7 +301,7 @@ def run_b200(args):
                        "parallelism": "single GPU" if world == 1 else
                        (f"dof-ownership z-slabs x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
                         f"(CUDA IPC windows), NCCL for the per-step phi halo" if peer_path else
-                        f"dof-ownership z-slabs x{world}, NCCL halo + allreduce"),
+                        f"dof-ownership z-slabs x{world}, NCCL halo + allreduce") + (f", cuts at {args.cut}" if world > 1 else ""),
                        "assembly": {2: "element matrices + ordered gather (deterministic)", 0: "fp64 atomic scatter"}.get(
                            asm_info["last_mode"], str(asm_info["last_mode"])) + f", {asm_info['last_chunks']} chunk(s)",
                        "l2": "working set (matrix + vectors) is far larger than the 126 MB L2, no flush needed"
@@ -414,6 +415,8 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=2, help="z-layers of cells in the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cut", default="planes", choices=["planes", "rows"],
+                    help="multi-GPU ownership cuts: at grid-plane boundaries (one-plane halos) or at equal row counts (balanced)")
     ap.add_argument("--precond", default="none", choices=["none", "jacobi"], help="inner CG preconditioner (SURVEY 8f-2)")
     args = ap.parse_args()
     if args.warmup < 3:
