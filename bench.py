@@ -415,7 +415,7 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=2, help="z-layers of cells in the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cut", default="planes", choices=["planes", "rows"],
+    ap.add_argument("--cut", default="rows", choices=["planes", "rows"],
                     help="multi-GPU ownership cuts: at grid-plane boundaries (one-plane halos) or at equal row counts (balanced)")
     ap.add_argument("--precond", default="none", choices=["none", "jacobi"], help="inner CG preconditioner (SURVEY 8f-2)")
     args = ap.parse_args()

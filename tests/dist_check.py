@@ -51,7 +51,9 @@ def main():
     it1 = [st1.step(u1, float(s), 1.0)[0] for s in range(5)]
     ref = u1.to_host()
     # --- partitioned ---------------------------------------------------------------------------------
-    part = tbd.partition_mesh(dev, full, dist, plane=(nel[0] + 1) * (nel[1] + 1))
+    # DIST_CUT=rows: ownership cut at equal row counts instead of grid planes (ragged halos of up to two planes)
+    plane = None if os.environ.get("DIST_CUT", "planes") == "rows" else (nel[0] + 1) * (nel[1] + 1)
+    part = tbd.partition_mesh(dev, full, dist, plane=plane)
     lm = part.mesh
     lo, hi = int(part.bounds[rank]), int(part.bounds[rank + 1])
     gids = np.concatenate([np.arange(lo, hi), lm.ghost_global])       # local -> global dof id
