@@ -326,16 +326,18 @@ static double map_qp(int nv, int dim, const double *X, const double *dN, double 
     double det;
     if (dim == 2) {
         det = J[0] * J[3] - J[1] * J[2];
-        if (G) {
-            Ji[0] = J[3] / det; Ji[1] = -J[1] / det; Ji[2] = -J[2] / det; Ji[3] = J[0] / det;
+        if (G) { /* Tensors.jl inv(::Tensor{2,dim}): dinv = 1 / det(t), every cofactor TIMES dinv */
+            double dinv = 1.0 / det;
+            Ji[0] = J[3] * dinv; Ji[1] = -J[1] * dinv; Ji[2] = -J[2] * dinv; Ji[3] = J[0] * dinv;
         }
     } else {
         double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
         det = J[0] * c00 + J[1] * c01 + J[2] * c02;
         if (G) {
-            Ji[0] = c00 / det; Ji[1] = (J[2] * J[7] - J[1] * J[8]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
-            Ji[3] = c01 / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (J[2] * J[3] - J[0] * J[5]) / det;
-            Ji[6] = c02 / det; Ji[7] = (J[1] * J[6] - J[0] * J[7]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+            double dinv = 1.0 / det;
+            Ji[0] = c00 * dinv; Ji[1] = (J[2] * J[7] - J[1] * J[8]) * dinv; Ji[2] = (J[1] * J[5] - J[2] * J[4]) * dinv;
+            Ji[3] = c01 * dinv; Ji[4] = (J[0] * J[8] - J[2] * J[6]) * dinv; Ji[5] = (J[2] * J[3] - J[0] * J[5]) * dinv;
+            Ji[6] = c02 * dinv; Ji[7] = (J[1] * J[6] - J[0] * J[7]) * dinv; Ji[8] = (J[0] * J[4] - J[1] * J[3]) * dinv;
         }
     }
     if (G)

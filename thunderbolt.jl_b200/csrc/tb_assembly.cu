@@ -344,6 +344,8 @@ __global__ void __launch_bounds__(AS_BLOCK)
     for (int i = threadIdx.x; i < nq * NV; i += AS_BLOCK) sN[i] = gT->N[i];
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
     const tb_tables_view sT_tab{nq, sW, sN, sdN};
+    __shared__ double sD[9];                       // constant diffusion tensor, evaluated once per CTA
+    if (OP == 1 && kind != 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
     const int64_t ncl = c1 - c0;
     const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
                         sT[(i * NV + j) * EA_PAD + lane] = i <= j ? acc[tb_sym<NV>(i, j)] : acc[tb_sym<NV>(j, i)];
             } else {
                 double Ke[NE];
-                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT_tab, sX + threadIdx.x, kind, ddata, cmchi, e, Ke);
+                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT_tab, sX + threadIdx.x, kind, ddata, cmchi, e, Ke, kind != 2 ? sD : nullptr);
 #pragma unroll
                 for (int i = 0; i < NE; i++) sT[i * EA_PAD + lane] = Ke[i];
             }

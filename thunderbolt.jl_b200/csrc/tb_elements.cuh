@@ -155,15 +155,17 @@ TB_HD double tb_map_qp(const double *X, const double *dNq, double *G) {
     if constexpr (DIM == 2) {
         det = J[0] * J[3] - J[1] * J[2];
         if (WANT_G) {
-            Ji[0] = J[3] / det; Ji[1] = -J[1] / det; Ji[2] = -J[2] / det; Ji[3] = J[0] / det;
+            const double dinv = 1.0 / det;   // Tensors.jl inv(::Tensor{2,dim}): dinv = 1 / det(t), every cofactor TIMES dinv
+            Ji[0] = J[3] * dinv; Ji[1] = -J[1] * dinv; Ji[2] = -J[2] * dinv; Ji[3] = J[0] * dinv;
         }
     } else {
         const double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
         det = J[0] * c00 + J[1] * c01 + J[2] * c02;
         if (WANT_G) {
-            Ji[0] = c00 / det; Ji[1] = (J[2] * J[7] - J[1] * J[8]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
-            Ji[3] = c01 / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (J[2] * J[3] - J[0] * J[5]) / det;
-            Ji[6] = c02 / det; Ji[7] = (J[1] * J[6] - J[0] * J[7]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+            const double dinv = 1.0 / det;
+            Ji[0] = c00 * dinv; Ji[1] = (J[2] * J[7] - J[1] * J[8]) * dinv; Ji[2] = (J[1] * J[5] - J[2] * J[4]) * dinv;
+            Ji[3] = c01 * dinv; Ji[4] = (J[0] * J[8] - J[2] * J[6]) * dinv; Ji[5] = (J[2] * J[3] - J[0] * J[5]) * dinv;
+            Ji[6] = c02 * dinv; Ji[7] = (J[1] * J[6] - J[0] * J[7]) * dinv; Ji[8] = (J[0] * J[4] - J[1] * J[3]) * dinv;
         }
     }
     if (WANT_G) {
@@ -256,10 +258,12 @@ TB_HD void tb_element_diffusion(const tb_tables_view T, const double *X, int kin
                                 int64_t cell, double *acc) {
 #pragma unroll
     for (int i = 0; i < NV * (NV + 1) / 2; i++) acc[i] = 0.0;
+    double D[DIM * DIM];
+    if (kind != 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N, D);   // constant coefficients: same value at every point
     for (int q = 0; q < T.nq; q++) {
-        double G[NV * DIM], D[DIM * DIM];
+        double G[NV * DIM];
         const double dO = tb_map_qp<NV, DIM, XS, true>(X, T.dN + q * NV * DIM, G) * T.w[q];
-        tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
+        if (kind == 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             if (kind == 0) {
@@ -297,13 +301,18 @@ TB_HD void tb_element_diffusion(const tb_tables_view T, const double *X, int kin
 // floating point, and the gather assembly (tb_assembly.cu) reproduces the CPU path bit for bit with this.
 template <int NV, int DIM, int XS>
 TB_HD void tb_element_diffusion_full(const tb_tables_view T, const double *X, int kind, const double *data, double cmchi,
-                                     int64_t cell, double *Ke) {
+                                     int64_t cell, double *Ke, const double *Dconst = nullptr) {
 #pragma unroll
     for (int i = 0; i < NV * NV; i++) Ke[i] = 0.0;
+    // constant coefficients (kind 0, 1) have the same value at every point: evaluated once -- by the caller into shared
+    // memory (Dconst; no registers held across the loop) or here
+    double Dloc[DIM * DIM];
+    if (kind != 2 && !Dconst) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N, Dloc);
     for (int q = 0; q < T.nq; q++) {
-        double G[NV * DIM], D[DIM * DIM];
+        double G[NV * DIM];
         const double dO = tb_map_qp<NV, DIM, XS, true>(X, T.dN + q * NV * DIM, G) * T.w[q];
-        tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
+        if (kind == 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, Dloc);
+        const double *D = (kind != 2 && Dconst) ? Dconst : Dloc;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             if (kind == 0) {
