@@ -50,6 +50,10 @@ extern "C" int32_t tb_quadrature(int32_t celltype, int32_t qorder, int32_t *nq, 
     return TB_OK;
 }
 
+struct SrcParams {
+    double p[8];
+};
+
 struct SellView {
     const int64_t *rowptr;
     const int64_t *slice_ptr;
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
 template <int NV, int DIM>
 __global__ void __launch_bounds__(AS_BLOCK)
     k_assemble_source(const int *__restrict__ conn, const int *__restrict__ celldofs, const double *__restrict__ coords,
-                      int64_t ncells, const tb_elem_tables *__restrict__ gT, int nq, int kind, const double *__restrict__ prm,
+                      int64_t ncells, const tb_elem_tables *__restrict__ gT, int nq, int kind, const SrcParams prm,
                       double t, const double *__restrict__ fq, double *__restrict__ b, int64_t nrows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared memory: the nq used rows of the quadrature/shape tables, then the coordinate tile, then the dof tile
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
     const tb_tables_view sT{nq, sW, sN, sdN};
     __shared__ double sprm[8];
-    if (threadIdx.x < 8) sprm[threadIdx.x] = prm ? prm[threadIdx.x] : 0.0;
+    if (threadIdx.x < 8) sprm[threadIdx.x] = prm.p[threadIdx.x];
     const int64_t ntiles = (ncells + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = tile * AS_BLOCK;
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
 template <int NV, int DIM>
 __global__ void __launch_bounds__(AS_BLOCK)
     k_element_vectors(const int *__restrict__ conn, const double *__restrict__ coords, int64_t c0, int64_t c1,
-                      const tb_elem_tables *__restrict__ gT, int nq, int kind, const double *__restrict__ prm, double t,
+                      const tb_elem_tables *__restrict__ gT, int nq, int kind, const SrcParams prm, double t,
                       const double *__restrict__ fq, double *__restrict__ EAb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sW = reinterpret_cast<double *>(smem_raw);
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
     const tb_tables_view sT{nq, sW, sN, sdN};
     __shared__ double sprm[8];
-    if (threadIdx.x < 8) sprm[threadIdx.x] = prm ? prm[threadIdx.x] : 0.0;
+    if (threadIdx.x < 8) sprm[threadIdx.x] = prm.p[threadIdx.x];
     const int64_t ncl = c1 - c0;
     const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -608,16 +612,28 @@ static size_t assembly_smem(int nv, int dim, int nq) {
     return sizeof(double) * nq * (1 + nv + nv * dim) + sizeof(double) * nv * dim * AS_BLOCK + sizeof(int) * nv * AS_BLOCK;
 }
 
-static int32_t upload_tables(tb_ctx *ctx, int celltype, int qorder, tb_elem_tables **d_T, int *nq) {
-    tb_elem_tables T;
-    memset(&T, 0, sizeof(T));
-    if (tb_build_tables(celltype, qorder, &T))
+// Quadrature/shape tables live on the device for the lifetime of the context: one upload per (cell type, order).
+int32_t tb_get_tables(tb_ctx *ctx, int celltype, int qorder, const tb_elem_tables **d_T, int *nq) {
+    if (celltype < 0 || celltype > 3 || qorder < 1 || qorder > 4)
         return tb_fail(TB_ERR_UNSUPPORTED, "assembly: quadrature order %d not available for cell type %d", qorder, celltype);
-    TB_CUDA(cudaMalloc(d_T, sizeof(T)));
-    // stream-ordered: the context stream is non-blocking, a plain cudaMemcpy is not ordered against its kernels
-    TB_CUDA(cudaMemcpyAsync(*d_T, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (nq) *nq = T.nq;
+    if (!ctx->d_tables[celltype][qorder]) {
+        tb_elem_tables T;
+        memset(&T, 0, sizeof(T));
+        if (tb_build_tables(celltype, qorder, &T))
+            return tb_fail(TB_ERR_UNSUPPORTED, "assembly: quadrature order %d not available for cell type %d", qorder, celltype);
+        tb_elem_tables *d = nullptr;
+        TB_CUDA(cudaMalloc(&d, sizeof(T)));
+        // stream-ordered: the context stream is non-blocking, a plain cudaMemcpy is not ordered against its kernels
+        if (cudaMemcpyAsync(d, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            cudaFree(d);
+            return tb_fail(TB_ERR_CUDA, "assembly: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        ctx->d_tables[celltype][qorder] = d;
+        ctx->tables_nq[celltype][qorder] = T.nq;
+    }
+    *d_T = ctx->d_tables[celltype][qorder];
+    if (nq) *nq = ctx->tables_nq[celltype][qorder];
     return TB_OK;
 }
 
@@ -642,12 +658,7 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     TB_REQUIRE(A->pat->nrows == mesh->ndofs_owned && A->pat->ncols == mesh->ndofs,
                "assemble: operator is %lld x %lld but the mesh has %lld owned / %lld total dofs", (long long)A->pat->nrows,
                (long long)A->pat->ncols, (long long)mesh->ndofs_owned, (long long)mesh->ndofs);
-    TB_DEV(ctx);
-    tb_elem_tables *d_T = nullptr;
-    int nq = 0;
-    TB_TRY(upload_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
-    double *d_data = nullptr;
-    if (op == 1) {
+    if (op == 1) {   // argument checks before anything is allocated
         const int64_t need = kind == TB_D_SCALAR ? 1 : kind == TB_D_TENSOR ? mesh->dim * mesh->dim
                                                                           : 3 + mesh->ncells * mesh->nv * 9;
         TB_REQUIRE(kind >= TB_D_SCALAR && kind <= TB_D_SPECTRAL, "tb_assemble_diffusion: unknown coefficient kind %d", kind);
@@ -655,8 +666,21 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         TB_REQUIRE(data && ndata == need, "tb_assemble_diffusion: coefficient kind %d needs %lld doubles, got %lld", kind,
                    (long long)need, (long long)ndata);
         TB_REQUIRE(cmchi != 0.0, "tb_assemble_diffusion: Cm*chi must be non-zero");
-        TB_CUDA(cudaMalloc(&d_data, sizeof(double) * (size_t)ndata));
-        TB_CUDA(cudaMemcpyAsync(d_data, data, sizeof(double) * (size_t)ndata, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TB_DEV(ctx);
+    const tb_elem_tables *d_T = nullptr;
+    int nq = 0;
+    TB_TRY(tb_get_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
+    double *d_data = nullptr;
+    if (op == 1) {
+        if (cudaMalloc(&d_data, sizeof(double) * (size_t)ndata) != cudaSuccess) {
+            cudaGetLastError();
+            return tb_fail(TB_ERR_NOMEM, "tb_assemble_diffusion: cannot allocate %lld coefficient values", (long long)ndata);
+        }
+        if (cudaMemcpyAsync(d_data, data, sizeof(double) * (size_t)ndata, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            cudaFree(d_data);
+            return tb_fail(TB_ERR_CUDA, "tb_assemble_diffusion: coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
     SellView S{A->pat->d_rowptr, A->pat->d_slice_ptr, A->pat->d_col, A->d_val, A->pat->nrows};
     int32_t st = TB_OK;
@@ -710,7 +734,6 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         }
         if (gathered || st != TB_OK) {
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
-            cudaFree(d_T);
             cudaFree(d_data);
             if (st != TB_OK) return st;
             if (e != cudaSuccess) return tb_fail(TB_ERR_CUDA, "assemble (gather): kernel failed: %s", cudaGetErrorString(e));
@@ -732,7 +755,6 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     }
 #undef DISPATCH
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_T);
     cudaFree(d_data);
     if (st != TB_OK) return st;
     if (e != cudaSuccess) return tb_fail(TB_ERR_CUDA, "assemble: kernel failed: %s", cudaGetErrorString(e));
@@ -749,7 +771,7 @@ extern "C" int32_t tb_assemble_diffusion(tb_ctx *ctx, const tb_mesh *mesh, int32
 }
 
 template <int NV, int DIM>
-static int32_t launch_source(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, int kind, const double *d_prm,
+static int32_t launch_source(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, int kind, const SrcParams &d_prm,
                              double t, const double *d_fq, double *b) {
     const size_t smem = assembly_smem(NV, DIM, nq);
     TB_CUDA(cudaFuncSetAttribute(k_assemble_source<NV, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -762,7 +784,7 @@ static int32_t launch_source(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables
 
 template <int NV, int DIM>
 static int32_t launch_element_vectors(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, int kind,
-                                      const double *d_prm, double t, const double *d_fq, int64_t c0, int64_t c1, double *EAb) {
+                                      const SrcParams &d_prm, double t, const double *d_fq, int64_t c0, int64_t c1, double *EAb) {
     const size_t smem = element_smem(NV, DIM, nq);
     TB_CUDA(cudaFuncSetAttribute(k_element_vectors<NV, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (c1 - c0 + AS_BLOCK - 1) / AS_BLOCK;
@@ -779,14 +801,12 @@ static int32_t assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int
     TB_REQUIRE(fq || (kind >= TB_SRC_NONE && kind <= TB_SRC_ENDO), "tb_assemble_source: unknown source kind %d", kind);
     TB_REQUIRE(nprm >= 0 && nprm <= 8, "tb_assemble_source: at most 8 parameters");
     TB_DEV(ctx);
-    tb_elem_tables *d_T = nullptr;
+    const tb_elem_tables *d_T = nullptr;
     int nq = 0;
-    TB_TRY(upload_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
-    double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < nprm; i++) hp[i] = prm[i];
-    double *d_prm = nullptr, *d_fq = nullptr;
-    TB_CUDA(cudaMalloc(&d_prm, sizeof(hp)));
-    TB_CUDA(cudaMemcpyAsync(d_prm, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+    TB_TRY(tb_get_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
+    SrcParams d_prm;                      // travels as a kernel argument: no allocation, no copy, nothing to free
+    for (int i = 0; i < 8; i++) d_prm.p[i] = i < nprm ? prm[i] : 0.0;
+    double *d_fq = nullptr;
     if (fq) {
         const size_t bytes = sizeof(double) * (size_t)(mesh->ncells * nq);
         TB_CUDA(cudaMalloc(&d_fq, bytes));
@@ -862,9 +882,8 @@ static int32_t assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int
             }
         }
     }
+    if (!d_fq) return st;                 // built-in families: fully stream-ordered, the step that consumes b follows on the same stream
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_T);
-    cudaFree(d_prm);
     cudaFree(d_fq);
     if (st != TB_OK) return st;
     if (e != cudaSuccess) return tb_fail(TB_ERR_CUDA, "tb_assemble_source: kernel failed: %s", cudaGetErrorString(e));

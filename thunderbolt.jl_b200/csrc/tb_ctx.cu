@@ -82,6 +82,8 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     cudaFreeHost(ctx->h_cg);
     cudaFree(ctx->d_scalar);
     cudaFreeHost(ctx->h_scalar);
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 5; b++) cudaFree(ctx->d_tables[a][b]);
     cudaFree(ctx->d_flush);
     cudaFree(ctx->d_dinv);
     cudaFree(ctx->d_ea);

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(ECG_BLOCK)
     for (int i = threadIdx.x; i < nq; i += ECG_BLOCK) sW[i] = gT->w[i];
     for (int i = threadIdx.x; i < nq * NV; i += ECG_BLOCK) sN[i] = gT->N[i];
     for (int i = threadIdx.x; i < nq * NV * DIM; i += ECG_BLOCK) sdN[i] = gT->dN[i];
+    __shared__ double sD[9];                       // constant coefficient: evaluated once per CTA
+    if (kind != 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
     double acc[ECG_NE];
 #pragma unroll
     for (int k = 0; k < ECG_NE; k++) acc[k] = 0.0;
@@ -59,10 +61,11 @@ __global__ void __launch_bounds__(ECG_BLOCK)
 #pragma unroll
             for (int k = 0; k < ECG_NE; k++) local[k] = 0.0;
             for (int q = 0; q < nq; q++) {
-                double G[NV * DIM], D[DIM * DIM], f[DIM], xq[DIM];
+                double G[NV * DIM], Dloc[DIM * DIM], f[DIM], xq[DIM];
                 const double *Nq = sN + q * NV;
                 const double dO = tb_map_qp<NV, DIM, ECG_BLOCK, true>(X, sdN + q * NV * DIM, G) * sW[q];
-                tb_eval_D<NV, DIM>(kind, ddata, cmchi, e, Nq, D);
+                if (kind == 2) tb_eval_D<NV, DIM>(kind, ddata, cmchi, e, Nq, Dloc);
+                const double *D = kind == 2 ? Dloc : sD;
 #pragma unroll
                 for (int r = 0; r < DIM; r++) f[r] = 0.0;
 #pragma unroll
@@ -154,15 +157,12 @@ extern "C" int32_t tb_ecg_plonsey(tb_ctx *ctx, const tb_mesh *mesh, int32_t qord
     TB_REQUIRE(data && ndata == need, "tb_ecg_plonsey: coefficient kind %d needs %lld doubles, got %lld", kind, (long long)need, (long long)ndata);
     TB_REQUIRE(cm_chi != 0.0 && kappa_t != 0.0, "tb_ecg_plonsey: Cm*chi and kappa_t must be non-zero");
     TB_DEV(ctx);
-    tb_elem_tables T, *d_T = nullptr;
-    memset(&T, 0, sizeof(T));
-    if (tb_build_tables(mesh->celltype, qorder, &T))
-        return tb_fail(TB_ERR_UNSUPPORTED, "tb_ecg_plonsey: quadrature order %d not available for cell type %d", qorder, mesh->celltype);
+    const tb_elem_tables *d_T = nullptr;
+    int nq_tab = 0;
+    TB_TRY(tb_get_tables(ctx, mesh->celltype, qorder, &d_T, &nq_tab));
     double *d_data = nullptr, *d_out = nullptr;
-    TB_CUDA(cudaMalloc(&d_T, sizeof(T)));
     TB_CUDA(cudaMalloc(&d_data, sizeof(double) * (size_t)ndata));
     TB_CUDA(cudaMalloc(&d_out, sizeof(double) * ECG_NE));
-    TB_CUDA(cudaMemcpyAsync(d_T, &T, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     TB_CUDA(cudaMemcpyAsync(d_data, data, sizeof(double) * (size_t)ndata, cudaMemcpyHostToDevice, ctx->stream));
     const double *ph = phi->d + (size_t)phicol * phi->ld;
     int32_t st = TB_OK;
@@ -174,10 +174,10 @@ extern "C" int32_t tb_ecg_plonsey(tb_ctx *ctx, const tb_mesh *mesh, int32_t qord
         for (int k = 0; k < el.n; k++)
             for (int d = 0; d < mesh->dim; d++) el.x[k * 3 + d] = electrodes[(size_t)(k0 + k) * mesh->dim + d];
         switch (mesh->celltype) {
-        case TB_QUAD4: st = launch_ecg<4, 2>(ctx, mesh, d_T, T.nq, kind, d_data, cm_chi, ph, el, d_out); break;
-        case TB_HEX8: st = launch_ecg<8, 3>(ctx, mesh, d_T, T.nq, kind, d_data, cm_chi, ph, el, d_out); break;
-        case TB_TRI3: st = launch_ecg<3, 2>(ctx, mesh, d_T, T.nq, kind, d_data, cm_chi, ph, el, d_out); break;
-        default: st = launch_ecg<4, 3>(ctx, mesh, d_T, T.nq, kind, d_data, cm_chi, ph, el, d_out); break;
+        case TB_QUAD4: st = launch_ecg<4, 2>(ctx, mesh, d_T, nq_tab, kind, d_data, cm_chi, ph, el, d_out); break;
+        case TB_HEX8: st = launch_ecg<8, 3>(ctx, mesh, d_T, nq_tab, kind, d_data, cm_chi, ph, el, d_out); break;
+        case TB_TRI3: st = launch_ecg<3, 2>(ctx, mesh, d_T, nq_tab, kind, d_data, cm_chi, ph, el, d_out); break;
+        default: st = launch_ecg<4, 3>(ctx, mesh, d_T, nq_tab, kind, d_data, cm_chi, ph, el, d_out); break;
         }
         if (st == TB_OK) {
             double h[ECG_NE];
@@ -189,7 +189,6 @@ extern "C" int32_t tb_ecg_plonsey(tb_ctx *ctx, const tb_mesh *mesh, int32_t qord
         }
     }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_T);
     cudaFree(d_data);
     cudaFree(d_out);
     return st;

@@ -145,6 +145,8 @@ struct tb_ctx {
     int assembly_last_mode = -1;      // what the last assembly call really ran (2 falls back to 0 when the scratch cannot fit)
     int assembly_last_chunks = 0;
     size_t ea_budget_bytes = (size_t)8 << 30;   // scratch for element matrices per chunk (env TB_EA_BUDGET_MB)
+    struct tb_elem_tables *d_tables[4][5] = {};   // quadrature/shape tables per (cell type, order), uploaded once (tb_assembly.cu)
+    int tables_nq[4][5] = {};
     void *d_ea = nullptr;             // cached scratch of the vector (per-step source) assembly
     size_t ea_bytes = 0;
     int spmv_variant = 1;             // 0: LDG kernel, 1..: bulk-async (TMA) staged kernel configurations (env TB_SPMV_VARIANT)
@@ -420,5 +422,6 @@ int32_t tb_spmv_raw(tb_ctx *ctx, const tb_csr *A, double *x, double *y);
 int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int nparams, double *u, int64_t n, int64_t ld,
                          int phi_idx, const double *phi_src, double t, double dt, int substeps, double thr,
                          double *max_dphi);
+int32_t tb_get_tables(tb_ctx *ctx, int celltype, int qorder, const struct tb_elem_tables **d_T, int *nq);
 int32_t tb_exclusive_scan_i64(tb_ctx *ctx, const int64_t *in, int64_t *out, int64_t n);
 int tb_grid_for(tb_ctx *ctx, int64_t work_items, int block, int blocks_per_sm);
