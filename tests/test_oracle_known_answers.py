@@ -152,3 +152,68 @@ def test_ltg_order_heat_then_cells(oracle):
     orc.step(u, 0.0, 0.25)
     O.cell_step(O.FHN, prm, u_ref, m.ndofs, 0.0, 0.25)
     assert np.allclose(u, u_ref, rtol=1e-12, atol=1e-14)
+
+
+def test_spectral_tensor_coefficient_known_tensors(oracle):
+    """test/test_coefficients.jl:107-141 (SpectralTensorCoefficient): eigenvector e1 with eigenvalues (-1, 0) gives
+    diag(-1, 0[, 0]); equal eigenvalues give -I whatever the frame.  Checked through the element matrix: the spectral
+    coefficient over a constant frame must assemble exactly what the equivalent constant tensor assembles; a rotated
+    frame gives R diag(lambda) R^T; and orthogonalize_system (microstructure.jl:176-187) makes a skewed input frame
+    equivalent to its Gram-Schmidt image."""
+    O = oracle
+    from conftest import DISTORTED_HEX
+    X = DISTORTED_HEX
+    nv = 8
+
+    def spectral(lam, f, s, n, cell=0):
+        frame = np.tile(np.concatenate([f, s, n]), (nv, 1)).ravel()
+        return O.element_diffusion(O.HEX8, 2, X, O.D_SPECTRAL, np.concatenate([lam, frame]), cell=cell)
+
+    e1, e2, e3 = np.eye(3)
+    K = spectral([-1.0, 0.0, 0.0], e1, e2, e3)
+    assert np.allclose(K, O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, np.diag([-1.0, 0.0, 0.0]).ravel()), rtol=0, atol=1e-15)
+    K = spectral([-1.0, -1.0, -1.0], e1, e2, e3)
+    assert np.allclose(K, O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, (-np.eye(3)).ravel()), rtol=0, atol=1e-15)
+    assert np.allclose(K, O.element_diffusion(O.HEX8, 2, X, O.D_SCALAR, [-1.0]), rtol=0, atol=1e-15)
+    # rotated orthonormal frame
+    rng = np.random.default_rng(0)
+    Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    lam = np.array([0.1334, 0.0176, 0.0051])
+    D = Q @ np.diag(lam) @ Q.T
+    K = spectral(lam, Q[:, 0], Q[:, 1], Q[:, 2])
+    Kt = O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, D.ravel())
+    assert np.allclose(K, Kt, rtol=0, atol=1e-13 * np.abs(Kt).max())
+    # skewed, unnormalised input frame: normalise each, then Gram-Schmidt without renormalising (utils.jl:131-139);
+    # f stays, s loses its f-component (the result is orthogonal but s, n are no longer unit vectors)
+    f, s, n = 2.0 * Q[:, 0], Q[:, 1] + 0.4 * Q[:, 0], 0.5 * Q[:, 2] + 0.3 * Q[:, 1]
+    fh, sh, nh = f / np.linalg.norm(f), s / np.linalg.norm(s), n / np.linalg.norm(n)
+    w1 = fh
+    w2 = sh - (w1 @ sh) * w1
+    w3 = nh - (w1 @ nh) * w1 - (w2 @ nh) * w2
+    D = lam[0] * np.outer(w1, w1) + lam[1] * np.outer(w2, w2) + lam[2] * np.outer(w3, w3)
+    K = spectral(lam, f, s, n)
+    Kt = O.element_diffusion(O.HEX8, 2, X, O.D_TENSOR, D.ravel())
+    assert np.allclose(K, Kt, rtol=0, atol=1e-13 * np.abs(Kt).max())
+
+
+def test_field_coefficient_interpolates_nodal_data(oracle):
+    """test/test_coefficients.jl:39-71 (FieldCoefficient): per-element nodal data are interpolated with the shape values
+    at the quadrature point.  A frame that varies linearly over the element must give, at order-1 quadrature (one point,
+    the centroid), exactly the tensor of the nodal average."""
+    O = oracle
+    m = O.generate_grid(O.HEX8, (1, 1, 1), (0, 0, 0), (1, 1, 1))
+    X = m.coords[m.conn[0]]
+    rng = np.random.default_rng(1)
+    f = np.tile([1.0, 0.0, 0.0], (8, 1)) + 0.2 * rng.standard_normal((8, 3))
+    s = np.tile([0.0, 1.0, 0.0], (8, 1))
+    n = np.tile([0.0, 0.0, 1.0], (8, 1))
+    lam = np.array([0.3, 0.1, 0.05])
+    data = np.concatenate([lam, np.concatenate([f, s, n], axis=1).ravel()])
+    K = O.element_diffusion(O.HEX8, 1, X, O.D_SPECTRAL, data)
+    fa = f.mean(axis=0)                      # shape values at the centroid are all 1/8
+    fh = fa / np.linalg.norm(fa)
+    w2 = s[0] - (fh @ s[0]) * fh
+    w3 = n[0] - (fh @ n[0]) * fh - (w2 @ n[0]) * w2
+    D = lam[0] * np.outer(fh, fh) + lam[1] * np.outer(w2, w2) + lam[2] * np.outer(w3, w3)
+    Kt = O.element_diffusion(O.HEX8, 1, X, O.D_TENSOR, D.ravel())
+    assert np.allclose(K, Kt, rtol=0, atol=1e-14 * np.abs(Kt).max())
