@@ -300,7 +300,8 @@ def run_b200(args):
                        "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
                        "parallelism": "single GPU" if world == 1 else
                        (f"dof-ownership z-slabs x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
-                        f"(CUDA IPC windows), NCCL for the per-step phi halo" if peer_path else
+                        f"(CUDA IPC windows; collects and halo push fused into the update kernels unless TB_P2P_FUSED=0), NCCL for "
+                        f"the per-step phi halo" if peer_path else
                         f"dof-ownership z-slabs x{world}, NCCL halo + allreduce") + (f", cuts at {args.cut}" if world > 1 else ""),
                        "assembly": {2: "element matrices + ordered gather (deterministic)", 0: "fp64 atomic scatter"}.get(
                            asm_info["last_mode"], str(asm_info["last_mode"])) + f", {asm_info['last_chunks']} chunk(s)",

@@ -296,6 +296,130 @@ __global__ void __launch_bounds__(256) k_cg_p(const double *__restrict__ r, doub
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = (dinv ? dinv[n - 1] * r[n - 1] : r[n - 1]) + beta * p[n - 1];
 }
 
+// ---- fused multi-GPU variants (peer path): the all-reduce collects and the halo push live INSIDE the CG kernels --------
+// k_cg_xr_fused : every CTA collects p.Ap from the window (all ranks' partials, rank order), forms alpha itself, updates
+//                 x and r, and the last CTA publishes this rank's r.z partial.
+// k_cg_p_fused  : every CTA collects r.z, forms beta / the stopping decision itself, updates p and -- for the rows a
+//                 neighbour needs -- stores the new value straight into that neighbour's ghost block; the last CTA
+//                 raises the neighbours' halo flags.  CTA 0 writes the advanced scalars into the OTHER CGState (ping-pong:
+//                 a CTA that starts late must still read the old gamma), which the next iteration's kernels then read.
+// Three launches per iteration, like the single-GPU path; no NCCL call, no helper kernel.
+__global__ void __launch_bounds__(256) k_cg_xr_fused(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                                                     const double *__restrict__ Ap, int64_t n, const CGState *sin, double *partials,
+                                                     unsigned *ticket, const tb_ar_args ar_in, const tb_ar_args ar_out,
+                                                     const double *__restrict__ dinv) {
+    if (sin->done) return;
+    __shared__ double sm[32];
+    __shared__ double s_alpha;
+    if (threadIdx.x == 0) s_alpha = sin->gamma / tb_ar_collect(ar_in);
+    __syncthreads();
+    const double alpha = s_alpha;
+    const int64_t n2 = n >> 1;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 xv = reinterpret_cast<double2 *>(x)[i], rv = reinterpret_cast<double2 *>(r)[i];
+        const double2 pv = reinterpret_cast<const double2 *>(p)[i], av = reinterpret_cast<const double2 *>(Ap)[i];
+        xv.x += alpha * pv.x;
+        xv.y += alpha * pv.y;
+        rv.x -= alpha * av.x;
+        rv.y -= alpha * av.y;
+        reinterpret_cast<double2 *>(x)[i] = xv;
+        reinterpret_cast<double2 *>(r)[i] = rv;
+        if (dinv) {
+            const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+            acc += rv.x * (dv.x * rv.x);
+            acc += rv.y * (dv.y * rv.y);
+        } else {
+            acc += rv.x * rv.x;
+            acc += rv.y * rv.y;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * Ap[i];
+        x[i] = xn;
+        r[i] = rn;
+        acc += dinv ? rn * (dinv[i] * rn) : rn * rn;
+    }
+    const double bs = tb_block_sum(acc, sm);
+    double total;
+    if (tb_grid_sum(bs, partials, ticket, sm, &total) && threadIdx.x == 0) tb_ar_publish(ar_out, total);
+}
+
+__device__ __forceinline__ void tb_push_row(const tb_push_args &pa, int64_t row, double v) {
+    for (int k = 0; k < pa.n; k++) {
+        const long long o = row - pa.lo[k];
+        if (o >= 0 && o < pa.len[k]) pa.dst[k][o] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cg_p_fused(const double *__restrict__ r, double *__restrict__ p, int64_t n,
+                                                    const CGState *sin, CGState *sout, const tb_ar_args ar_in,
+                                                    const double *__restrict__ dinv, const tb_push_args pa, unsigned *ticket) {
+    if (sin->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *sout = *sin;
+        return;
+    }
+    __shared__ double s_beta, s_gnext;
+    __shared__ int s_solved, s_last;
+    if (threadIdx.x == 0) {
+        const double gnext = tb_ar_collect(ar_in);
+        s_gnext = gnext;
+        s_solved = sqrt(gnext) <= sin->eps;
+        s_beta = gnext / sin->gamma;
+    }
+    __syncthreads();
+    const bool solved = s_solved != 0;
+    if (!solved) {
+        const double beta = s_beta;
+        const int64_t n2 = n >> 1;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+            double2 rv = reinterpret_cast<const double2 *>(r)[i];
+            if (dinv) {
+                const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
+                rv.x = dv.x * rv.x;
+                rv.y = dv.y * rv.y;
+            }
+            double2 pv = reinterpret_cast<double2 *>(p)[i];
+            pv.x = rv.x + beta * pv.x;
+            pv.y = rv.y + beta * pv.y;
+            reinterpret_cast<double2 *>(p)[i] = pv;
+            tb_push_row(pa, 2 * i, pv.x);
+            tb_push_row(pa, 2 * i + 1, pv.y);
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+            const double v = (dinv ? dinv[n - 1] * r[n - 1] : r[n - 1]) + beta * p[n - 1];
+            p[n - 1] = v;
+            tb_push_row(pa, n - 1, v);
+        }
+        // all pushes of this CTA are out before its ticket; the last CTA raises the neighbours' flags
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicInc(ticket, gridDim.x - 1);
+            s_last = (t == gridDim.x - 1);
+            if (s_last) {
+                __threadfence_system();
+                for (int k = 0; k < pa.n; k++) *(volatile unsigned long long *)pa.flag[k] = pa.epoch;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CGState s = *sin;
+        const double gnext = s_gnext;
+        s.gamma_next = gnext;
+        s.rnorm = sqrt(gnext);
+        s.solved = solved;
+        if (!solved) {
+            s.beta = gnext / s.gamma;
+            s.gamma = gnext;
+        }
+        s.iter += 1;
+        s.done = solved || (s.iter >= s.itmax);
+        *sout = s;
+    }
+}
+
 // ---- Jacobi preconditioner: dinv = 1 / diag(A) ------------------------------------------------------------------
 __global__ void k_diag_slot(const int64_t *__restrict__ rowptr, const int64_t *__restrict__ slice_ptr,
                             const int *__restrict__ col, int64_t nrows, int *__restrict__ slot) {
@@ -394,6 +518,10 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const int grid_im = TB_GRID(ctx, k_cg_init_Mphi, 256, 0, need_s);
     const bool tma = ctx->spmv_variant > 0 && pat->max_width_tma > 0;   // slices above TB_TMA_WCAP take the LDG row kernel inside the sweep
     const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
+    // fused peer path: collects and halo push inside k_cg_xr_fused / k_cg_p_fused, scalars ping-pong between st[0] and st[1]
+    const bool fused = peer_halo && pat->halo.contiguous && ctx->p2p_fused;
+    const int grid_xrf = fused ? TB_GRID(ctx, k_cg_xr_fused, 256, 0, need_v) : 0;
+    const int grid_pf = fused ? TB_GRID(ctx, k_cg_p_fused, 256, 0, need_v) : 0;
 
     TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);
     {
@@ -417,7 +545,28 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     CGState *h = ctx->h_cg;
     for (;;) {
         if (chunk > itmax - enq) chunk = itmax - enq;
-        for (int64_t k = 0; k < chunk; k++) {
+        for (int64_t k = 0; k < chunk && fused; k++) {
+            const int64_t it = enq + k;
+            CGState *sin = st + (it & 1), *sout = st + ((it + 1) & 1);
+            tb_hwait_args hw = nowait;
+            if (it == 0) TB_TRY(tb_halo_push(ctx, pat, p, sin, &hw));   // p of iteration 0 comes from the init kernel
+            else hw = ctx->peer.hw_next;                                 // ... later ones were pushed by k_cg_p_fused
+            const bool prof = ctx->profile && it < TB_PROF_MAX;
+            if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * it], ctx->stream));
+            const tb_ar_args ar1 = cg_next_ar(ctx, true);
+            if (tma)
+                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, sin, part, tick, dist, ar1, hw, nullptr));
+            else
+                TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
+                          pat->nslices, sin, part, tick, dist, ar1, hw);
+            if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * it + 1], ctx->stream));
+            const tb_ar_args ar2 = cg_next_ar(ctx, true);
+            TB_LAUNCH(ctx, k_cg_xr_fused, grid_xrf, 256, 0, x, r, p, Ap, n, sin, part + TB_MAX_PARTIALS, tick + 1, ar1, ar2, dinv);
+            tb_push_args pa;
+            TB_TRY(tb_halo_push_args(ctx, pat, &pa, &ctx->peer.hw_next));
+            TB_LAUNCH(ctx, k_cg_p_fused, grid_pf, 256, 0, r, p, n, sin, sout, ar2, dinv, pa, ctx->d_ticket + 6);
+        }
+        for (int64_t k = 0; k < chunk && !fused; k++) {
             tb_hwait_args hw = nowait;
             if (peer_halo) TB_TRY(tb_halo_push(ctx, pat, p, st, &hw));
             else if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));
@@ -437,7 +586,7 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
             TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, r, p, n, st, dinv);
         }
         enq += chunk;
-        TB_CUDA(cudaMemcpyAsync(h, st, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
+        TB_CUDA(cudaMemcpyAsync(h, fused ? st + (enq & 1) : st, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
         TB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (h->done || enq >= itmax) break;
         chunk = 4;

@@ -54,14 +54,15 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 4 * TB_MAX_PARTIALS));
     TB_CUDA(cudaMalloc(&ctx->d_ticket, sizeof(unsigned) * 8));
     TB_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned) * 8, ctx->stream));
-    TB_CUDA(cudaMalloc(&ctx->d_cg, sizeof(CGState)));
-    TB_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(CGState), ctx->stream));
+    TB_CUDA(cudaMalloc(&ctx->d_cg, 2 * sizeof(CGState)));   // [1] is the ping-pong partner of the fused multi-GPU path
+    TB_CUDA(cudaMemsetAsync(ctx->d_cg, 0, 2 * sizeof(CGState), ctx->stream));
     TB_CUDA(cudaMallocHost(&ctx->h_cg, sizeof(CGState)));
     TB_CUDA(cudaMalloc(&ctx->d_scalar, sizeof(double) * 16));
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));
     if (const char *v = getenv("TB_SPMV_VARIANT")) ctx->spmv_variant = atoi(v);
     if (const char *v = getenv("TB_SPMV_COMPRESS")) ctx->spmv_compress = atoi(v);
     if (const char *v = getenv("TB_CG_PERSISTENT")) ctx->cg_persistent = atoi(v) < 0 ? 0 : atoi(v) > 2 ? 2 : atoi(v);
+    if (const char *v = getenv("TB_P2P_FUSED")) ctx->p2p_fused = atoi(v);
     if (const char *v = getenv("TB_CG_PERSISTENT_MAX_ROWS")) ctx->cg_persistent_max_rows = atoll(v);
     if (const char *v = getenv("TB_ASSEMBLY_MODE")) ctx->assembly_mode = atoi(v) == 0 ? 0 : 2;
     if (const char *v = getenv("TB_EA_BUDGET_MB")) ctx->ea_budget_bytes = (size_t)(atof(v) * 1048576.0);

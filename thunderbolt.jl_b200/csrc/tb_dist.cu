@@ -200,7 +200,41 @@ extern "C" int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const
         TB_REQUIRE(h.dst_off[i] >= 0 && h.dst_off[i] + ns <= ctx->peer.peer_ld[h.ranks[i]],
                    "tb_csr_set_halo_peer: destination range outside the neighbour's work vector");
     }
+    // slab partitions send one run of consecutive rows to each neighbour: then the p-update kernel can push in line
+    h.contiguous = true;
+    h.range_lo.assign((size_t)h.nneigh, 0);
+    {
+        std::vector<int> rows((size_t)h.nsend);
+        TB_CUDA(cudaMemcpy(rows.data(), h.d_send_rows, sizeof(int) * (size_t)h.nsend, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < h.nneigh; i++) {
+            const int64_t a = h.send_ptr[i], b = h.send_ptr[i + 1];
+            h.range_lo[(size_t)i] = b > a ? rows[(size_t)a] : 0;
+            for (int64_t k = a; k < b; k++)
+                if (rows[(size_t)k] != rows[(size_t)a] + (k - a)) h.contiguous = false;
+        }
+    }
     h.peer_ready = true;
+    return TB_OK;
+}
+
+// arguments of the in-line push (k_cg_p_fused) for the next halo epoch
+int32_t tb_halo_push_args(tb_ctx *ctx, const tb_pattern *pat, tb_push_args *out, tb_hwait_args *wait_out) {
+    const tb_halo &h = pat->halo;
+    tb_peer &P = ctx->peer;
+    const unsigned long long epoch = ++P.halo_epoch;
+    out->n = h.nneigh;
+    out->epoch = epoch;
+    for (int i = 0; i < h.nneigh; i++) {
+        const int q = h.ranks[i];
+        out->lo[i] = h.range_lo[(size_t)i];
+        out->len[i] = h.send_ptr[i + 1] - h.send_ptr[i];
+        out->dst[i] = P.peer_cgwork[q] + P.peer_ld[q] + h.dst_off[i];
+        out->flag[i] = &P.peer_win[q]->hflag[h.dst_slot[i]];
+    }
+    wait_out->hflag = P.win->hflag;
+    wait_out->n = h.nneigh;
+    wait_out->epoch = epoch;
+    wait_out->err = &P.win->err;
     return TB_OK;
 }
 

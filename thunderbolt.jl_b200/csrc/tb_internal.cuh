@@ -95,6 +95,13 @@ struct tb_peer_window {
     unsigned long long err;          // set by a waiter that timed out
     unsigned long long pad[15];
 };
+// halo wait of an SpMV kernel (n == 0: nothing to wait for)
+struct tb_hwait_args {
+    const unsigned long long *hflag;
+    int n;
+    unsigned long long epoch;
+    unsigned long long *err;
+};
 struct tb_peer {
     bool on = false;
     tb_peer_window *win = nullptr;                     // this rank's window
@@ -103,6 +110,7 @@ struct tb_peer {
     int64_t peer_ld[TB_MAX_RANKS] = {};
     tb_peer_window **d_peer_win = nullptr;             // device copy of peer_win
     unsigned long long ar_epoch = 0, halo_epoch = 0;
+    tb_hwait_args hw_next = {nullptr, 0, 0, nullptr};   // fused path: what the next SpMV waits for (set when k_cg_p_fused is enqueued)
 };
 // what a reducing / consuming kernel needs to take part in the window all-reduce (wins == nullptr: NCCL path)
 struct tb_ar_args {
@@ -110,12 +118,13 @@ struct tb_ar_args {
     int rank, nranks, slot;
     unsigned long long epoch;
 };
-// halo wait of an SpMV kernel (n == 0: nothing to wait for)
-struct tb_hwait_args {
-    const unsigned long long *hflag;
+// in-line halo push of k_cg_p_fused: neighbour k wants rows [lo, lo+len) of p at dst[0..len)
+struct tb_push_args {
     int n;
+    long long lo[TB_MAX_RANKS], len[TB_MAX_RANKS];
+    double *dst[TB_MAX_RANKS];
+    unsigned long long *flag[TB_MAX_RANKS];
     unsigned long long epoch;
-    unsigned long long *err;
 };
 
 struct tb_ctx {
@@ -154,6 +163,7 @@ struct tb_ctx {
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
     int cg_persistent = 1;            // 0: never; 1: auto (small: register-resident kernel, mid-size: TMA kernel); 2: TMA kernel whenever eligible (tests); env TB_CG_PERSISTENT
     int last_cg_persistent = 0;       // path of the last solve: 0 multi-kernel, 1 persistent (registers), 2 persistent (TMA sweep, vectors in L2)
+    int p2p_fused = 1;                // multi-GPU peer path: 1 = collects and halo push inside the CG kernels (3 launches per iteration), 0 = separate tiny kernels (env TB_P2P_FUSED)
     int64_t cg_persistent_max_rows = 4000000;   // above this the multi-kernel path is used (env TB_CG_PERSISTENT_MAX_ROWS)
     // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
     bool profile = false;
@@ -235,6 +245,8 @@ struct tb_halo {
     bool peer_ready = false;
     std::vector<int64_t> dst_off;
     std::vector<int> dst_slot;
+    bool contiguous = false;          // every neighbour's send list is one run of consecutive rows (slab partitions):
+    std::vector<int64_t> range_lo;    // first row of that run -- lets k_cg_p_fused push while it updates
 };
 
 // sparsity pattern shared by M, K and A (sliced ELL image of the reference's CSR pattern)
@@ -361,6 +373,7 @@ int32_t tb_ctx_ensure_cgwork(tb_ctx *ctx, int64_t n);
 int32_t tb_halo_exchange(tb_ctx *ctx, const tb_pattern *pat, double *x);
 int32_t tb_peer_release(tb_ctx *ctx);
 int32_t tb_halo_push(tb_ctx *ctx, const tb_pattern *pat, const double *p, const struct CGState *st, tb_hwait_args *wait_out);
+int32_t tb_halo_push_args(tb_ctx *ctx, const tb_pattern *pat, tb_push_args *out, tb_hwait_args *wait_out);
 
 // ---- device side of the window protocol -------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long tb_ld_acquire_sys(const unsigned long long *p) {
