@@ -202,19 +202,11 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
     wide.slices = pat->d_wide_slices;
     wide.n = (int)pat->n_wide;
     if (cc) {
-        static size_t configured = 0;
-        if (configured < g.smem) {
-            TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-            configured = g.smem;
-        }
+        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_tma<STAGES, INIT, true>, g.smem));
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_ccol,
                   pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv, wide);
     } else {
-        static size_t configured = 0;
-        if (configured < g.smem) {
-            TB_CUDA(cudaFuncSetAttribute(k_cg_spmv_tma<STAGES, INIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-            configured = g.smem;
-        }
+        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_tma<STAGES, INIT, false>, g.smem));
         TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_col, nullptr,
                   val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv, wide);
     }

@@ -355,11 +355,7 @@ template <bool FROM_B, bool CC>
 static int32_t launch_pcg_tma(tb_ctx *ctx, int grid, int threads, size_t smem, const PcgTmaArgs &P, const double *Aval,
                               const double *Mval, const double *src, const double *bS, double *x, double *r, double *p, double *Ap,
                               int64_t nrows, int64_t nslices, const double *dinv) {
-    static size_t configured = 0;
-    if (configured < smem) {
-        TB_CUDA(cudaFuncSetAttribute(k_cg_persistent_tma<FROM_B, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_persistent_tma<FROM_B, CC>, smem));
     CGState *st = ctx->d_cg;
     double *partials = ctx->d_partials;
     void *args[] = {(void *)&P, (void *)&Aval, (void *)&Mval, (void *)&src, (void *)&bS, (void *)&x, (void *)&r, (void *)&p,

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <utility>
 #include <new>
 
 #include "../../include/tbolt_b200.h"
@@ -175,6 +176,9 @@ struct tb_ctx {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     tb_peer peer;
+    // per-context record of cudaFuncAttributeMaxDynamicSharedMemorySize settings (the attribute is per device, and a
+    // process may hold contexts on several devices)
+    std::vector<std::pair<const void *, size_t>> smem_set;
 };
 
 // device-resident scalars of a CG solve; mirrors the locals of Krylov.jl's cg!
@@ -365,6 +369,20 @@ __device__ __forceinline__ bool tb_grid_sum(double block_value /* valid in threa
     s = tb_block_sum(s, sm);
     if (threadIdx.x == 0) *total = s;
     return true;
+}
+
+// raise a kernel's dynamic shared-memory limit once per context
+static inline cudaError_t tb_ensure_smem(tb_ctx *ctx, const void *func, size_t smem) {
+    for (auto &e : ctx->smem_set)
+        if (e.first == func) {
+            if (e.second >= smem) return cudaSuccess;
+            cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (r == cudaSuccess) e.second = smem;
+            return r;
+        }
+    cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r == cudaSuccess) ctx->smem_set.emplace_back(func, smem);
+    return r;
 }
 
 // internal cross-TU helpers
