@@ -140,12 +140,20 @@ qorder(i) = Thunderbolt.getorder(i.qrc)
 function update_operator!(op::B200BilinearOperator{<:BilinearMassIntegrator}, t)
     @tb tb_assemble_mass (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, Ptr{Cvoid}) op.A.dev.h op.mesh.h Int32(qorder(op.integrator)) Float64(op.integrator.ρ.val) op.A.h
 end
-function update_operator!(op::B200BilinearOperator{<:BilinearDiffusionIntegrator}, t)
-    D = op.integrator.D                                   # ConductivityToDiffusivityCoefficient(κ, Cₘ, χ)
-    κ = D.conductivity_tensor_coefficient.val
-    cmχ = D.capacitance_coefficient.val * D.χ_coefficient.val
+# lower the coefficient tree of a diffusion integrator to (kind, data, Cₘχ) of the C ABI
+function diffusion_data(D, mesh)
+    cmχ = 1.0
+    if D isa ConductivityToDiffusivityCoefficient                                  # coefficients.jl:122-162
+        cmχ = D.capacitance_coefficient.val * D.χ_coefficient.val
+        D = D.conductivity_tensor_coefficient
+    end
+    κ = D.val                                                                       # ConstantCoefficient
     data = κ isa Number ? Float64[κ] : Float64[κ[i, j] for i in 1:size(κ, 1) for j in 1:size(κ, 2)]
-    kind = κ isa Number ? 0 : 1                           # TB_D_SCALAR / TB_D_TENSOR; spectral: kind 2, see tbolt_b200.h
+    kind = κ isa Number ? Int32(0) : Int32(1)             # TB_D_SCALAR / TB_D_TENSOR; SpectralTensorCoefficient: kind 2 with
+    return kind, data, Float64(cmχ)                       # λ[3] + per-cell nodal f,s,n (see tbolt_b200.h), same call
+end
+function update_operator!(op::B200BilinearOperator{<:BilinearDiffusionIntegrator}, t)
+    kind, data, cmχ = diffusion_data(op.integrator.D, op.mesh)
     @tb tb_assemble_diffusion (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Float64, Ptr{Cvoid}) op.A.dev.h op.mesh.h Int32(qorder(op.integrator)) Int32(kind) data length(data) Float64(cmχ) op.A.h
 end
 # A Julia closure cannot cross the C ABI: evaluate f at the quadrature points on the host, ship the values.
@@ -164,7 +172,9 @@ Base.@kwdef struct B200CG <: LinearSolve.SciMLLinearSolveAlgorithm
     atol::Float64 = sqrt(eps(Float64))
     rtol::Float64 = sqrt(eps(Float64))
     maxiters::Int = 0            # 0 -> length(b), LinearSolve's default
+    precs::Symbol = :none        # :none or :jacobi -- where KrylovJL_CG takes `precs = ..., ldiv = false` (bak/examples-gpu/spiral-wave.jl:95-105)
 end
+precond_id(alg::B200CG) = alg.precs === :jacobi ? Int32(1) : Int32(0)   # TB_PRECOND_NONE / TB_PRECOND_JACOBI
 mutable struct B200CGCache
     iters::Int64
     resid::Float64
@@ -174,7 +184,7 @@ function SciMLBase.solve!(cache::LinearSolve.LinearCache, alg::B200CG; kwargs...
     A, b, u = cache.A::B200CSRMatrix, cache.b::B200Vector, cache.u::B200Vector
     it, rn, conv = Ref{Int64}(0), Ref{Float64}(0.0), Ref{Int32}(0)
     itmax = alg.maxiters == 0 ? length(b) : alg.maxiters
-    @tb tb_cg_solve (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Float64, Float64, Int64, Ref{Int64}, Ref{Float64}, Ref{Int32}) A.dev.h A.h b.h Int32(0) u.h Int32(0) alg.atol alg.rtol itmax it rn conv
+    @tb tb_cg_solve_pc (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Int32, Float64, Float64, Int64, Ref{Int64}, Ref{Float64}, Ref{Int32}) A.dev.h A.h b.h Int32(0) u.h Int32(0) precond_id(alg) alg.atol alg.rtol itmax it rn conv
     cache.cacheval.iters, cache.cacheval.resid = it[], rn[]
     # non-convergence is a retcode, not an exception: euler.jl:95-100 then returns false and the integrator rolls back
     SciMLBase.build_linear_solution(alg, u, nothing, cache; retcode = conv[] == 1 ? ReturnCode.Success : ReturnCode.MaxIters, iters = it[])
@@ -183,6 +193,7 @@ end
 # ---- cell sweep (partitioned_solver.jl:38-52; the method CuThunderboltExt.jl:111-124 had for CuVector) -----------
 model_id(::ParametrizedFHNModel) = Int32(0)
 model_id(::ParametrizedPCG2019Model) = Int32(1)
+model_id(::Thunderbolt.ParametrizedAlievPanfilovModel) = Int32(2)   # states (s, φₘ): transmembranepotential_index == 2
 params(m) = Float64[getfield(m, f) for f in fieldnames(typeof(m))]
 substeps(c::ForwardEulerCellSolverCache) = (Int32(1), 0.1)
 substeps(c::AdaptiveForwardEulerSubstepperCache) = (Int32(c.substeps), Float64(c.reaction_threshold))
@@ -206,6 +217,30 @@ reaction_tangent(cache::AbstractPointwiseSolverCache) = get(REACTION_TANGENT, ob
 # upstream change (one method, rtc.jl:64-67):
 #   R = max(R, subintegrator.cache.uₙ isa B200Vector ? reaction_tangent(subintegrator.cache) :
 #                                                       maximum(@view subintegrator.cache.dumat[:, φₘidx]))
+
+# ---- pseudo-ECG (src/modeling/electrophysiology/ecg.jl:55-160) -------------------------------------------------------
+# Plonsey1964ECGGaussCache keeps κ∇φₘ at every quadrature point between update_ecg! and evaluate_ecg; for a
+# B200-backed diffusion operator the cache keeps a device copy of φₘ instead and the flux is formed in registers inside
+# the one element sweep tb_ecg_plonsey launches.
+struct B200PlonseyECGCache{O}
+    op::O                       # B200BilinearOperator{<:BilinearDiffusionIntegrator}
+    φₘ::B200Vector{Float64}
+end
+function Thunderbolt.Plonsey1964ECGGaussCache(op::B200BilinearOperator{<:BilinearDiffusionIntegrator}, φₘ::B200Vector)
+    c = B200PlonseyECGCache(op, B200Vector{Float64}(φₘ.dev, φₘ.n, 1))
+    Thunderbolt.update_ecg!(c, φₘ)
+    c
+end
+Thunderbolt.update_ecg!(c::B200PlonseyECGCache, φₘ::B200Vector) =
+    @tb tb_vec_copy (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32) c.φₘ.h Int32(0) φₘ.h Int32(0)
+function Thunderbolt.evaluate_ecg(c::B200PlonseyECGCache, x::AbstractVector{<:Ferrite.Vec{sdim}}, κₜ::Real) where {sdim}
+    kind, data, cmchi = diffusion_data(c.op.integrator.D, c.op.mesh)      # same lowering as update_operator! uses
+    pts = Float64[xi[d] for xi in x for d in 1:sdim]
+    out = zeros(length(x))
+    @tb tb_ecg_plonsey (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Float64, Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Float64, Ptr{Float64}) c.op.mesh.dev.h c.op.mesh.h Int32(qorder(c.op.integrator)) kind data Int64(length(data)) cmchi c.φₘ.h Int32(0) pts Int32(length(x)) Float64(κₜ) out
+    out
+end
+Thunderbolt.evaluate_ecg(c::B200PlonseyECGCache, x::Ferrite.Vec, κₜ::Real) = Thunderbolt.evaluate_ecg(c, [x], κₜ)[1]
 
 # ---- assembly strategy knobs ------------------------------------------------------------------------------------
 # 2 = per-element results + ordered row gather (default: deterministic, bitwise the sequential CPU assembly),
