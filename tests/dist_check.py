@@ -83,10 +83,20 @@ def main():
     err_phi = np.abs(got[:no] - ref[lo:hi]).max() / np.abs(ref[:N]).max()
     err_s = np.abs(got[nl:nl + no] - ref[N + lo:N + hi]).max()
     ok = err_phi <= 1e-9 and err_s <= 1e-10 and max(abs(a - b) for a, b in zip(its, it1)) <= 1
+    # Jacobi-preconditioned CG through the same (fused / unfused / NCCL) communication path
+    st1.set_preconditioner(tb._lib.PRECOND_JACOBI)
+    st.set_preconditioner(tb._lib.PRECOND_JACOBI)
+    u1.upload(u0)
+    u.upload(ul)
+    itp1 = [st1.step(u1, float(s), 1.0)[0] for s in range(3)]
+    itp = [st.step(u, float(s), 1.0)[0] for s in range(3)]
+    refp, gotp = u1.to_host(), u.to_host()
+    err_pc = np.abs(gotp[:no] - refp[lo:hi]).max() / np.abs(refp[:N]).max()
+    ok = ok and err_pc <= 1e-9 and max(abs(a - b) for a, b in zip(itp, itp1)) <= 1 and max(itp1) <= max(it1)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print(f"rank {rank}/{world}: owned [{lo},{hi}) ghosts {lm.ghost_global.size} iters {its} vs {it1} "
-          f"err_phi {err_phi:.2e} err_s {err_s:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+          f"err_phi {err_phi:.2e} err_s {err_s:.2e} | jacobi iters {itp} vs {itp1} err {err_pc:.2e} {'OK' if ok else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
