@@ -6,8 +6,10 @@
  * int32 status (TB_OK = 0) and never throws.  The message of the last failure is available from
  * tb_last_error().  Host pointers are borrowed for the duration of the call only; device memory is
  * owned by the library behind the handles and released by the matching *_destroy.  A tb_ctx is
- * used from one host thread at a time; all work is ordered on the context's CUDA stream; only
- * *_download, tb_cg_solve, tb_monodomain_step (they return scalars) and tb_sync block the host.
+ * used from one host thread at a time; all work is ordered on the context's CUDA stream (a non-blocking
+ * stream unless the caller supplies one); only *_download, the solves and steps that return scalars
+ * (tb_cg_solve*, tb_monodomain_step*, tb_monodomain_run*, tb_ecg_plonsey), the matrix assemblies and
+ * tb_sync block the host -- tb_assemble_source with a built-in stimulus family is fully stream-ordered.
  *
  * Each declaration cites the reference interface (file:line under JuliaHealth/Thunderbolt.jl
  * v0.0.4) that a Julia `ccall` of it replaces; INTEGRATION.md shows those bindings.
@@ -36,7 +38,7 @@ extern "C" {
 #define TB_ERR_INVALID 1     /* bad argument (null handle, size mismatch, unsupported enum) */
 #define TB_ERR_CUDA 2        /* a CUDA runtime call or kernel failed */
 #define TB_ERR_NOMEM 3       /* device or host allocation failed */
-#define TB_ERR_COMM 4        /* NCCL failure */
+#define TB_ERR_COMM 4        /* NCCL failure, or a wait on a peer rank's data timed out (peer-memory path) */
 #define TB_ERR_UNSUPPORTED 5 /* valid request the library does not implement */
 
 /* cell types (Ferrite Quadrilateral / Hexahedron / Triangle / Tetrahedron, Lagrange order 1) */
