@@ -91,3 +91,20 @@ def test_unsupported_kwargs_are_refused(tb):
     """test/test_time_integrator.jl:43-273 ('unsupported kwargs refused')"""
     with pytest.raises(TypeError):
         tb.init(None, None, dt=0.1, callback=None)
+
+
+def test_cell_model_tables_and_solver_options(tb):
+    """Host-side facts of the API mirror that need no GPU: state layouts of the three ionic models
+    (fhn.jl:14-19, pcg2019.jl:136, aliev-panfilov.jl:11-14), the preconditioner switch, the RTC unwrapping."""
+    import numpy as np
+    assert tb.state_symbols(tb.FHNModel()) == ("φₘ", "s") and tb.transmembranepotential_index(tb.FHNModel()) == 1
+    assert tb.num_states(tb.PCG2019()) == 7 and tb.transmembranepotential_index(tb.PCG2019()) == 1
+    ap = tb.AlievPanfilovModel()
+    assert tb.state_symbols(ap) == ("s", "φₘ") and tb.transmembranepotential_index(ap) == 2 and tb.num_states(ap) == 2
+    assert np.array_equal(ap.params(), [1.0 / 12.9, 8.0, 0.05, 0.002, 0.2, 0.3])
+    assert np.array_equal(tb.default_initial_state(ap), [0.0, 0.0])
+    assert tb.B200CG().precond == tb._lib.PRECOND_NONE
+    assert tb.B200CG(precs=tb.JacobiPreconditioner()).precond == tb._lib.PRECOND_JACOBI
+    ltg = tb.LieTrotterGodunov((tb.BackwardEulerSolver(), tb.AdaptiveForwardEulerSubstepper()))
+    rtc = tb.ReactionTangentController(ltg, 0.5, 1.0, (0.5, 2.0))
+    assert rtc.inner_algs is ltg.inner_algs and 0.5 <= rtc.next_dt(3.0) < rtc.next_dt(0.0) <= 2.0
