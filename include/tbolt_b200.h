@@ -194,6 +194,13 @@ int32_t tb_peer_export(tb_ctx *ctx, int64_t ncols, void *blob_out);
 int32_t tb_peer_attach(tb_ctx *ctx, const void *blobs, int32_t nranks);
 int32_t tb_peer_enabled(tb_ctx *ctx, int32_t *on);
 int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const int32_t *dst_slot);
+/* The fused communication path (collects and halo push inside the CG update kernels, 3 launches per iteration) consumes
+ * a different number of halo epochs per solve than the unfused one, so ALL ranks must take the same path.
+ * tb_csr_halo_fused_capable reports whether THIS rank could (every send list one run of consecutive rows, fusion not
+ * disabled); the host reduces that with MIN over the ranks and hands the agreed value to tb_csr_set_halo_fused.
+ * Until that call the unfused path is used. */
+int32_t tb_csr_halo_fused_capable(const tb_csr *A, int32_t *capable);
+int32_t tb_csr_set_halo_fused(tb_csr *A, int32_t on);
 
 /* ---- assembly ---------------------------------------------------------------------------------
  * update_operator!(op, t) of the FerriteOperators element loop (called at euler.jl:173-175) with the
@@ -265,7 +272,8 @@ int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *path);
  * ext/CuThunderboltExt.jl:111-124 provided for CuVector).  substeps <= 1: ForwardEulerCellSolver
  * (:80-99); substeps > 1: AdaptiveForwardEulerSubstepper (:196-234) with `reaction_threshold`.
  * `u` holds num_states columns; phi_idx is the 0-based state column of the transmembrane potential.
- * max_dphi (nullable) receives max_i du[i, phi] of the first rhs evaluation (rtc.jl:64-67). */
+ * max_dphi (nullable) receives the signed max_i du[i, phi] of the LAST rhs evaluation of the sweep, i.e. what the
+ * reference's cache.dumat holds afterwards (rtc.jl:64-67); -inf when the vector has no rows. */
 int32_t tb_cell_step(tb_ctx *ctx, int32_t model, const double *params, int32_t nparams, tb_vec *u, int32_t phi_idx,
                      double t, double dt, int32_t substeps, double reaction_threshold, double *max_dphi);
 
@@ -285,7 +293,8 @@ int32_t tb_monodomain_set_source(tb_monodomain *md, const tb_vec *bS, int32_t co
 int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                            int32_t *converged);
 /* the same step, also returning the reaction tangent R = max_i du[i, phi_m] left by the cell sweep's last rhs
- * evaluation, maximum over all ranks: the input of ReactionTangentController (src/solver/time/rtc.jl:51-78,121-133) */
+ * evaluation, maximum over all ranks and clamped at 0 like _get_reaction_tangent (R = 0.0; R = max(R, maximum(...))):
+ * the input of ReactionTangentController (src/solver/time/rtc.jl:51-78,121-133) */
 int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                               int32_t *converged, double *reaction_tangent);
 /* `nsteps` steps back to back with one host round trip at the end (iters = total, converged = all) */

@@ -385,6 +385,6 @@ class MonodomainOracle:
         return int(it), rn.value, bool(conv.value)
 
     def reaction_tangent(self):
-        """get_reaction_tangent (rtc.jl:51-78): maximum (not maximum(abs)) of the phi_m column of the cell solver's
-        du left by the last step."""
-        return float(self.du[self.phi_idx * self.n:(self.phi_idx + 1) * self.n].max())
+        """get_reaction_tangent (rtc.jl:51-78): R = 0.0; R = max(R, maximum(dumat[:, phi_m])) -- the signed maximum
+        (not maximum(abs)) of the phi_m column of the cell solver's du left by the last step, never below zero."""
+        return max(0.0, float(self.du[self.phi_idx * self.n:(self.phi_idx + 1) * self.n].max()))

@@ -114,6 +114,8 @@ _SIGNATURES = {
     "tb_peer_attach": [_vp, _vp, C.c_int32],
     "tb_peer_enabled": [_vp, _pi32],
     "tb_csr_set_halo_peer": [_vp, _vp, _vp],
+    "tb_csr_halo_fused_capable": [_vp, _pi32],
+    "tb_csr_set_halo_fused": [_vp, C.c_int32],
     "tb_quadrature": [C.c_int32, C.c_int32, _pi32, _vp, _vp],
     "tb_assemble_mass": [_vp, _vp, C.c_int32, C.c_double, _vp],
     "tb_assemble_diffusion": [_vp, _vp, C.c_int32, C.c_int32, _f64p, C.c_int64, C.c_double, _vp],

@@ -893,7 +893,7 @@ class ThunderboltTimeIntegrator:
                     ok = False
                     break
             if self.controller is not None and ok:
-                self.R = self.dev.allreduce_max(self.caches[-1].R)
+                self.R = max(0.0, self.dev.allreduce_max(self.caches[-1].R))   # rtc.jl:57-66: R starts at 0.0
         self.iter += 1
         if ok:
             self.stats.naccept += 1

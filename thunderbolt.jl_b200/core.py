@@ -334,6 +334,14 @@ class B200CSRMatrix:
         ds = np.ascontiguousarray(dst_slot, dtype=np.int32)
         L.call("tb_csr_set_halo_peer", self.h, L.ptr(do), L.ptr(ds))
 
+    def halo_fused_capable(self) -> bool:
+        v = C.c_int32()
+        L.call("tb_csr_halo_fused_capable", self.h, C.byref(v))
+        return bool(v.value)
+
+    def set_halo_fused(self, on: bool):
+        L.call("tb_csr_set_halo_fused", self.h, int(bool(on)))
+
     def free(self):
         if getattr(self, "h", None):
             L.lib().tb_csr_destroy(self.h)

@@ -98,7 +98,10 @@ int32_t tb_cell_step_raw(tb_ctx *ctx, int model, const double *params, int npara
     TB_REQUIRE(phi_idx == tb_model_phi(model), "tb_cell_step: model %d keeps the transmembrane potential in state %d, not %d", model,
                tb_model_phi(model), phi_idx);
     TB_REQUIRE((ld & 1) == 0, "tb_cell_step: column stride must be even");
-    if (n == 0) return TB_OK;
+    if (n == 0) {   // a rank that owns no points contributes the identity of the max-reduction
+        if (max_dphi) *max_dphi = -INFINITY;
+        return TB_OK;
+    }
     tb_cell_params prm;
     for (int i = 0; i < 36; i++) prm.p[i] = i < np ? params[i] : 0.0;
     if (model == TB_FHN) TB_TRY((launch_cell<0>(ctx, prm, u, n, ld, phi_src, t, dt, substeps, thr, max_dphi != nullptr)));

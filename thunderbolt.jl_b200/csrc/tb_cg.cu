@@ -29,9 +29,17 @@ __device__ __forceinline__ void cg_after_init(CGState *st, double gamma) {
     st->iter = 0;
     st->done = st->solved || (st->iter >= st->itmax);
 }
+// A NaN scalar or a non-positive curvature can never satisfy the stopping rule; without an exit the host would keep
+// enqueueing iterations up to itmax (= nrows by default).  Same exit as the persistent kernels: tired, not solved.
+__device__ __forceinline__ void cg_give_up(CGState *st) {
+    st->solved = 0;
+    st->iter = st->itmax;
+    st->done = 1;
+}
 __device__ __forceinline__ void cg_after_pAp(CGState *st, double pAp) {
     st->pAp = pAp;
     st->alpha = st->gamma / pAp;
+    if (!(pAp > 0.0)) cg_give_up(st);
 }
 __device__ __forceinline__ void cg_after_rr(CGState *st, double gnext) {
     st->gamma_next = gnext;
@@ -45,6 +53,7 @@ __device__ __forceinline__ void cg_after_rr(CGState *st, double gnext) {
     }
     st->iter += 1;
     st->done = solved || (st->iter >= st->itmax);
+    if (gnext != gnext) cg_give_up(st);
 }
 
 // which: 0 init, 1 pAp, 2 rr.  Used on the multi-GPU path after the NCCL all-reduce of st->local[0].
@@ -303,11 +312,15 @@ __global__ void __launch_bounds__(256) k_cg_xr_fused(double *__restrict__ x, dou
     if (sin->done) return;
     __shared__ double sm[32];
     __shared__ double s_alpha;
-    if (threadIdx.x == 0) s_alpha = sin->gamma / tb_ar_collect(ar_in);
+    if (threadIdx.x == 0) {
+        const double pAp = tb_ar_collect(ar_in);
+        s_alpha = pAp > 0.0 ? sin->gamma / pAp : NAN;   // NaN / non-positive curvature: leave x and r alone, poison r.z so that
+    }                                                   // k_cg_p_fused gives up (same outcome as cg_after_pAp on one GPU)
     __syncthreads();
     const double alpha = s_alpha;
-    const int64_t n2 = n >> 1;
-    double acc = 0.0;
+    const bool bad = alpha != alpha;
+    const int64_t n2 = bad ? 0 : n >> 1;
+    double acc = bad ? NAN : 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
         double2 xv = reinterpret_cast<double2 *>(x)[i], rv = reinterpret_cast<double2 *>(r)[i];
         const double2 pv = reinterpret_cast<const double2 *>(p)[i], av = reinterpret_cast<const double2 *>(Ap)[i];
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(256) k_cg_xr_fused(double *__restrict__ x, dou
             acc += rv.y * rv.y;
         }
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (!bad && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = n - 1;
         const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * Ap[i];
         x[i] = xn;
@@ -408,6 +421,11 @@ __global__ void __launch_bounds__(256) k_cg_p_fused(const double *__restrict__ r
         }
         s.iter += 1;
         s.done = solved || (s.iter >= s.itmax);
+        if (gnext != gnext) {   // NaN right-hand side or pAp <= 0 upstream (alpha = inf/NaN poisons r): tired, not solved
+            s.solved = 0;
+            s.iter = s.itmax;
+            s.done = 1;
+        }
         *sout = s;
     }
 }
@@ -511,7 +529,7 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const bool tma = ctx->spmv_variant > 0 && pat->max_width_tma > 0;   // slices above TB_TMA_WCAP take the LDG row kernel inside the sweep
     const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
     // fused peer path: collects and halo push inside k_cg_xr_fused / k_cg_p_fused, scalars ping-pong between st[0] and st[1]
-    const bool fused = peer_halo && pat->halo.contiguous && ctx->p2p_fused;
+    const bool fused = peer_ar && pat->halo.peer_ready && pat->halo.fused;   // agreed by all ranks (tb_csr_set_halo_fused)
     const int grid_xrf = fused ? TB_GRID(ctx, k_cg_xr_fused, 256, 0, need_v) : 0;
     const int grid_pf = fused ? TB_GRID(ctx, k_cg_p_fused, 256, 0, need_v) : 0;
 

@@ -3,6 +3,8 @@
 #include "tb_internal.cuh"
 #include <string.h>
 
+#define TB_DEV(ctx) TB_CUDA(cudaSetDevice((ctx)->device))
+
 static thread_local char g_last_error[1024] = "";
 
 int32_t tb_fail(int32_t code, const char *fmt, ...) {
@@ -24,6 +26,8 @@ int tb_grid_for(tb_ctx *ctx, int64_t work_items, int block, int blocks_per_sm) {
     return (int)(need < cap ? need : cap);
 }
 
+static int32_t ctx_init(tb_ctx *ctx, int32_t device, void *stream);
+
 extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     TB_REQUIRE(out != nullptr, "tb_ctx_create: out is NULL");
     *out = nullptr;
@@ -34,6 +38,16 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     tb_ctx *ctx = new (std::nothrow) tb_ctx();
     if (!ctx) return tb_fail(TB_ERR_NOMEM, "tb_ctx_create: host allocation failed");
     ctx->device = device;
+    const int32_t st = ctx_init(ctx, device, stream);
+    if (st != TB_OK) {   // free whatever was built (tb_ctx_destroy tolerates a partially initialised context)
+        tb_ctx_destroy(ctx);
+        return st;
+    }
+    *out = ctx;
+    return TB_OK;
+}
+
+static int32_t ctx_init(tb_ctx *ctx, int32_t device, void *stream) {
     cudaDeviceProp prop;
     TB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -66,14 +80,13 @@ extern "C" int32_t tb_ctx_create(int32_t device, void *stream, tb_ctx **out) {
     if (const char *v = getenv("TB_CG_PERSISTENT_MAX_ROWS")) ctx->cg_persistent_max_rows = atoll(v);
     if (const char *v = getenv("TB_ASSEMBLY_MODE")) ctx->assembly_mode = atoi(v) == 0 ? 0 : 2;
     if (const char *v = getenv("TB_EA_BUDGET_MB")) ctx->ea_budget_bytes = (size_t)(atof(v) * 1048576.0);
-    *out = ctx;
     return TB_OK;
 }
 
 extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     if (!ctx) return TB_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     tb_peer_release(ctx);
     if (ctx->has_comm) ncclCommDestroy(ctx->comm);
     cudaFree(ctx->d_partials);
@@ -88,11 +101,11 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_flush);
     cudaFree(ctx->d_dinv);
     cudaFree(ctx->d_ea);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * TB_PROF_MAX; i++)
         if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TB_OK;
 }
@@ -210,6 +223,7 @@ extern "C" int32_t tb_vec_sizes(const tb_vec *v, int64_t *n, int32_t *ncols) {
 
 extern "C" int32_t tb_vec_upload(tb_vec *v, const double *host) {
     TB_REQUIRE(v && host, "tb_vec_upload: NULL argument");
+    TB_DEV(v->ctx);
     TB_CUDA(cudaMemcpy2DAsync(v->d, sizeof(double) * v->ld, host, sizeof(double) * v->n, sizeof(double) * v->n,
                               v->ncols, cudaMemcpyHostToDevice, v->ctx->stream));
     TB_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -218,6 +232,7 @@ extern "C" int32_t tb_vec_upload(tb_vec *v, const double *host) {
 
 extern "C" int32_t tb_vec_download(const tb_vec *v, double *host) {
     TB_REQUIRE(v && host, "tb_vec_download: NULL argument");
+    TB_DEV(v->ctx);
     TB_CUDA(cudaMemcpy2DAsync(host, sizeof(double) * v->n, v->d, sizeof(double) * v->ld, sizeof(double) * v->n,
                               v->ncols, cudaMemcpyDeviceToHost, v->ctx->stream));
     TB_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -228,6 +243,7 @@ extern "C" int32_t tb_vec_upload_col(tb_vec *v, int32_t col, const double *host,
     TB_REQUIRE(v && host, "tb_vec_upload_col: NULL argument");
     TB_REQUIRE(col >= 0 && col < v->ncols && offset >= 0 && count >= 0 && offset + count <= v->n,
                "tb_vec_upload_col: range out of bounds");
+    TB_DEV(v->ctx);
     TB_CUDA(cudaMemcpyAsync(v->d + (size_t)col * v->ld + offset, host, sizeof(double) * count, cudaMemcpyHostToDevice,
                             v->ctx->stream));
     TB_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -238,6 +254,7 @@ extern "C" int32_t tb_vec_download_col(const tb_vec *v, int32_t col, double *hos
     TB_REQUIRE(v && host, "tb_vec_download_col: NULL argument");
     TB_REQUIRE(col >= 0 && col < v->ncols && offset >= 0 && count >= 0 && offset + count <= v->n,
                "tb_vec_download_col: range out of bounds");
+    TB_DEV(v->ctx);
     TB_CUDA(cudaMemcpyAsync(host, v->d + (size_t)col * v->ld + offset, sizeof(double) * count, cudaMemcpyDeviceToHost,
                             v->ctx->stream));
     TB_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -247,6 +264,7 @@ extern "C" int32_t tb_vec_download_col(const tb_vec *v, int32_t col, double *hos
 extern "C" int32_t tb_vec_fill(tb_vec *v, int32_t col, double value) {
     TB_REQUIRE(v, "tb_vec_fill: v is NULL");
     TB_REQUIRE(col >= 0 && col < v->ncols, "tb_vec_fill: column out of range");
+    TB_DEV(v->ctx);
     if (v->n == 0) return TB_OK;
     tb_ctx *ctx = v->ctx;
     TB_LAUNCH(ctx, tb_flush_kernel, tb_grid_for(ctx, v->n, 256, 8), 256, 0, v->d + (size_t)col * v->ld, v->n, value);
@@ -257,6 +275,7 @@ extern "C" int32_t tb_vec_copy(tb_vec *dst, int32_t dcol, const tb_vec *src, int
     TB_REQUIRE(dst && src, "tb_vec_copy: NULL argument");
     TB_REQUIRE(dst->n == src->n && dcol >= 0 && dcol < dst->ncols && scol >= 0 && scol < src->ncols,
                "tb_vec_copy: shape mismatch");
+    TB_DEV(dst->ctx);
     TB_CUDA(cudaMemcpyAsync(dst->d + (size_t)dcol * dst->ld, src->d + (size_t)scol * src->ld, sizeof(double) * src->n,
                             cudaMemcpyDeviceToDevice, dst->ctx->stream));
     return TB_OK;
@@ -270,6 +289,7 @@ __global__ void tb_axpy_kernel(double *__restrict__ y, const double *__restrict_
 extern "C" int32_t tb_vec_axpy(tb_vec *y, int32_t ycol, double a, const tb_vec *x, int32_t xcol) {
     TB_REQUIRE(y && x, "tb_vec_axpy: NULL argument");
     TB_REQUIRE(ycol >= 0 && ycol < y->ncols && xcol >= 0 && xcol < x->ncols && x->n == y->n, "tb_vec_axpy: shape mismatch");
+    TB_DEV(y->ctx);
     if (y->n == 0) return TB_OK;
     tb_ctx *ctx = y->ctx;
     TB_LAUNCH(ctx, tb_axpy_kernel, tb_grid_for(ctx, y->n, 256, 8), 256, 0, y->d + (size_t)ycol * y->ld,

@@ -190,7 +190,12 @@ extern "C" int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const
     tb_halo &h = A->pat->halo;
     tb_ctx *ctx = A->pat->ctx;
     TB_REQUIRE(ctx->peer.on, "tb_csr_set_halo_peer: peers are not attached");
-    TB_REQUIRE(h.nneigh > 0 && h.nneigh <= TB_MAX_RANKS, "tb_csr_set_halo_peer: set the halo plan first");
+    TB_REQUIRE(h.nneigh <= TB_MAX_RANKS, "tb_csr_set_halo_peer: too many neighbours");
+    if (h.nneigh == 0) {   // a rank whose rows reference no foreign dof: nothing to push or to wait for
+        h.contiguous = true;
+        h.peer_ready = true;
+        return TB_OK;
+    }
     TB_REQUIRE(A->pat->ncols <= ctx->cgwork_ld, "tb_csr_set_halo_peer: operator has more columns than the exported work vectors");
     h.dst_off.assign(dst_off, dst_off + h.nneigh);
     h.dst_slot.assign(dst_slot, dst_slot + h.nneigh);
@@ -214,6 +219,22 @@ extern "C" int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const
         }
     }
     h.peer_ready = true;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_csr_halo_fused_capable(const tb_csr *A, int32_t *capable) {
+    TB_REQUIRE(A && capable, "tb_csr_halo_fused_capable: NULL argument");
+    const tb_halo &h = A->pat->halo;
+    // a rank without neighbours never pushes or waits: it can follow either path
+    *capable = (A->pat->ctx->p2p_fused && (h.nneigh == 0 || (h.peer_ready && h.contiguous))) ? 1 : 0;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_csr_set_halo_fused(tb_csr *A, int32_t on) {
+    TB_REQUIRE(A, "tb_csr_set_halo_fused: matrix is NULL");
+    tb_halo &h = A->pat->halo;
+    if (on) TB_REQUIRE(h.nneigh == 0 || (h.peer_ready && h.contiguous), "tb_csr_set_halo_fused: this rank's send lists are not contiguous runs");
+    h.fused = on != 0;
     return TB_OK;
 }
 
@@ -281,7 +302,8 @@ int32_t tb_halo_push(tb_ctx *ctx, const tb_pattern *pat, const double *p, const 
         hp.flag[i] = &P.peer_win[q]->hflag[h.dst_slot[i]];
     }
     hp.begin[h.nneigh] = h.nsend;
-    TB_LAUNCH(ctx, k_halo_push, tb_grid_for(ctx, h.nsend, 256, 4), 256, 0, p, h.d_send_rows, hp, epoch, ctx->d_ticket + 4, st);
+    if (h.nneigh > 0)
+        TB_LAUNCH(ctx, k_halo_push, tb_grid_for(ctx, h.nsend, 256, 4), 256, 0, p, h.d_send_rows, hp, epoch, ctx->d_ticket + 4, st);
     wait_out->hflag = P.win->hflag;
     wait_out->n = h.nneigh;
     wait_out->epoch = epoch;

@@ -251,6 +251,8 @@ struct tb_halo {
     std::vector<int> dst_slot;
     bool contiguous = false;          // every neighbour's send list is one run of consecutive rows (slab partitions):
     std::vector<int64_t> range_lo;    // first row of that run -- lets k_cg_p_fused push while it updates
+    bool fused = false;               // decision agreed by ALL ranks (tb_csr_set_halo_fused): the fused and the unfused path
+                                      // consume different numbers of halo epochs, a per-rank choice would desynchronise them
 };
 
 // sparsity pattern shared by M, K and A (sliced ELL image of the reference's CSR pattern)

@@ -139,7 +139,10 @@ extern "C" int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t,
                                          int32_t *converged, double *reaction_tangent) {
     TB_REQUIRE(reaction_tangent, "tb_monodomain_step_rt: reaction_tangent is NULL");
     TB_TRY(monodomain_step_impl(md, u, t, dt, iters, rnorm, converged, reaction_tangent));
-    return tb_comm_allreduce_max(md->ctx, reaction_tangent);
+    TB_TRY(tb_comm_allreduce_max(md->ctx, reaction_tangent));
+    // _get_reaction_tangent starts from R = 0.0 and takes max(R, maximum(dumat[:, phi])) (rtc.jl:57-66): never negative
+    if (!(*reaction_tangent > 0.0)) *reaction_tangent = 0.0;
+    return TB_OK;
 }
 
 static int32_t monodomain_step_impl(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,

@@ -101,6 +101,7 @@ class Partition:
     nranks: int
     dist: object = None
     peer: bool = False        # True once the NVLink peer-memory path is active
+    fused: bool = False       # all ranks agreed on the fused (3 launches per iteration) communication path
 
     def attach_halo(self, A: B200CSRMatrix, p2p: bool | None = None):
         """M, K and A share one pattern object, so attaching to one attaches to all.
@@ -141,6 +142,11 @@ class Partition:
         off, slot = peer_targets(self.rank, p, [g[2] for g in gathered], [g[3] for g in gathered])
         A.set_halo_peer(off, slot)
         self.peer = True
+        # fused vs unfused consume different numbers of halo epochs per solve: the choice must be collective
+        caps = [None] * self.nranks
+        dist.all_gather_object(caps, bool(A.halo_fused_capable()))
+        self.fused = all(caps)
+        A.set_halo_fused(self.fused)
 
 
 def partition_mesh(dev: B200Device, mesh: DeviceMesh, dist, plane: int | None = None) -> Partition:

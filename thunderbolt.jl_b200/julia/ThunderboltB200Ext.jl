@@ -71,6 +71,7 @@ adapt_vector_type(::Type{<:B200Vector}, v::Vector) = v   # coordinates stay on t
 const CELLTYPE = Dict(Ferrite.Quadrilateral => 0, Ferrite.Hexahedron => 1, Ferrite.Triangle => 2, Ferrite.Tetrahedron => 3)
 mutable struct B200Mesh
     h::Ptr{Cvoid}
+    dev::B200Device
 end
 function B200Mesh(dev::B200Device, dh::Ferrite.DofHandler)
     grid = Ferrite.get_grid(dh)
@@ -81,7 +82,7 @@ function B200Mesh(dev::B200Device, dh::Ferrite.DofHandler)
     cdofs = Int64[d for c in 1:Ferrite.getncells(grid) for d in Ferrite.celldofs(dh, c)]
     r = Ref{Ptr{Cvoid}}(C_NULL)
     @tb tb_mesh_create (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Int64, Int32, Ref{Ptr{Cvoid}}) dev.h Int32(CELLTYPE[CT]) length(grid.cells) length(grid.nodes) conn coords cdofs Ferrite.ndofs(dh) Int32(1) r
-    finalizer(m -> ccall((:tb_mesh_destroy, LIB[]), Int32, (Ptr{Cvoid},), m.h), B200Mesh(r[]))
+    finalizer(m -> ccall((:tb_mesh_destroy, LIB[]), Int32, (Ptr{Cvoid},), m.h), B200Mesh(r[], dev))
 end
 
 # ---- matrices (src/solver/interface.jl:159-173) --------------------------------------------------------
@@ -135,7 +136,10 @@ end
 function setup_operator(s::ElementAssemblyStrategy{<:B200Device}, i::LinearIntegrator, dh)
     B200LinearOperator(B200Vector{Float64}(s.device, Ferrite.ndofs(dh)), i, dh, mesh_of(s.device, dh))
 end
-qorder(i) = Thunderbolt.getorder(i.qrc)
+# FerriteOperators' QuadratureRuleCollection carries its order as the type parameter (`QuadratureRuleCollection(2)` ==
+# `QuadratureRuleCollection{2}()`, fem.jl:52-55) -- no upstream helper needed
+qorder_of(::Thunderbolt.QuadratureRuleCollection{order}) where {order} = order
+qorder(i) = qorder_of(i.qrc)
 
 function update_operator!(op::B200BilinearOperator{<:BilinearMassIntegrator}, t)
     @tb tb_assemble_mass (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, Ptr{Cvoid}) op.A.dev.h op.mesh.h Int32(qorder(op.integrator)) Float64(op.integrator.ρ.val) op.A.h
@@ -157,9 +161,31 @@ function update_operator!(op::B200BilinearOperator{<:BilinearDiffusionIntegrator
     @tb tb_assemble_diffusion (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64, Float64, Ptr{Cvoid}) op.A.dev.h op.mesh.h Int32(qorder(op.integrator)) Int32(kind) data length(data) Float64(cmχ) op.A.h
 end
 # A Julia closure cannot cross the C ABI: evaluate f at the quadrature points on the host, ship the values.
+# x_q = Σ_a M_a(ξ_q) x_a exactly as AnalyticalCoefficientElementCache does (coefficients.jl:279-292), through Ferrite's
+# own CellValues / spatial_coordinate -- nothing here is missing upstream.  The result is ncells × nq doubles in
+# cell-major order; it is re-evaluated only while t lies in a nonzero interval (needs_update below).
+function evaluate_at_quadrature_points(f, dh::Ferrite.DofHandler, qorder::Integer, t)
+    grid = Ferrite.get_grid(dh)
+    sdh = first(dh.subdofhandlers)
+    CT = typeof(Ferrite.getcells(grid, first(sdh.cellset)))
+    RS = Ferrite.getrefshape(CT)
+    ip = Ferrite.geometric_interpolation(CT)
+    qr = Ferrite.QuadratureRule{RS}(qorder)
+    cv = Ferrite.CellValues(qr, Ferrite.Lagrange{RS, 1}(), ip)
+    nq = Ferrite.getnquadpoints(cv)
+    fq = Matrix{Float64}(undef, nq, Ferrite.getncells(grid))
+    for cell in Ferrite.CellIterator(dh)
+        Ferrite.reinit!(cv, cell)
+        x = Ferrite.getcoordinates(cell)
+        for q in 1:nq
+            fq[q, Ferrite.cellid(cell)] = f(Ferrite.spatial_coordinate(cv, q, x), t)
+        end
+    end
+    return fq
+end
 function update_operator!(op::B200LinearOperator, t)
     proto = op.integrator.integrand::AnalyticalTransmembraneStimulationProtocol
-    fq = Thunderbolt.evaluate_at_quadrature_points(proto.f, op.dh, op.integrator.qrc, t)   # ncells × nq, helper to add
+    fq = evaluate_at_quadrature_points(proto.f.f, op.dh, qorder(op.integrator), t)
     @tb tb_assemble_source_qp (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}, Int32) op.b.dev.h op.mesh.h Int32(qorder(op.integrator)) fq op.b.h Int32(0)
 end
 needs_update(op::B200LinearOperator, t) = any(iv -> iv[1] ≤ t ≤ iv[2], op.integrator.integrand.nonzero_intervals)
@@ -214,7 +240,8 @@ end
 # pointwise cache the value was already reduced on the device by the sweep above.
 const REACTION_TANGENT = Dict{UInt, Float64}()
 reaction_tangent(cache::AbstractPointwiseSolverCache) = get(REACTION_TANGENT, objectid(cache), 0.0)
-# upstream change (one method, rtc.jl:64-67):
+# REQUIRES AN UPSTREAM PATCH (get_reaction_tangent indexes cache.dumat directly and offers no dispatch point); the one
+# changed expression, rtc.jl:64-67:
 #   R = max(R, subintegrator.cache.uₙ isa B200Vector ? reaction_tangent(subintegrator.cache) :
 #                                                       maximum(@view subintegrator.cache.dumat[:, φₘidx]))
 
