@@ -100,9 +100,38 @@ def initial_state(x, model, lengths, tb):
     return u
 
 
+if __name__ != "__main__":
+    sys.modules.setdefault("bench", sys.modules[__name__])
+
+
+def host_cores():
+    """Physical cores this process may use (lscpu sockets x cores/socket, capped by the affinity mask).  OMP_NUM_THREADS is
+    deliberately ignored: torchrun exports OMP_NUM_THREADS=1 to every rank, which silently made the CPU arm single-threaded."""
+    phys = None
+    try:
+        out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=10).stdout
+        f = {k.strip(): v.strip() for k, v in (ln.split(":", 1) for ln in out.splitlines() if ":" in ln)}
+        phys = int(f["Socket(s)"]) * int(f["Core(s) per socket"])
+    except Exception:
+        pass
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    return max(1, min(phys, aff) if phys else aff)
+
+
 def bytes_per_row(nnz, n):
     """SpMV = nnzr*12 + 8 (rowptr) + 8 (x) + 8 (y) per row."""
     return nnz / n * 12.0 + 24.0
+
+
+def config_of(args, W, nel):
+    """What is configured (identical for the b200 and the reference arm); measured quantities go to `run_info`."""
+    return {"workload": W["name"] if not args.grid else f"{W['name']} [grid override {list(nel)}]", "nel": list(nel),
+            "cell_model": W["model"], "dt": W["dt"],
+            "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
+            "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "preconditioner": args.precond}}
 
 
 def run_b200(args):
@@ -179,7 +208,8 @@ def run_b200(args):
         u0[:mesh.ndofs] = np.where(x[:, 2] > x[:, 2].max() - 0.15 * lengths[2], 20.0, u0[:mesh.ndofs])
     else:
         u0 = initial_state(x, W["model"], lengths, tb)
-    del x
+    if args.no_parity:
+        del x
     u = tb.B200Vector.from_host(dev, u0, ns)
     nnz = M.nnz
     dev.sync()
@@ -257,11 +287,11 @@ def run_b200(args):
     # ---- e2e: same steps through the host-buffer entry point: the state lives in PINNED HOST memory between steps; every
     # step uploads the whole state and downloads the whole result (tb_monodomain_run_host pipelines the copies) ----
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps != 0:
         hin = torch.empty(ns * n_local, dtype=torch.float64, pin_memory=True)
         hout = torch.empty(ns * n_local, dtype=torch.float64, pin_memory=True)
         hin.numpy()[:] = u.to_host()
-        ke = max(1, min(args.steps, args.e2e_steps))
+        ke = max(1, args.steps if args.e2e_steps < 0 else args.e2e_steps)   # default: the same K steps as the device-timed region
         st.run_host(u, hin.numpy(), hout.numpy(), t, dt, 1)          # warm-up (creates the copy streams)
         barrier()
         t0 = time.perf_counter()
@@ -283,6 +313,16 @@ def run_b200(args):
                "api": "tb_monodomain_run_host (C ABI): state in pinned host buffers between steps, full state H2D + D2H every "
                       "step, copies pipelined on two copy streams (phi download/upload full duplex in chunks, other columns under CG)"}
 
+    # ---- parity evidence on the benchmarked configuration, at this GPU count (scripts/parity_block.py) ----
+    parity = None
+    if not args.no_parity:
+        from scripts import parity_block
+        gname = ("c5" if args.workload == "c5" else args.workload) + "_checksum.json"
+        parity = parity_block.run(tb, dev, mesh, M, K, st, ion, W, nel, u, u0, x, dist=dist if world > 1 else None, world=world,
+                                  rank=rank, precond=tb._lib.PRECOND_JACOBI if args.precond == "jacobi" else 0,
+                                  write_golden=args.write_golden, golden_path=ROOT / "tests" / "golden" / gname)
+        del x
+
     # ---- CPU baseline: the oracle on this box's host cores, bounded z-slab of the same mesh ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and W["celltype"] != "lv":
@@ -293,21 +333,21 @@ def run_b200(args):
             "metric": "monodomain DoF*steps/s", "value": value, "unit": "DoF*steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": W["name"] if not args.grid else f"{W['name']} [grid override {nel}]", "nel": list(nel),
-                       "dofs": N_global, "nnz": int(nnz) if world == 1 else None, "cell_model": W["model"], "dt": dt,
-                       "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "preconditioner": args.precond, "iters_per_step_mean": k_mean,
-                              "iters_min": int(min(iters)), "iters_max": int(max(iters)), "all_converged": bool(conv_all)},
-                       "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
-                       "parallelism": "single GPU" if world == 1 else
-                       (f"dof-ownership z-slabs x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
-                        f"(CUDA IPC windows; collects and halo push fused into the update kernels unless TB_P2P_FUSED=0), NCCL for "
-                        f"the per-step phi halo" if peer_path else
-                        f"dof-ownership z-slabs x{world}, NCCL halo + allreduce") + (f", cuts at {args.cut}" if world > 1 else ""),
-                       "assembly": {2: "element matrices + ordered gather (deterministic)", 0: "fp64 atomic scatter"}.get(
-                           asm_info["last_mode"], str(asm_info["last_mode"])) + f", {asm_info['last_chunks']} chunk(s)",
-                       "l2": "working set (matrix + vectors) is far larger than the 126 MB L2, no flush needed"
-                             if nnz * 12 > 4e8 else "working set fits L2: tb_l2_flush not applied between steps (steady-state regime)",
-                       "setup_s": t_setup},
+            "config": config_of(args, W, nel),
+            "run_info": {"dofs": N_global, "nnz": int(nnz) if world == 1 else None,
+                         "cg_iters_per_step_mean": k_mean, "cg_iters_min": int(min(iters)), "cg_iters_max": int(max(iters)),
+                         "all_converged": bool(conv_all),
+                         "parallelism": "single GPU" if world == 1 else
+                         (f"dof-ownership z-slabs x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
+                          f"(CUDA IPC windows; {'collects and halo push fused into the update kernels' if part.fused else 'separate push/collect kernels'}), "
+                          f"NCCL for the per-step phi halo" if peer_path else
+                          f"dof-ownership z-slabs x{world}, NCCL halo + allreduce") + (f", cuts at {args.cut}" if world > 1 else ""),
+                         "assembly": {2: "element matrices + ordered gather (deterministic)", 0: "fp64 atomic scatter"}.get(
+                             asm_info["last_mode"], str(asm_info["last_mode"])) + f", {asm_info['last_chunks']} chunk(s)",
+                         "l2": "working set (matrix + vectors) is far larger than the 126 MB L2, no flush needed"
+                               if nnz * 12 > 4e8 else "working set fits L2: tb_l2_flush not applied between steps (steady-state regime)",
+                         "setup_s": t_setup},
+            "parity": parity,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -319,17 +359,19 @@ def cpu_baseline(args, W, nel, all_threads=True):
     """Oracle (CPU restatement of the reference's algorithm, threads over nodes/rows like the reference)
     on a thin z-slab (or sub-square) of the SAME mesh spacing/physics: ~10-30 s of CPU work."""
     import oracle as O
+    cores = host_cores()
+    O.set_num_threads(cores)
     dim = len(nel)
     if dim == 3:
-        snel = (min(nel[0], 512), min(nel[1], 512), min(nel[2], args.cpu_layers))
+        snel = (min(nel[0], 512), min(nel[1], 512), min(nel[2], args.cpu_inline_layers))
         ct = O.HEX8
     else:
         snel = (min(nel[0], 256), min(nel[1], 256))
         ct = O.QUAD4
     lengths = tuple(n * W["h"] for n in snel)
     m = O.generate_grid(ct, snel, (0.0,) * dim, lengths)
-    Mv = O.assemble_mass(m, 2)
-    Kv = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag(W["kappa"][:dim]))
+    Mv = O.assemble_mass(m, 2, threaded=True)
+    Kv = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag(W["kappa"][:dim]), threaded=True)
     model = O.FHN if W["model"] == "fhn" else O.PCG2019
 
     class _T:
@@ -350,7 +392,7 @@ def cpu_baseline(args, W, nel, all_threads=True):
         dtw = time.perf_counter() - t0
         out[name] = m.ndofs * nst / dtw
         out[name + "_iters"] = float(np.mean(orc.iters[1:]))
-    return {"value": out["threaded_blas1"], "unit": "DoF*steps/s", "cores": O.num_threads(), "kind": "port",
+    return {"value": out["threaded_blas1"], "unit": "DoF*steps/s", "cores": cores, "cores_physical": cores, "kind": "port",
             "sample": f"{'x'.join(map(str, snel))} cells ({m.ndofs} DoFs) of the same mesh, {args.cpu_steps} steps after 1 warm-up; "
                       f"oracle = C/OpenMP restatement of the reference's CPU algorithm (not Julia)",
             "serial_blas1_value": out["serial_blas1"], "cg_iters_mean": out["threaded_blas1_iters"]}
@@ -369,13 +411,17 @@ def run_reference(args):
         return
     nel = tuple(int(v) for v in args.grid.split(",")) if args.grid else W["nel"]
     import oracle as O
+    cores = host_cores()
+    O.set_num_threads(cores)        # explicit: torchrun exports OMP_NUM_THREADS=1
     dim = len(nel)
     snel = (min(nel[0], 512), min(nel[1], 512), min(nel[2], args.cpu_layers)) if dim == 3 else (min(nel[0], 256), min(nel[1], 256))
     ct = O.HEX8 if dim == 3 else O.QUAD4
     lengths = tuple(n * W["h"] for n in snel)
+    t_setup = time.time()
     m = O.generate_grid(ct, snel, (0.0,) * dim, lengths)
-    Mv = O.assemble_mass(m, 2)
-    Kv = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag(W["kappa"][:dim]))
+    Mv = O.assemble_mass(m, 2, threaded=True)
+    Kv = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag(W["kappa"][:dim]), threaded=True)
+    t_setup = time.time() - t_setup
     model = O.FHN if W["model"] == "fhn" else O.PCG2019
 
     class _T:
@@ -391,14 +437,17 @@ def run_reference(args):
         orc.step(u, t, W["dt"]); t += W["dt"]
     el = time.perf_counter() - t0
     value = m.ndofs * args.steps / el
-    sample = f"{'x'.join(map(str, snel))} cells ({m.ndofs} DoFs) of the same mesh spacing and physics"
+    frac = f"1/{nel[2] // snel[2]} slab" if dim == 3 and snel[2] < nel[2] else "whole mesh"
+    sample = (f"{'x'.join(map(str, snel))} cells ({m.ndofs} DoFs, {frac}) of the same mesh spacing, physics and initial condition; "
+              f"oracle = C/OpenMP restatement of the reference's CPU algorithm (threads over nodes / rows, threaded BLAS-1), not Julia; "
+              f"DoF*steps/s is size-intensive once the working set ({(Mv.nbytes * 2 + m.pattern()[1].nbytes) / 1e9:.1f} GB) is out of cache")
     print(json.dumps({
         "impl": "reference", "metric": "monodomain DoF*steps/s", "value": value, "unit": "DoF*steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": W["name"], "nel": list(nel), "sample": sample,
-                   "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "iters_per_step_mean": float(np.mean(orc.iters[-args.steps:]))}},
-        "cpu_baseline": {"value": value, "unit": "DoF*steps/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "config": config_of(args, W, nel),
+        "run_info": {"sample_dofs": m.ndofs, "cg_iters_per_step_mean": float(np.mean(orc.iters[-args.steps:])), "setup_s": t_setup},
+        "cpu_baseline": {"value": value, "unit": "DoF*steps/s", "cores": cores, "cores_physical": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "DoF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -412,9 +461,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--grid", default="", help="override cells per direction, e.g. 128,128,32")
-    ap.add_argument("--e2e-steps", type=int, default=4)
-    ap.add_argument("--cpu-layers", type=int, default=2, help="z-layers of cells in the CPU baseline sample")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end (host-buffer) measurement; -1 = same as --steps, 0 = skip")
+    ap.add_argument("--cpu-layers", type=int, default=48,
+                    help="z-layers of cells in the --impl reference sample (48 = the 1/8 slab of C5 BASELINE.md states)")
+    ap.add_argument("--cpu-inline-layers", type=int, default=16, help="z-layers of the cpu_baseline sample printed by the b200 arm")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
+    ap.add_argument("--write-golden", action="store_true", help="N=1 only: store this run's parity sequence as the gpu_n1 section of the golden file")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cut", default="rows", choices=["planes", "rows"],
                     help="multi-GPU ownership cuts: at grid-plane boundaries (one-plane halos) or at equal row counts (balanced)")

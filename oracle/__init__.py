@@ -67,6 +67,8 @@ def lib():
         L.orc_source_eval.restype = C.c_double
         L.orc_assemble_bilinear.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _i64p, _f64p, _i64p, C.c_double,
                                             C.c_int, _f64p, C.c_double, _i64p, _i64p, _f64p]
+        L.orc_assemble_bilinear_par.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _i64p, _f64p, _i64p, C.c_int64, C.c_double,
+                                                C.c_int, _f64p, C.c_double, _i64p, _i64p, _f64p]
         L.orc_assemble_source.argtypes = [C.c_int, C.c_int, C.c_int64, _i64p, _f64p, _i64p, C.c_int, _f64p,
                                           C.c_double, C.c_void_p, C.c_int64, _f64p]
         L.orc_ecg_plonsey.argtypes = [C.c_int, C.c_int, C.c_int64, _i64p, _f64p, _i64p, C.c_int, _f64p, C.c_double, _f64p,
@@ -92,6 +94,13 @@ def lib():
                                    C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                                    C.c_double, C.c_int64, C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.orc_ltg_step.restype = C.c_int64
+        L.orc_stencil_apply.argtypes = [_i64p, _f64p, _f64p, C.c_double, C.c_double, _f64p, _f64p]
+        L.orc_stencil_entry.argtypes = [_i64p, _f64p, _f64p, C.c_int, _i64p, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
+        L.orc_stencil_entry.restype = C.c_double
+        L.orc_stencil_ltg_step.argtypes = [_i64p, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, C.c_double,
+                                           C.c_int, C.c_double, C.c_double, C.c_double, C.c_int64, _f64p,
+                                           C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+        L.orc_stencil_ltg_step.restype = C.c_int64
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -212,20 +221,29 @@ def source_eval(kind, prm, x, t):
     return lib().orc_source_eval(kind, _ddata(prm), x.size, x, t)
 
 
-def assemble_mass(mesh: Mesh, qorder=2, rho=1.0):
+def assemble_mass(mesh: Mesh, qorder=2, rho=1.0, threaded=False):
+    """threaded=True: same values bit for bit (orc_assemble_bilinear_par), for the large parity cases / CPU baseline."""
     rowptr, colidx = mesh.pattern()
     vals = np.zeros(colidx.size)
-    lib().orc_assemble_bilinear(0, mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs, rho, 0,
-                                np.zeros(1), 1.0, rowptr, colidx, vals)
+    if threaded:
+        lib().orc_assemble_bilinear_par(0, mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs,
+                                        mesh.ndofs, rho, 0, np.zeros(1), 1.0, rowptr, colidx, vals)
+    else:
+        lib().orc_assemble_bilinear(0, mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs, rho, 0,
+                                    np.zeros(1), 1.0, rowptr, colidx, vals)
     return vals
 
 
-def assemble_diffusion(mesh: Mesh, qorder, kind, data, cmchi=1.0):
+def assemble_diffusion(mesh: Mesh, qorder, kind, data, cmchi=1.0, threaded=False):
     """K as the reference assembles it: NEGATIVE semi-definite (diffusion.jl:28-50)."""
     rowptr, colidx = mesh.pattern()
     vals = np.zeros(colidx.size)
-    lib().orc_assemble_bilinear(1, mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs, 1.0, kind,
-                                _ddata(data), cmchi, rowptr, colidx, vals)
+    if threaded:
+        lib().orc_assemble_bilinear_par(1, mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs,
+                                        mesh.ndofs, 1.0, kind, _ddata(data), cmchi, rowptr, colidx, vals)
+    else:
+        lib().orc_assemble_bilinear(1, mesh.celltype, qorder, mesh.ncells, mesh.conn, mesh.coords, mesh.celldofs, 1.0, kind,
+                                    _ddata(data), cmchi, rowptr, colidx, vals)
     return vals
 
 
@@ -388,3 +406,46 @@ class MonodomainOracle:
         """get_reaction_tangent (rtc.jl:51-78): R = 0.0; R = max(R, maximum(dumat[:, phi_m])) -- the signed maximum
         (not maximum(abs)) of the phi_m column of the cell solver's du left by the last step, never below zero."""
         return max(0.0, float(self.du[self.phi_idx * self.n:(self.phi_idx + 1) * self.n].max()))
+
+
+class StencilOracle:
+    """Matrix-free twin of MonodomainOracle for a UNIFORM hexahedral grid with a diagonal diffusion tensor (closed-form
+    27-point operator, tb_oracle.c: orc_stencil_*).  Exists because the assembled CSR image of BASELINE config 5
+    (2.7 G nonzeros) does not fit the host; vectors are in grid order (node a + (nx+1)*(b + (ny+1)*c))."""
+
+    def __init__(self, nel, h, kappa, model, prm, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, substeps=1, threshold=0.1, phi_idx=0):
+        self.nel = np.ascontiguousarray(nel, dtype=np.int64)
+        self.h = np.ascontiguousarray(np.broadcast_to(np.asarray(h, dtype=np.float64), (3,)))
+        self.kappa = np.ascontiguousarray(kappa, dtype=np.float64)
+        self.n = int(np.prod(self.nel + 1))
+        self.model, self.prm = model, np.ascontiguousarray(prm, dtype=np.float64)
+        self.atol, self.rtol, self.itmax = atol, rtol, self.n if itmax is None else itmax
+        self.substeps, self.threshold, self.phi_idx = substeps, threshold, phi_idx
+        self.work = np.empty(5 * self.n)
+        self.du = np.zeros(cell_nstates(model) * self.n)
+        self.iters = []
+
+    def node_id(self, a, b, c):
+        return a + (self.nel[0] + 1) * (b + (self.nel[1] + 1) * c)
+
+    def node_coords(self):
+        ax = [np.arange(int(n) + 1) * hh for n, hh in zip(self.nel, self.h)]
+        Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+        return np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+    def apply(self, x, cm=1.0, ck=0.0):
+        y = np.empty(self.n)
+        lib().orc_stencil_apply(self.nel, self.h, self.kappa, cm, ck, np.ascontiguousarray(x, dtype=np.float64), y)
+        return y
+
+    def entry(self, which, node, off):
+        return lib().orc_stencil_entry(self.nel, self.h, self.kappa, which, np.ascontiguousarray(node, dtype=np.int64),
+                                       np.ascontiguousarray(off, dtype=np.int32))
+
+    def step(self, u, t, dt):
+        rn, conv = C.c_double(), C.c_int32()
+        it = lib().orc_stencil_ltg_step(self.nel, self.h, self.kappa, self.model, self.prm, u, self.du, self.phi_idx, t, dt,
+                                        self.substeps, self.threshold, self.atol, self.rtol, self.itmax, self.work,
+                                        C.byref(rn), C.byref(conv))
+        self.iters.append(int(it))
+        return int(it), rn.value, bool(conv.value)

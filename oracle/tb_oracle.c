@@ -168,41 +168,67 @@ static int cmp_i64(const void *a, const void *b) {
     return x < y ? -1 : x > y;
 }
 
-int64_t orc_pattern(int64_t ndofs, int64_t ncells, int nv, const int64_t *celldofs, int64_t *rowptr, int64_t *colidx) {
-    /* dof -> cells adjacency */
-    int64_t *adjptr = (int64_t *)calloc((size_t)ndofs + 1, sizeof(int64_t));
+/* dof -> cells adjacency (cells ascending per dof).  adjptr: ndofs+1, adj: ncells*nv. */
+static void dof_cell_adjacency(int64_t ndofs, int64_t ncells, int nv, const int64_t *celldofs, int64_t *adjptr, int64_t *adj) {
+    for (int64_t d = 0; d <= ndofs; d++) adjptr[d] = 0;
     for (int64_t p = 0; p < ncells * nv; p++) adjptr[celldofs[p] + 1]++;
     for (int64_t d = 0; d < ndofs; d++) adjptr[d + 1] += adjptr[d];
-    int64_t *adj = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ncells * nv));
-    int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)ndofs);
+    int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ndofs + 1));
     memcpy(cur, adjptr, sizeof(int64_t) * (size_t)ndofs);
     for (int64_t c = 0; c < ncells; c++)
-        for (int a = 0; a < nv; a++) adj[cur[celldofs[c * nv + a]]++] = c;
-    int64_t cap = 1024;
-    int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
-    int64_t nnz = 0;
-    rowptr[0] = 0;
-    for (int64_t d = 0; d < ndofs; d++) {
-        int64_t m = 0;
-        int64_t need = (adjptr[d + 1] - adjptr[d]) * nv;
-        if (need > cap) {
-            cap = need * 2;
-            buf = (int64_t *)realloc(buf, sizeof(int64_t) * (size_t)cap);
-        }
-        for (int64_t q = adjptr[d]; q < adjptr[d + 1]; q++)
-            for (int a = 0; a < nv; a++) buf[m++] = celldofs[adj[q] * nv + a];
-        qsort(buf, (size_t)m, sizeof(int64_t), cmp_i64);
-        int64_t u = 0;
-        for (int64_t q = 0; q < m; q++)
-            if (q == 0 || buf[q] != buf[q - 1]) {
-                if (colidx) colidx[nnz + u] = buf[q];
-                u++;
-            }
-        nnz += u;
-        rowptr[d + 1] = nnz;
-    }
-    free(buf);
+        for (int a = 0; a < nv; a++) adj[cur[celldofs[c * nv + a]]++] = c * nv + a;
     free(cur);
+}
+
+/* sorted union of the dofs of the cells around dof d; returns its size */
+static int64_t pattern_row(int64_t d, int nv, const int64_t *celldofs, const int64_t *adjptr, const int64_t *adj, int64_t **buf,
+                           int64_t *cap, int64_t *out) {
+    int64_t m = 0;
+    const int64_t need = (adjptr[d + 1] - adjptr[d]) * nv;
+    if (need > *cap) {
+        *cap = need * 2;
+        *buf = (int64_t *)realloc(*buf, sizeof(int64_t) * (size_t)*cap);
+    }
+    int64_t *b = *buf;
+    for (int64_t q = adjptr[d]; q < adjptr[d + 1]; q++)
+        for (int a = 0; a < nv; a++) b[m++] = celldofs[(adj[q] / nv) * nv + a];
+    qsort(b, (size_t)m, sizeof(int64_t), cmp_i64);
+    int64_t u = 0;
+    for (int64_t q = 0; q < m; q++)
+        if (q == 0 || b[q] != b[q - 1]) {
+            if (out) out[u] = b[q];
+            u++;
+        }
+    return u;
+}
+
+/* Rows are independent, so the two passes (count, fill) run threads over rows; the result does not depend on the
+ * thread count. */
+int64_t orc_pattern(int64_t ndofs, int64_t ncells, int nv, const int64_t *celldofs, int64_t *rowptr, int64_t *colidx) {
+    int64_t *adjptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ndofs + 1));
+    int64_t *adj = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ncells * nv + 1));
+    dof_cell_adjacency(ndofs, ncells, nv, celldofs, adjptr, adj);
+    rowptr[0] = 0;
+#pragma omp parallel
+    {
+        int64_t cap = 1024;
+        int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
+#pragma omp for schedule(static)
+        for (int64_t d = 0; d < ndofs; d++) rowptr[d + 1] = pattern_row(d, nv, celldofs, adjptr, adj, &buf, &cap, NULL);
+        free(buf);
+    }
+    for (int64_t d = 0; d < ndofs; d++) rowptr[d + 1] += rowptr[d];
+    const int64_t nnz = rowptr[ndofs];
+    if (colidx) {
+#pragma omp parallel
+        {
+            int64_t cap = 1024;
+            int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * (size_t)cap);
+#pragma omp for schedule(static)
+            for (int64_t d = 0; d < ndofs; d++) pattern_row(d, nv, celldofs, adjptr, adj, &buf, &cap, colidx + rowptr[d]);
+            free(buf);
+        }
+    }
     free(adj);
     free(adjptr);
     return nnz;
@@ -519,6 +545,56 @@ void orc_assemble_bilinear(int op, int ct, int qorder, int64_t ncells, const int
             }
         }
     }
+}
+
+/* Threaded twin of orc_assemble_bilinear with BITWISE the same result: the sequential element loop adds the
+ * contributions to one stored entry in ascending cell order, so (1) the element matrices of a chunk of consecutive
+ * cells are computed by all threads into a scratch array, (2) threads over rows add, for every adjacent cell of the
+ * chunk in ascending order, row `a` of that cell's matrix to the row's entries.  Chunks are processed in ascending
+ * order, hence every entry still sees its contributions in the order of the sequential loop.  Test infrastructure
+ * only (large parity cases and the CPU baseline's setup); tests/test_oracle_independent.py checks it against the
+ * sequential loop. */
+void orc_assemble_bilinear_par(int op, int ct, int qorder, int64_t ncells, const int64_t *conn, const double *coords,
+                               const int64_t *celldofs, int64_t ndofs, double rho, int kind, const double *data, double cmchi,
+                               const int64_t *rowptr, const int64_t *colidx, double *vals) {
+    const int nv = cell_nv(ct), dim = cell_dim(ct);
+    int64_t *adjptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ndofs + 1));
+    int64_t *adj = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ncells * nv + 1));
+    dof_cell_adjacency(ndofs, ncells, nv, celldofs, adjptr, adj);
+    int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ndofs + 1));
+    memcpy(cur, adjptr, sizeof(int64_t) * (size_t)(ndofs + 1));
+    const int64_t chunk = 1 << 20;
+    double *EA = (double *)malloc(sizeof(double) * (size_t)(chunk * nv * nv));
+    for (int64_t c0 = 0; c0 < ncells; c0 += chunk) {
+        const int64_t c1 = c0 + chunk < ncells ? c0 + chunk : ncells;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = c0; c < c1; c++) {
+            double X[ORC_MAXNV * 3];
+            for (int a = 0; a < nv; a++)
+                for (int d = 0; d < dim; d++) X[a * dim + d] = coords[conn[c * nv + a] * dim + d];
+            double *Ke = EA + (c - c0) * nv * nv;
+            if (op == 0) orc_element_mass(ct, qorder, X, rho, Ke);
+            else orc_element_diffusion(ct, qorder, X, kind, data, cmchi, c, Ke);
+        }
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (int64_t r = 0; r < ndofs; r++) {
+            int64_t q = cur[r];
+            for (; q < adjptr[r + 1] && adj[q] / nv < c1; q++) {
+                const int64_t c = adj[q] / nv;
+                const int i = (int)(adj[q] % nv);
+                const double *Ke = EA + (c - c0) * nv * nv;
+                for (int j = 0; j < nv; j++) {
+                    int64_t p = find_col(colidx, rowptr[r], rowptr[r + 1], celldofs[c * nv + j]);
+                    vals[p] += Ke[i * nv + j];
+                }
+            }
+            cur[r] = q;
+        }
+    }
+    free(EA);
+    free(cur);
+    free(adj);
+    free(adjptr);
 }
 
 /* b is zeroed first, as update_operator! of a LinearFerriteOperator does */
@@ -859,4 +935,116 @@ int64_t orc_ltg_step(int64_t n, const int64_t *rowptr, const int64_t *colidx, co
     memcpy(phi, x, sizeof(double) * (size_t)n);
     orc_cell_step(model, prm, u, du, n, ld, t, dt, substeps, threshold, phi_idx);
     return it;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Closed-form operator of a UNIFORM hexahedral grid with a diagonal diffusion tensor -- a second, matrix-free
+ * restatement used where the assembled CSR image does not fit the host (BASELINE config 5: 101 M dofs, 2.7 G
+ * nonzeros).  For Lagrange-1 on a uniform grid the 2x2x2 Gauss rule integrates mass and stiffness exactly, so
+ *     M = Mx (x) My (x) Mz,   K_ref = -( kx Kx(x)My(x)Mz + ky Mx(x)Ky(x)Mz + kz Mx(x)My(x)Kz )      (negative, a-7)
+ * with the 1D matrices  M1 = h*[1/6 2/3 1/6] (ends h*[1/3 1/6]),  K1 = (1/h)*[-1 2 -1] (ends (1/h)*[1 -1]).
+ * Vectors are in GRID ORDER (node a + (nx+1)*(b + (ny+1)*c)), not in dof order: this oracle never numbers dofs; the
+ * harness matches nodes by coordinates.  tests/test_oracle_independent.py pins the closed form against the assembled
+ * oracle matrices (orc_assemble_bilinear) on small grids.
+ *   y = cm * M x + ck * K_ref x
+ * ---------------------------------------------------------------------------------------- */
+static void stencil_1d(int64_t n, double h, int64_t i, double *m3, double *k3) {
+    /* row i of the (n+1)x(n+1) 1D mass / stiffness matrices, offsets -1, 0, +1 */
+    const int lo = i > 0, hi = i < n;
+    m3[0] = lo ? h / 6.0 : 0.0;
+    m3[2] = hi ? h / 6.0 : 0.0;
+    m3[1] = (lo ? h / 3.0 : 0.0) + (hi ? h / 3.0 : 0.0);
+    k3[0] = lo ? -1.0 / h : 0.0;
+    k3[2] = hi ? -1.0 / h : 0.0;
+    k3[1] = (lo ? 1.0 / h : 0.0) + (hi ? 1.0 / h : 0.0);
+}
+
+void orc_stencil_apply(const int64_t *nel, const double *h, const double *kappa, double cm, double ck, const double *x,
+                       double *y) {
+    const int64_t nx = nel[0], ny = nel[1], nz = nel[2];
+    const int64_t sx = nx + 1, sy = ny + 1, sz = nz + 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < sz; c++) {
+        double mz[3], kz[3];
+        stencil_1d(nz, h[2], c, mz, kz);
+        for (int64_t b = 0; b < sy; b++) {
+            double my[3], ky[3];
+            stencil_1d(ny, h[1], b, my, ky);
+            for (int64_t a = 0; a < sx; a++) {
+                double mx[3], kx[3];
+                stencil_1d(nx, h[0], a, mx, kx);
+                double acc = 0.0;
+                for (int dc = -1; dc <= 1; dc++) {
+                    if (c + dc < 0 || c + dc >= sz) continue;
+                    for (int db = -1; db <= 1; db++) {
+                        if (b + db < 0 || b + db >= sy) continue;
+                        for (int da = -1; da <= 1; da++) {
+                            if (a + da < 0 || a + da >= sx) continue;
+                            const double m = mx[da + 1] * my[db + 1] * mz[dc + 1];
+                            const double k = -(kappa[0] * (kx[da + 1] * my[db + 1] * mz[dc + 1]) +
+                                               kappa[1] * (mx[da + 1] * ky[db + 1] * mz[dc + 1]) +
+                                               kappa[2] * (mx[da + 1] * my[db + 1] * kz[dc + 1]));
+                            acc += (cm * m + ck * k) * x[(a + da) + sx * ((b + db) + sy * (c + dc))];
+                        }
+                    }
+                }
+                y[a + sx * (b + sy * c)] = acc;
+            }
+        }
+    }
+}
+
+/* one stored entry of the closed-form M (which = 0) or K_ref (which = 1) between grid nodes (a,b,c) and (a+da,b+db,c+dc) */
+double orc_stencil_entry(const int64_t *nel, const double *h, const double *kappa, int which, const int64_t *node,
+                         const int *off) {
+    double m[3][3], k[3][3];
+    for (int d = 0; d < 3; d++) stencil_1d(nel[d], h[d], node[d], m[d], k[d]);
+    for (int d = 0; d < 3; d++)
+        if (off[d] < -1 || off[d] > 1 || node[d] + off[d] < 0 || node[d] + off[d] > nel[d]) return 0.0;
+    const double mx = m[0][off[0] + 1], my = m[1][off[1] + 1], mz = m[2][off[2] + 1];
+    const double kx = k[0][off[0] + 1], ky = k[1][off[1] + 1], kz = k[2][off[2] + 1];
+    if (which == 0) return mx * my * mz;
+    return -(kappa[0] * (kx * my * mz) + kappa[1] * (mx * ky * mz) + kappa[2] * (mx * my * kz));
+}
+
+/* orc_ltg_step with the closed-form operator: b = M phi; CG (same recurrence and stopping rule as orc_cg, threaded
+ * dot products) on A = M - dt*K_ref; phi <- x; cell sweep.  u, du: SoA in grid order; work: 5n doubles. */
+int64_t orc_stencil_ltg_step(const int64_t *nel, const double *h, const double *kappa, int model, const double *prm,
+                             double *u, double *du, int phi_idx, double t, double dt, int substeps, double threshold,
+                             double atol, double rtol, int64_t itmax, double *work, double *rnorm, int32_t *converged) {
+    const int64_t n = (nel[0] + 1) * (nel[1] + 1) * (nel[2] + 1);
+    double *b = work, *x = work + n, *r = work + 2 * n, *p = work + 3 * n, *Ap = work + 4 * n;
+    double *phi = u + (int64_t)phi_idx * n;
+    orc_stencil_apply(nel, h, kappa, 1.0, 0.0, phi, b);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) { x[i] = 0.0; r[i] = b[i]; p[i] = b[i]; }
+    double gamma = dot_omp(n, r, r);
+    double rn = sqrt(gamma);
+    const double eps = atol + rtol * rn;
+    int solved = rn <= eps;
+    int64_t iter = 0;
+    int tired = iter >= itmax;
+    while (!(solved || tired)) {
+        orc_stencil_apply(nel, h, kappa, 1.0, -dt, p, Ap);
+        const double pAp = dot_omp(n, p, Ap);
+        const double alpha = gamma / pAp;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; i++) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
+        const double gnext = dot_omp(n, r, r);
+        rn = sqrt(gnext);
+        solved = rn <= eps;
+        if (!solved) {
+            const double beta = gnext / gamma;
+            gamma = gnext;
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < n; i++) p[i] = r[i] + beta * p[i];
+        }
+        iter++;
+        tired = iter >= itmax;
+    }
+    *rnorm = rn;
+    *converged = solved;
+    memcpy(phi, x, sizeof(double) * (size_t)n);
+    orc_cell_step(model, prm, u, du, n, n, t, dt, substeps, threshold, phi_idx);
+    return iter;
 }

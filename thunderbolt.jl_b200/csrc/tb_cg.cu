@@ -59,9 +59,11 @@ __device__ __forceinline__ void cg_after_rr(CGState *st, double gnext) {
 // which: 0 init, 1 pAp, 2 rr.  Used on the multi-GPU path after the NCCL all-reduce of st->local[0].
 // With a peer window (ar.wins != nullptr) this one thread IS the all-reduce: it waits for every rank's partial of this
 // epoch and adds them in rank order, so all ranks advance with bitwise identical scalars.
-__global__ void k_cg_scalar(CGState *st, int which, const tb_ar_args ar) {
+__global__ void k_cg_scalar(CGState *st, int which, const tb_ar_args ar, bool exact) {
     if (which != 0 && st->done) return;
-    const double total = ar.wins ? tb_ar_collect(ar) : st->local[0];
+    // NCCL path in exact mode: local[0] / local[1] hold the all-reduced high and low words (summed separately)
+    const double total = ar.wins ? (exact ? tb_ar_collect_acc<true>(ar) : tb_ar_collect(ar))
+                                 : (exact ? st->local[0] + st->local[1] : st->local[0]);
     if (which == 0) cg_after_init(st, total);
     else if (which == 1) cg_after_pAp(st, total);
     else cg_after_rr(st, total);
@@ -78,50 +80,53 @@ __global__ void k_cg_set_tol(CGState *st, double atol, double rtol, long long it
 
 // finishing step shared by the reducing kernels: single GPU -> advance the scalars here;
 // multi GPU -> leave the rank-local sum for the all-reduce
-template <int WHICH>
-__device__ __forceinline__ void cg_finish(double block_value, CGState *st, double *partials, unsigned *ticket, double *sm,
+template <int WHICH, bool X>
+__device__ __forceinline__ void cg_finish(tb_acc<X> block_value, CGState *st, double *partials, unsigned *ticket, double *sm,
                                           bool dist, const tb_ar_args &ar) {
-    double total;
-    if (tb_grid_sum(block_value, partials, ticket, sm, &total) && threadIdx.x == 0) {
-        if (dist && ar.wins) tb_ar_publish(ar, total);
-        else if (dist) st->local[0] = total;
-        else if (WHICH == 0) cg_after_init(st, total);
-        else if (WHICH == 1) cg_after_pAp(st, total);
-        else cg_after_rr(st, total);
+    tb_acc<X> total;
+    if (tb_grid_sum_acc<X>(block_value, partials, ticket, sm, &total) && threadIdx.x == 0) {
+        if (dist && ar.wins) tb_ar_publish_acc<X>(ar, total);
+        else if (dist) {
+            st->local[0] = total.hi;
+            st->local[1] = total.low();
+        } else if (WHICH == 0) cg_after_init(st, total.value());
+        else if (WHICH == 1) cg_after_pAp(st, total.value());
+        else cg_after_rr(st, total.value());
     }
 }
 
 // ---- init from a given right-hand side: x = 0, r = p = b, gamma = b.b ------------------------------
+template <bool X>
 __global__ void __launch_bounds__(256) k_cg_init_b(const double *__restrict__ b, double *__restrict__ x,
                                                    double *__restrict__ r, double *__restrict__ p, int64_t n, CGState *st,
                                                    double *partials, unsigned *ticket, bool dist, const tb_ar_args ar,
                                                    const double *__restrict__ dinv) {
-    __shared__ double sm[32];
-    double acc = 0.0;
+    __shared__ double sm[64];
+    tb_acc<X> acc;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double v = b[i];
         const double z = dinv ? dinv[i] * v : v;      // z = M r (Jacobi), p = z, gamma = r.z
         x[i] = 0.0;
         r[i] = v;
         p[i] = z;
-        acc += v * z;
+        acc.add_prod(v, z);
     }
-    const double bs = tb_block_sum(acc, sm);
-    cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
+    cg_finish<0, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
 }
 
 // ---- init fused with the backward-Euler right-hand side: r = p = M*phi (+ bS), x = 0 ----------------
 // ("b = M u_{n-1}" + add!(b, source), src/solver/time/euler.jl:85-91)
+template <bool X>
 __global__ void __launch_bounds__(256)
     k_cg_init_Mphi(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ Mval,
                    const double *__restrict__ phi, const double *__restrict__ bS, double *__restrict__ x,
                    double *__restrict__ r, double *__restrict__ p, int64_t nrows, int64_t nslices, CGState *st,
                    double *partials, unsigned *ticket, bool dist, const tb_ar_args ar, const double *__restrict__ dinv) {
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    double acc = 0.0;
+    tb_acc<X> acc;
     for (int64_t s = warp; s < nslices; s += nwarps) {
         double v = tb_sell_row(slice_ptr, col, Mval, phi, s, lane);
         const int64_t row = s * TB_SLICE + lane;
@@ -131,41 +136,40 @@ __global__ void __launch_bounds__(256)
             x[row] = 0.0;
             r[row] = v;
             p[row] = z;
-            acc += v * z;
+            acc.add_prod(v, z);
         }
     }
-    const double bs = tb_block_sum(acc, sm);
-    cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
+    cg_finish<0, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
 }
 
 // ---- Ap = A p, p.Ap -------------------------------------------------------------------------------
+template <bool X>
 __global__ void __launch_bounds__(256)
     k_cg_spmv_dot(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ val,
                   const double *__restrict__ p, double *__restrict__ Ap, int64_t nrows, int64_t nslices, CGState *st,
                   double *partials, unsigned *ticket, bool dist, const tb_ar_args ar, const tb_hwait_args hw) {
     if (st->done) return;
     tb_halo_wait(hw);
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    double acc = 0.0;
+    tb_acc<X> acc;
     for (int64_t s = warp; s < nslices; s += nwarps) {
         const double v = tb_sell_row(slice_ptr, col, val, p, s, lane);
         const int64_t row = s * TB_SLICE + lane;
         if (row < nrows) {
             Ap[row] = v;
-            acc += p[row] * v;
+            acc.add_prod(p[row], v);
         }
     }
-    const double bs = tb_block_sum(acc, sm);
-    cg_finish<1>(bs, st, partials, ticket, sm, dist, ar);
+    cg_finish<1, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
 }
 
 // ---- bulk-async (TMA) variants of the two SpMV-shaped kernels ------------------------------------------
 // Same arithmetic and summation order as above; the matrix stream comes through cp.async.bulk + mbarrier
 // (tb_spmv.cuh).  INIT = true: r = p = M*phi (+bS), x = 0, gamma; false: Ap = A p, p.Ap.
-template <int STAGES, bool INIT, bool CC>
+template <int STAGES, bool INIT, bool CC, bool X>
 __global__ void __launch_bounds__(1024, 1)
     k_cg_spmv_tma(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const int *__restrict__ cstream,
                   const int64_t *__restrict__ cptr,
@@ -176,8 +180,8 @@ __global__ void __launch_bounds__(1024, 1)
     if (!INIT && st->done) return;
     tb_halo_wait(hw);
     extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
-    __shared__ double sm[32];
-    double acc = 0.0;
+    __shared__ double sm[64];
+    tb_acc<X> acc;
     auto epi = [&](int64_t row, double v) {
         if (row < nrows) {
             if (INIT) {
@@ -186,17 +190,17 @@ __global__ void __launch_bounds__(1024, 1)
                 xout[row] = 0.0;
                 r[row] = v;
                 pout[row] = z;
-                acc += v * z;
+                acc.add_prod(v, z);
             } else {
                 r[row] = v;              // r aliases Ap here
-                acc += xin[row] * v;
+                acc.add_prod(xin[row], v);
             }
         }
     };
     tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, epi, nullptr, col, wide);
-    const double bs = tb_block_sum(acc, sm);
-    if (INIT) cg_finish<0>(bs, st, partials, ticket, sm, dist, ar);
-    else cg_finish<1>(bs, st, partials, ticket, sm, dist, ar);
+    const tb_acc<X> bs = tb_block_sum_acc<X>(acc, sm);
+    if (INIT) cg_finish<0, X>(bs, st, partials, ticket, sm, dist, ar);
+    else cg_finish<1, X>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 template <int STAGES, bool INIT>
@@ -210,15 +214,21 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
     tb_wide_list wide;
     wide.slices = pat->d_wide_slices;
     wide.n = (int)pat->n_wide;
+#define TB_SPMV_TMA_LAUNCH(CCV, XV, colstream, cptrv)                                                                          \
+    do {                                                                                                                      \
+        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_tma<STAGES, INIT, CCV, XV>, g.smem));                             \
+        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, CCV, XV>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, colstream, \
+                  cptrv, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, \
+                  hw, dinv, wide);                                                                                            \
+    } while (0)
     if (cc) {
-        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_tma<STAGES, INIT, true>, g.smem));
-        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, true>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_ccol,
-                  pat->d_cptr, val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv, wide);
+        if (ctx->exact_dot) TB_SPMV_TMA_LAUNCH(true, true, pat->d_ccol, pat->d_cptr);
+        else TB_SPMV_TMA_LAUNCH(true, false, pat->d_ccol, pat->d_cptr);
     } else {
-        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_tma<STAGES, INIT, false>, g.smem));
-        TB_LAUNCH(ctx, (k_cg_spmv_tma<STAGES, INIT, false>), grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_col, nullptr,
-                  val, xin, bS, xout, r, pout, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, dist, ar, hw, dinv, wide);
+        if (ctx->exact_dot) TB_SPMV_TMA_LAUNCH(false, true, pat->d_col, nullptr);
+        else TB_SPMV_TMA_LAUNCH(false, false, pat->d_col, nullptr);
     }
+#undef TB_SPMV_TMA_LAUNCH
     return TB_OK;
 }
 
@@ -238,15 +248,16 @@ static int32_t dispatch_spmv_tma(tb_ctx *ctx, const tb_pattern *pat, const doubl
 }
 
 // ---- x += alpha p; r -= alpha Ap; r.r  (128-bit loads/stores) --------------------------------------
+template <bool X>
 __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                                                const double *__restrict__ Ap, int64_t n, CGState *st, double *partials,
                                                unsigned *ticket, bool dist, const tb_ar_args ar,
                                                const double *__restrict__ dinv) {
     if (st->done) return;
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     const double alpha = st->alpha;
     const int64_t n2 = n >> 1;
-    double acc = 0.0;
+    tb_acc<X> acc;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
         double2 xv = reinterpret_cast<double2 *>(x)[i], rv = reinterpret_cast<double2 *>(r)[i];
         const double2 pv = reinterpret_cast<const double2 *>(p)[i], av = reinterpret_cast<const double2 *>(Ap)[i];
@@ -258,11 +269,11 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
         reinterpret_cast<double2 *>(r)[i] = rv;
         if (dinv) {   // gamma' = r.z, z = M r
             const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
-            acc += rv.x * (dv.x * rv.x);
-            acc += rv.y * (dv.y * rv.y);
+            acc.add_prod(rv.x, dv.x * rv.x);
+            acc.add_prod(rv.y, dv.y * rv.y);
         } else {
-            acc += rv.x * rv.x;
-            acc += rv.y * rv.y;
+            acc.add_prod(rv.x, rv.x);
+            acc.add_prod(rv.y, rv.y);
         }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -270,10 +281,9 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
         const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * Ap[i];
         x[i] = xn;
         r[i] = rn;
-        acc += dinv ? rn * (dinv[i] * rn) : rn * rn;
+        acc.add_prod(rn, dinv ? dinv[i] * rn : rn);
     }
-    const double bs = tb_block_sum(acc, sm);
-    cg_finish<2>(bs, st, partials, ticket, sm, dist, ar);
+    cg_finish<2, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
 }
 
 // ---- p = r + beta p ---------------------------------------------------------------------------------
@@ -305,22 +315,24 @@ __global__ void __launch_bounds__(256) k_cg_p(const double *__restrict__ r, doub
 //                 raises the neighbours' halo flags.  CTA 0 writes the advanced scalars into the OTHER CGState (ping-pong:
 //                 a CTA that starts late must still read the old gamma), which the next iteration's kernels then read.
 // Three launches per iteration, like the single-GPU path; no NCCL call, no helper kernel.
+template <bool X>
 __global__ void __launch_bounds__(256) k_cg_xr_fused(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                                                      const double *__restrict__ Ap, int64_t n, const CGState *sin, double *partials,
                                                      unsigned *ticket, const tb_ar_args ar_in, const tb_ar_args ar_out,
                                                      const double *__restrict__ dinv) {
     if (sin->done) return;
-    __shared__ double sm[32];
+    __shared__ double sm[64];
     __shared__ double s_alpha;
     if (threadIdx.x == 0) {
-        const double pAp = tb_ar_collect(ar_in);
+        const double pAp = tb_ar_collect_acc<X>(ar_in);
         s_alpha = pAp > 0.0 ? sin->gamma / pAp : NAN;   // NaN / non-positive curvature: leave x and r alone, poison r.z so that
     }                                                   // k_cg_p_fused gives up (same outcome as cg_after_pAp on one GPU)
     __syncthreads();
     const double alpha = s_alpha;
     const bool bad = alpha != alpha;
     const int64_t n2 = bad ? 0 : n >> 1;
-    double acc = bad ? NAN : 0.0;
+    tb_acc<X> acc;
+    if (bad) acc.set(NAN, 0.0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
         double2 xv = reinterpret_cast<double2 *>(x)[i], rv = reinterpret_cast<double2 *>(r)[i];
         const double2 pv = reinterpret_cast<const double2 *>(p)[i], av = reinterpret_cast<const double2 *>(Ap)[i];
@@ -332,11 +344,11 @@ __global__ void __launch_bounds__(256) k_cg_xr_fused(double *__restrict__ x, dou
         reinterpret_cast<double2 *>(r)[i] = rv;
         if (dinv) {
             const double2 dv = reinterpret_cast<const double2 *>(dinv)[i];
-            acc += rv.x * (dv.x * rv.x);
-            acc += rv.y * (dv.y * rv.y);
+            acc.add_prod(rv.x, dv.x * rv.x);
+            acc.add_prod(rv.y, dv.y * rv.y);
         } else {
-            acc += rv.x * rv.x;
-            acc += rv.y * rv.y;
+            acc.add_prod(rv.x, rv.x);
+            acc.add_prod(rv.y, rv.y);
         }
     }
     if (!bad && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -344,11 +356,11 @@ __global__ void __launch_bounds__(256) k_cg_xr_fused(double *__restrict__ x, dou
         const double xn = x[i] + alpha * p[i], rn = r[i] - alpha * Ap[i];
         x[i] = xn;
         r[i] = rn;
-        acc += dinv ? rn * (dinv[i] * rn) : rn * rn;
+        acc.add_prod(rn, dinv ? dinv[i] * rn : rn);
     }
-    const double bs = tb_block_sum(acc, sm);
-    double total;
-    if (tb_grid_sum(bs, partials, ticket, sm, &total) && threadIdx.x == 0) tb_ar_publish(ar_out, total);
+    tb_acc<X> total;
+    if (tb_grid_sum_acc<X>(tb_block_sum_acc<X>(acc, sm), partials, ticket, sm, &total) && threadIdx.x == 0)
+        tb_ar_publish_acc<X>(ar_out, total);
 }
 
 __device__ __forceinline__ void tb_push_row(const tb_push_args &pa, int64_t row, double v) {
@@ -358,6 +370,7 @@ __device__ __forceinline__ void tb_push_row(const tb_push_args &pa, int64_t row,
     }
 }
 
+template <bool X>
 __global__ void __launch_bounds__(256) k_cg_p_fused(const double *__restrict__ r, double *__restrict__ p, int64_t n,
                                                     const CGState *sin, CGState *sout, const tb_ar_args ar_in,
                                                     const double *__restrict__ dinv, const tb_push_args pa, unsigned *ticket) {
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(256) k_cg_p_fused(const double *__restrict__ r
     __shared__ double s_beta, s_gnext;
     __shared__ int s_solved, s_last;
     if (threadIdx.x == 0) {
-        const double gnext = tb_ar_collect(ar_in);
+        const double gnext = tb_ar_collect_acc<X>(ar_in);
         s_gnext = gnext;
         s_solved = sqrt(gnext) <= sin->eps;
         s_beta = gnext / sin->gamma;

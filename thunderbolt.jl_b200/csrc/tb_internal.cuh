@@ -91,6 +91,7 @@ int32_t tb_fail(int32_t code, const char *fmt, ...);
 #define TB_AR_SLOTS 8
 struct tb_peer_window {
     double val[TB_AR_SLOTS][TB_MAX_RANKS];
+    double val_lo[TB_AR_SLOTS][TB_MAX_RANKS];   // low words of the partial sums (exact-dot mode, see tb_acc)
     unsigned long long flag[TB_AR_SLOTS][TB_MAX_RANKS];
     unsigned long long hflag[TB_MAX_RANKS];
     unsigned long long err;          // set by a waiter that timed out
@@ -138,7 +139,7 @@ struct tb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     // scratch for deterministic two-stage reductions (block partials + last-block ticket)
-    double *d_partials = nullptr;   // 4 * TB_MAX_PARTIALS
+    double *d_partials = nullptr;   // 4 * TB_MAX_PARTIALS, followed by the same layout again for the low words (exact-dot mode)
     unsigned *d_ticket = nullptr;   // 8 tickets
     // CG workspace (grown on demand): r, p, Ap as one tb_vec-like allocation
     double *d_cgwork = nullptr;
@@ -164,6 +165,7 @@ struct tb_ctx {
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
     int cg_persistent = 1;            // 0: never; 1: auto (small: register-resident kernel, mid-size: TMA kernel); 2: TMA kernel whenever eligible (tests); env TB_CG_PERSISTENT
     int last_cg_persistent = 0;       // path of the last solve: 0 multi-kernel, 1 persistent (registers), 2 persistent (TMA sweep, vectors in L2)
+    int exact_dot = 0;                // 1: CG dot products accumulated in double-double (order-independent after rounding; env TB_DOT_EXACT)
     int p2p_fused = 1;                // multi-GPU peer path: 1 = collects and halo push inside the CG kernels (3 launches per iteration), 0 = separate tiny kernels (env TB_P2P_FUSED)
     int64_t cg_persistent_max_rows = 4000000;   // above this the multi-kernel path is used (env TB_CG_PERSISTENT_MAX_ROWS)
     // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
@@ -191,7 +193,7 @@ struct CGState {
     double rnorm;
     double eps;         // atol + rtol*|r0|
     double atol, rtol;
-    double local[2];    // per-rank partial sums awaiting the allreduce (multi-GPU)
+    double local[2];    // per-rank partial sums awaiting the allreduce (multi-GPU); [1] = low word in exact-dot mode
     long long iter;
     long long itmax;
     int done;           // solved || tired
@@ -329,6 +331,72 @@ __device__ __forceinline__ double tb_warp_max(double v) {
     return v;
 }
 
+// ---- dot-product accumulators ------------------------------------------------------------------------------------
+// tb_acc<false>: plain fp64 accumulation (the default; fastest).  tb_acc<true>: double-double accumulation with exact
+// products (TwoProd by fma) and error-free additions (TwoSum), i.e. the sum is carried to ~2^-104 relative accuracy and
+// only the FINAL value is rounded to fp64.  Two different summation orders then round to the same double except when
+// the exact sum lies within ~1e-24 (relative) of a rounding boundary, so the CG scalars -- and with them every
+// iterate, the stopping decision and the iteration count -- no longer depend on the grid size, on the number of GPUs
+// or on whether the sum was formed sequentially on a CPU (the oracle's "exact" mode).  SURVEY 7 hard part 1.
+__device__ __forceinline__ void tb_two_sum(double a, double b, double &s, double &e) {
+    s = a + b;
+    const double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+}
+template <bool X> struct tb_acc;
+template <> struct tb_acc<false> {
+    double hi = 0.0;
+    __device__ __forceinline__ void add_prod(double a, double b) { hi += a * b; }
+    __device__ __forceinline__ void add(const tb_acc &o) { hi += o.hi; }
+    __device__ __forceinline__ void set(double h, double) { hi = h; }
+    __device__ __forceinline__ double low() const { return 0.0; }
+    __device__ __forceinline__ double value() const { return hi; }
+};
+template <> struct tb_acc<true> {
+    double hi = 0.0, lo = 0.0;
+    __device__ __forceinline__ void add_pair(double h, double l) {
+        double s, e;
+        tb_two_sum(hi, h, s, e);
+        e += lo + l;
+        hi = s + e;               // renormalise (fast two-sum)
+        lo = e - (hi - s);
+    }
+    __device__ __forceinline__ void add_prod(double a, double b) {
+        const double p = a * b;
+        add_pair(p, __fma_rn(a, b, -p));
+    }
+    __device__ __forceinline__ void add(const tb_acc &o) { add_pair(o.hi, o.lo); }
+    __device__ __forceinline__ void set(double h, double l) { hi = h; lo = l; }
+    __device__ __forceinline__ double low() const { return lo; }
+    __device__ __forceinline__ double value() const { return hi + lo; }
+};
+template <bool X> __device__ __forceinline__ tb_acc<X> tb_warp_sum_acc(tb_acc<X> v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tb_acc<X> w;
+        w.set(__shfl_xor_sync(0xffffffffu, v.hi, o), X ? __shfl_xor_sync(0xffffffffu, v.low(), o) : 0.0);
+        v.add(w);
+    }
+    return v;
+}
+// Sum over the block; result valid in every thread of warp 0.  `sm` has >= 64 doubles.
+template <bool X> __device__ __forceinline__ tb_acc<X> tb_block_sum_acc(tb_acc<X> v, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = tb_warp_sum_acc<X>(v);
+    __syncthreads();
+    if (lane == 0) {
+        sm[warp] = v.hi;
+        if (X) sm[32 + warp] = v.low();
+    }
+    __syncthreads();
+    tb_acc<X> r;
+    if (warp == 0) {
+        if (lane < nw) r.set(sm[lane], X ? sm[32 + lane] : 0.0);
+        r = tb_warp_sum_acc<X>(r);
+    }
+    return r;
+}
+
 // Sum over the block; result valid in every thread of warp 0.  `sm` has >= 32 doubles.
 __device__ __forceinline__ double tb_block_sum(double v, double *sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -369,6 +437,33 @@ __device__ __forceinline__ bool tb_grid_sum(double block_value /* valid in threa
     double s = 0.0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += ((volatile double *)partials)[i];
     s = tb_block_sum(s, sm);
+    if (threadIdx.x == 0) *total = s;
+    return true;
+}
+
+// tb_grid_sum for accumulators: partials[] holds the high words, partials[4*TB_MAX_PARTIALS + ...] the low words.
+template <bool X>
+__device__ __forceinline__ bool tb_grid_sum_acc(tb_acc<X> block_value /* valid in thread 0 */, double *partials, unsigned *ticket,
+                                                double *sm, tb_acc<X> *total) {
+    __shared__ int s_last_acc;
+    double *plo = partials + 4 * TB_MAX_PARTIALS;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = block_value.hi;
+        if (X) plo[blockIdx.x] = block_value.low();
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);
+        s_last_acc = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last_acc) return false;
+    __threadfence();
+    tb_acc<X> s;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        tb_acc<X> w;
+        w.set(((volatile double *)partials)[i], X ? ((volatile double *)plo)[i] : 0.0);
+        s.add(w);
+    }
+    s = tb_block_sum_acc<X>(s, sm);
     if (threadIdx.x == 0) *total = s;
     return true;
 }
@@ -422,6 +517,26 @@ __device__ __forceinline__ void tb_ar_publish(const tb_ar_args &a, double v) {
     for (int q = 0; q < a.nranks; q++) a.wins[q]->val[a.slot][a.rank] = v;
     __threadfence_system();
     for (int q = 0; q < a.nranks; q++) *(volatile unsigned long long *)&a.wins[q]->flag[a.slot][a.rank] = a.epoch;
+}
+// the same two steps for (hi, lo) pairs
+template <bool X> __device__ __forceinline__ void tb_ar_publish_acc(const tb_ar_args &a, const tb_acc<X> &v) {
+    for (int q = 0; q < a.nranks; q++) {
+        a.wins[q]->val[a.slot][a.rank] = v.hi;
+        if (X) a.wins[q]->val_lo[a.slot][a.rank] = v.low();
+    }
+    __threadfence_system();
+    for (int q = 0; q < a.nranks; q++) *(volatile unsigned long long *)&a.wins[q]->flag[a.slot][a.rank] = a.epoch;
+}
+template <bool X> __device__ __forceinline__ double tb_ar_collect_acc(const tb_ar_args &a) {
+    tb_peer_window *w = a.wins[a.rank];
+    tb_acc<X> s;
+    for (int q = 0; q < a.nranks; q++) {
+        tb_wait_flag(&w->flag[a.slot][q], a.epoch, &w->err);
+        tb_acc<X> t;
+        t.set(*(volatile double *)&w->val[a.slot][q], X ? *(volatile double *)&w->val_lo[a.slot][q] : 0.0);
+        s.add(t);
+    }
+    return s.value();
 }
 // one thread: wait for all ranks' partials of this epoch and add them in rank order
 __device__ __forceinline__ double tb_ar_collect(const tb_ar_args &a) {
