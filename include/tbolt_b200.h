@@ -266,6 +266,15 @@ int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bc
  * tb_cg_last_path reports the path of the last solve. */
 int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t mode);
 int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *path);
+/* Order-independent dot products (off by default; env TB_DOT_EXACT=1).  Krylov's cg! forms r.r and p.Ap with BLAS `dot`
+ * (euler.jl:94 -> KrylovJL_CG); any two implementations differ in summation order, and on ill-conditioned operators
+ * (LV meshes) that rounding noise decides on which side of `atol + rtol |r0|` an iterate falls -- hence the +-1 in the
+ * iteration rule.  With exact = 1 every CG dot product is accumulated in double-double (exact products by fma, error-free
+ * additions) and rounded once at the end, across blocks and across GPUs, so alpha, beta, the residual norms, the stopping
+ * decision and therefore every iterate are the same bits for any grid size and any number of GPUs -- and equal to a CPU
+ * reference that rounds its dot products the same way.  Costs ~20 extra fp64 operations per row in kernels that are
+ * bandwidth bound; forces solver path 0. */
+int32_t tb_cg_set_exact_dot(tb_ctx *ctx, int32_t on);
 
 /* ---- cell sweep -------------------------------------------------------------------------------
  * _pointwise_step_outer_kernel! (src/solver/time/partitioned_solver.jl:38-52; the method

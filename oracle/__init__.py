@@ -79,7 +79,7 @@ def lib():
                              C.c_int, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.orc_cg.restype = C.c_int64
         L.orc_pcg_jacobi.argtypes = [C.c_int64, _i64p, _i64p, _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_int64,
-                                     _f64p, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+                                     _f64p, _f64p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int]
         L.orc_pcg_jacobi.restype = C.c_int64
         L.orc_cell_nstates.argtypes = [C.c_int]
         L.orc_cell_nstates.restype = C.c_int
@@ -283,7 +283,9 @@ SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
 
 
 def cg(rowptr, colidx, vals, b, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, threaded_blas1=False):
-    """LinearSolve.KrylovJL_CG defaults: abstol = reltol = sqrt(eps), maxiters = length(b), x0 = 0."""
+    """LinearSolve.KrylovJL_CG defaults: abstol = reltol = sqrt(eps), maxiters = length(b), x0 = 0.
+    threaded_blas1: False/0 serial sums (Krylov on Vector), True/1 threaded, 2 = order-free "exact" dot products
+    (double-double, rounded once; the product's tb_cg_set_exact_dot meets it bit for bit)."""
     n = rowptr.size - 1
     itmax = n if itmax is None else itmax
     x, work = np.empty(n), np.empty(3 * n)
@@ -293,14 +295,15 @@ def cg(rowptr, colidx, vals, b, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, thread
     return x, int(it), rn.value, bool(conv.value)
 
 
-def pcg_jacobi(rowptr, colidx, vals, b, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None):
+def pcg_jacobi(rowptr, colidx, vals, b, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None, dot_mode=0):
     """KrylovJL_CG with a Jacobi preconditioner (precs, ldiv = false): stops on sqrt(r.z) <= atol + rtol*sqrt(r0.z0)."""
     n = rowptr.size - 1
     itmax = n if itmax is None else itmax
     x, work, dinv = np.empty(n), np.empty(4 * n), np.empty(n)
     rn, conv = C.c_double(), C.c_int32()
     it = lib().orc_pcg_jacobi(n, rowptr, colidx, np.ascontiguousarray(vals, dtype=np.float64),
-                              np.ascontiguousarray(b, dtype=np.float64), x, atol, rtol, itmax, dinv, work, C.byref(rn), C.byref(conv))
+                              np.ascontiguousarray(b, dtype=np.float64), x, atol, rtol, itmax, dinv, work, C.byref(rn), C.byref(conv),
+                              int(dot_mode))
     return x, int(it), rn.value, bool(conv.value)
 
 
@@ -389,7 +392,8 @@ class MonodomainOracle:
             b = spmv(self.rowptr, self.colidx, self.M, u[pi * n:(pi + 1) * n])
             if self.bS is not None:
                 b += self.bS
-            x, it, rnv, cv = pcg_jacobi(self.rowptr, self.colidx, self.A, b, self.atol, self.rtol, self.itmax)
+            x, it, rnv, cv = pcg_jacobi(self.rowptr, self.colidx, self.A, b, self.atol, self.rtol, self.itmax,
+                                        dot_mode=2 if int(self.threaded_blas1) == 2 else 0)
             u[pi * n:(pi + 1) * n] = x
             lib().orc_cell_step(self.model, self.prm, u, self.du, n, n, t, dt, self.substeps, self.threshold, pi)
             self.iters.append(int(it))

@@ -713,12 +713,47 @@ static double dot_omp(int64_t n, const double *a, const double *b) {
     return s;
 }
 
+/* "Exact" dot product (threaded_blas1 == 2): double-double accumulation -- exact products by fma (TwoProd), error-free
+ * additions (TwoSum) -- rounded to fp64 once at the end.  The value no longer depends on the summation order (up to a
+ * ~1e-24 relative chance per call of sitting on a rounding boundary), which is what lets a CPU run and a GPU run --
+ * whose sums are formed in completely different orders -- produce the same CG scalars, hence the same iterates and the
+ * same iteration counts.  Not what Julia's BLAS dot does (no implementation can reproduce that order); it is the
+ * order-free reference both sides can meet.  Product side: tb_cg_set_exact_dot. */
+typedef struct { double hi, lo; } orc_dd;
+static inline void dd_add_pair(orc_dd *a, double h, double l) {
+    double s = a->hi + h;
+    double bb = s - a->hi;
+    double e = (a->hi - (s - bb)) + (h - bb);
+    e += a->lo + l;
+    double hi = s + e;
+    a->lo = e - (hi - s);
+    a->hi = hi;
+}
+static double dot_exact(int64_t n, const double *a, const double *b) {
+    orc_dd tot = {0.0, 0.0};
+#pragma omp parallel
+    {
+        orc_dd acc = {0.0, 0.0};
+#pragma omp for schedule(static) nowait
+        for (int64_t i = 0; i < n; i++) {
+            double p = a[i] * b[i];
+            dd_add_pair(&acc, p, fma(a[i], b[i], -p));
+        }
+#pragma omp critical
+        dd_add_pair(&tot, acc.hi, acc.lo);
+    }
+    return tot.hi + tot.lo;
+}
+static double dot_mode(int mode, int64_t n, const double *a, const double *b) {
+    return mode == 2 ? dot_exact(n, a, b) : mode == 1 ? dot_omp(n, a, b) : dot_serial(n, a, b);
+}
+
 int64_t orc_cg(int64_t n, const int64_t *rowptr, const int64_t *colidx, const double *vals, const double *b, double *x,
                double atol, double rtol, int64_t itmax, int threaded_blas1, double *work, double *rnorm,
                int32_t *converged) {
     double *r = work, *p = work + n, *Ap = work + 2 * n;
     for (int64_t i = 0; i < n; i++) { x[i] = 0.0; r[i] = b[i]; p[i] = b[i]; }
-    double gamma = threaded_blas1 ? dot_omp(n, r, r) : dot_serial(n, r, r);
+    double gamma = dot_mode(threaded_blas1, n, r, r);
     double rn = sqrt(gamma);
     double eps = atol + rtol * rn;
     int solved = rn <= eps;
@@ -726,7 +761,7 @@ int64_t orc_cg(int64_t n, const int64_t *rowptr, const int64_t *colidx, const do
     int tired = iter >= itmax;
     while (!(solved || tired)) {
         orc_spmv(n, rowptr, colidx, vals, p, Ap);
-        double pAp = threaded_blas1 ? dot_omp(n, p, Ap) : dot_serial(n, p, Ap);
+        double pAp = dot_mode(threaded_blas1, n, p, Ap);
         double alpha = gamma / pAp;
         if (threaded_blas1) {
 #pragma omp parallel for schedule(static)
@@ -735,7 +770,7 @@ int64_t orc_cg(int64_t n, const int64_t *rowptr, const int64_t *colidx, const do
             for (int64_t i = 0; i < n; i++) x[i] += alpha * p[i];
             for (int64_t i = 0; i < n; i++) r[i] -= alpha * Ap[i];
         }
-        double gnext = threaded_blas1 ? dot_omp(n, r, r) : dot_serial(n, r, r);
+        double gnext = dot_mode(threaded_blas1, n, r, r);
         rn = sqrt(gnext);
         solved = rn <= eps;
         if (!solved) {
@@ -763,7 +798,7 @@ int64_t orc_cg(int64_t n, const int64_t *rowptr, const int64_t *colidx, const do
  * dinv: n doubles, 1/a_ii.  work: 4n doubles. */
 int64_t orc_pcg_jacobi(int64_t n, const int64_t *rowptr, const int64_t *colidx, const double *vals, const double *b,
                        double *x, double atol, double rtol, int64_t itmax, double *dinv, double *work, double *rnorm,
-                       int32_t *converged) {
+                       int32_t *converged, int dmode) {
     double *r = work, *p = work + n, *Ap = work + 2 * n, *z = work + 3 * n;
     for (int64_t i = 0; i < n; i++) {
         dinv[i] = 0.0;
@@ -771,7 +806,7 @@ int64_t orc_pcg_jacobi(int64_t n, const int64_t *rowptr, const int64_t *colidx, 
             if (colidx[k] == i) dinv[i] = 1.0 / vals[k];
     }
     for (int64_t i = 0; i < n; i++) { x[i] = 0.0; r[i] = b[i]; z[i] = dinv[i] * r[i]; p[i] = z[i]; }
-    double gamma = dot_serial(n, r, z);
+    double gamma = dot_mode(dmode, n, r, z);
     double rn = sqrt(gamma);
     double eps = atol + rtol * rn;
     int solved = rn <= eps;
@@ -779,12 +814,12 @@ int64_t orc_pcg_jacobi(int64_t n, const int64_t *rowptr, const int64_t *colidx, 
     int tired = iter >= itmax;
     while (!(solved || tired)) {
         orc_spmv(n, rowptr, colidx, vals, p, Ap);
-        double pAp = dot_serial(n, p, Ap);
+        double pAp = dot_mode(dmode, n, p, Ap);
         double alpha = gamma / pAp;
         for (int64_t i = 0; i < n; i++) x[i] += alpha * p[i];
         for (int64_t i = 0; i < n; i++) r[i] -= alpha * Ap[i];
         for (int64_t i = 0; i < n; i++) z[i] = dinv[i] * r[i];
-        double gnext = dot_serial(n, r, z);
+        double gnext = dot_mode(dmode, n, r, z);
         rn = sqrt(gnext);
         solved = rn <= eps;
         if (!solved) {

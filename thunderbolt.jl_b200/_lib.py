@@ -132,6 +132,7 @@ _SIGNATURES = {
     "tb_monodomain_set_preconditioner": [_vp, C.c_int32],
     "tb_cg_set_persistent": [_vp, C.c_int32],
     "tb_cg_last_path": [_vp, _pi32],
+    "tb_cg_set_exact_dot": [_vp, C.c_int32],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                      _pf64],
     "tb_monodomain_create": [_vp, _vp, _vp, C.c_int32, _f64p, C.c_int32, C.c_int32, _pp],

@@ -74,6 +74,10 @@ class B200Device:
         L.call("tb_cg_last_path", self.h, C.byref(v))
         return v.value
 
+    def cg_set_exact_dot(self, on=True):
+        """CG dot products in double-double, rounded once: iterates independent of grid size / GPU count (solver path 0)"""
+        L.call("tb_cg_set_exact_dot", self.h, int(bool(on)))
+
     def cg_last_path_persistent(self) -> bool:
         return self.cg_last_path() != 0
 

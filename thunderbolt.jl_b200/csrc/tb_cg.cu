@@ -505,9 +505,11 @@ static tb_ar_args cg_next_ar(tb_ctx *ctx, bool peer) {
 
 // finish a distributed dot product: window path = one single-thread kernel that collects; NCCL path = all-reduce + scalar kernel
 static int32_t cg_allreduce_then(tb_ctx *ctx, int which, const tb_ar_args &ar) {
+    // NCCL path: in exact mode the high and low words are all-reduced separately (the high words' rounding error is not
+    // recovered, so this path is deterministic but not order-independent; the peer-window path is both)
     if (!ar.wins)
-        TB_NCCL(ncclAllReduce(ctx->d_cg->local, ctx->d_cg->local, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
-    TB_LAUNCH(ctx, k_cg_scalar, 1, 1, 0, ctx->d_cg, which, ar);
+        TB_NCCL(ncclAllReduce(ctx->d_cg->local, ctx->d_cg->local, ctx->exact_dot ? 2 : 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    TB_LAUNCH(ctx, k_cg_scalar, 1, 1, 0, ctx->d_cg, which, ar, ctx->exact_dot != 0);
     return TB_OK;
 }
 
@@ -520,7 +522,8 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const double *dinv = nullptr;
     if (precond == TB_PRECOND_JACOBI) TB_TRY(cg_build_dinv(ctx, A, &dinv));
     int pgrid = 0;
-    const int pkind = tb_cg_persistent_kind(ctx, pat, &pgrid);   // small / mid-size operator: one persistent cooperative kernel
+    // exact-dot mode lives in the multi-kernel path only (the persistent kernels keep plain fp64 partial sums)
+    const int pkind = ctx->exact_dot ? 0 : tb_cg_persistent_kind(ctx, pat, &pgrid);   // small / mid-size operator: one persistent cooperative kernel
     if (pkind == 1) return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
     if (pkind == 2) return tb_cg_run_persistent_tma(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
     ctx->last_cg_persistent = 0;
@@ -534,29 +537,34 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     double *part = ctx->d_partials;
     unsigned *tick = ctx->d_ticket;
     const int64_t need_v = (n / 2 + 256) / 256, need_s = (pat->nslices + 7) / 8;
-    const int grid_xr = TB_GRID(ctx, k_cg_xr, 256, 0, need_v);
+    const int grid_xr = TB_GRID(ctx, k_cg_xr<true>, 256, 0, need_v);
     const int grid_p = TB_GRID(ctx, k_cg_p, 256, 0, need_v);
-    const int grid_ib = TB_GRID(ctx, k_cg_init_b, 256, 0, (n + 255) / 256);
-    const int grid_s = TB_GRID(ctx, k_cg_spmv_dot, 256, 0, need_s);
-    const int grid_im = TB_GRID(ctx, k_cg_init_Mphi, 256, 0, need_s);
+    const int grid_ib = TB_GRID(ctx, k_cg_init_b<true>, 256, 0, (n + 255) / 256);
+    const int grid_s = TB_GRID(ctx, k_cg_spmv_dot<true>, 256, 0, need_s);
+    const int grid_im = TB_GRID(ctx, k_cg_init_Mphi<true>, 256, 0, need_s);
     const bool tma = ctx->spmv_variant > 0 && pat->max_width_tma > 0;   // slices above TB_TMA_WCAP take the LDG row kernel inside the sweep
     const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
     // fused peer path: collects and halo push inside k_cg_xr_fused / k_cg_p_fused, scalars ping-pong between st[0] and st[1]
     const bool fused = peer_ar && pat->halo.peer_ready && pat->halo.fused;   // agreed by all ranks (tb_csr_set_halo_fused)
-    const int grid_xrf = fused ? TB_GRID(ctx, k_cg_xr_fused, 256, 0, need_v) : 0;
-    const int grid_pf = fused ? TB_GRID(ctx, k_cg_p_fused, 256, 0, need_v) : 0;
+    const int grid_xrf = fused ? TB_GRID(ctx, k_cg_xr_fused<true>, 256, 0, need_v) : 0;
+    const int grid_pf = fused ? TB_GRID(ctx, k_cg_p_fused<true>, 256, 0, need_v) : 0;
+    const bool X = ctx->exact_dot != 0;
 
     TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);
     {
         const tb_ar_args ar = cg_next_ar(ctx, peer_ar);
         if (b) {
-            TB_LAUNCH(ctx, k_cg_init_b, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist, ar, dinv);
+            if (X) TB_LAUNCH(ctx, k_cg_init_b<true>, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist, ar, dinv);
+            else TB_LAUNCH(ctx, k_cg_init_b<false>, grid_ib, 256, 0, b, x, r, p, n, st, part, tick, dist, ar, dinv);
         } else {
             if (M->pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, M->pat, phi));   // phi lives in the caller's vector: NCCL
             if (tma)
                 TB_TRY(dispatch_spmv_tma<true>(ctx, pat, M->d_val, phi, bS, x, r, p, st, part, tick, dist, ar, nowait, dinv));
+            else if (X)
+                TB_LAUNCH(ctx, k_cg_init_Mphi<true>, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
+                          pat->nslices, st, part, tick, dist, ar, dinv);
             else
-                TB_LAUNCH(ctx, k_cg_init_Mphi, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
+                TB_LAUNCH(ctx, k_cg_init_Mphi<false>, grid_im, 256, 0, pat->d_slice_ptr, pat->d_col, M->d_val, phi, bS, x, r, p, n,
                           pat->nslices, st, part, tick, dist, ar, dinv);
         }
         if (dist) TB_TRY(cg_allreduce_then(ctx, 0, ar));
@@ -579,15 +587,20 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
             const tb_ar_args ar1 = cg_next_ar(ctx, true);
             if (tma)
                 TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, sin, part, tick, dist, ar1, hw, nullptr));
+            else if (X)
+                TB_LAUNCH(ctx, k_cg_spmv_dot<true>, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
+                          pat->nslices, sin, part, tick, dist, ar1, hw);
             else
-                TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
+                TB_LAUNCH(ctx, k_cg_spmv_dot<false>, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
                           pat->nslices, sin, part, tick, dist, ar1, hw);
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * it + 1], ctx->stream));
             const tb_ar_args ar2 = cg_next_ar(ctx, true);
-            TB_LAUNCH(ctx, k_cg_xr_fused, grid_xrf, 256, 0, x, r, p, Ap, n, sin, part + TB_MAX_PARTIALS, tick + 1, ar1, ar2, dinv);
+            if (X) TB_LAUNCH(ctx, k_cg_xr_fused<true>, grid_xrf, 256, 0, x, r, p, Ap, n, sin, part + TB_MAX_PARTIALS, tick + 1, ar1, ar2, dinv);
+            else TB_LAUNCH(ctx, k_cg_xr_fused<false>, grid_xrf, 256, 0, x, r, p, Ap, n, sin, part + TB_MAX_PARTIALS, tick + 1, ar1, ar2, dinv);
             tb_push_args pa;
             TB_TRY(tb_halo_push_args(ctx, pat, &pa, &ctx->peer.hw_next));
-            TB_LAUNCH(ctx, k_cg_p_fused, grid_pf, 256, 0, r, p, n, sin, sout, ar2, dinv, pa, ctx->d_ticket + 6);
+            if (X) TB_LAUNCH(ctx, k_cg_p_fused<true>, grid_pf, 256, 0, r, p, n, sin, sout, ar2, dinv, pa, ctx->d_ticket + 6);
+            else TB_LAUNCH(ctx, k_cg_p_fused<false>, grid_pf, 256, 0, r, p, n, sin, sout, ar2, dinv, pa, ctx->d_ticket + 6);
         }
         for (int64_t k = 0; k < chunk && !fused; k++) {
             tb_hwait_args hw = nowait;
@@ -598,13 +611,17 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
             const tb_ar_args ar1 = cg_next_ar(ctx, peer_ar);
             if (tma)
                 TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, p, nullptr, nullptr, Ap, nullptr, st, part, tick, dist, ar1, hw, nullptr));
+            else if (X)
+                TB_LAUNCH(ctx, k_cg_spmv_dot<true>, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
+                          pat->nslices, st, part, tick, dist, ar1, hw);
             else
-                TB_LAUNCH(ctx, k_cg_spmv_dot, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
+                TB_LAUNCH(ctx, k_cg_spmv_dot<false>, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, p, Ap, n,
                           pat->nslices, st, part, tick, dist, ar1, hw);
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k) + 1], ctx->stream));
             if (dist) TB_TRY(cg_allreduce_then(ctx, 1, ar1));
             const tb_ar_args ar2 = cg_next_ar(ctx, peer_ar);
-            TB_LAUNCH(ctx, k_cg_xr, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, dinv);
+            if (X) TB_LAUNCH(ctx, k_cg_xr<true>, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, dinv);
+            else TB_LAUNCH(ctx, k_cg_xr<false>, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, dinv);
             if (dist) TB_TRY(cg_allreduce_then(ctx, 2, ar2));
             TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, r, p, n, st, dinv);
         }

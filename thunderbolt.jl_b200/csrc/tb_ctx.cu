@@ -65,7 +65,7 @@ static int32_t ctx_init(tb_ctx *ctx, int32_t device, void *stream) {
     }
     TB_CUDA(cudaEventCreate(&ctx->ev0));
     TB_CUDA(cudaEventCreate(&ctx->ev1));
-    TB_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 4 * TB_MAX_PARTIALS));
+    TB_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * 8 * TB_MAX_PARTIALS));   // high words | low words (exact-dot mode)
     TB_CUDA(cudaMalloc(&ctx->d_ticket, sizeof(unsigned) * 8));
     TB_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned) * 8, ctx->stream));
     TB_CUDA(cudaMalloc(&ctx->d_cg, 2 * sizeof(CGState)));   // [1] is the ping-pong partner of the fused multi-GPU path
@@ -77,6 +77,7 @@ static int32_t ctx_init(tb_ctx *ctx, int32_t device, void *stream) {
     if (const char *v = getenv("TB_SPMV_COMPRESS")) ctx->spmv_compress = atoi(v);
     if (const char *v = getenv("TB_CG_PERSISTENT")) ctx->cg_persistent = atoi(v) < 0 ? 0 : atoi(v) > 2 ? 2 : atoi(v);
     if (const char *v = getenv("TB_P2P_FUSED")) ctx->p2p_fused = atoi(v);
+    if (const char *v = getenv("TB_DOT_EXACT")) ctx->exact_dot = atoi(v) != 0;
     if (const char *v = getenv("TB_CG_PERSISTENT_MAX_ROWS")) ctx->cg_persistent_max_rows = atoll(v);
     if (const char *v = getenv("TB_ASSEMBLY_MODE")) ctx->assembly_mode = atoi(v) == 0 ? 0 : 2;
     if (const char *v = getenv("TB_EA_BUDGET_MB")) ctx->ea_budget_bytes = (size_t)(atof(v) * 1048576.0);
@@ -319,6 +320,12 @@ extern "C" int32_t tb_profile_get(tb_ctx *ctx, double *spmv_ms_total, int64_t *s
     TB_REQUIRE(ctx && spmv_ms_total && spmv_launches, "tb_profile_get: NULL argument");
     *spmv_ms_total = ctx->prof_spmv_ms;
     *spmv_launches = ctx->prof_spmv_n;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_cg_set_exact_dot(tb_ctx *ctx, int32_t on) {
+    TB_REQUIRE(ctx, "tb_cg_set_exact_dot: ctx is NULL");
+    ctx->exact_dot = on != 0;
     return TB_OK;
 }
 
