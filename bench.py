@@ -131,7 +131,9 @@ def config_of(args, W, nel):
     return {"workload": W["name"] if not args.grid else f"{W['name']} [grid override {list(nel)}]", "nel": list(nel),
             "cell_model": W["model"], "dt": W["dt"],
             "cell_solver": "ForwardEulerCellSolver" if W["substeps"] == 1 else f"AdaptiveForwardEulerSubstepper({W['substeps']})",
-            "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "preconditioner": args.precond}}
+            "cg": {"atol": SQRT_EPS, "rtol": SQRT_EPS, "x0": "zero", "preconditioner": args.precond,
+                   **({"bj_rows": args.bj_rows} if args.precond == "block_jacobi" else {}),
+                   **({"degree": args.cheb_degree, "ratio": args.cheb_ratio} if args.precond == "chebyshev" else {})}}
 
 
 def run_b200(args):
@@ -197,8 +199,13 @@ def run_b200(args):
     dev.assembly_release_scratch()
     st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
     st.set_cg(SQRT_EPS, SQRT_EPS, None)
-    if args.precond == "jacobi":
-        st.set_preconditioner(tb._lib.PRECOND_JACOBI)
+    PC = {"none": tb._lib.PRECOND_NONE, "jacobi": tb._lib.PRECOND_JACOBI, "block_jacobi": tb._lib.PRECOND_BLOCK_JACOBI,
+          "chebyshev": tb._lib.PRECOND_CHEBYSHEV}[args.precond]
+    if args.precond == "block_jacobi":
+        dev.cg_set_block_jacobi(mesh.ndofs_owned, max(1, mesh.ndofs_owned // args.bj_rows), None)
+    if args.precond == "chebyshev":
+        dev.cg_set_chebyshev(args.cheb_degree, args.cheb_ratio)
+    st.set_preconditioner(PC)
     st.set_cell_solver(W["substeps"], 0.1)
     x = mesh.dof_coords()
     n_local = mesh.ndofs                                    # owned + ghosts
@@ -319,7 +326,7 @@ def run_b200(args):
         from scripts import parity_block
         gname = ("c5" if args.workload == "c5" else args.workload) + "_checksum.json"
         parity = parity_block.run(tb, dev, mesh, M, K, st, ion, W, nel, u, u0, x, dist=dist if world > 1 else None, world=world,
-                                  rank=rank, precond=tb._lib.PRECOND_JACOBI if args.precond == "jacobi" else 0,
+                                  rank=rank, precond=PC,
                                   write_golden=args.write_golden, golden_path=ROOT / "tests" / "golden" / gname)
         del x
 
@@ -471,7 +478,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cut", default="rows", choices=["planes", "rows"],
                     help="multi-GPU ownership cuts: at grid-plane boundaries (one-plane halos) or at equal row counts (balanced)")
-    ap.add_argument("--precond", default="none", choices=["none", "jacobi"], help="inner CG preconditioner (SURVEY 8f-2)")
+    ap.add_argument("--precond", default="none", choices=["none", "jacobi", "block_jacobi", "chebyshev"], help="inner CG preconditioner (SURVEY 8f-2)")
+    ap.add_argument("--bj-rows", type=int, default=64, help="block_jacobi: rows per block (contiguous ranges of the dof numbering)")
+    ap.add_argument("--cheb-degree", type=int, default=8)
+    ap.add_argument("--cheb-ratio", type=float, default=100.0)
     args = ap.parse_args()
     if args.warmup < 3:
         print("note: the timing rules ask for >= 3 warm-up steps", file=sys.stderr)

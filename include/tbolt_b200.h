@@ -253,8 +253,20 @@ int32_t tb_cg_solve(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol,
  * (KrylovPreconditioners' BlockJacobi with blocks of one row), rebuilt from the operator at every solve. */
 #define TB_PRECOND_NONE 0
 #define TB_PRECOND_JACOBI 1
+/* BlockJacobiPreconditioner(A, nblocks) as used by the reference's GPU example (bak/examples-gpu/spiral-wave.jl:95-105):
+ * dense fp64 inverses of the diagonal blocks, z = blockdiag(A)^-1 r as a batched dense mat-vec.  Configure the row
+ * partition once with tb_cg_set_block_jacobi; the inverses are rebuilt from the operator at every solve (update!(P, A)). */
+#define TB_PRECOND_BLOCK_JACOBI 2
+/* z = q_d(D^-1 A) D^-1 r: degree-d Chebyshev polynomial over [lmax/ratio, lmax], lmax = Gershgorin bound of D^-1 A.
+ * Configure with tb_cg_set_chebyshev (default degree 8, ratio 30). */
+#define TB_PRECOND_CHEBYSHEV 3
 int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b, int32_t bcol, tb_vec *x, int32_t xcol, int32_t precond,
                        double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm, int32_t *converged);
+
+/* row_block: nrows block ids in [0, nblocks) (the reference takes them from Metis), or NULL for equal contiguous ranges of
+ * the dof numbering.  Blocks may have different sizes (<= 2048 rows); memory = sum of squares of the block sizes. */
+int32_t tb_cg_set_block_jacobi(tb_ctx *ctx, int64_t nrows, int64_t nblocks, const int32_t *row_block);
+int32_t tb_cg_set_chebyshev(tb_ctx *ctx, int32_t degree, double ratio);
 
 /* Single-GPU solves of small and mid-size operators run as ONE persistent cooperative kernel per solve (grid-wide
  * barriers instead of kernel boundaries; same recurrence, same stopping rule):

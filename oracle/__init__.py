@@ -453,3 +453,104 @@ class StencilOracle:
                                         C.byref(rn), C.byref(conv))
         self.iters.append(int(it))
         return int(it), rn.value, bool(conv.value)
+
+
+# ---- general preconditioned CG (KrylovJL_CG(precs = ..., ldiv = false)) -----------------------------------
+def pcg(rowptr, colidx, vals, b, apply_pc, atol=SQRT_EPS, rtol=SQRT_EPS, itmax=None):
+    """Krylov.jl cg! with a preconditioner given as a function z = P(r) (P applies the INVERSE, ldiv = false):
+    gamma = r.z, stop on sqrt(r.z) <= atol + rtol*sqrt(r0.z0), p = z + beta p.  Vector algebra in numpy, SpMV in C."""
+    n = rowptr.size - 1
+    itmax = n if itmax is None else itmax
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    x, r = np.zeros(n), np.array(b, dtype=np.float64)
+    z = apply_pc(r)
+    p = z.copy()
+    gamma = float(np.dot(r, z))
+    rn = np.sqrt(gamma)
+    eps = atol + rtol * rn
+    solved, it = rn <= eps, 0
+    while not (solved or it >= itmax):
+        Ap = spmv(rowptr, colidx, vals, p)
+        alpha = gamma / float(np.dot(p, Ap))
+        x += alpha * p
+        r -= alpha * Ap
+        z = apply_pc(r)
+        gnext = float(np.dot(r, z))
+        rn = np.sqrt(gnext)
+        solved = rn <= eps
+        if not solved:
+            beta = gnext / gamma
+            gamma = gnext
+            p = z + beta * p
+        it += 1
+    return x, it, float(rn), bool(solved)
+
+
+def _diag(rowptr, colidx, vals):
+    n = rowptr.size - 1
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    d = np.zeros(n)
+    m = colidx == rows
+    d[rows[m]] = vals[m]
+    return d
+
+
+def gershgorin_lmax(rowptr, colidx, vals):
+    """max_i sum_j |a_ij| / a_ii: an upper bound of the spectrum of D^-1 A."""
+    n = rowptr.size - 1
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    s = np.bincount(rows, weights=np.abs(vals), minlength=n)
+    return float((s / _diag(rowptr, colidx, vals)).max())
+
+
+def chebyshev_preconditioner(rowptr, colidx, vals, degree=8, ratio=30.0):
+    """z = q_d(D^-1 A) D^-1 r: `degree` terms of the Chebyshev iteration for A z = r on [lmax/ratio, lmax] (Saad, Iterative
+    Methods, Alg. 12.1 with the Jacobi splitting), lmax = Gershgorin bound.  Returns the apply function."""
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    dinv = 1.0 / _diag(rowptr, colidx, vals)
+    hi = gershgorin_lmax(rowptr, colidx, vals)
+    lo = hi / ratio
+    theta, delta = 0.5 * (hi + lo), 0.5 * (hi - lo)
+    sigma1 = theta / delta
+
+    def apply(r):
+        res = r.copy()
+        d = (1.0 / theta) * (dinv * res)
+        z = d.copy()
+        rho = 1.0 / sigma1
+        for _ in range(1, degree):
+            res = res - spmv(rowptr, colidx, vals, d)
+            rho_new = 1.0 / (2.0 * sigma1 - rho)
+            d = (rho_new * rho) * d + (2.0 * rho_new / delta) * (dinv * res)
+            z = z + d
+            rho = rho_new
+        return z
+    return apply
+
+
+def block_jacobi_preconditioner(rowptr, colidx, vals, nblocks, row_block=None):
+    """KrylovPreconditioners.BlockJacobiPreconditioner(A, nblocks) (bak/examples-gpu/spiral-wave.jl:95-105): dense inverses of
+    the diagonal blocks.  row_block = block id per row (the reference: Metis), None = equal contiguous ranges."""
+    n = rowptr.size - 1
+    blk = (np.arange(n) * nblocks) // n if row_block is None else np.asarray(row_block)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    same = blk[rows] == blk[colidx]
+    order = np.argsort(blk, kind="stable")
+    pos = np.empty(n, dtype=np.int64)
+    counts = np.bincount(blk, minlength=nblocks)
+    start = np.concatenate([[0], np.cumsum(counts)])
+    pos[order] = np.arange(n) - start[blk[order]]
+    inv = []
+    for b in range(nblocks):
+        B = np.zeros((counts[b], counts[b]))
+        m = same & (blk[rows] == b)
+        B[pos[rows[m]], pos[colidx[m]]] = vals[m]
+        inv.append(np.linalg.inv(B))
+    members = [order[start[b]:start[b + 1]] for b in range(nblocks)]
+
+    def apply(r):
+        z = np.empty_like(r)
+        for b in range(nblocks):
+            z[members[b]] = inv[b] @ r[members[b]]
+        return z
+    return apply

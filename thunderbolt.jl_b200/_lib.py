@@ -25,7 +25,7 @@ QUAD4, HEX8, TRI3, TET4 = 0, 1, 2, 3
 FHN, PCG2019, ALIEV_PANFILOV = 0, 1, 2
 D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
 PEER_BLOB_BYTES = 160
-PRECOND_NONE, PRECOND_JACOBI = 0, 1
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_CHEBYSHEV = 0, 1, 2, 3
 SRC_NONE, SRC_BOX, SRC_BALL, SRC_COSEXP, SRC_NORMT, SRC_ENDO = 0, 1, 2, 3, 4, 5
 
 
@@ -133,6 +133,8 @@ _SIGNATURES = {
     "tb_cg_set_persistent": [_vp, C.c_int32],
     "tb_cg_last_path": [_vp, _pi32],
     "tb_cg_set_exact_dot": [_vp, C.c_int32],
+    "tb_cg_set_block_jacobi": [_vp, C.c_int64, C.c_int64, _vp],
+    "tb_cg_set_chebyshev": [_vp, C.c_int32, C.c_double],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                      _pf64],
     "tb_monodomain_create": [_vp, _vp, _vp, C.c_int32, _f64p, C.c_int32, C.c_int32, _pp],

@@ -621,17 +621,49 @@ class B200CG:
     atol: float = SQRT_EPS
     rtol: float = SQRT_EPS
     maxiters: int | None = None
-    precs: object = None          # None, or JacobiPreconditioner() (LinearSolve's `precs`, used with ldiv = false)
+    precs: object = None          # None, JacobiPreconditioner(), BlockJacobiPreconditioner(nblocks) or ChebyshevPreconditioner(...)
+                                  # (LinearSolve's `precs`, used with ldiv = false)
 
     @property
     def precond(self) -> int:
-        return L.PRECOND_JACOBI if isinstance(self.precs, JacobiPreconditioner) else L.PRECOND_NONE
+        if isinstance(self.precs, JacobiPreconditioner):
+            return L.PRECOND_JACOBI
+        if isinstance(self.precs, BlockJacobiPreconditioner):
+            return L.PRECOND_BLOCK_JACOBI
+        if isinstance(self.precs, ChebyshevPreconditioner):
+            return L.PRECOND_CHEBYSHEV
+        return L.PRECOND_NONE
+
+    def configure(self, dev, nrows: int):
+        """what `precs(A, p)` does at init_cacheval time: hand the preconditioner's parameters to the device"""
+        if isinstance(self.precs, BlockJacobiPreconditioner):
+            dev.cg_set_block_jacobi(nrows, self.precs.nblocks, self.precs.row_block)
+        elif isinstance(self.precs, ChebyshevPreconditioner):
+            dev.cg_set_chebyshev(self.precs.degree, self.precs.ratio)
 
 
 @dataclass
 class JacobiPreconditioner:
     """M = diag(A)^-1, rebuilt from the operator at every solve; stands where the reference's examples put
     KrylovPreconditioners.BlockJacobiPreconditioner (bak/examples-gpu/spiral-wave.jl:95-105) with one-row blocks."""
+
+
+@dataclass
+class BlockJacobiPreconditioner:
+    """KrylovPreconditioners.BlockJacobiPreconditioner(A, nblocks, backend) as used at bak/examples-gpu/spiral-wave.jl:95-105:
+    dense inverses of `nblocks` diagonal blocks, updated from A at every solve.  row_block = block id per row (the reference
+    partitions with Metis); None = equal contiguous ranges of the dof numbering."""
+    nblocks: int = 1000
+    row_block: object = None
+
+
+@dataclass
+class ChebyshevPreconditioner:
+    """z = q_d(D^-1 A) D^-1 r over [lmax/ratio, lmax] (lmax: Gershgorin) -- the polynomial smoother the reference's multigrid
+    configuration defaults to ("damped Jacobi with Chebyshev-optimal omega", src/solver/linear/multigrid.jl:29-33), used as a
+    stand-alone preconditioner."""
+    degree: int = 8
+    ratio: float = 30.0
 
 
 KrylovJL_CG = B200CG
@@ -778,6 +810,7 @@ def perform_step_(f, cache, t, Δt, want_tangent=False) -> bool:
         if not isinstance(cache.source_term, LinearNullOperator):    # add!(b, S) is unconditional, euler.jl:88-91
             _add(dev, cache.b, cache.source_term.b)
         s = cache.solver.inner_solver
+        s.configure(dev, cache.A.nrows)
         it, rn, conv = core.cg_solve(dev, cache.A, cache.b, cache.uₙ, s.atol, s.rtol, s.maxiters, xcol=cache.ucol,
                                      precond=s.precond)
         cache.iters.append(it)
@@ -831,6 +864,7 @@ class ThunderboltTimeIntegrator:
                 st = core.MonodomainStepper(dev, hc.M.A, hc.K.A, odefun.ode.model_id, odefun.ode.params(), φcol)
                 s = heat_alg.inner_solver
                 st.set_cg(s.atol, s.rtol, s.maxiters)
+                s.configure(dev, hc.M.A.nrows)
                 st.set_preconditioner(s.precond)
                 st.set_cell_solver(cc.substeps, cc.threshold)
                 self.fused = st

@@ -78,6 +78,15 @@ class B200Device:
         """CG dot products in double-double, rounded once: iterates independent of grid size / GPU count (solver path 0)"""
         L.call("tb_cg_set_exact_dot", self.h, int(bool(on)))
 
+    def cg_set_block_jacobi(self, nrows: int, nblocks: int, row_block=None):
+        """BlockJacobiPreconditioner(A, nblocks): row_block = block id per row, None = equal contiguous dof ranges"""
+        rb = None if row_block is None else np.ascontiguousarray(row_block, dtype=np.int32)
+        L.call("tb_cg_set_block_jacobi", self.h, int(nrows), int(nblocks), L.ptr(rb))
+        self._bj_keepalive = rb
+
+    def cg_set_chebyshev(self, degree: int = 8, ratio: float = 30.0):
+        L.call("tb_cg_set_chebyshev", self.h, int(degree), float(ratio))
+
     def cg_last_path_persistent(self) -> bool:
         return self.cg_last_path() != 0
 

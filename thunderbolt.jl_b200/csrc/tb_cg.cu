@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256)
             acc.add_prod(p[row], v);
         }
     }
-    cg_finish<1, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
+    if (partials) cg_finish<1, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);   // nullptr: plain y = A x
 }
 
 // ---- bulk-async (TMA) variants of the two SpMV-shaped kernels ------------------------------------------
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(1024, 1)
         }
     };
     tb_sell_sweep_tma<STAGES, CC>(slice_ptr, val, cstream, cptr, xin, nslices, val_bytes, col_bytes, tb_dyn_smem, epi, nullptr, col, wide);
+    if (!partials) return;   // plain y = A x (inner sweeps of the Chebyshev preconditioner): no reduction, scalars untouched
     const tb_acc<X> bs = tb_block_sum_acc<X>(acc, sm);
     if (INIT) cg_finish<0, X>(bs, st, partials, ticket, sm, dist, ar);
     else cg_finish<1, X>(bs, st, partials, ticket, sm, dist, ar);
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
                                                const double *__restrict__ Ap, int64_t n, CGState *st, double *partials,
                                                unsigned *ticket, bool dist, const tb_ar_args ar,
                                                const double *__restrict__ dinv) {
+    // partials == nullptr: update only (general preconditioners form r.z in k_cg_dot after z = P r)
     if (st->done) return;
     __shared__ double sm[64];
     const double alpha = st->alpha;
@@ -283,7 +285,21 @@ __global__ void __launch_bounds__(256) k_cg_xr(double *__restrict__ x, double *_
         r[i] = rn;
         acc.add_prod(rn, dinv ? dinv[i] * rn : rn);
     }
-    cg_finish<2, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
+    if (partials) cg_finish<2, X>(tb_block_sum_acc<X>(acc, sm), st, partials, ticket, sm, dist, ar);
+}
+
+// ---- gamma = a.b for an explicit preconditioned residual (WHICH 0: initial, 2: per iteration) --------------------------
+template <bool X>
+__global__ void __launch_bounds__(256) k_cg_dot(const double *__restrict__ a, const double *__restrict__ b, int64_t n, CGState *st,
+                                                double *partials, unsigned *ticket, bool dist, const tb_ar_args ar, int which) {
+    if (st->done) return;
+    __shared__ double sm[64];
+    tb_acc<X> acc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc.add_prod(a[i], b[i]);
+    const tb_acc<X> bs = tb_block_sum_acc<X>(acc, sm);
+    if (which == 0) cg_finish<0, X>(bs, st, partials, ticket, sm, dist, ar);
+    else cg_finish<2, X>(bs, st, partials, ticket, sm, dist, ar);
 }
 
 // ---- p = r + beta p ---------------------------------------------------------------------------------
@@ -520,10 +536,43 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const tb_pattern *pat = A->pat;
     const int64_t n = pat->nrows;
     const double *dinv = nullptr;
-    if (precond == TB_PRECOND_JACOBI) TB_TRY(cg_build_dinv(ctx, A, &dinv));
+    const bool gen_pc = precond == TB_PRECOND_BLOCK_JACOBI || precond == TB_PRECOND_CHEBYSHEV;   // z = P r is an explicit vector
+    if (precond == TB_PRECOND_JACOBI || precond == TB_PRECOND_CHEBYSHEV) TB_TRY(cg_build_dinv(ctx, A, &dinv));
+    const double *pc_dinv = dinv;                   // Chebyshev's D^-1
+    if (gen_pc) dinv = nullptr;                     // the CG kernels themselves run the unpreconditioned forms on (r, z)
+    double cheb_c1[64], cheb_c2[64], cheb_inv_theta = 0.0;
+    const int cheb_d = ctx->cheb_degree;
+    if (precond == TB_PRECOND_BLOCK_JACOBI) TB_TRY(tb_pc_bj_update(ctx, A));
+    if (precond == TB_PRECOND_CHEBYSHEV) {
+        double lmax = 0.0;
+        TB_TRY(tb_pc_gershgorin(ctx, A, &lmax));
+        TB_REQUIRE(lmax > 0.0, "Chebyshev preconditioner: operator has no positive diagonal");
+        const double hi = lmax, lo = lmax / ctx->cheb_ratio;
+        const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma1 = theta / delta;
+        cheb_inv_theta = 1.0 / theta;
+        double rho = 1.0 / sigma1;
+        for (int k = 1; k < cheb_d; k++) {
+            const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+            cheb_c1[k] = rho_new * rho;
+            cheb_c2[k] = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+    }
+    if (gen_pc) {
+        const int64_t ld = tb_round_up(pat->ncols, 32);
+        if (ctx->pcwork_ld < ld) {
+            TB_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_pcwork);
+            ctx->d_pcwork = nullptr;
+            ctx->pcwork_ld = 0;
+            TB_CUDA(cudaMalloc(&ctx->d_pcwork, sizeof(double) * 4 * (size_t)ld));
+            TB_CUDA(cudaMemsetAsync(ctx->d_pcwork, 0, sizeof(double) * 4 * (size_t)ld, ctx->stream));
+            ctx->pcwork_ld = ld;
+        }
+    }
     int pgrid = 0;
-    // exact-dot mode lives in the multi-kernel path only (the persistent kernels keep plain fp64 partial sums)
-    const int pkind = ctx->exact_dot ? 0 : tb_cg_persistent_kind(ctx, pat, &pgrid);   // small / mid-size operator: one persistent cooperative kernel
+    // exact-dot mode and the general preconditioners live in the multi-kernel path only
+    const int pkind = (ctx->exact_dot || gen_pc) ? 0 : tb_cg_persistent_kind(ctx, pat, &pgrid);   // small / mid-size operator: one persistent cooperative kernel
     if (pkind == 1) return tb_cg_run_persistent(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
     if (pkind == 2) return tb_cg_run_persistent_tma(ctx, pgrid, A, b, M, phi, bS, x, atol, rtol, itmax, iters, rnorm, converged, dinv);
     ctx->last_cg_persistent = 0;
@@ -545,10 +594,28 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const bool tma = ctx->spmv_variant > 0 && pat->max_width_tma > 0;   // slices above TB_TMA_WCAP take the LDG row kernel inside the sweep
     const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
     // fused peer path: collects and halo push inside k_cg_xr_fused / k_cg_p_fused, scalars ping-pong between st[0] and st[1]
-    const bool fused = peer_ar && pat->halo.peer_ready && pat->halo.fused;   // agreed by all ranks (tb_csr_set_halo_fused)
+    const bool fused = peer_ar && pat->halo.peer_ready && pat->halo.fused && !gen_pc;   // agreed by all ranks (tb_csr_set_halo_fused)
     const int grid_xrf = fused ? TB_GRID(ctx, k_cg_xr_fused<true>, 256, 0, need_v) : 0;
     const int grid_pf = fused ? TB_GRID(ctx, k_cg_p_fused<true>, 256, 0, need_v) : 0;
     const bool X = ctx->exact_dot != 0;
+    double *pc_z = ctx->d_pcwork, *pc_d = pc_z + ctx->pcwork_ld, *pc_res = pc_d + ctx->pcwork_ld, *pc_w = pc_res + ctx->pcwork_ld;
+    const int grid_dot = TB_GRID(ctx, k_cg_dot<true>, 256, 0, (n + 255) / 256);
+    // z = P r (every kernel in here returns at once when the solve is already done)
+    auto apply_pc = [&](const double *rr, double *zz, CGState *state) -> int32_t {
+        if (precond == TB_PRECOND_BLOCK_JACOBI) return tb_pc_bj_apply(ctx, rr, zz, state);
+        TB_TRY(tb_pc_cheb_first(ctx, rr, pc_dinv, pc_d, zz, pc_res, cheb_inv_theta, n, state));
+        for (int k = 1; k < cheb_d; k++) {
+            if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, pc_d));   // the inner direction lives outside the peer-mapped vectors: NCCL
+            const tb_ar_args ar0 = cg_next_ar(ctx, false);
+            if (tma)
+                TB_TRY(dispatch_spmv_tma<false>(ctx, pat, A->d_val, pc_d, nullptr, nullptr, pc_w, nullptr, state, nullptr, tick, false, ar0, nowait, nullptr));
+            else
+                TB_LAUNCH(ctx, k_cg_spmv_dot<false>, grid_s, 256, 0, pat->d_slice_ptr, pat->d_col, A->d_val, pc_d, pc_w, n, pat->nslices,
+                          state, nullptr, tick, false, ar0, nowait);
+            TB_TRY(tb_pc_cheb_step(ctx, pc_w, pc_dinv, pc_d, zz, pc_res, cheb_c1[k], cheb_c2[k], n, state));
+        }
+        return TB_OK;
+    };
 
     TB_LAUNCH(ctx, k_cg_set_tol, 1, 1, 0, st, atol, rtol, (long long)itmax);
     {
@@ -568,6 +635,14 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
                           pat->nslices, st, part, tick, dist, ar, dinv);
         }
         if (dist) TB_TRY(cg_allreduce_then(ctx, 0, ar));
+        if (gen_pc) {   // z0 = P r0, gamma = r0.z0 (stopping rule on sqrt(r.z) like Krylov's PCG), p0 = z0
+            TB_TRY(apply_pc(r, pc_z, st));
+            const tb_ar_args arz = cg_next_ar(ctx, peer_ar);
+            if (X) TB_LAUNCH(ctx, k_cg_dot<true>, grid_dot, 256, 0, r, pc_z, n, st, part, tick, dist, arz, 0);
+            else TB_LAUNCH(ctx, k_cg_dot<false>, grid_dot, 256, 0, r, pc_z, n, st, part, tick, dist, arz, 0);
+            if (dist) TB_TRY(cg_allreduce_then(ctx, 0, arz));
+            TB_CUDA(cudaMemcpyAsync(p, pc_z, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     }
 
     int64_t enq = 0;
@@ -619,6 +694,17 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
                           pat->nslices, st, part, tick, dist, ar1, hw);
             if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * (enq + k) + 1], ctx->stream));
             if (dist) TB_TRY(cg_allreduce_then(ctx, 1, ar1));
+            if (gen_pc) {   // x, r update; z = P r; gamma' = r.z; p = z + beta p
+                const tb_ar_args arn = cg_next_ar(ctx, false);
+                TB_LAUNCH(ctx, k_cg_xr<false>, grid_xr, 256, 0, x, r, p, Ap, n, st, nullptr, tick + 1, false, arn, nullptr);
+                TB_TRY(apply_pc(r, pc_z, st));
+                const tb_ar_args ar2 = cg_next_ar(ctx, peer_ar);
+                if (X) TB_LAUNCH(ctx, k_cg_dot<true>, grid_dot, 256, 0, r, pc_z, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, 2);
+                else TB_LAUNCH(ctx, k_cg_dot<false>, grid_dot, 256, 0, r, pc_z, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, 2);
+                if (dist) TB_TRY(cg_allreduce_then(ctx, 2, ar2));
+                TB_LAUNCH(ctx, k_cg_p, grid_p, 256, 0, pc_z, p, n, st, nullptr);
+                continue;
+            }
             const tb_ar_args ar2 = cg_next_ar(ctx, peer_ar);
             if (X) TB_LAUNCH(ctx, k_cg_xr<true>, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, dinv);
             else TB_LAUNCH(ctx, k_cg_xr<false>, grid_xr, 256, 0, x, r, p, Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, dist, ar2, dinv);
@@ -667,7 +753,7 @@ extern "C" int32_t tb_cg_solve_pc(tb_ctx *ctx, const tb_csr *A, const tb_vec *b,
                                   int32_t precond, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                                   int32_t *converged) {
     TB_REQUIRE(ctx && A && b && x, "tb_cg_solve: NULL argument");
-    TB_REQUIRE(precond == TB_PRECOND_NONE || precond == TB_PRECOND_JACOBI, "tb_cg_solve: unknown preconditioner %d", precond);
+    TB_REQUIRE(precond >= TB_PRECOND_NONE && precond <= TB_PRECOND_CHEBYSHEV, "tb_cg_solve: unknown preconditioner %d", precond);
     TB_REQUIRE(bcol >= 0 && bcol < b->ncols && xcol >= 0 && xcol < x->ncols, "tb_cg_solve: column out of range");
     TB_REQUIRE(b->n >= A->pat->nrows && x->n >= A->pat->nrows, "tb_cg_solve: vector shorter than the operator");
     TB_REQUIRE(itmax >= 0, "tb_cg_solve: itmax must be >= 0");

@@ -101,6 +101,8 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
         for (int b = 0; b < 5; b++) cudaFree(ctx->d_tables[a][b]);
     cudaFree(ctx->d_flush);
     cudaFree(ctx->d_dinv);
+    cudaFree(ctx->d_pcwork);
+    tb_bj_free(ctx->bj);
     cudaFree(ctx->d_ea);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -150,6 +150,11 @@ struct tb_ctx {
     double *h_scalar = nullptr;       // pinned
     double *d_dinv = nullptr;         // Jacobi preconditioner: 1/diag(A) of the operator being solved
     int64_t dinv_len = 0;
+    struct tb_bj *bj = nullptr;       // block-Jacobi plan + dense inverses (tb_precond.cu)
+    int cheb_degree = 8;              // Chebyshev preconditioner: polynomial degree and lmax/lmin of the target interval
+    double cheb_ratio = 30.0;
+    double *d_pcwork = nullptr;       // z | d | res | w of the general preconditioners
+    int64_t pcwork_ld = 0;
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
     int assembly_mode = 2;            // 0: fp64-atomic scatter, 2: element matrices + ordered row gather (deterministic; env TB_ASSEMBLY_MODE)
@@ -555,6 +560,14 @@ __device__ __forceinline__ void tb_halo_wait(const tb_hwait_args &h) {
         __syncthreads();
     }
 }
+void tb_bj_free(struct tb_bj *b);
+int32_t tb_pc_gershgorin(tb_ctx *ctx, const tb_csr *A, double *lmax);
+int32_t tb_pc_cheb_first(tb_ctx *ctx, const double *r, const double *dinv, double *d, double *z, double *res, double inv_theta,
+                         int64_t n, const struct CGState *st);
+int32_t tb_pc_cheb_step(tb_ctx *ctx, const double *w, const double *dinv, double *d, double *z, double *res, double c1, double c2,
+                        int64_t n, const struct CGState *st);
+int32_t tb_pc_bj_update(tb_ctx *ctx, const tb_csr *A);
+int32_t tb_pc_bj_apply(tb_ctx *ctx, const double *r, double *z, const struct CGState *st);
 int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                        int32_t *converged, int precond = 0);

@@ -86,7 +86,7 @@ extern "C" int32_t tb_monodomain_set_cg(tb_monodomain *md, double atol, double r
 
 extern "C" int32_t tb_monodomain_set_preconditioner(tb_monodomain *md, int32_t precond) {
     TB_REQUIRE(md, "tb_monodomain_set_preconditioner: handle is NULL");
-    TB_REQUIRE(precond == TB_PRECOND_NONE || precond == TB_PRECOND_JACOBI, "tb_monodomain_set_preconditioner: unknown preconditioner %d", precond);
+    TB_REQUIRE(precond >= TB_PRECOND_NONE && precond <= TB_PRECOND_CHEBYSHEV, "tb_monodomain_set_preconditioner: unknown preconditioner %d", precond);
     md->precond = precond;
     return TB_OK;
 }
