@@ -161,24 +161,31 @@ def run_b200(args):
     lengths = tuple(n * W["h"] for n in nel)
     t_setup = time.time()
     lv_data = None
+    part = None
     if W["celltype"] == "lv":
-        if world > 1:
-            raise SystemExit("workload c4 (unstructured LV) is single-GPU in this bench: its numbering has no plane structure to cut")
         from thunderbolt_jl_b200 import lv
         nodes, hexes, wedges, prm = lv.generate_ideal_lv_mesh(*nel)
         tets = lv.tetrahedralize(nodes, hexes, wedges)
-        fsn = lv.odb25lt_fibres(prm, tets)
-        lv_data = np.concatenate([np.asarray(W["kappa"], dtype=np.float64), np.ascontiguousarray(fsn).reshape(-1)])
-        del fsn
-        mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+        fsn = np.ascontiguousarray(lv.odb25lt_fibres(prm, tets)).reshape(tets.shape[0], -1)
         dim = 3
         lengths = tuple(float(v) for v in (nodes.max(axis=0) - nodes.min(axis=0)))
+        if world > 1:
+            # general mesh: RCB ownership of the dofs, renumbering, HOST-side cut -- only the local cells reach the GPU
+            celldofs, N_global = tb.api.close_dofs(tets)
+            part = tbd.partition_host_mesh(dev, tb.Tetrahedron, tets, nodes, celldofs, N_global, dist)
+            mesh = part.mesh
+            fsn = fsn[part.cells]
+        else:
+            mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+            N_global = mesh.ndofs
+        lv_data = np.concatenate([np.asarray(W["kappa"], dtype=np.float64), fsn.reshape(-1)])
+        del fsn
     else:
         mesh = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
-    N_global = mesh.ndofs
+        N_global = mesh.ndofs
     ion = tb.FHNModel() if W["model"] == "fhn" else tb.PCG2019()
     ns = tb.num_states(ion)
-    if world > 1:
+    if world > 1 and part is None:
         plane = (nel[0] + 1) * (nel[1] + 1) if dim == 3 else nel[0] + 1
         part = tbd.partition_mesh(dev, mesh, dist, plane=plane if args.cut == "planes" else None)
         mesh.free()
@@ -212,7 +219,8 @@ def run_b200(args):
     n_owned = mesh.ndofs_owned
     if W["celltype"] == "lv":   # rest, apex region depolarised
         u0 = np.repeat(tb.default_initial_state(tb.PCG2019()), mesh.ndofs)
-        u0[:mesh.ndofs] = np.where(x[:, 2] > x[:, 2].max() - 0.15 * lengths[2], 20.0, u0[:mesh.ndofs])
+        zmax = float(nodes[:, 2].max())                      # global, not this rank's
+        u0[:mesh.ndofs] = np.where(x[:, 2] > zmax - 0.15 * lengths[2], 20.0, u0[:mesh.ndofs])
     else:
         u0 = initial_state(x, W["model"], lengths, tb)
     if args.no_parity:
@@ -345,7 +353,7 @@ def run_b200(args):
                          "cg_iters_per_step_mean": k_mean, "cg_iters_min": int(min(iters)), "cg_iters_max": int(max(iters)),
                          "all_converged": bool(conv_all),
                          "parallelism": "single GPU" if world == 1 else
-                         (f"dof-ownership z-slabs x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
+                         (f"{'RCB dof ownership (general mesh, host-side cut)' if W['celltype'] == 'lv' else 'dof-ownership z-slabs'} x{world}, halo of p and dot products by NVLink peer stores from the CG kernels "
                           f"(CUDA IPC windows; {'collects and halo push fused into the update kernels' if part.fused else 'separate push/collect kernels'}), "
                           f"NCCL for the per-step phi halo" if peer_path else
                           f"dof-ownership z-slabs x{world}, NCCL halo + allreduce") + (f", cuts at {args.cut}" if world > 1 else ""),

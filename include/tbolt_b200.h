@@ -151,6 +151,10 @@ int32_t tb_mesh_dof_coords(const tb_mesh *m, double *host);
  * the ghosts' global ids; *nghost their count. */
 int32_t tb_mesh_extract_local(const tb_mesh *global, int64_t dof_lo, int64_t dof_hi, tb_mesh **out, int64_t *nghost);
 int32_t tb_mesh_ghosts(const tb_mesh *local, int64_t *ghost_global);
+/* the same ownership marking for a LOCAL mesh that was cut on the host and uploaded with tb_mesh_create (general
+ * partitions: no global replica in HBM): dofs 0 .. ndofs_owned-1 are owned (global ids dof_lo ..), the rest are ghosts with
+ * the given ascending global ids.  Call before the first assembly on this mesh. */
+int32_t tb_mesh_set_ownership(tb_mesh *m, int64_t ndofs_owned, int64_t dof_lo, const int64_t *ghost_global, int64_t nghost);
 
 /* ---- CSR operators ----------------------------------------------------------------------------
  * create_system_matrix (src/solver/interface.jl:159-173; ext/CuThunderboltExt.jl:129-139). */

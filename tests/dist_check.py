@@ -25,12 +25,78 @@ def build(dev, mesh, ion, D):
     return M, K
 
 
+def main_general(rank, world, local, dev):
+    """DIST_MESH=lv: an unstructured mesh (idealized LV, tetrahedra, fibre tensor) partitioned by RCB on the host
+    (dist.partition_host_mesh: renumbering + local cut, no global mesh in HBM) against the single-GPU solve."""
+    from thunderbolt_jl_b200 import lv
+    nodes, hexes, wedges, prm = lv.generate_ideal_lv_mesh(24, 3, 12)
+    tets = lv.tetrahedralize(nodes, hexes, wedges)
+    fsn = np.ascontiguousarray(lv.odb25lt_fibres(prm, tets)).reshape(tets.shape[0], -1)
+    kap = [0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24), 0.019 * 0.24 / (0.019 + 0.24)]
+    ion = tb.FHNModel()
+    dev1 = tb.B200Device(local)
+    full1 = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev1)
+    N = full1.ndofs
+
+    def build_lv(d, mesh, cellsel):
+        M = tb.B200CSRMatrix.from_mesh(d, mesh)
+        K = M.like()
+        tb.core.assemble_mass(d, mesh, M, 2, 1.0)
+        tb.core.assemble_diffusion(d, mesh, K, 2, tb._lib.D_SPECTRAL, np.concatenate([kap, fsn[cellsel].ravel()]), 1.0)
+        return M, K
+    x = full1.dof_coords()
+    u0 = np.concatenate([np.where(x[:, 2] > x[:, 2].max() - 0.4, 1.0, 0.0), np.zeros(N)])
+    M1, K1 = build_lv(dev1, full1, slice(None))
+    st1 = tb.MonodomainStepper(dev1, M1, K1, ion.model_id, ion.params())
+    u1 = tb.B200Vector.from_host(dev1, u0, 2)
+    it1 = [st1.step(u1, 0.05 * s, 0.05)[0] for s in range(5)]
+    ref = u1.to_host()
+    celldofs, nd = tb.api.close_dofs(tets)
+    assert nd == N
+    part = tbd.partition_host_mesh(dev, tb.Tetrahedron, tets, nodes, celldofs, N, dist)
+    lm = part.mesh
+    no, nl = lm.ndofs_owned, lm.ndofs
+    assert np.array_equal(lm.dof_coords(), x[part.gids_old])
+    M, K = build_lv(dev, lm, part.cells)
+    part.attach_halo(M)
+    if rank == 0:
+        print(("peer path on" if part.peer else "peer path off (NCCL)") + (", fused" if part.fused else ", unfused"), flush=True)
+    st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+    u = tb.B200Vector.from_host(dev, part.local_vector(u0, 2), 2)
+    its = [st.step(u, 0.05 * s, 0.05)[0] for s in range(5)]
+    got = u.to_host()
+    own = part.gids_old[:no]
+    err_phi = np.abs(got[:no] - ref[own]).max() / np.abs(ref[:N]).max()
+    err_s = np.abs(got[nl:nl + no] - ref[N + own]).max()
+    ok = err_phi <= 1e-8 and err_s <= 1e-9 and max(abs(a - b) for a, b in zip(its, it1)) <= 1
+    # Chebyshev-preconditioned CG across the partition (inner SpMVs exchange their halo through NCCL)
+    for d_, s_ in ((dev1, st1), (dev, st)):
+        d_.cg_set_chebyshev(6, 30.0)
+        s_.set_preconditioner(tb._lib.PRECOND_CHEBYSHEV)
+    u1.upload(u0)
+    u.upload(part.local_vector(u0, 2))
+    itc1 = [st1.step(u1, 0.05 * s, 0.05)[0] for s in range(3)]
+    itc = [st.step(u, 0.05 * s, 0.05)[0] for s in range(3)]
+    refc, gotc = u1.to_host(), u.to_host()
+    err_c = np.abs(gotc[:no] - refc[own]).max() / np.abs(refc[:N]).max()
+    ok = ok and err_c <= 1e-8 and max(abs(a - b) for a, b in zip(itc, itc1)) <= 1 and max(itc1) < max(it1)
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    print(f"rank {rank}/{world} [lv, rcb]: owned {no} ghosts {nl - no} neighbours {list(part.plan.neigh_ranks)} iters {its} vs {it1} "
+          f"err_phi {err_phi:.2e} err_s {err_s:.2e} | chebyshev iters {itc} vs {itc1} err {err_c:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = tb.B200Device(local)
     tbd.init_comm(dev, dist)
+    if os.environ.get("DIST_MESH", "grid") == "lv":
+        return main_general(rank, world, local, dev)
     nel = (24, 20, 4 * world + 3)
     lengths = tuple(0.25 * n for n in nel)
     D = np.diag([0.0295, 0.0131, 0.0131])

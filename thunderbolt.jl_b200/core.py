@@ -254,6 +254,12 @@ class DeviceMesh:
             L.call("tb_mesh_ghosts", h, m.ghost_global)
         return m
 
+    def set_ownership(self, ndofs_owned: int, dof_lo: int, ghost_global):
+        """mark a host-cut local mesh: owned dofs first (global ids dof_lo ..), ghosts after (ascending global ids)"""
+        gg = np.ascontiguousarray(ghost_global, dtype=np.int64)
+        L.call("tb_mesh_set_ownership", self.h, int(ndofs_owned), int(dof_lo), L.ptr(gg), int(gg.size))
+        self.ndofs_owned, self.dof_lo, self.ghost_global = int(ndofs_owned), int(dof_lo), gg
+
     def download(self):
         conn = np.empty((self.ncells, self.nv), dtype=np.int64)
         coords = np.empty((self.nnodes, self.dim))

@@ -442,6 +442,31 @@ extern "C" int32_t tb_mesh_extract_local(const tb_mesh *g, int64_t dof_lo, int64
     return TB_OK;
 }
 
+// Marks a mesh uploaded with tb_mesh_create as the LOCAL part of a partitioned mesh: its dofs are numbered owned-first
+// (0 .. ndofs_owned-1 = global ids dof_lo ..), ghosts after (ascending global id).  What tb_mesh_extract_local produces on
+// the device, for callers that cut the mesh on the host (general partitions, no global replica in HBM).
+extern "C" int32_t tb_mesh_set_ownership(tb_mesh *m, int64_t ndofs_owned, int64_t dof_lo, const int64_t *ghost_global,
+                                         int64_t nghost) {
+    TB_REQUIRE(m, "tb_mesh_set_ownership: mesh is NULL");
+    TB_REQUIRE(ndofs_owned > 0 && nghost >= 0 && ndofs_owned + nghost == m->ndofs,
+               "tb_mesh_set_ownership: %lld owned + %lld ghosts != %lld dofs of the mesh", (long long)ndofs_owned, (long long)nghost,
+               (long long)m->ndofs);
+    TB_REQUIRE(nghost == 0 || ghost_global, "tb_mesh_set_ownership: ghost list is NULL");
+    for (int64_t i = 1; i < nghost; i++)
+        TB_REQUIRE(ghost_global[i - 1] < ghost_global[i], "tb_mesh_set_ownership: ghost ids must be strictly ascending");
+    tb_ctx *ctx = m->ctx;
+    TB_DEV(ctx);
+    TB_REQUIRE(!m->d_adjptr, "tb_mesh_set_ownership: call before the first assembly");
+    cudaFree(m->d_ghost_global);
+    m->d_ghost_global = nullptr;
+    TB_CUDA(cudaMalloc(&m->d_ghost_global, sizeof(int64_t) * (size_t)(nghost + 1)));
+    if (nghost) TB_CUDA(cudaMemcpy(m->d_ghost_global, ghost_global, sizeof(int64_t) * (size_t)nghost, cudaMemcpyHostToDevice));
+    m->ndofs_owned = ndofs_owned;
+    m->nghost = nghost;
+    m->dof_lo = dof_lo;
+    return TB_OK;
+}
+
 extern "C" int32_t tb_mesh_ghosts(const tb_mesh *m, int64_t *ghost_global) {
     TB_REQUIRE(m && ghost_global, "tb_mesh_ghosts: NULL argument");
     if (m->nghost == 0) return TB_OK;

@@ -256,24 +256,53 @@ __global__ void __launch_bounds__(512) k_bj_invert(const int64_t *__restrict__ b
     }
 }
 
-// z_b = inv_b * r_b.  One CTA per block; r_b in shared memory; lane i sums row i left to right, reading column i of the
-// symmetric inverse (coalesced across the warp).
+// z_b = inv_b * r_b.  One CTA per block; r_b in shared memory.  The 256 threads split into G = 256 / roundup32(n) groups;
+// lane i of group g sums the terms j of its slice of the block's columns for row i, reading column i of the (symmetric)
+// inverse -- 32 lanes read 256 contiguous bytes per term -- and the G partial sums of a row are added in group order
+// (fixed order: deterministic).  The kernel streams sum(n_b^2) * 8 bytes per application: HBM bound.
 __global__ void __launch_bounds__(256) k_bj_apply(const double *__restrict__ r, double *__restrict__ z, const int *__restrict__ perm,
                                                   const int64_t *__restrict__ bptr, const int64_t *__restrict__ iptr,
                                                   const double *__restrict__ inv, int64_t nblocks, const CGState *st) {
     if (st && st->done) return;
-    extern __shared__ double s_r[];
+    extern __shared__ double s_r[];          // max_bs doubles, then 512 doubles of partial sums
     for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const int64_t p0 = bptr[b];
         const int n = (int)(bptr[b + 1] - p0);
         const double *a = inv + iptr[b];
+        const int n32 = (n + 31) & ~31;
+        double *s_part = s_r + ((n + 1) & ~1);
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) s_r[i] = r[perm[p0 + i]];
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            double acc = 0.0;
-            for (int j = 0; j < n; j++) acc += a[(int64_t)j * n + i] * s_r[j];
-            z[perm[p0 + i]] = acc;
+        if (n32 <= 128) {
+            const int G = 256 / n32, g = threadIdx.x / n32, i = threadIdx.x - g * n32;
+            if (g < G && i < n) {
+                const int j0 = (int)(((int64_t)n * g) / G), j1 = (int)(((int64_t)n * (g + 1)) / G);
+                double acc = 0.0;
+                int j = j0;
+                for (; j + 4 <= j1; j += 4) {
+                    const double a0 = a[(int64_t)j * n + i], a1 = a[(int64_t)(j + 1) * n + i], a2 = a[(int64_t)(j + 2) * n + i],
+                                 a3 = a[(int64_t)(j + 3) * n + i];
+                    acc += a0 * s_r[j];
+                    acc += a1 * s_r[j + 1];
+                    acc += a2 * s_r[j + 2];
+                    acc += a3 * s_r[j + 3];
+                }
+                for (; j < j1; j++) acc += a[(int64_t)j * n + i] * s_r[j];
+                s_part[g * n32 + i] = acc;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < n) {
+                double acc = s_part[threadIdx.x];
+                for (int g2 = 1; g2 < G; g2++) acc += s_part[g2 * n32 + threadIdx.x];
+                z[perm[p0 + threadIdx.x]] = acc;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double acc = 0.0;
+                for (int j = 0; j < n; j++) acc += a[(int64_t)j * n + i] * s_r[j];
+                z[perm[p0 + i]] = acc;
+            }
         }
     }
 }
@@ -301,7 +330,7 @@ int32_t tb_pc_bj_update(tb_ctx *ctx, const tb_csr *A) {
 
 int32_t tb_pc_bj_apply(tb_ctx *ctx, const double *r, double *z, const CGState *st) {
     tb_bj *B = ctx->bj;
-    const size_t smem = sizeof(double) * (size_t)B->max_bs;
+    const size_t smem = sizeof(double) * ((size_t)B->max_bs + 2 + 512);
     const int64_t cap = (int64_t)ctx->sm_count * 8;
     const int grid = (int)(B->nblocks < cap ? B->nblocks : cap);
     TB_LAUNCH(ctx, k_bj_apply, grid, 256, smem, r, z, B->d_perm, B->d_bptr, B->d_iptr, B->d_inv, B->nblocks, st);

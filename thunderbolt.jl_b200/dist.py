@@ -158,3 +158,106 @@ def partition_mesh(dev: B200Device, mesh: DeviceMesh, dist, plane: int | None = 
     dist.all_gather_object(gathered, local.ghost_global)
     plan = build_halo_plan(rank, bounds, local.ghost_global, gathered)
     return Partition(local, bounds, plan, rank, world, dist)
+
+
+# =====================================================================================================================
+# General meshes ("general meshes via a host-side graph partition"): ownership by recursive coordinate
+# bisection of the dof coordinates, a global renumbering that makes every rank's dofs one contiguous range (so the halo
+# plan, the peer windows and the kernels above are reused unchanged), and a HOST-side cut of the mesh so that no rank ever
+# holds the global mesh in HBM.  The renumbering is a symmetric permutation of the reference's operator: iteration counts
+# agree within the +-1 rule, vectors map back through `GeneralPartition.gids_old`.
+# =====================================================================================================================
+def rcb_partition(x: np.ndarray, nparts: int) -> np.ndarray:
+    """Recursive coordinate bisection: part id per point, sizes equal up to one, deterministic (stable sorts, ties by
+    index) so that every rank computes the same partition from the same coordinates."""
+    x = np.asarray(x, dtype=np.float64)
+    part = np.empty(x.shape[0], dtype=np.int32)
+
+    def rec(idx, nparts, first):
+        if nparts == 1:
+            part[idx] = first
+            return
+        nl = nparts // 2
+        ext = x[idx].max(axis=0) - x[idx].min(axis=0)
+        ax = int(np.argmax(ext))
+        order = np.argsort(x[idx, ax], kind="stable")
+        k = (idx.size * nl) // nparts
+        rec(idx[order[:k]], nl, first)
+        rec(idx[order[k:]], nparts - nl, first + nl)
+
+    rec(np.arange(x.shape[0]), int(nparts), 0)
+    return part
+
+
+def renumber_by_part(part: np.ndarray, nparts: int):
+    """(new_of_old, old_of_new, bounds): dofs of part 0 first, then part 1, ... (old order kept inside a part)."""
+    old_of_new = np.argsort(part, kind="stable").astype(np.int64)
+    new_of_old = np.empty_like(old_of_new)
+    new_of_old[old_of_new] = np.arange(part.size, dtype=np.int64)
+    bounds = np.concatenate([[0], np.cumsum(np.bincount(part, minlength=nparts))]).astype(np.int64)
+    return new_of_old, old_of_new, bounds
+
+
+def cut_local_mesh(conn: np.ndarray, coords: np.ndarray, celldofs_new: np.ndarray, lo: int, hi: int):
+    """Host twin of tb_mesh_extract_local for renumbered dofs: the cells touching [lo, hi) (ascending global cell id, so the
+    ordered-gather assembly adds element contributions in the reference's order), local node / dof numbering (owned dofs
+    first, ghosts after in ascending global id).  Returns (cells, lconn, lcoords, lcelldofs, ghost_global)."""
+    cd = np.asarray(celldofs_new)
+    touch = ((cd >= lo) & (cd < hi)).any(axis=1)
+    cells = np.flatnonzero(touch)
+    cdl = cd[cells]
+    out = (cdl < lo) | (cdl >= hi)
+    ghosts = np.unique(cdl[out])
+    ldofs = np.where(out, (hi - lo) + np.searchsorted(ghosts, cdl), cdl - lo)
+    cl = np.asarray(conn)[cells]
+    used = np.unique(cl)
+    lconn = np.searchsorted(used, cl)
+    return cells, lconn.astype(np.int64), np.asarray(coords)[used], ldofs.astype(np.int64), ghosts.astype(np.int64)
+
+
+@dataclass
+class GeneralPartition(Partition):
+    cells: np.ndarray = None        # global ids of the local cells (per-cell coefficient data is subset with this)
+    gids_old: np.ndarray = None     # local dof -> dof id in the REFERENCE's numbering (owned first, then ghosts)
+    new_of_old: np.ndarray = None
+    part: np.ndarray = None
+
+    def local_vector(self, v_old: np.ndarray, ncols: int = 1) -> np.ndarray:
+        """state-blocked host vector in the reference's numbering -> this rank's local image (owned + ghosts)"""
+        n = v_old.size // ncols
+        return np.concatenate([v_old[c * n:(c + 1) * n][self.gids_old] for c in range(ncols)])
+
+
+def host_cut(rank: int, nranks: int, conn, coords, celldofs, ndofs: int, part: np.ndarray | None = None):
+    """Pure host logic of partition_host_mesh (CPU-testable): ownership, renumbering and this rank's local cut."""
+    conn, celldofs = np.asarray(conn), np.asarray(celldofs)
+    if part is None:
+        xd = np.empty((ndofs, np.asarray(coords).shape[1]))
+        xd[celldofs.ravel()] = np.asarray(coords)[conn.ravel()]          # Lagrange-1: a dof sits on its vertex
+        part = rcb_partition(xd, nranks)
+    new_of_old, old_of_new, bounds = renumber_by_part(part, nranks)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    cells, lconn, lcoords, ldofs, ghosts = cut_local_mesh(conn, coords, new_of_old[celldofs], lo, hi)
+    gids_old = old_of_new[np.concatenate([np.arange(lo, hi), ghosts])]
+    return dict(part=part, new_of_old=new_of_old, old_of_new=old_of_new, bounds=bounds, lo=lo, hi=hi, cells=cells, lconn=lconn,
+                lcoords=lcoords, ldofs=ldofs, ghosts=ghosts, gids_old=gids_old)
+
+
+def partition_host_mesh(dev: B200Device, celltype, conn, coords, celldofs, ndofs: int, dist=None, rank: int | None = None,
+                        nranks: int | None = None, part: np.ndarray | None = None) -> GeneralPartition:
+    """conn / coords / celldofs: the whole mesh in HOST memory with the reference's dof numbering (what Ferrite hands
+    over).  `part` (owner rank per dof) defaults to RCB of the dof coordinates.  Only the local cut is uploaded."""
+    rank = dist.get_rank() if rank is None else rank
+    nranks = dist.get_world_size() if nranks is None else nranks
+    c = host_cut(rank, nranks, conn, coords, celldofs, ndofs, part)
+    lo, hi, ghosts = c["lo"], c["hi"], c["ghosts"]
+    mesh = DeviceMesh.from_host(dev, celltype, c["lconn"], c["lcoords"], c["ldofs"], (hi - lo) + ghosts.size)
+    mesh.set_ownership(hi - lo, lo, ghosts)
+    if dist is not None and nranks > 1:
+        gathered = [None] * nranks
+        dist.all_gather_object(gathered, ghosts)
+        plan = build_halo_plan(rank, c["bounds"], ghosts, gathered)
+    else:
+        plan = HaloPlan(np.empty(0, np.int32), np.zeros(1, np.int64), np.empty(0, np.int64), np.zeros(1, np.int64))
+    return GeneralPartition(mesh, c["bounds"], plan, rank, nranks, dist, cells=c["cells"], gids_old=c["gids_old"],
+                            new_of_old=c["new_of_old"], part=c["part"])
