@@ -118,6 +118,41 @@ def c2_full():
     np.savez_compressed(HERE / "c2_full.npz", **out)
 
 
+def c2_full_1000():
+    """config 2 at FULL size and FULL length: 1000 steps of dt = 0.01, adaptive substepper, corner stimulus
+    with its [0, 2.1] window (needs_update gating, stale source afterwards: euler.jl:88-91).  Stored: phi_m at every 61st
+    dof after steps 1 and 1000, the h gate after 1000, all CG iteration counts, activation steps (first step with
+    phi_m >= 0 mV) of the sampled dofs."""
+    m = O.generate_grid(O.HEX8, (128, 128, 32), (0, 0, 0), (32.0, 32.0, 8.0))
+    k1 = 0.17 * 0.62 / (0.17 + 0.62)
+    kr = 0.019 * 0.24 / (0.019 + 0.24)
+    M = O.assemble_mass(m, 2, threaded=True)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag([k1, kr, kr]), threaded=True)
+    N = m.ndofs
+    u = np.repeat(O.default_initial_state(O.PCG2019), N)
+    orc = O.MonodomainOracle(m, O.PCG2019, O.default_params(O.PCG2019), M, K, substeps=10, threaded_blas1=True)
+    out, t, dt = {}, 0.0, 0.01
+    act = np.full(u[:N:61].size, -1, dtype=np.int16)
+    for step in range(1000):
+        if 0.0 <= t + dt <= 2.1:
+            orc.bS = O.assemble_source(m, 2, O.SRC_BOX, [1.5, 2.0, 0.5], t + dt)
+        it, rn, conv = orc.step(u, t, dt)
+        assert conv
+        t += dt
+        ph = u[:N:61]
+        act[(act < 0) & (ph >= 0.0)] = step + 1
+        if step == 0:
+            out["phi1"] = ph.copy()
+        if step % 100 == 99:
+            print("step", step + 1, "iters", it, "activated", int((act > 0).sum()), flush=True)
+    out["phi1000"] = u[:N:61].copy()
+    out["h1000"] = u[N:2 * N:61].copy()
+    out["iters"] = np.array(orc.iters, dtype=np.int16)
+    out["act"] = act
+    out["n_above"] = np.array([(u[:N] > -84.0).sum()])
+    np.savez_compressed(HERE / "c2_full_1000.npz", **out)
+
+
 def c2_small():
     """config 2 (conduction-velocity-benchmark.jl) on 16x16x4 hexes, h = 0.25: PCG2019, corner stimulus."""
     m = O.generate_grid(O.HEX8, (16, 16, 4), (0, 0, 0), (4.0, 4.0, 1.0))
@@ -152,6 +187,11 @@ def c2_small():
 if __name__ == "__main__" and "--c2-full" in sys.argv:
     c2_full()
     print("wrote", HERE / "c2_full.npz")
+    sys.exit(0)
+
+if __name__ == "__main__" and "--c2-full-1000" in sys.argv:
+    c2_full_1000()
+    print("wrote", HERE / "c2_full_1000.npz")
     sys.exit(0)
 
 if __name__ == "__main__" and "--c1-full" in sys.argv:

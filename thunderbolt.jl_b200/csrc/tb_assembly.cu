@@ -655,6 +655,7 @@ static int32_t launch_bilinear(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tabl
 static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int op, double rho, int kind,
                                  const double *data, int64_t ndata, double cmchi, tb_csr *A) {
     TB_REQUIRE(ctx && mesh && A, "assemble: NULL argument");
+    A->version++;
     TB_REQUIRE(A->pat->nrows == mesh->ndofs_owned && A->pat->ncols == mesh->ndofs,
                "assemble: operator is %lld x %lld but the mesh has %lld owned / %lld total dofs", (long long)A->pat->nrows,
                (long long)A->pat->ncols, (long long)mesh->ndofs_owned, (long long)mesh->ndofs);

@@ -542,10 +542,12 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     if (gen_pc) dinv = nullptr;                     // the CG kernels themselves run the unpreconditioned forms on (r, z)
     double cheb_c1[64], cheb_c2[64], cheb_inv_theta = 0.0;
     const int cheb_d = ctx->cheb_degree;
-    if (precond == TB_PRECOND_BLOCK_JACOBI) TB_TRY(tb_pc_bj_update(ctx, A));
+    // update!(P, A) only when the operator's values changed since the setup was built (A = M - dt K is rebuilt only when dt moves)
+    const bool pc_stale = !(ctx->pc_uid == A->uid && ctx->pc_version == A->version && ctx->pc_kind == precond);
+    if (precond == TB_PRECOND_BLOCK_JACOBI && pc_stale) TB_TRY(tb_pc_bj_update(ctx, A));
     if (precond == TB_PRECOND_CHEBYSHEV) {
-        double lmax = 0.0;
-        TB_TRY(tb_pc_gershgorin(ctx, A, &lmax));
+        if (pc_stale) TB_TRY(tb_pc_gershgorin(ctx, A, &ctx->pc_lmax));
+        const double lmax = ctx->pc_lmax;
         TB_REQUIRE(lmax > 0.0, "Chebyshev preconditioner: operator has no positive diagonal");
         const double hi = lmax, lo = lmax / ctx->cheb_ratio;
         const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma1 = theta / delta;
@@ -559,6 +561,9 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
         }
     }
     if (gen_pc) {
+        ctx->pc_uid = A->uid;
+        ctx->pc_version = A->version;
+        ctx->pc_kind = precond;
         const int64_t ld = tb_round_up(pat->ncols, 32);
         if (ctx->pcwork_ld < ld) {
             TB_CUDA(cudaStreamSynchronize(ctx->stream));

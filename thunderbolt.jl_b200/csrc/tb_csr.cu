@@ -217,10 +217,16 @@ int32_t tb_pattern_release(tb_pattern *p) {
     return TB_OK;
 }
 
+uint64_t tb_next_uid() {
+    static uint64_t next = 0;
+    return ++next;
+}
+
 static int32_t csr_from_pattern(tb_pattern *p, tb_csr **out) {
     tb_csr *a = new (std::nothrow) tb_csr();
     if (!a) return tb_fail(TB_ERR_NOMEM, "tb_csr: host allocation failed");
     a->pat = p;
+    a->uid = tb_next_uid();
     a->d_val = nullptr;
     cudaError_t e = cudaMalloc(&a->d_val, sizeof(double) * (size_t)(p->sell_len + 32));
     if (e != cudaSuccess) {
@@ -512,6 +518,7 @@ extern "C" int32_t tb_csr_values_download(const tb_csr *a, double *vals) {
 
 extern "C" int32_t tb_csr_values_upload(tb_csr *a, const double *vals) {
     TB_REQUIRE(a && vals, "tb_csr_values_upload: NULL argument");
+    a->version++;
     tb_pattern *p = a->pat;
     tb_ctx *ctx = p->ctx;
     TB_DEV(ctx);
@@ -528,6 +535,7 @@ extern "C" int32_t tb_csr_values_upload(tb_csr *a, const double *vals) {
 
 extern "C" int32_t tb_csr_zero(tb_csr *a) {
     TB_REQUIRE(a, "tb_csr_zero: matrix is NULL");
+    a->version++;
     TB_CUDA(cudaMemsetAsync(a->d_val, 0, sizeof(double) * (size_t)a->pat->sell_len, a->pat->ctx->stream));
     return TB_OK;
 }
@@ -549,6 +557,7 @@ __global__ void __launch_bounds__(256) k_axpby_values(const double2 *__restrict_
 extern "C" int32_t tb_csr_axpby_values(tb_csr *A, const tb_csr *M, const tb_csr *K, double dt) {
     TB_REQUIRE(A && M && K, "tb_csr_axpby_values: NULL argument");
     TB_REQUIRE(A->pat == M->pat && A->pat == K->pat, "tb_csr_axpby_values: A, M, K must share one pattern");
+    A->version++;
     tb_ctx *ctx = A->pat->ctx;
     TB_DEV(ctx);
     int64_t n2 = A->pat->sell_len / 2;   // sell_len is a multiple of 32

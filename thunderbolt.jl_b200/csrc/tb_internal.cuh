@@ -151,6 +151,9 @@ struct tb_ctx {
     double *d_dinv = nullptr;         // Jacobi preconditioner: 1/diag(A) of the operator being solved
     int64_t dinv_len = 0;
     struct tb_bj *bj = nullptr;       // block-Jacobi plan + dense inverses (tb_precond.cu)
+    uint64_t pc_uid = 0, pc_version = ~0ull;   // operator the cached Chebyshev bound / block inverses were built from
+    int pc_kind = -1;
+    double pc_lmax = 0.0;
     int cheb_degree = 8;              // Chebyshev preconditioner: polynomial degree and lmax/lmin of the target interval
     double cheb_ratio = 30.0;
     double *d_pcwork = nullptr;       // z | d | res | w of the general preconditioners
@@ -289,7 +292,10 @@ struct tb_pattern {
 struct tb_csr {
     tb_pattern *pat;
     double *d_val;   // sell_len
+    uint64_t version = 0;   // bumped by every entry point that writes values: lets the preconditioners cache their setup
+    uint64_t uid = 0;       // distinguishes handles that reuse an address
 };
+uint64_t tb_next_uid();
 
 struct tb_monodomain {
     tb_ctx *ctx;

@@ -198,6 +198,8 @@ extern "C" int32_t tb_cg_set_block_jacobi(tb_ctx *ctx, int64_t nrows, int64_t nb
                        cudaGetErrorString(e), (double)B->inv_len * 8e-6);
     }
     ctx->bj = B;
+    ctx->pc_version = ~0ull;   // the inverses have to be rebuilt for the new plan
+    ctx->pc_uid = 0;
     return TB_OK;
 }
 
@@ -256,53 +258,39 @@ __global__ void __launch_bounds__(512) k_bj_invert(const int64_t *__restrict__ b
     }
 }
 
-// z_b = inv_b * r_b.  One CTA per block; r_b in shared memory.  The 256 threads split into G = 256 / roundup32(n) groups;
-// lane i of group g sums the terms j of its slice of the block's columns for row i, reading column i of the (symmetric)
-// inverse -- 32 lanes read 256 contiguous bytes per term -- and the G partial sums of a row are added in group order
-// (fixed order: deterministic).  The kernel streams sum(n_b^2) * 8 bytes per application: HBM bound.
+// z_b = inv_b * r_b as a batched dense mat-vec.  One CTA per block, one warp per tile of 32 rows: lane i owns row i and walks
+// the columns j = 0 .. n-1 left to right (fixed order: deterministic), reading column i of the (symmetric) inverse so that
+// the 32 lanes fetch 256 contiguous bytes per term; r_b never touches shared memory -- a warp keeps 32 entries in
+// registers and broadcasts them with shuffles.  No barriers, eight independent 256-byte loads in flight per warp: the
+// kernel streams sum(n_b^2) * 8 bytes per application and is HBM bound.
 __global__ void __launch_bounds__(256) k_bj_apply(const double *__restrict__ r, double *__restrict__ z, const int *__restrict__ perm,
                                                   const int64_t *__restrict__ bptr, const int64_t *__restrict__ iptr,
                                                   const double *__restrict__ inv, int64_t nblocks, const CGState *st) {
     if (st && st->done) return;
-    extern __shared__ double s_r[];          // max_bs doubles, then 512 doubles of partial sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const int64_t p0 = bptr[b];
         const int n = (int)(bptr[b + 1] - p0);
         const double *a = inv + iptr[b];
-        const int n32 = (n + 31) & ~31;
-        double *s_part = s_r + ((n + 1) & ~1);
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_r[i] = r[perm[p0 + i]];
-        __syncthreads();
-        if (n32 <= 128) {
-            const int G = 256 / n32, g = threadIdx.x / n32, i = threadIdx.x - g * n32;
-            if (g < G && i < n) {
-                const int j0 = (int)(((int64_t)n * g) / G), j1 = (int)(((int64_t)n * (g + 1)) / G);
-                double acc = 0.0;
-                int j = j0;
-                for (; j + 4 <= j1; j += 4) {
-                    const double a0 = a[(int64_t)j * n + i], a1 = a[(int64_t)(j + 1) * n + i], a2 = a[(int64_t)(j + 2) * n + i],
-                                 a3 = a[(int64_t)(j + 3) * n + i];
-                    acc += a0 * s_r[j];
-                    acc += a1 * s_r[j + 1];
-                    acc += a2 * s_r[j + 2];
-                    acc += a3 * s_r[j + 3];
+        for (int i0 = warp * 32; i0 < n; i0 += nw * 32) {
+            const int i = i0 + lane;
+            const int ic = i < n ? i : n - 1;              // idle lanes read a valid column, their sum is dropped
+            double acc = 0.0;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int jj = j0 + lane;
+                const double xv = jj < n ? r[perm[p0 + jj]] : 0.0;
+                const int jn = n - j0 < 32 ? n - j0 : 32;
+                int j = 0;
+                for (; j + 8 <= jn; j += 8) {
+                    double av[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) av[q] = a[(int64_t)(j0 + j + q) * n + ic];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc += av[q] * __shfl_sync(0xffffffffu, xv, j + q);
                 }
-                for (; j < j1; j++) acc += a[(int64_t)j * n + i] * s_r[j];
-                s_part[g * n32 + i] = acc;
+                for (; j < jn; j++) acc += a[(int64_t)(j0 + j) * n + ic] * __shfl_sync(0xffffffffu, xv, j);
             }
-            __syncthreads();
-            if ((int)threadIdx.x < n) {
-                double acc = s_part[threadIdx.x];
-                for (int g2 = 1; g2 < G; g2++) acc += s_part[g2 * n32 + threadIdx.x];
-                z[perm[p0 + threadIdx.x]] = acc;
-            }
-        } else {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                double acc = 0.0;
-                for (int j = 0; j < n; j++) acc += a[(int64_t)j * n + i] * s_r[j];
-                z[perm[p0 + i]] = acc;
-            }
+            if (i < n) z[perm[p0 + i]] = acc;
         }
     }
 }
@@ -330,10 +318,11 @@ int32_t tb_pc_bj_update(tb_ctx *ctx, const tb_csr *A) {
 
 int32_t tb_pc_bj_apply(tb_ctx *ctx, const double *r, double *z, const CGState *st) {
     tb_bj *B = ctx->bj;
-    const size_t smem = sizeof(double) * ((size_t)B->max_bs + 2 + 512);
-    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    int threads = (B->max_bs + 31) / 32 * 32;          // one warp per 32-row tile of the largest block, at most 8 warps
+    if (threads > 256) threads = 256;
+    const int64_t cap = (int64_t)ctx->sm_count * (2048 / threads);
     const int grid = (int)(B->nblocks < cap ? B->nblocks : cap);
-    TB_LAUNCH(ctx, k_bj_apply, grid, 256, smem, r, z, B->d_perm, B->d_bptr, B->d_iptr, B->d_inv, B->nblocks, st);
+    TB_LAUNCH(ctx, k_bj_apply, grid, threads, 0, r, z, B->d_perm, B->d_bptr, B->d_iptr, B->d_inv, B->nblocks, st);
     return TB_OK;
 }
 

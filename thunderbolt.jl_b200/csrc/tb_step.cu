@@ -226,7 +226,8 @@ extern "C" int32_t tb_monodomain_step_host(tb_monodomain *md, tb_vec *u_dev, con
     return TB_OK;
 }
 
-#define RH_CHUNKS 8
+#define RH_CHUNKS 16
+#define RH_TRACE_MAX 64
 extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *buf0, double *buf1, double t0, double dt,
                                           int64_t nsteps, int64_t *iters_total, int32_t *all_converged) {
     TB_REQUIRE(md && u && buf0 && buf1 && nsteps >= 0, "tb_monodomain_run_host: bad argument");
@@ -242,6 +243,18 @@ extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *
     const int64_t n = u->n, ld = u->ld;
     const int nc = u->ncols, phic = md->phi_idx;
     const int64_t csz = tb_round_up((n + RH_CHUNKS - 1) / RH_CHUNKS, 32);
+    // TB_RUNHOST_TRACE=<file>: per-step timeline from CUDA events on the three streams (ms since the first step started):
+    // compute start | CG + cells done | phi download done | phi upload (next step's input) done | other columns down | up
+    const char *trace_path = getenv("TB_RUNHOST_TRACE");
+    std::vector<cudaEvent_t> tev;
+    const int64_t ntrace = trace_path ? (nsteps < RH_TRACE_MAX ? nsteps : RH_TRACE_MAX) : 0;
+    if (ntrace > 0) {
+        tev.resize((size_t)ntrace * 6);
+        for (auto &e : tev) TB_CUDA(cudaEventCreate(&e));
+    }
+    auto trace = [&](int64_t step, int k, cudaStream_t st) {
+        if (step < ntrace) cudaEventRecord(tev[(size_t)step * 6 + k], st);
+    };
     double *buf[2] = {buf0, buf1};
     int64_t total = 0;
     int32_t all = 1;
@@ -258,8 +271,10 @@ extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *
         int64_t it = 0;
         int32_t conv = 0;
         TB_CUDA(cudaStreamWaitEvent(ctx->stream, md->e_phi, 0));
+        trace(s, 0, ctx->stream);
         TB_TRY(monodomain_step_impl(md, u, t0, dt, &it, nullptr, &conv, nullptr, md->e_s));
         TB_CUDA(cudaEventRecord(md->e_done, ctx->stream));
+        trace(s, 1, ctx->stream);
         t0 += dt;
         total += it;
         all &= conv;
@@ -276,11 +291,14 @@ extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *
                 TB_CUDA(cudaMemcpyAsync(u->d + (size_t)phic * ld + o, out + (size_t)phic * n + o, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, md->s_in));
             }
         }
+        trace(s, 2, md->s_out);
         if (more) TB_CUDA(cudaEventRecord(md->e_phi, md->s_in));
+        trace(s, 3, md->s_in);
         for (int c = 0; c < nc; c++)
             if (c != phic)
                 TB_CUDA(cudaMemcpyAsync(out + (size_t)c * n, u->d + (size_t)c * ld, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, md->s_out));
         TB_CUDA(cudaEventRecord(md->o_s, md->s_out));
+        trace(s, 4, md->s_out);
         if (more) {
             TB_CUDA(cudaStreamWaitEvent(md->s_in, md->o_s, 0));
             for (int c = 0; c < nc; c++)
@@ -288,10 +306,27 @@ extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *
                     TB_CUDA(cudaMemcpyAsync(u->d + (size_t)c * ld, out + (size_t)c * n, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, md->s_in));
             TB_CUDA(cudaEventRecord(md->e_s, md->s_in));
         }
+        trace(s, 5, md->s_in);
     }
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
     TB_CUDA(cudaStreamSynchronize(md->s_out));
     TB_CUDA(cudaStreamSynchronize(md->s_in));
+    if (ntrace > 0) {
+        if (FILE *f = fopen(trace_path, ctx->rank == 0 ? "w" : "a")) {
+            fprintf(f, "# rank %d: step, compute_start, compute_done, phi_d2h_done, phi_h2d_done, rest_d2h_done, rest_h2d_done [ms]\n", ctx->rank);
+            for (int64_t k = 0; k < ntrace; k++) {
+                fprintf(f, "%d,%lld", ctx->rank, (long long)k);
+                for (int j = 0; j < 6; j++) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, tev[0], tev[(size_t)k * 6 + j]);
+                    fprintf(f, ",%.3f", ms);
+                }
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     if (iters_total) *iters_total = total;
     if (all_converged) *all_converged = all;
     return TB_OK;
