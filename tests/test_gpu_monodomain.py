@@ -311,6 +311,34 @@ def test_c2_full_size_40_steps_against_golden(tb, dev):
     assert (integ.u.column(0) > -84.0).sum() == int(g["n_above"][0])
 
 
+def test_c2_full_size_1000_steps_against_golden(tb, dev):
+    """BASELINE config 2 at its FULL size AND full length (1000 steps of dt = 0.01): 1e-10 after one step,
+    1e-6 after 1000, CG iterations +-1 on every step, activation steps identical (sampled at every 61st dof)."""
+    g = np.load(GOLD / "c2_full_1000.npz")
+    md = tb.generate_mesh(tb.Hexahedron, (128, 128, 32), (0, 0, 0), (32.0, 32.0, 8.0), device=dev)
+    k1, kr = 0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24)
+    proto = tb.AnalyticalTransmembraneStimulationProtocol(
+        tb.AnalyticalCoefficient(tb.BoxStimulus(1.5, 2.0, 0.5), tb.CartesianCoordinateSystem()), [(0.0, 2.1)])
+    model = tb.MonodomainModel(tb.ConstantCoefficient(1.0), tb.ConstantCoefficient(1.0),
+                               tb.ConstantCoefficient(np.diag([k1, kr, kr])), proto, tb.PCG2019(), "φₘ", "s")
+    odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(model), tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1)}), md)
+    u0 = tb.create_initial_condition(odeform)
+    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0, (0.0, 10.0)),
+                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(), tb.AdaptiveForwardEulerSubstepper())), dt=0.01)
+    act = np.full(g["act"].shape, -1, dtype=np.int16)
+    for step in range(1000):
+        assert tb.step_(integ)
+        if step == 0:
+            assert rel_linf(integ.u.column(0)[::61], g["phi1"]) <= 1e-10
+        ph = integ.u.column(0)[::61]
+        act[(act < 0) & (ph >= 0.0)] = step + 1
+    assert rel_linf(integ.u.column(0)[::61], g["phi1000"]) <= 1e-6
+    assert rel_linf(integ.u.column(1)[::61], g["h1000"]) <= 1e-6
+    assert np.abs(np.array(integ.cg_iterations) - g["iters"]).max() <= 1
+    assert np.array_equal(act, g["act"]) and (act > 0).sum() > 50                # activation steps identical at time-step resolution
+    assert (integ.u.column(0) > -84.0).sum() == int(g["n_above"][0])
+
+
 def test_c2_full_size_properties(tb, dev):
     """BASELINE config 2 at FULL size (128x128x32, PCG2019): properties that need no oracle.
     Pure-Neumann diffusion conserves 1^T M phi; the CG residual really is below tolerance; resting
