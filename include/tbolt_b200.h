@@ -302,6 +302,45 @@ int32_t tb_cg_set_exact_dot(tb_ctx *ctx, int32_t on);
 int32_t tb_cell_step(tb_ctx *ctx, int32_t model, const double *params, int32_t nparams, tb_vec *u, int32_t phi_idx,
                      double t, double dt, int32_t substeps, double reaction_threshold, double *max_dphi);
 
+/* ---- multi-subdomain splits (PointwiseMultiODEFunction, heat_dofrange views, interface diffusion) -------------------
+ * semidiscretize(::ReactionDiffusionSplit{<:Dict}) (src/discretization/fem.jl:434-542) packs the solution vector
+ * subdomain by subdomain, every block in PointBlockedLayout (src/modeling/solution_variables.jl:41-68), and gives the
+ * heat sub-problem the scattered index set heat_dofrange; perform_step!(::PointwiseMultiODEFunction, ...) sweeps the
+ * blocks one after the other (src/solver/time/partitioned_solver.jl:23-35,126-155). */
+typedef struct tb_index tb_index;
+int32_t tb_index_create(tb_ctx *ctx, const int64_t *idx, int64_t n, int32_t index_base, tb_index **out);
+int32_t tb_index_destroy(tb_index *ix);
+/* dst[i, dcol] = src[idx[i], scol]  -- the copy behind `view(u, heat_dofrange)` handed to the heat solver */
+int32_t tb_vec_gather(tb_vec *dst, int32_t dcol, const tb_vec *src, int32_t scol, const tb_index *ix);
+/* dst[idx[i], dcol] = src[i, scol] */
+int32_t tb_vec_scatter(tb_vec *dst, int32_t dcol, const tb_index *ix, const tb_vec *src, int32_t scol);
+
+#define TB_LAYOUT_STATE_BLOCKED 0 /* StateBlockedLayout: state s of point k at offset + s*npoints + k */
+#define TB_LAYOUT_POINT_BLOCKED 1 /* PointBlockedLayout: state s of point k at offset + k*nstates + s */
+typedef struct tb_cell_block {   /* StateBlock(offset, npoints, nstates, layout) + the PointwiseODEFunction's model */
+    int64_t offset;              /* 0-based, in doubles, into the flat state vector */
+    int64_t npoints;
+    int32_t model;               /* TB_FHN | TB_PCG2019 | TB_ALIEV_PANFILOV */
+    int32_t layout;
+    int32_t nparams;
+    int32_t reserved;
+    double params[36];
+} tb_cell_block;
+/* one cell sweep per block, in order; `u` is ONE flat column.  max_dphi (nullable): max over all blocks of the phi_m
+ * component of the last rhs evaluation (rtc.jl:68-73 loops the children the same way). */
+int32_t tb_cell_step_blocks(tb_ctx *ctx, const tb_cell_block *blocks, int32_t nblocks, tb_vec *u, double t, double dt,
+                            int32_t substeps, double reaction_threshold, double *max_dphi);
+
+/* BilinearInterfaceDiffusionIntegrator (src/modeling/core/diffusion.jl:81-140): K_e[i,j] -= [[N_i]] D [[N_j]] dGamma over
+ * interface cells, each a pair of coincident facets ("here", "there") whose nodes were duplicated.  dofs: nif x 2k ids
+ * (here side first), coords_*: nif x k x sdim.  K is zeroed first like every update_operator!; combine it with the bulk
+ * operator through tb_csr_axpby_values.  The scatter runs in interface-cell order (bitwise the sequential loop). */
+#define TB_FACET_LINE2 0
+#define TB_FACET_QUAD4 1
+int32_t tb_assemble_interface_diffusion(tb_ctx *ctx, int32_t facet_type, int32_t sdim, int64_t nif, const int64_t *dofs,
+                                        int32_t index_base, const double *coords_here, const double *coords_there,
+                                        int32_t qorder, double D, tb_csr *K);
+
 /* ---- fused LieTrotterGodunov step -------------------------------------------------------------
  * One OS.LieTrotterGodunov((BackwardEulerSolver, cell solver)) step (operatorsplitting-interface.jl:23-232;
  * perform_backward_euler_step!, euler.jl:71-101; partitioned_solver.jl:14-21): refresh A when dt

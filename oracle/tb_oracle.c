@@ -1083,3 +1083,109 @@ int64_t orc_stencil_ltg_step(const int64_t *nel, const double *h, const double *
     orc_cell_step(model, prm, u, du, n, n, t, dt, substeps, threshold, phi_idx);
     return iter;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-subdomain splits (src/discretization/fem.jl:434-542).
+ * orc_cell_step_strided: the cell solvers over one StateBlock with an arbitrary layout (solution_variables.jl:60-68):
+ * state s of point k at u[k*pstride + s*sstride] (PointBlockedLayout: pstride = nstates, sstride = 1).  du uses the
+ * same indexing.  Same arithmetic as orc_cell_step.
+ * ---------------------------------------------------------------------------------------- */
+void orc_cell_step_strided(int model, const double *p, double *u, double *du, int64_t n, int64_t pstride, int64_t sstride,
+                           double t, double dt, int substeps, double threshold, int phi_idx) {
+    int ns = orc_cell_nstates(model);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        double ul[8], dl[8];
+        for (int s = 0; s < ns; s++) ul[s] = u[i * pstride + s * sstride];
+        orc_cell_rhs(model, p, ul, t, dl);
+        if (substeps <= 1 || fabs(dl[phi_idx]) < threshold) {
+            for (int s = 0; s < ns; s++) ul[s] += dt * dl[s];
+        } else {
+            double dts = dt / substeps;
+            for (int s = 0; s < ns; s++) ul[s] += dts * dl[s];
+            for (int k = 2; k <= substeps; k++) {
+                double ts = t + (k - 1) * dts;
+                orc_cell_rhs(model, p, ul, ts, dl);
+                for (int s = 0; s < ns; s++) ul[s] += dts * dl[s];
+            }
+        }
+        for (int s = 0; s < ns; s++) { u[i * pstride + s * sstride] = ul[s]; du[i * pstride + s * sstride] = dl[s]; }
+    }
+}
+
+/* BilinearInterfaceDiffusionElementCache / assemble_element! (src/modeling/core/diffusion.jl:81-140): an interface cell is a
+ * pair of coincident facets; basis functions 0..k-1 live on the "here" side, k..2k-1 on the "there" side;
+ * shape_value_jump = value_there - value_here, i.e. -N_i on the here side and +N_i on the there side (⚠ mem:
+ * FerriteInterfaceElements' convention; the element matrix is a product of two jumps, so the sign cancels);
+ * dOmega = getdetJdV_average = (detJ_here + detJ_there)/2 * w.  Facets: line (2 nodes) in 2D, quadrilateral (4 nodes) in 3D;
+ * Gauss-Legendre `qorder` points per direction, first coordinate fastest.  Ke: (2k) x (2k), row-major. */
+void orc_interface_diffusion_element(int k, int sdim, int qorder, const double *Xh, const double *Xt, double D, double *Ke) {
+    double gp[8], gw[8];
+    int ng = gauss_1d(qorder, gp, gw);
+    int fd = sdim - 1, nd = 2 * k;
+    int nq = fd == 1 ? ng : ng * ng;
+    for (int i = 0; i < nd * nd; i++) Ke[i] = 0;
+    static const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+    for (int q = 0; q < nq; q++) {
+        double N[4], dN[4][2], w;
+        if (fd == 1) {
+            N[0] = 0.5 * (1.0 - gp[q]); N[1] = 0.5 * (1.0 + gp[q]);
+            dN[0][0] = -0.5; dN[1][0] = 0.5;
+            w = gw[q];
+        } else {
+            int a = q % ng, b = q / ng;
+            for (int v = 0; v < 4; v++) {
+                N[v] = 0.25 * (1.0 + sx[v] * gp[a]) * (1.0 + sy[v] * gp[b]);
+                dN[v][0] = 0.25 * sx[v] * (1.0 + sy[v] * gp[b]);
+                dN[v][1] = 0.25 * (1.0 + sx[v] * gp[a]) * sy[v];
+            }
+            w = gw[a] * gw[b];
+        }
+        double dO = 0;
+        for (int side = 0; side < 2; side++) {
+            const double *X = side ? Xt : Xh;
+            double t0[3] = {0, 0, 0}, t1[3] = {0, 0, 0};
+            for (int a = 0; a < k; a++)
+                for (int d = 0; d < sdim; d++) {
+                    t0[d] += X[a * sdim + d] * dN[a][0];
+                    if (fd == 2) t1[d] += X[a * sdim + d] * dN[a][1];
+                }
+            double dj;
+            if (fd == 1) dj = sqrt(t0[0] * t0[0] + t0[1] * t0[1]);
+            else {
+                double n0 = t0[1] * t1[2] - t0[2] * t1[1], n1 = t0[2] * t1[0] - t0[0] * t1[2], n2 = t0[0] * t1[1] - t0[1] * t1[0];
+                dj = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+            }
+            dO += dj * w;
+        }
+        dO = dO / 2.0;
+        for (int i = 0; i < nd; i++) {
+            double ji = i < k ? -N[i] : N[i - k];
+            for (int j = 0; j < nd; j++) {
+                double jj = j < k ? -N[j] : N[j - k];
+                Ke[i * nd + j] -= (ji * D * jj) * dO;
+            }
+        }
+    }
+}
+
+/* sequential interface-cell loop scattering into a CSR pattern that already holds the interface couplings; vals is NOT
+ * zeroed (the caller adds the interface operator on top of the bulk one, as BilinearMultiIntegrator assembles them into
+ * one matrix, subdomain after subdomain) */
+int orc_assemble_interface_diffusion(int k, int sdim, int qorder, int64_t nif, const int64_t *dofs, const double *Xh,
+                                     const double *Xt, double D, const int64_t *rowptr, const int64_t *colidx, double *vals) {
+    int nd = 2 * k, miss = 0;
+    double Ke[64];
+    for (int64_t c = 0; c < nif; c++) {
+        orc_interface_diffusion_element(k, sdim, qorder, Xh + c * k * sdim, Xt + c * k * sdim, D, Ke);
+        for (int i = 0; i < nd; i++) {
+            int64_t r = dofs[c * nd + i];
+            for (int j = 0; j < nd; j++) {
+                int64_t p = find_col(colidx, rowptr[r], rowptr[r + 1], dofs[c * nd + j]);
+                if (p < rowptr[r + 1] && colidx[p] == dofs[c * nd + j]) vals[p] += Ke[i * nd + j];
+                else miss = 1;
+            }
+        }
+    }
+    return miss;
+}

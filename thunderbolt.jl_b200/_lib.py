@@ -26,6 +26,16 @@ FHN, PCG2019, ALIEV_PANFILOV = 0, 1, 2
 D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
 PEER_BLOB_BYTES = 160
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_CHEBYSHEV = 0, 1, 2, 3
+LAYOUT_STATE_BLOCKED, LAYOUT_POINT_BLOCKED = 0, 1
+FACET_LINE2, FACET_QUAD4 = 0, 1
+
+
+class CellBlock(C.Structure):
+    """tb_cell_block"""
+    _fields_ = [("offset", C.c_int64), ("npoints", C.c_int64), ("model", C.c_int32), ("layout", C.c_int32),
+                ("nparams", C.c_int32), ("reserved", C.c_int32), ("params", C.c_double * 36)]
+
+
 SRC_NONE, SRC_BOX, SRC_BALL, SRC_COSEXP, SRC_NORMT, SRC_ENDO = 0, 1, 2, 3, 4, 5
 
 
@@ -138,6 +148,12 @@ _SIGNATURES = {
     "tb_cg_set_chebyshev": [_vp, C.c_int32, C.c_double],
     "tb_cell_step": [_vp, C.c_int32, _f64p, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                      _pf64],
+    "tb_index_create": [_vp, _vp, C.c_int64, C.c_int32, _pp],
+    "tb_index_destroy": [_vp],
+    "tb_vec_gather": [_vp, C.c_int32, _vp, C.c_int32, _vp],
+    "tb_vec_scatter": [_vp, C.c_int32, _vp, _vp, C.c_int32],
+    "tb_cell_step_blocks": [_vp, _vp, C.c_int32, _vp, C.c_double, C.c_double, C.c_int32, C.c_double, _pf64],
+    "tb_assemble_interface_diffusion": [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, C.c_int32, _vp, _vp, C.c_int32, C.c_double, _vp],
     "tb_monodomain_create": [_vp, _vp, _vp, C.c_int32, _f64p, C.c_int32, C.c_int32, _pp],
     "tb_monodomain_destroy": [_vp],
     "tb_monodomain_set_cg": [_vp, C.c_double, C.c_double, C.c_int64],

@@ -418,6 +418,10 @@ def semidiscretize(model, discretization: FiniteElementDiscretization, mesh: Dev
             BilinearMassIntegrator(ConstantCoefficient(1.0), discretization.qrcs.get("mass", qrc), sym),
             BilinearDiffusionIntegrator(model.κ, qrc, sym), LinearIntegrator(model.source, qrc), mesh,
             discretization.assembly_strategy)
+    if isinstance(model, ReactionDiffusionSplit) and isinstance(model.model, dict):
+        from . import multidomain                                   # fem.jl:434-542: one model per subdomain (+ interfaces)
+        import sys as _sys
+        return multidomain.semidiscretize_multidomain(model.model, discretization, mesh, default_device(), _sys.modules[__name__])
     if isinstance(model, ReactionDiffusionSplit):
         ep = model.model
         heatfun = semidiscretize(
@@ -434,6 +438,10 @@ def semidiscretize(model, discretization: FiniteElementDiscretization, mesh: Dev
 
 def create_initial_condition(f) -> np.ndarray:
     """functions.jl:312-339: zeros + every model's default_initial_state, state blocked."""
+    if isinstance(f, GenericSplitFunction) and hasattr(f.functions[1], "functions"):
+        from . import multidomain
+        import sys as _sys
+        return multidomain.create_initial_condition_multidomain(f, _sys.modules[__name__])
     if isinstance(f, GenericSplitFunction):
         odefun = f.functions[1]
         n = len(odefun.associated_states) // num_states(odefun.ode)
@@ -947,6 +955,12 @@ def init(prob, alg, dt=None, **kw) -> ThunderboltTimeIntegrator:
     unsupported = set(kw) - {"verbose", "maxiters", "fused"}
     if unsupported:
         raise TypeError(f"unsupported keyword arguments: {sorted(unsupported)}")
+    if isinstance(prob.f, GenericSplitFunction) and hasattr(prob.f.functions[1], "functions"):
+        from . import multidomain                                   # PointwiseMultiODEFunction: multi-subdomain split
+        import sys as _sys
+        if dt is None or not (dt == dt):
+            raise ValueError("dt must be given and finite")
+        return multidomain.MultiDomainIntegrator(prob, alg, dt, _sys.modules[__name__], maxiters=kw.get("maxiters", 10**9))
     return ThunderboltTimeIntegrator(prob, alg, dt, fused=kw.get("fused", True), maxiters=kw.get("maxiters", 10**9))
 
 
