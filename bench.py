@@ -213,6 +213,8 @@ def run_b200(args):
     if args.precond == "chebyshev":
         dev.cg_set_chebyshev(args.cheb_degree, args.cheb_ratio)
     st.set_preconditioner(PC)
+    if args.cell_substeps:
+        W = dict(W, substeps=args.cell_substeps)
     st.set_cell_solver(W["substeps"], 0.1)
     x = mesh.dof_coords()
     n_local = mesh.ndofs                                    # owned + ghosts
@@ -508,6 +510,7 @@ def main():
     ap.add_argument("--cpu-inline-layers", type=int, default=16, help="z-layers of the cpu_baseline sample printed by the b200 arm")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block")
+    ap.add_argument("--cell-substeps", type=int, default=0, help="override the workload's cell solver: N > 1 = AdaptiveForwardEulerSubstepper(N)")
     ap.add_argument("--write-golden", action="store_true", help="N=1 only: store this run's parity sequence as the gpu_n1 section of the golden file")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cut", default="rows", choices=["planes", "rows"],

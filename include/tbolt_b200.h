@@ -62,6 +62,7 @@ extern "C" {
 #define TB_D_SCALAR 0
 #define TB_D_TENSOR 1
 #define TB_D_SPECTRAL 2
+#define TB_D_CELL_TENSOR 3 /* data = one dim x dim tensor per cell (piecewise-constant coefficient fields) */
 
 /* built-in stimulus families f(x,t); a Julia closure cannot cross a C ABI, so either one of these
  * or host-evaluated values per quadrature point (tb_assemble_source_qp).  prm[]:
@@ -340,6 +341,19 @@ int32_t tb_cell_step_blocks(tb_ctx *ctx, const tb_cell_block *blocks, int32_t nb
 int32_t tb_assemble_interface_diffusion(tb_ctx *ctx, int32_t facet_type, int32_t sdim, int64_t nif, const int64_t *dofs,
                                         int32_t index_base, const double *coords_here, const double *coords_there,
                                         int32_t qorder, double D, tb_csr *K);
+
+/* ---- building blocks of the Poisson / Geselowitz ECG reconstructions (src/modeling/electrophysiology/ecg.jl:166-619) ----
+ * Everything else they need already exists: rectangular operators for the heart -> torso transfer and the electrode
+ * evaluation (tb_csr_create with ncols != nrows + tb_csr_values_upload + tb_spmv), tb_assemble_diffusion on the torso
+ * mesh (TB_D_CELL_TENSOR for the heart conductivity extended by zero), tb_cg_solve for the lead fields and for phi_e. */
+/* out[c] = sum_i Z[i, c] * v[i, vcol] for every column c of Z: `-Z * kappa_grad_phi` (ecg.jl:617-619); blocks until done */
+int32_t tb_vec_dots(tb_ctx *ctx, const tb_vec *Z, const tb_vec *v, int32_t vcol, double *out);
+/* d[r, col] = A[r, r] */
+int32_t tb_csr_diagonal(const tb_csr *A, tb_vec *d, int32_t col);
+/* Ferrite apply_zero!(K, f, ch), matrix half: zero the rows and columns of the constrained dofs, put diag_value on their
+ * diagonal (Ferrite: mean |K_ii|); right-hand-side half: tb_vec_fill_at(f, col, constrained, 0.0) */
+int32_t tb_csr_apply_zero(tb_csr *A, const tb_index *constrained, double diag_value);
+int32_t tb_vec_fill_at(tb_vec *v, int32_t col, const tb_index *ix, double value);
 
 /* ---- fused LieTrotterGodunov step -------------------------------------------------------------
  * One OS.LieTrotterGodunov((BackwardEulerSolver, cell solver)) step (operatorsplitting-interface.jl:23-232;

@@ -398,6 +398,8 @@ static void eval_D(int kind, const double *data, double cmchi, int dim, int nv, 
         for (int i = 0; i < dim; i++) D[i * dim + i] = data[0] / cmchi;
     } else if (kind == 1) {
         for (int i = 0; i < dim * dim; i++) D[i] = data[i] / cmchi;
+    } else if (kind == 3) { /* one tensor per cell: a piecewise-constant coefficient field (e.g. the AnalyticalCoefficient of test_ecg.jl:27-33) */
+        for (int i = 0; i < dim * dim; i++) D[i] = data[cell * dim * dim + i] / cmchi;
     } else {
         const double *lam = data;
         const double *fsn = data + 3 + cell * nv * 9;

@@ -23,7 +23,7 @@ STATUS_NAMES = {0: "TB_OK", 1: "TB_ERR_INVALID", 2: "TB_ERR_CUDA", 3: "TB_ERR_NO
 
 QUAD4, HEX8, TRI3, TET4 = 0, 1, 2, 3
 FHN, PCG2019, ALIEV_PANFILOV = 0, 1, 2
-D_SCALAR, D_TENSOR, D_SPECTRAL = 0, 1, 2
+D_SCALAR, D_TENSOR, D_SPECTRAL, D_CELL_TENSOR = 0, 1, 2, 3
 PEER_BLOB_BYTES = 160
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_JACOBI, PRECOND_CHEBYSHEV = 0, 1, 2, 3
 LAYOUT_STATE_BLOCKED, LAYOUT_POINT_BLOCKED = 0, 1
@@ -154,6 +154,10 @@ _SIGNATURES = {
     "tb_vec_scatter": [_vp, C.c_int32, _vp, _vp, C.c_int32],
     "tb_cell_step_blocks": [_vp, _vp, C.c_int32, _vp, C.c_double, C.c_double, C.c_int32, C.c_double, _pf64],
     "tb_assemble_interface_diffusion": [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, C.c_int32, _vp, _vp, C.c_int32, C.c_double, _vp],
+    "tb_vec_dots": [_vp, _vp, _vp, C.c_int32, _f64p],
+    "tb_csr_diagonal": [_vp, _vp, C.c_int32],
+    "tb_csr_apply_zero": [_vp, _vp, C.c_double],
+    "tb_vec_fill_at": [_vp, C.c_int32, _vp, C.c_double],
     "tb_monodomain_create": [_vp, _vp, _vp, C.c_int32, _f64p, C.c_int32, C.c_int32, _pp],
     "tb_monodomain_destroy": [_vp],
     "tb_monodomain_set_cg": [_vp, C.c_double, C.c_double, C.c_int64],

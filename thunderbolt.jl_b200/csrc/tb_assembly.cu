@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
     const tb_tables_view sT_tab{nq, sW, sN, sdN};
     __shared__ double sD[9];                       // constant diffusion tensor, evaluated once per CTA
-    if (OP == 1 && kind != 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
+    if (OP == 1 && kind < 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
     const int64_t ncl = c1 - c0;
     const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
                         sT[(i * NV + j) * EA_PAD + lane] = i <= j ? acc[tb_sym<NV>(i, j)] : acc[tb_sym<NV>(j, i)];
             } else {
                 double Ke[NE];
-                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT_tab, sX + threadIdx.x, kind, ddata, cmchi, e, Ke, kind != 2 ? sD : nullptr);
+                tb_element_diffusion_full<NV, DIM, AS_BLOCK>(sT_tab, sX + threadIdx.x, kind, ddata, cmchi, e, Ke, kind < 2 ? sD : nullptr);
 #pragma unroll
                 for (int i = 0; i < NE; i++) sT[i * EA_PAD + lane] = Ke[i];
             }
@@ -661,8 +661,8 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
                (long long)A->pat->ncols, (long long)mesh->ndofs_owned, (long long)mesh->ndofs);
     if (op == 1) {   // argument checks before anything is allocated
         const int64_t need = kind == TB_D_SCALAR ? 1 : kind == TB_D_TENSOR ? mesh->dim * mesh->dim
-                                                                          : 3 + mesh->ncells * mesh->nv * 9;
-        TB_REQUIRE(kind >= TB_D_SCALAR && kind <= TB_D_SPECTRAL, "tb_assemble_diffusion: unknown coefficient kind %d", kind);
+                             : kind == TB_D_CELL_TENSOR ? mesh->ncells * mesh->dim * mesh->dim : 3 + mesh->ncells * mesh->nv * 9;
+        TB_REQUIRE(kind >= TB_D_SCALAR && kind <= TB_D_CELL_TENSOR, "tb_assemble_diffusion: unknown coefficient kind %d", kind);
         TB_REQUIRE(kind != TB_D_SPECTRAL || mesh->dim == 3, "tb_assemble_diffusion: spectral coefficient needs a 3D mesh");
         TB_REQUIRE(data && ndata == need, "tb_assemble_diffusion: coefficient kind %d needs %lld doubles, got %lld", kind,
                    (long long)need, (long long)ndata);

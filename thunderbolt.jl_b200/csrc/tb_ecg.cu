@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(ECG_BLOCK)
     for (int i = threadIdx.x; i < nq * NV; i += ECG_BLOCK) sN[i] = gT->N[i];
     for (int i = threadIdx.x; i < nq * NV * DIM; i += ECG_BLOCK) sdN[i] = gT->dN[i];
     __shared__ double sD[9];                       // constant coefficient: evaluated once per CTA
-    if (kind != 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
+    if (kind < 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
     double acc[ECG_NE];
 #pragma unroll
     for (int k = 0; k < ECG_NE; k++) acc[k] = 0.0;
@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(ECG_BLOCK)
                 double G[NV * DIM], Dloc[DIM * DIM], f[DIM], xq[DIM];
                 const double *Nq = sN + q * NV;
                 const double dO = tb_map_qp<NV, DIM, ECG_BLOCK, true>(X, sdN + q * NV * DIM, G) * sW[q];
-                if (kind == 2) tb_eval_D<NV, DIM>(kind, ddata, cmchi, e, Nq, Dloc);
-                const double *D = kind == 2 ? Dloc : sD;
+                if (kind >= 2) tb_eval_D<NV, DIM>(kind, ddata, cmchi, e, Nq, Dloc);
+                const double *D = kind >= 2 ? Dloc : sD;
 #pragma unroll
                 for (int r = 0; r < DIM; r++) f[r] = 0.0;
 #pragma unroll
@@ -151,9 +151,10 @@ extern "C" int32_t tb_ecg_plonsey(tb_ctx *ctx, const tb_mesh *mesh, int32_t qord
     TB_REQUIRE(ctx && mesh && phi && electrodes && phi_e, "tb_ecg_plonsey: NULL argument");
     TB_REQUIRE(ne >= 0, "tb_ecg_plonsey: negative electrode count");
     TB_REQUIRE(phicol >= 0 && phicol < phi->ncols && phi->n >= mesh->ndofs, "tb_ecg_plonsey: phi is smaller than the mesh's dof count");
-    TB_REQUIRE(kind >= TB_D_SCALAR && kind <= TB_D_SPECTRAL, "tb_ecg_plonsey: unknown coefficient kind %d", kind);
+    TB_REQUIRE(kind >= TB_D_SCALAR && kind <= TB_D_CELL_TENSOR, "tb_ecg_plonsey: unknown coefficient kind %d", kind);
     TB_REQUIRE(kind != TB_D_SPECTRAL || mesh->dim == 3, "tb_ecg_plonsey: spectral coefficient needs a 3D mesh");
-    const int64_t need = kind == TB_D_SCALAR ? 1 : kind == TB_D_TENSOR ? mesh->dim * mesh->dim : 3 + mesh->ncells * mesh->nv * 9;
+    const int64_t need = kind == TB_D_SCALAR ? 1 : kind == TB_D_TENSOR ? mesh->dim * mesh->dim
+                         : kind == TB_D_CELL_TENSOR ? mesh->ncells * mesh->dim * mesh->dim : 3 + mesh->ncells * mesh->nv * 9;
     TB_REQUIRE(data && ndata == need, "tb_ecg_plonsey: coefficient kind %d needs %lld doubles, got %lld", kind, (long long)need, (long long)ndata);
     TB_REQUIRE(cm_chi != 0.0 && kappa_t != 0.0, "tb_ecg_plonsey: Cm*chi and kappa_t must be non-zero");
     TB_DEV(ctx);

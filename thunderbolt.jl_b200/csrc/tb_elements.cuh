@@ -200,6 +200,9 @@ TB_HD void tb_eval_D(int kind, const double *data, double cmchi, int64_t cell, c
     } else if (kind == 1) {
 #pragma unroll
         for (int i = 0; i < DIM * DIM; i++) D[i] = data[i] / cmchi;
+    } else if (kind == 3) {   // one tensor per cell (a piecewise-constant AnalyticalCoefficient / per-subdomain conductivity)
+#pragma unroll
+        for (int i = 0; i < DIM * DIM; i++) D[i] = data[cell * (DIM * DIM) + i] / cmchi;
     } else if constexpr (DIM == 3) {
         const double *lam = data;
         const double *fsn = data + 3 + cell * NV * 9;
@@ -259,11 +262,11 @@ TB_HD void tb_element_diffusion(const tb_tables_view T, const double *X, int kin
 #pragma unroll
     for (int i = 0; i < NV * (NV + 1) / 2; i++) acc[i] = 0.0;
     double D[DIM * DIM];
-    if (kind != 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N, D);   // constant coefficients: same value at every point
+    if (kind < 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N, D);   // constant coefficients: same value at every point
     for (int q = 0; q < T.nq; q++) {
         double G[NV * DIM];
         const double dO = tb_map_qp<NV, DIM, XS, true>(X, T.dN + q * NV * DIM, G) * T.w[q];
-        if (kind == 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
+        if (kind >= 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, D);
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             if (kind == 0) {
@@ -307,12 +310,12 @@ TB_HD void tb_element_diffusion_full(const tb_tables_view T, const double *X, in
     // constant coefficients (kind 0, 1) have the same value at every point: evaluated once -- by the caller into shared
     // memory (Dconst; no registers held across the loop) or here
     double Dloc[DIM * DIM];
-    if (kind != 2 && !Dconst) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N, Dloc);
+    if (kind < 2 && !Dconst) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N, Dloc);
     for (int q = 0; q < T.nq; q++) {
         double G[NV * DIM];
         const double dO = tb_map_qp<NV, DIM, XS, true>(X, T.dN + q * NV * DIM, G) * T.w[q];
-        if (kind == 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, Dloc);
-        const double *D = (kind != 2 && Dconst) ? Dconst : Dloc;
+        if (kind >= 2) tb_eval_D<NV, DIM>(kind, data, cmchi, cell, T.N + q * NV, Dloc);
+        const double *D = (kind < 2 && Dconst) ? Dconst : Dloc;
 #pragma unroll
         for (int j = 0; j < NV; j++) {
             if (kind == 0) {

@@ -336,3 +336,118 @@ extern "C" int32_t tb_assemble_interface_diffusion(tb_ctx *ctx, int32_t facet_ty
     if (fail) return tb_fail(TB_ERR_INVALID, "tb_assemble_interface_diffusion: the pattern has no entry for an interface dof pair");
     return TB_OK;
 }
+
+// ---- pieces of the lead-field / Poisson ECG reconstructions (src/modeling/electrophysiology/ecg.jl:166-619) -----------------
+// out[c] = sum_i Z[i, c] * v[i] for every column c of Z: `-cache.Z * cache.κ∇φₘ_t` (ecg.jl:617-619) with the lead fields stored
+// as the columns of one device vector.  One column per blockIdx.y, deterministic two-stage sums.
+__global__ void __launch_bounds__(256) k_vec_dots(const double *__restrict__ Z, int64_t ld, const double *__restrict__ v, int64_t n,
+                                                  double *partials) {
+    __shared__ double sm[32];
+    const double *z = Z + (int64_t)blockIdx.y * ld;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += z[i] * v[i];
+    const double b = tb_block_sum(acc, sm);
+    if (threadIdx.x == 0) partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = b;
+}
+__global__ void k_vec_dots_finish(const double *partials, int nb, double *out) {
+    double s = 0.0;
+    for (int i = 0; i < nb; i++) s += partials[(int64_t)blockIdx.x * nb + i];
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+extern "C" int32_t tb_vec_dots(tb_ctx *ctx, const tb_vec *Z, const tb_vec *v, int32_t vcol, double *out) {
+    TB_REQUIRE(ctx && Z && v && out, "tb_vec_dots: NULL argument");
+    TB_REQUIRE(vcol >= 0 && vcol < v->ncols && v->n >= Z->n, "tb_vec_dots: shape mismatch");
+    TB_DEV(ctx);
+    const int nb = 64;
+    double *part = nullptr, *d_out = nullptr;
+    TB_CUDA(cudaMalloc(&part, sizeof(double) * (size_t)(nb * Z->ncols)));
+    TB_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)Z->ncols));
+    TB_LAUNCH(ctx, k_vec_dots, dim3(nb, Z->ncols), 256, 0, Z->d, Z->ld, v->d + (size_t)vcol * v->ld, Z->n, part);
+    TB_LAUNCH(ctx, k_vec_dots_finish, Z->ncols, 1, 0, part, nb, d_out);
+    TB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)Z->ncols, cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(part);
+    cudaFree(d_out);
+    return TB_OK;
+}
+
+// d[r] = A[r, r]
+__global__ void k_csr_diag(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const double *__restrict__ val, int64_t nrows,
+                           int64_t nslices, double *__restrict__ d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp; s < nslices; s += nwarps) {
+        const int64_t base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5, row = s * TB_SLICE + lane;
+        double dv = 0.0;
+        for (int64_t j = 0; j < w; j++)
+            if (col[base + j * TB_SLICE + lane] == (int)row) dv += val[base + j * TB_SLICE + lane];   // padding adds 0
+        if (row < nrows) d[row] = dv;
+    }
+}
+extern "C" int32_t tb_csr_diagonal(const tb_csr *A, tb_vec *d, int32_t col) {
+    TB_REQUIRE(A && d && col >= 0 && col < d->ncols && d->n >= A->pat->nrows, "tb_csr_diagonal: bad argument");
+    tb_ctx *ctx = A->pat->ctx;
+    TB_DEV(ctx);
+    const tb_pattern *p = A->pat;
+    TB_LAUNCH(ctx, k_csr_diag, tb_grid_for(ctx, p->nslices * 32, 256, 8), 256, 0, p->d_slice_ptr, p->d_col, A->d_val, p->nrows, p->nslices,
+              d->d + (size_t)col * d->ld);
+    return TB_OK;
+}
+
+// Ferrite's apply_zero!(K, f, ch) on the matrix (ecg.jl:338): rows and columns of the constrained dofs are zeroed and their
+// diagonal entries set to `diag_value` (Ferrite uses the mean of |diag(K)|, which the caller computes from tb_csr_diagonal)
+__global__ void k_mark(const int64_t *__restrict__ idx, int64_t n, unsigned char *flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) flag[idx[i]] = 1;
+}
+__global__ void __launch_bounds__(256)
+    k_apply_zero(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, double *__restrict__ val, int64_t nrows, int64_t nslices,
+                 const unsigned char *__restrict__ flag, double diag_value) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp; s < nslices; s += nwarps) {
+        const int64_t base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5, row = s * TB_SLICE + lane;
+        if (row >= nrows) continue;
+        const bool fr = flag[row] != 0;
+        bool diag_done = false;
+        for (int64_t j = 0; j < w; j++) {
+            const int c = col[base + j * TB_SLICE + lane];
+            if (fr || flag[c]) {
+                double nv = 0.0;
+                if (fr && c == (int)row && !diag_done) {   // the first stored (row, row) entry is the real diagonal; padding repeats the own column
+                    nv = diag_value;
+                    diag_done = true;
+                }
+                val[base + j * TB_SLICE + lane] = nv;
+            } else if (c == (int)row) diag_done = true;
+        }
+    }
+}
+extern "C" int32_t tb_csr_apply_zero(tb_csr *A, const tb_index *constrained, double diag_value) {
+    TB_REQUIRE(A && constrained, "tb_csr_apply_zero: NULL argument");
+    tb_ctx *ctx = A->pat->ctx;
+    TB_DEV(ctx);
+    const tb_pattern *p = A->pat;
+    A->version++;
+    unsigned char *flag = nullptr;
+    TB_CUDA(cudaMalloc(&flag, (size_t)p->ncols + 1));
+    TB_CUDA(cudaMemsetAsync(flag, 0, (size_t)p->ncols + 1, ctx->stream));
+    if (constrained->n) TB_LAUNCH(ctx, k_mark, tb_grid_for(ctx, constrained->n, 256, 4), 256, 0, constrained->d, constrained->n, flag);
+    TB_LAUNCH(ctx, k_apply_zero, tb_grid_for(ctx, p->nslices * 32, 256, 8), 256, 0, p->d_slice_ptr, p->d_col, A->d_val, p->nrows, p->nslices,
+              flag, diag_value);
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(flag);
+    return TB_OK;
+}
+
+__global__ void k_fill_at(double *__restrict__ v, const int64_t *__restrict__ idx, int64_t n, double value) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[idx[i]] = value;
+}
+// v[idx[i], col] = value   (the right-hand-side half of apply_zero!)
+extern "C" int32_t tb_vec_fill_at(tb_vec *v, int32_t col, const tb_index *ix, double value) {
+    TB_REQUIRE(v && ix && col >= 0 && col < v->ncols, "tb_vec_fill_at: bad argument");
+    tb_ctx *ctx = v->ctx;
+    TB_DEV(ctx);
+    if (ix->n) TB_LAUNCH(ctx, k_fill_at, tb_grid_for(ctx, ix->n, 256, 4), 256, 0, v->d + (size_t)col * v->ld, ix->d, ix->n, value);
+    return TB_OK;
+}
