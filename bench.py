@@ -121,6 +121,28 @@ def host_cores():
     return max(1, min(phys, aff) if phys else aff)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and therefore the first-touch placement of its pinned buffers) to the CPUs of the NUMA
+    node its GPU hangs off: /sys/bus/pci/devices/<bdf>/local_cpulist.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / bdf
+        node = (base / "numa_node").read_text().strip()
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node}, {len(cpus)} cpus"
+        return f"numa node {node}, affinity unchanged"
+    except Exception as e:                                  # noqa: BLE001 - best effort, containers often hide sysfs
+        return f"not bound ({type(e).__name__})"
+
+
 def bytes_per_row(nnz, n):
     """SpMV = nnzr*12 + 8 (rowptr) + 8 (x) + 8 (y) per row."""
     return nnz / n * 12.0 + 24.0
@@ -149,6 +171,7 @@ def run_b200(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single GPU: not bound"
     dev = tb.B200Device(local)
     tb.set_default_device(dev)
     if world > 1:
@@ -346,7 +369,7 @@ def run_b200(args):
             link = float(lk.item())
         del dprobe
         phi_bytes_rank = n_local * 8
-        e2e = {"link_gbs_per_direction_per_gpu_all_ranks_active": link,
+        e2e = {"host_binding": numa, "link_gbs_per_direction_per_gpu_all_ranks_active": link,
                "exposed_ms_model": phi_bytes_rank / (link * 1e9) * 1e3,
                "exposed_ms_measured": te / ke * 1e3 - ms / args.steps,
                "value": N_global * ke / te, "unit": "DoF*steps/s", "h2d_bytes_per_step": bytes_step,
