@@ -153,6 +153,48 @@ def c2_full_1000():
     np.savez_compressed(HERE / "c2_full_1000.npz", **out)
 
 
+def c4_mid_1000():
+    """BASELINE config 4 at a realistic size and FULL length: idealized LV 120 x 12 x 80 rings, tetrahedralised (0.7 M tets,
+    126 k dofs), ODB25LT fibres, spectral tensor, PCG2019, ForwardEulerCellSolver, endocardial stimulus, default CG
+    tolerances, 1000 steps of dt = 0.01.  Stored: phi_m at every 13th dof after steps 1, 100 and 1000, all CG iteration
+    counts, activation steps (phi_m >= 0 mV) of the sampled dofs."""
+    sys.path.insert(0, str(HERE.parent.parent))
+    from thunderbolt_jl_b200 import lv
+    nodes, hexes, wedges, prm = lv.generate_ideal_lv_mesh(120, 12, 80)
+    tets = lv.tetrahedralize(nodes, hexes, wedges)
+    fsn = lv.odb25lt_fibres(prm, tets)
+    k1, kr = 0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24)
+    data = np.concatenate([[k1, kr, kr], np.ascontiguousarray(fsn).reshape(tets.shape[0], 4, 9).ravel()])
+    m = O.Mesh(O.TET4, tets, nodes)
+    M = O.assemble_mass(m, 2, threaded=True)
+    K = O.assemble_diffusion(m, 2, O.D_SPECTRAL, data, threaded=True)
+    N = m.ndofs
+    print("dofs", N, "tets", tets.shape[0], flush=True)
+    u = np.repeat(O.default_initial_state(O.PCG2019), N)
+    orc = O.MonodomainOracle(m, O.PCG2019, O.default_params(O.PCG2019), M, K, threaded_blas1=True)
+    SRC = [0.0, 0.2, 0.3, 0.25]
+    out, t, dt = {}, 0.0, 0.01
+    act = np.full(u[:N:13].size, -1, dtype=np.int16)
+    for step in range(1000):
+        orc.bS = O.assemble_source(m, 2, O.SRC_ENDO, SRC, t + dt)
+        it, rn, conv = orc.step(u, t, dt)
+        assert conv
+        t += dt
+        ph = u[:N:13]
+        act[(act < 0) & (ph >= 0.0)] = step + 1
+        if step == 0:
+            out["phi1"] = ph.copy()
+        if step == 99:
+            out["phi100"] = ph.copy()
+        if step % 50 == 49:
+            print("step", step + 1, "iters", it, "activated", int((act > 0).sum()), "phi max", float(u[:N].max()), flush=True)
+    out["phi1000"] = u[:N:13].copy()
+    out["h1000"] = u[N:2 * N:13].copy()
+    out["iters"] = np.array(orc.iters, dtype=np.int16)
+    out["act"] = act
+    np.savez_compressed(HERE / "c4_mid_1000.npz", **out)
+
+
 def c2_small():
     """config 2 (conduction-velocity-benchmark.jl) on 16x16x4 hexes, h = 0.25: PCG2019, corner stimulus."""
     m = O.generate_grid(O.HEX8, (16, 16, 4), (0, 0, 0), (4.0, 4.0, 1.0))
@@ -192,6 +234,11 @@ if __name__ == "__main__" and "--c2-full" in sys.argv:
 if __name__ == "__main__" and "--c2-full-1000" in sys.argv:
     c2_full_1000()
     print("wrote", HERE / "c2_full_1000.npz")
+    sys.exit(0)
+
+if __name__ == "__main__" and "--c4-mid-1000" in sys.argv:
+    c4_mid_1000()
+    print("wrote", HERE / "c4_mid_1000.npz")
     sys.exit(0)
 
 if __name__ == "__main__" and "--c1-full" in sys.argv:

@@ -84,9 +84,12 @@ def _oracle_operators(O, grid, order, celldofs, ndofs, rowptr, colidx, D2, G):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cell_solver", ["fe", "adaptive"])
-def test_pacemaker_subdomain_against_oracle(tb, dev, oracle, cell_solver):
+@pytest.mark.parametrize("cell_solver,tight", [("fe", False), ("adaptive", False), ("fe", True)])
+def test_pacemaker_subdomain_against_oracle(tb, dev, oracle, cell_solver, tight):
+    """tight = False: LinearSolve's default tolerances -- CG iterations +-1, phi to the CG stopping error; tight = True: the
+    linear solves converged far below 1e-10 on both sides, then the 1e-10-after-one-step rule applies to the whole split step"""
     O = oracle
+    tol = dict(atol=1e-14, rtol=1e-13) if tight else {}
     grid = _pacemaker_grid(tb, O, 64)
     models = _models(tb)
     odeform = tb.semidiscretize(tb.ReactionDiffusionSplit(models),
@@ -103,7 +106,8 @@ def test_pacemaker_subdomain_against_oracle(tb, dev, oracle, cell_solver):
     u0 = tb.create_initial_condition(odeform)
     u0[hd - 1] = np.maximum(1.0 - np.linalg.norm(heat.dof_coords, axis=1), 0.0)
     cs = tb.ForwardEulerCellSolver() if cell_solver == "fe" else tb.AdaptiveForwardEulerSubstepper()
-    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 10.0)), tb.LieTrotterGodunov((tb.BackwardEulerSolver(), cs)), dt=1.0)
+    integ = tb.init(tb.OperatorSplittingProblem(odeform, u0.copy(), (0.0, 10.0)),
+                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(inner_solver=tb.B200CG(**tol)), cs)), dt=1.0)
     # ---- oracle: same numbering, same operators, same split -------------------------------------------------------
     rowptr, colidx = heat.rowptr, heat.colidx
     D2 = np.array([[4.5e-4, 0.0], [0.0, 2.0e-4]])
@@ -126,8 +130,8 @@ def test_pacemaker_subdomain_against_oracle(tb, dev, oracle, cell_solver):
     for step in range(10):
         assert tb.step_(integ)
         phi = uo[hd - 1].copy()
-        x, ito, rno, convo = O.cg(rowptr, colidx, Ao, O.spmv(rowptr, colidx, Mo, phi))
-        assert convo and abs(integ.cg_iterations[-1] - ito) <= 1
+        x, ito, rno, convo = O.cg(rowptr, colidx, Ao, O.spmv(rowptr, colidx, Mo, phi), **tol)
+        assert convo and abs(integ.cg_iterations[-1] - ito) <= (3 if tight else 1)
         uo[hd - 1] = x
         for f, p in zip(ionic.functions, prm):
             b = f.block
@@ -136,9 +140,9 @@ def test_pacemaker_subdomain_against_oracle(tb, dev, oracle, cell_solver):
             L_.orc_cell_step_strided(O.FHN, p, seg, dseg, b.npoints, 2, 1, float(step), 1.0, sub, 0.1, 0)
         if step == 0:
             h = integ.u.to_host()
-            assert np.abs(h - uo).max() <= 1e-10 * np.abs(uo).max()
+            assert np.abs(h - uo).max() <= (1e-10 if tight else 1e-7) * np.abs(uo).max()
     h = integ.u.to_host()
-    assert np.abs(h - uo).max() <= 1e-8 * np.abs(uo).max()
+    assert np.abs(h - uo).max() <= (1e-9 if tight else 1e-6) * np.abs(uo).max()
     assert not np.allclose(h, u0)                                     # `integrator.u ≉ u₀`
     assert integ.stats.naccept == 10 and integ.t == 10.0
 

@@ -542,16 +542,7 @@ static size_t element_matrix_smem(int nv, int dim, int nq) {
 template <int NV, int DIM, int OP>
 static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, double rho, int kind,
                                  const double *d_data, double cmchi, const tb_pattern *pat, const SellView &S,
-                                 const GatherPlan &plan, double *EA0, size_t ea_stride) {
-    // Two scratch buffers, two streams: the element pass of chunk k+1 (fp64-pipe bound) runs while the ordered gather of
-    // chunk k (latency / L2 bound) drains the other buffer.  Every row still adds its cells in ascending order from one
-    // buffer, so the values are the same bits as with a single stream.
-    if (!ctx->stream2) {
-        TB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-        for (int i = 0; i < 5; i++) TB_CUDA(cudaEventCreateWithFlags(&ctx->asm_ev[i], cudaEventDisableTiming));
-    }
-    TB_CUDA(cudaEventRecord(ctx->asm_ev[4], ctx->stream));            // everything queued so far (coefficient upload, tables)
-    TB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->asm_ev[4], 0));
+                                 const GatherPlan &plan, double *EA) {
     const size_t smem1 = element_matrix_smem(NV, DIM, nq);
     TB_CUDA(cudaFuncSetAttribute(k_element_matrices<NV, DIM, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     int per_sm = 1;
@@ -597,24 +588,14 @@ static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_ta
         const int64_t r1 = r0 + plan.rows_per_chunk < pat->nrows ? r0 + plan.rows_per_chunk : pat->nrows;
         const int64_t s0 = r0 / TB_SLICE, s1 = (r1 + TB_SLICE - 1) / TB_SLICE;
         int64_t c0 = 0;
-        const int buf = ch & 1;
-        double *EA = EA0 + (size_t)buf * ea_stride;
         if (plan.cmax[ch] >= plan.cmin[ch]) {
             c0 = plan.cmin[ch];
             const int64_t c1 = (int64_t)plan.cmax[ch] + 1;
             const int64_t ntiles = (c1 - c0 + AS_BLOCK - 1) / AS_BLOCK;
             const int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
-            if (ch >= 2) TB_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->asm_ev[2 + buf], 0));   // the gather that last read this buffer
-            k_element_matrices<NV, DIM, OP><<<grid, AS_BLOCK, smem1, ctx->stream2>>>(m->d_conn, m->d_coords, c0, c1, d_T, nq, rho, kind,
-                                                                                    d_data, cmchi, EA);
-            ctx->launches++;
-            {
-                cudaError_t e__ = cudaGetLastError();
-                if (e__ != cudaSuccess) return tb_fail(TB_ERR_CUDA, "launch of k_element_matrices failed: %s", cudaGetErrorString(e__));
-            }
+            TB_LAUNCH(ctx, (k_element_matrices<NV, DIM, OP>), grid, AS_BLOCK, smem1, m->d_conn, m->d_coords, c0, c1, d_T, nq,
+                      rho, kind, d_data, cmchi, EA);
         }
-        TB_CUDA(cudaEventRecord(ctx->asm_ev[buf], ctx->stream2));
-        TB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->asm_ev[buf], 0));
         for (int k = 0; k < ngeom; k++) {
             const GatherGeom &G = gg[k];
             const int64_t need = (s1 - s0 + G.warps - 1) / G.warps;
@@ -623,7 +604,6 @@ static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_ta
                 TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, G.warps * 32, G.smem, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, S, s0,
                           s1, G.maxw, G.top_step, G.wlo);
         }
-        TB_CUDA(cudaEventRecord(ctx->asm_ev[2 + buf], ctx->stream));
     }
     return TB_OK;
 }
@@ -711,7 +691,6 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         const GatherPlan *planp = nullptr;
         bool ok = false;
         double *EA = nullptr;
-        size_t ea_stride = 0;
         st = mesh_ensure_adjacency(ctx, mesh);
         if (st == TB_OK) {
             size_t free_b = 0, total_b = 0;
@@ -719,18 +698,12 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
             size_t budget = ctx->ea_budget_bytes;
             if (budget > free_b / 2) budget = free_b / 2;
             const int64_t per_cell = (int64_t)mesh->nv * mesh->nv * (int64_t)sizeof(double);
-            // two buffers share the budget; large meshes are cut into >= 8 chunks so that the element pass of one chunk
-            // overlaps the gather of the previous one (gather_bilinear_t)
-            int64_t budget_cells = (int64_t)(budget / 2 / (size_t)per_cell);
-            const int64_t pipe_cells = mesh->ncells / 8 > 65536 ? mesh->ncells / 8 : 65536;
-            if (budget_cells > pipe_cells) budget_cells = pipe_cells;
-            st = plan_gather(ctx, mesh, budget_cells, 0, &planp);
+            st = plan_gather(ctx, mesh, (int64_t)(budget / (size_t)per_cell), 0, &planp);
             ok = st == TB_OK && planp->ok;
             if (ok) {
                 // the scratch is cached on the context (cudaMalloc/cudaFree of GBs costs 10-80 ms per call, measured);
                 // tb_assembly_release_scratch gives it back
-                ea_stride = (size_t)(planp->max_cells > 0 ? planp->max_cells : 1) * (size_t)(mesh->nv * mesh->nv);
-                const size_t bytes = 2 * ea_stride * sizeof(double);
+                const size_t bytes = (size_t)(planp->max_cells > 0 ? planp->max_cells : 1) * (size_t)per_cell;
                 if (ctx->ea_bytes < bytes) {
                     cudaFree(ctx->d_ea);
                     ctx->d_ea = nullptr;
@@ -747,8 +720,8 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         if (st == TB_OK && ok) {
             const GatherPlan &plan = *planp;
 #define DISPATCH_G(NV, DIM)                                                                                         \
-    st = op == 0 ? gather_bilinear_t<NV, DIM, 0>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, A->pat, S, plan, EA, ea_stride) \
-                 : gather_bilinear_t<NV, DIM, 1>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, A->pat, S, plan, EA, ea_stride)
+    st = op == 0 ? gather_bilinear_t<NV, DIM, 0>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, A->pat, S, plan, EA) \
+                 : gather_bilinear_t<NV, DIM, 1>(ctx, mesh, d_T, nq, rho, kind, d_data, cmchi, A->pat, S, plan, EA)
             switch (mesh->celltype) {
             case TB_QUAD4: DISPATCH_G(4, 2); break;
             case TB_HEX8: DISPATCH_G(8, 3); break;
