@@ -198,9 +198,26 @@ Base.@kwdef struct B200CG <: LinearSolve.SciMLLinearSolveAlgorithm
     atol::Float64 = sqrt(eps(Float64))
     rtol::Float64 = sqrt(eps(Float64))
     maxiters::Int = 0            # 0 -> length(b), LinearSolve's default
-    precs::Symbol = :none        # :none or :jacobi -- where KrylovJL_CG takes `precs = ..., ldiv = false` (bak/examples-gpu/spiral-wave.jl:95-105)
+    precs::Symbol = :none        # :none | :jacobi | :block_jacobi | :chebyshev -- where KrylovJL_CG takes `precs = ..., ldiv = false`
+                                 # (bak/examples-gpu/spiral-wave.jl:95-105: BlockJacobiPreconditioner(A, 1000, CUDABackend()))
+    nblocks::Int = 1000          # :block_jacobi -- number of diagonal blocks (equal contiguous dof ranges unless row_block is given)
+    row_block::Union{Nothing, Vector{Int32}} = nothing   # block id per row, e.g. a Metis partition (0-based)
+    degree::Int = 8              # :chebyshev -- polynomial degree and lmax / lmin of the target interval
+    ratio::Float64 = 30.0
 end
-precond_id(alg::B200CG) = alg.precs === :jacobi ? Int32(1) : Int32(0)   # TB_PRECOND_NONE / TB_PRECOND_JACOBI
+precond_id(alg::B200CG) = Int32(Dict(:none => 0, :jacobi => 1, :block_jacobi => 2, :chebyshev => 3)[alg.precs])   # TB_PRECOND_*
+# what `precs(A, p)` does in the reference: hand the preconditioner's parameters over (the inverses / the Gershgorin bound
+# are rebuilt by the library whenever the operator's values change -- update!(P, A))
+function configure!(alg::B200CG, A::B200CSRMatrix)
+    if alg.precs === :block_jacobi
+        rb = alg.row_block === nothing ? C_NULL : pointer(alg.row_block)
+        GC.@preserve alg @tb tb_cg_set_block_jacobi (Ptr{Cvoid}, Int64, Int64, Ptr{Int32}) A.dev.h Int64(A.n) Int64(alg.nblocks) rb
+    elseif alg.precs === :chebyshev
+        @tb tb_cg_set_chebyshev (Ptr{Cvoid}, Int32, Float64) A.dev.h Int32(alg.degree) alg.ratio
+    end
+end
+# order-independent CG dot products (double-double accumulation, rounded once): iterates independent of grid size / GPU count
+exact_dot!(dev::B200Device, on::Bool = true) = @tb tb_cg_set_exact_dot (Ptr{Cvoid}, Int32) dev.h Int32(on)
 mutable struct B200CGCache
     iters::Int64
     resid::Float64
@@ -208,6 +225,7 @@ end
 LinearSolve.init_cacheval(::B200CG, A, b, u, Pl, Pr, maxiters, abstol, reltol, verbose, assumptions) = B200CGCache(0, 0.0)
 function SciMLBase.solve!(cache::LinearSolve.LinearCache, alg::B200CG; kwargs...)
     A, b, u = cache.A::B200CSRMatrix, cache.b::B200Vector, cache.u::B200Vector
+    configure!(alg, A)
     it, rn, conv = Ref{Int64}(0), Ref{Float64}(0.0), Ref{Int32}(0)
     itmax = alg.maxiters == 0 ? length(b) : alg.maxiters
     @tb tb_cg_solve_pc (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Int32, Float64, Float64, Int64, Ref{Int64}, Ref{Float64}, Ref{Int32}) A.dev.h A.h b.h Int32(0) u.h Int32(0) precond_id(alg) alg.atol alg.rtol itmax it rn conv
@@ -268,6 +286,64 @@ function Thunderbolt.evaluate_ecg(c::B200PlonseyECGCache, x::AbstractVector{<:Fe
     out
 end
 Thunderbolt.evaluate_ecg(c::B200PlonseyECGCache, x::Ferrite.Vec, κₜ::Real) = Thunderbolt.evaluate_ecg(c, [x], κₜ)[1]
+
+# ---- multi-subdomain splits (fem.jl:434-542; partitioned_solver.jl:23-35,126-155) -----------------------------------------
+# A child of a PointwiseMultiODEFunction owns the slots `f.associated_states` of the flat solution vector in
+# PointBlockedLayout; perform_step!(::PointwiseMultiODEFunction) calls the outer kernel once per child.
+Base.@kwdef struct TBCellBlock            # tb_cell_block (include/tbolt_b200.h)
+    offset::Int64
+    npoints::Int64
+    model::Int32
+    layout::Int32                         # 0 StateBlockedLayout, 1 PointBlockedLayout
+    nparams::Int32
+    reserved::Int32 = 0
+    params::NTuple{36, Float64}
+end
+function cell_block(f::PointwiseODEFunction)
+    p = params(f.ode)
+    ns = num_states(f.ode)
+    TBCellBlock(offset = first(f.associated_states) - 1, npoints = length(f.associated_states) ÷ ns, model = model_id(f.ode),
+                layout = Int32(f.layout isa Thunderbolt.PointBlockedLayout), nparams = Int32(length(p)),
+                params = ntuple(i -> i <= length(p) ? p[i] : 0.0, 36))
+end
+function step_block!(f::PointwiseODEFunction, t::Real, Δt::Real, cache::AbstractPointwiseSolverCache, u::B200Vector)
+    ns, thr = substeps(cache)
+    blk = Ref(cell_block(f))
+    R = Ref{Float64}(0.0)
+    @tb tb_cell_step_blocks (Ptr{Cvoid}, Ptr{TBCellBlock}, Int32, Ptr{Cvoid}, Float64, Float64, Int32, Float64, Ptr{Float64}) u.dev.h blk Int32(1) u.h Float64(t) Float64(Δt) ns thr R
+    REACTION_TANGENT[objectid(cache)] = max(get(REACTION_TANGENT, objectid(cache), 0.0), R[])
+    return true
+end
+# the heat child's `view(u, heat_dofrange)` with a scattered index set: forward / backward sync of the OS integrator
+mutable struct B200Index
+    h::Ptr{Cvoid}
+end
+function B200Index(dev::B200Device, idx::Vector{Int})
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    @tb tb_index_create (Ptr{Cvoid}, Ptr{Int64}, Int64, Int32, Ref{Ptr{Cvoid}}) dev.h idx Int64(length(idx)) Int32(1) r
+    finalizer(i -> ccall((:tb_index_destroy, LIB[]), Int32, (Ptr{Cvoid},), i.h), B200Index(r[]))
+end
+gather!(dst::B200Vector, src::B200Vector, ix::B200Index) =
+    @tb tb_vec_gather (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int32, Ptr{Cvoid}) dst.h Int32(0) src.h Int32(0) ix.h
+scatter!(dst::B200Vector, ix::B200Index, src::B200Vector) =
+    @tb tb_vec_scatter (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int32) dst.h Int32(0) ix.h src.h Int32(0)
+# BilinearInterfaceDiffusionIntegrator (diffusion.jl:81-140): dofs = ninterfaces x 2k (here side first, 1-based), coordinates of the
+# two facets; K is zeroed first -- add it to the bulk operator with tb_csr_axpby_values(K, K_bulk, K_if, -1.0)
+function assemble_interface_diffusion!(K::B200CSRMatrix, facet::Symbol, sdim::Integer, dofs::Matrix{Int64}, xh::Array{Float64}, xt::Array{Float64}, qorder::Integer, D::Real)
+    @tb tb_assemble_interface_diffusion (Ptr{Cvoid}, Int32, Int32, Int64, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}) K.dev.h Int32(facet === :line ? 0 : 1) Int32(sdim) Int64(size(dofs, 2)) dofs Int32(1) xh xt Int32(qorder) Float64(D) K.h
+end
+
+# ---- lead-field / Poisson ECG building blocks (ecg.jl:166-619) ------------------------------------------------------------------
+# transfer and electrode evaluation are rectangular B200CSRMatrix (tb_csr_create with ncols != nrows + tb_csr_values_upload);
+# `-Z * κ∇φₘ_t` with the lead fields as the columns of one B200Vector:
+function lead_potentials(Z::B200Vector, src::B200Vector)
+    out = zeros(Z.ncols)
+    @tb tb_vec_dots (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}) Z.dev.h Z.h src.h Int32(0) out
+    return -out
+end
+# Ferrite.apply_zero!(K, f, ch): matrix half (diagonal of the constrained dofs := meandiag(K)) and right-hand-side half
+apply_zero!(K::B200CSRMatrix, ix::B200Index, meandiag::Real) = @tb tb_csr_apply_zero (Ptr{Cvoid}, Ptr{Cvoid}, Float64) K.h ix.h Float64(meandiag)
+apply_zero!(f::B200Vector, ix::B200Index) = @tb tb_vec_fill_at (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Float64) f.h Int32(0) ix.h 0.0
 
 # ---- assembly strategy knobs ------------------------------------------------------------------------------------
 # 2 = per-element results + ordered row gather (default: deterministic, bitwise the sequential CPU assembly),
