@@ -272,6 +272,8 @@ def run_b200(args):
         sampler.start()
     dev.profile_enable(True)
     launches0 = dev.launch_count()
+    if world > 1:
+        dev.peer_stats(reset=True)
     barrier()
     dev.timer_start()
     conv_all = True
@@ -283,6 +285,17 @@ def run_b200(args):
     ms = dev.timer_stop()
     barrier()
     launches = dev.launch_count() - launches0
+    comm = None
+    if world > 1:
+        ps = dev.peer_stats()
+        cw = torch.tensor([ps["ar_wait_ms"], ps["halo_wait_ms"]], dtype=torch.float64, device="cuda")
+        cmax, cmin = cw.clone(), cw.clone()
+        dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        comm = {"what": "time CTA 0 of a rank spent waiting for the other ranks inside the CG kernels (ld.acquire.sys spins), per step",
+                "allreduce_wait_ms_per_step_max_rank": float(cmax[0]) / args.steps, "allreduce_wait_ms_per_step_min_rank": float(cmin[0]) / args.steps,
+                "halo_wait_ms_per_step_max_rank": float(cmax[1]) / args.steps, "halo_wait_ms_per_step_min_rank": float(cmin[1]) / args.steps,
+                "waits_per_step": ps["ar_waits"] / args.steps}
     spmv_ms, spmv_n = dev.profile_get()
     dev.profile_enable(False)
     cg_path = dev.cg_last_path()
@@ -413,7 +426,7 @@ def run_b200(args):
                          "l2": "working set (matrix + vectors) is far larger than the 126 MB L2, no flush needed"
                                if nnz * 12 > 4e8 else "working set fits L2: tb_l2_flush not applied between steps (steady-state regime)",
                          "setup_s": t_setup},
-            "parity": parity,
+            "parity": parity, "comm": comm,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

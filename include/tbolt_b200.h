@@ -204,6 +204,9 @@ int32_t tb_csr_set_halo_peer(tb_csr *A, const int64_t *dst_off, const int32_t *d
  * tb_csr_halo_fused_capable reports whether THIS rank could (every send list one run of consecutive rows, fusion not
  * disabled); the host reduces that with MIN over the ranks and hands the agreed value to tb_csr_set_halo_fused.
  * Until that call the unfused path is used. */
+/* instrumentation of the peer path: time (ms) one CTA of this rank spent waiting for the other ranks' partial sums and
+ * halo flags since the last reset, and the number of waits -- what the slowest rank costs per iteration */
+int32_t tb_peer_stats(tb_ctx *ctx, double *ar_wait_ms, int64_t *ar_waits, double *halo_wait_ms, int64_t *halo_waits, int32_t reset);
 int32_t tb_csr_halo_fused_capable(const tb_csr *A, int32_t *capable);
 int32_t tb_csr_set_halo_fused(tb_csr *A, int32_t on);
 

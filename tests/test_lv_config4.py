@@ -239,3 +239,48 @@ def test_lv_high_valence_apex_rows(tb, dev, oracle, nc, nr, nl, cg_mode):
         dev.cg_set_persistent(1)
     for h in (M, K, A, xv, yv, bv, mesh):
         h.free()
+
+
+@pytest.mark.gpu
+def test_config4_mid_size_1000_steps_against_golden(tb, dev):
+    """BASELINE config 4 at a realistic size and its FULL length (126 k dofs / 0.7 M tets, 1000 steps of dt = 0.01, default CG
+    tolerances; golden: tests/golden/make_golden.py --c4-mid-1000): 1e-10 relative L-inf after one step is NOT demanded here
+    (plain partial sums, see tests/test_gpu_exact_dot.py for that rule on this mesh family) -- the checks are the other
+    three north_star rules at full length: CG iterations +-1 on every step, 1e-6 after 1000 steps, activation steps identical."""
+    g = np.load(Path(__file__).resolve().parent / "golden" / "c4_mid_1000.npz")
+    lv, nodes, hexes, wedges, prm, tets = _lv(120, 12, 80)
+    fsn = lv.odb25lt_fibres(prm, tets)
+    k1, kr = 0.17 * 0.62 / (0.17 + 0.62), 0.019 * 0.24 / (0.019 + 0.24)
+    data = np.concatenate([[k1, kr, kr], np.ascontiguousarray(fsn).reshape(tets.shape[0], 4, 9).ravel()])
+    mesh = tb.to_mesh(tb.Tetrahedron, tets, nodes, device=dev)
+    N = mesh.ndofs
+    assert N == 126373
+    M = tb.B200CSRMatrix.from_mesh(dev, mesh)
+    K = M.like()
+    tb.core.assemble_mass(dev, mesh, M, 2, 1.0)
+    tb.core.assemble_diffusion(dev, mesh, K, 2, tb._lib.D_SPECTRAL, data, 1.0)
+    ion = tb.PCG2019()
+    st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+    bS = tb.B200Vector(dev, N, 1)
+    u = tb.B200Vector.from_host(dev, np.repeat(tb.default_initial_state(ion), N), 7)
+    SRC = [0.0, 0.2, 0.3, 0.25]
+    act = np.full(g["act"].shape, -1, dtype=np.int16)
+    its = []
+    t, dt = 0.0, 0.01
+    for step in range(1000):
+        tb.core.assemble_source(dev, mesh, bS, 2, tb._lib.SRC_ENDO, SRC, t + dt)
+        st.set_source(bS)
+        it, rn, conv = st.step(u, t, dt)
+        assert conv
+        its.append(it)
+        t += dt
+        ph = u.column(0)[::13]
+        act[(act < 0) & (ph >= 0.0)] = step + 1
+        if step == 0:
+            assert np.abs(ph - g["phi1"]).max() / np.abs(g["phi1"]).max() <= 1e-6
+        if step == 99:
+            assert np.abs(ph - g["phi100"]).max() / np.abs(g["phi100"]).max() <= 1e-6
+    assert np.abs(np.array(its) - g["iters"]).max() <= 1
+    assert np.abs(u.column(0)[::13] - g["phi1000"]).max() / np.abs(g["phi1000"]).max() <= 1e-6
+    assert np.abs(u.column(1)[::13] - g["h1000"]).max() <= 1e-6
+    assert np.array_equal(act, g["act"]) and (act > 0).sum() > act.size // 2

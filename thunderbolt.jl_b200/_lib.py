@@ -125,6 +125,7 @@ _SIGNATURES = {
     "tb_peer_attach": [_vp, _vp, C.c_int32],
     "tb_peer_enabled": [_vp, _pi32],
     "tb_csr_set_halo_peer": [_vp, _vp, _vp],
+    "tb_peer_stats": [_vp, _pf64, _pi64, _pf64, _pi64, C.c_int32],
     "tb_csr_halo_fused_capable": [_vp, _pi32],
     "tb_csr_set_halo_fused": [_vp, C.c_int32],
     "tb_quadrature": [C.c_int32, C.c_int32, _pi32, _vp, _vp],

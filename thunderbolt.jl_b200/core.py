@@ -136,6 +136,12 @@ class B200Device:
         L.call("tb_peer_enabled", self.h, C.byref(on))
         return bool(on.value)
 
+    def peer_stats(self, reset=False):
+        """ms one CTA of this rank waited for peers (all-reduce collects, halo flags) since the last reset, and the wait counts"""
+        a, na, h, nh = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+        L.call("tb_peer_stats", self.h, C.byref(a), C.byref(na), C.byref(h), C.byref(nh), int(reset))
+        return {"ar_wait_ms": a.value, "ar_waits": na.value, "halo_wait_ms": h.value, "halo_waits": nh.value}
+
     def allreduce_max(self, v: float) -> float:
         x = C.c_double(v)
         L.call("tb_comm_allreduce_max", self.h, C.byref(x))

@@ -597,7 +597,7 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
     const int grid_s = TB_GRID(ctx, k_cg_spmv_dot<true>, 256, 0, need_s);
     const int grid_im = TB_GRID(ctx, k_cg_init_Mphi<true>, 256, 0, need_s);
     const bool tma = ctx->spmv_variant > 0 && pat->max_width_tma > 0;   // slices above TB_TMA_WCAP take the LDG row kernel inside the sweep
-    const tb_hwait_args nowait{nullptr, 0, 0, nullptr};
+    const tb_hwait_args nowait{nullptr, 0, 0, nullptr, nullptr};
     // fused peer path: collects and halo push inside k_cg_xr_fused / k_cg_p_fused, scalars ping-pong between st[0] and st[1]
     const bool fused = peer_ar && pat->halo.peer_ready && pat->halo.fused && !gen_pc;   // agreed by all ranks (tb_csr_set_halo_fused)
     const int grid_xrf = fused ? TB_GRID(ctx, k_cg_xr_fused<true>, 256, 0, need_v) : 0;

@@ -256,6 +256,7 @@ int32_t tb_halo_push_args(tb_ctx *ctx, const tb_pattern *pat, tb_push_args *out,
     wait_out->n = h.nneigh;
     wait_out->epoch = epoch;
     wait_out->err = &P.win->err;
+    wait_out->stat = &P.win->halo_wait_ns;
     return TB_OK;
 }
 
@@ -308,5 +309,23 @@ int32_t tb_halo_push(tb_ctx *ctx, const tb_pattern *pat, const double *p, const 
     wait_out->n = h.nneigh;
     wait_out->epoch = epoch;
     wait_out->err = &P.win->err;
+    wait_out->stat = &P.win->halo_wait_ns;
+    return TB_OK;
+}
+
+// time CTA 0 spent waiting for peers since the last reset: {all-reduce collects, halo flags} in ms, and the wait counts
+extern "C" int32_t tb_peer_stats(tb_ctx *ctx, double *ar_wait_ms, int64_t *ar_waits, double *halo_wait_ms, int64_t *halo_waits, int32_t reset) {
+    TB_REQUIRE(ctx, "tb_peer_stats: ctx is NULL");
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (ctx->peer.on) {
+        TB_DEV(ctx);
+        TB_CUDA(cudaStreamSynchronize(ctx->stream));
+        TB_CUDA(cudaMemcpy(v, &ctx->peer.win->ar_wait_ns, sizeof(v), cudaMemcpyDeviceToHost));
+        if (reset) TB_CUDA(cudaMemset(&ctx->peer.win->ar_wait_ns, 0, sizeof(v)));
+    }
+    if (ar_wait_ms) *ar_wait_ms = (double)v[0] * 1e-6;
+    if (ar_waits) *ar_waits = (int64_t)v[1];
+    if (halo_wait_ms) *halo_wait_ms = (double)v[2] * 1e-6;
+    if (halo_waits) *halo_waits = (int64_t)v[3];
     return TB_OK;
 }

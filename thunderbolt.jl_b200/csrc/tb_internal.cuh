@@ -95,7 +95,10 @@ struct tb_peer_window {
     unsigned long long flag[TB_AR_SLOTS][TB_MAX_RANKS];
     unsigned long long hflag[TB_MAX_RANKS];
     unsigned long long err;          // set by a waiter that timed out
-    unsigned long long pad[15];
+    // instrumentation (CTA 0 only, so the numbers are one CTA's view of the critical path): time spent waiting for the
+    // other ranks' partial sums / halo flags, and how often
+    unsigned long long ar_wait_ns, ar_waits, halo_wait_ns, halo_waits;
+    unsigned long long pad[11];
 };
 // halo wait of an SpMV kernel (n == 0: nothing to wait for)
 struct tb_hwait_args {
@@ -103,6 +106,7 @@ struct tb_hwait_args {
     int n;
     unsigned long long epoch;
     unsigned long long *err;
+    unsigned long long *stat;   // -> {halo_wait_ns, halo_waits} of this rank's window (nullable)
 };
 struct tb_peer {
     bool on = false;
@@ -112,7 +116,7 @@ struct tb_peer {
     int64_t peer_ld[TB_MAX_RANKS] = {};
     tb_peer_window **d_peer_win = nullptr;             // device copy of peer_win
     unsigned long long ar_epoch = 0, halo_epoch = 0;
-    tb_hwait_args hw_next = {nullptr, 0, 0, nullptr};   // fused path: what the next SpMV waits for (set when k_cg_p_fused is enqueued)
+    tb_hwait_args hw_next = {nullptr, 0, 0, nullptr, nullptr};   // fused path: what the next SpMV waits for (set when k_cg_p_fused is enqueued)
 };
 // what a reducing / consuming kernel needs to take part in the window all-reduce (wins == nullptr: NCCL path)
 struct tb_ar_args {
@@ -541,11 +545,16 @@ template <bool X> __device__ __forceinline__ void tb_ar_publish_acc(const tb_ar_
 template <bool X> __device__ __forceinline__ double tb_ar_collect_acc(const tb_ar_args &a) {
     tb_peer_window *w = a.wins[a.rank];
     tb_acc<X> s;
+    const unsigned long long t0 = blockIdx.x == 0 ? tb_globaltimer() : 0ull;
     for (int q = 0; q < a.nranks; q++) {
         tb_wait_flag(&w->flag[a.slot][q], a.epoch, &w->err);
         tb_acc<X> t;
         t.set(*(volatile double *)&w->val[a.slot][q], X ? *(volatile double *)&w->val_lo[a.slot][q] : 0.0);
         s.add(t);
+    }
+    if (blockIdx.x == 0) {
+        w->ar_wait_ns += tb_globaltimer() - t0;
+        w->ar_waits += 1;
     }
     return s.value();
 }
@@ -553,17 +562,27 @@ template <bool X> __device__ __forceinline__ double tb_ar_collect_acc(const tb_a
 __device__ __forceinline__ double tb_ar_collect(const tb_ar_args &a) {
     tb_peer_window *w = a.wins[a.rank];
     double s = 0.0;
+    const unsigned long long t0 = blockIdx.x == 0 ? tb_globaltimer() : 0ull;
     for (int q = 0; q < a.nranks; q++) {
         tb_wait_flag(&w->flag[a.slot][q], a.epoch, &w->err);
         s += *(volatile double *)&w->val[a.slot][q];
+    }
+    if (blockIdx.x == 0) {
+        w->ar_wait_ns += tb_globaltimer() - t0;
+        w->ar_waits += 1;
     }
     return s;
 }
 // kernel prologue of an SpMV that reads ghost entries pushed by the neighbours
 __device__ __forceinline__ void tb_halo_wait(const tb_hwait_args &h) {
     if (h.n > 0) {
+        const unsigned long long t0 = (blockIdx.x == 0 && threadIdx.x == 0 && h.stat) ? tb_globaltimer() : 0ull;
         if ((int)threadIdx.x < h.n) tb_wait_flag(h.hflag + threadIdx.x, h.epoch, h.err);
         __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0 && h.stat) {
+            h.stat[0] += tb_globaltimer() - t0;
+            h.stat[1] += 1;
+        }
     }
 }
 void tb_bj_free(struct tb_bj *b);
