@@ -203,6 +203,13 @@ def run_b200(args):
             N_global = mesh.ndofs
         lv_data = np.concatenate([np.asarray(W["kappa"], dtype=np.float64), fsn.reshape(-1)])
         del fsn
+    elif world > 1:
+        # structured grid: every rank generates only its own cells from the closed-form first-touch numbering -- the global
+        # grid never exists in HBM (tb_mesh_generate_grid_local)
+        plane = (nel[0] + 1) * (nel[1] + 1) if dim == 3 else nel[0] + 1
+        part = tbd.partition_structured_grid(dev, ct, nel, (0.0,) * dim, lengths, dist, plane=plane if args.cut == "planes" else None)
+        mesh = part.mesh
+        N_global = int(np.prod([n + 1 for n in nel]))
     else:
         mesh = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
         N_global = mesh.ndofs

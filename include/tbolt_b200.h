@@ -151,6 +151,11 @@ int32_t tb_mesh_dof_coords(const tb_mesh *m, double *host);
  * first (global id - dof_lo), ghosts after them sorted by global id.  ghost_global (nullable) gets
  * the ghosts' global ids; *nghost their count. */
 int32_t tb_mesh_extract_local(const tb_mesh *global, int64_t dof_lo, int64_t dof_hi, tb_mesh **out, int64_t *nghost);
+/* the same local mesh for a STRUCTURED Quadrilateral / Hexahedron grid, generated directly from Ferrite's closed-form first-touch
+ * numbering: identical arrays to tb_mesh_extract_local(tb_mesh_generate_grid(...), lo, hi), but no rank ever holds the global
+ * grid -- all temporaries are sized by the slab of cell layers that can touch [dof_lo, dof_hi) */
+int32_t tb_mesh_generate_grid_local(tb_ctx *ctx, int32_t celltype, const int64_t *nel3, const double *left3, const double *right3,
+                                    int64_t dof_lo, int64_t dof_hi, tb_mesh **out, int64_t *nghost);
 int32_t tb_mesh_ghosts(const tb_mesh *local, int64_t *ghost_global);
 /* the same ownership marking for a LOCAL mesh that was cut on the host and uploaded with tb_mesh_create (general
  * partitions: no global replica in HBM): dofs 0 .. ndofs_owned-1 are owned (global ids dof_lo ..), the rest are ghosts with

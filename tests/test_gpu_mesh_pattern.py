@@ -83,3 +83,28 @@ def test_c2_size_pattern_closed_form(tb, dev):
     P = sp.csr_matrix((np.ones(ci.size), ci, rp))
     assert (P != P.T).nnz == 0 and np.all(P.diagonal() == 1)
     A.free(); md.free()
+
+
+@pytest.mark.parametrize("celltype,nel", [("Hexahedron", (7, 5, 9)), ("Hexahedron", (3, 4, 2)), ("Hexahedron", (1, 1, 6)), ("Quadrilateral", (9, 11)),
+                                           ("Quadrilateral", (2, 3))])
+def test_local_structured_generator_equals_extract_of_the_global_grid(tb, dev, celltype, nel):
+    """tb_mesh_generate_grid_local (closed-form first-touch numbering, slab-sized temporaries) against
+    tb_mesh_extract_local(tb_mesh_generate_grid(...)): identical cells, nodes, coordinates, dofs and ghost lists"""
+    ct = getattr(tb, celltype)
+    dim = len(nel)
+    left, right = (0.0,) * dim, tuple(0.25 * n + 0.1 for n in nel)
+    full = tb.generate_mesh(ct, nel, left, right, device=dev)
+    n = full.ndofs
+    rng = np.random.default_rng(5)
+    cuts = sorted(set([0, n] + [int(v) for v in rng.integers(1, n, 4)] + [n // 2, n // 3]))
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        a = full.extract_local(lo, hi)
+        b = tb.DeviceMesh.generate_grid_local(dev, ct, nel, left, right, lo, hi)
+        assert (a.ncells, a.nnodes, a.ndofs, a.ndofs_owned) == (b.ncells, b.nnodes, b.ndofs, b.ndofs_owned)
+        assert np.array_equal(a.ghost_global, b.ghost_global)
+        for x, y in zip(a.download(), b.download()):
+            assert np.array_equal(x, y)
+        assert np.array_equal(a.dof_coords(), b.dof_coords())
+        a.free()
+        b.free()
+    full.free()

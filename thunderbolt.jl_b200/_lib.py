@@ -107,6 +107,7 @@ _SIGNATURES = {
     "tb_mesh_dof_coords": [_vp, _f64p],
     "tb_mesh_extract_local": [_vp, C.c_int64, C.c_int64, _pp, _pi64],
     "tb_mesh_ghosts": [_vp, _i64p],
+    "tb_mesh_generate_grid_local": [_vp, C.c_int32, _i64p, _f64p, _f64p, C.c_int64, C.c_int64, _pp, _pi64],
     "tb_mesh_set_ownership": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64],
     "tb_csr_create": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, C.c_int32, _pp],
     "tb_csr_create_from_mesh": [_vp, _vp, _pp],

@@ -235,6 +235,26 @@ class DeviceMesh:
         return m
 
     @classmethod
+    def generate_grid_local(cls, dev, celltype, nel, left, right, dof_lo: int, dof_hi: int):
+        """the local part [dof_lo, dof_hi) of a structured Quadrilateral / Hexahedron grid, built from the closed-form numbering:
+        the same mesh as generate_grid(...).extract_local(dof_lo, dof_hi) without the global grid in HBM"""
+        dim = 2 if celltype in (L.QUAD4, L.TRI3) else 3
+        nel3 = np.ones(3, dtype=np.int64)
+        nel3[:dim] = nel
+        l3, r3 = np.zeros(3), np.ones(3)
+        l3[:dim], r3[:dim] = left, right
+        h, ng = C.c_void_p(), C.c_int64()
+        L.call("tb_mesh_generate_grid_local", dev.h, int(celltype), nel3, l3, r3, int(dof_lo), int(dof_hi), C.byref(h), C.byref(ng))
+        m = cls(dev, h)
+        m.celltype = int(celltype)
+        m.ndofs_owned = int(dof_hi - dof_lo)
+        m.dof_lo = int(dof_lo)
+        m.ghost_global = np.empty(ng.value, dtype=np.int64)
+        if ng.value:
+            L.call("tb_mesh_ghosts", h, m.ghost_global)
+        return m
+
+    @classmethod
     def from_host(cls, dev, celltype, conn, coords, celldofs, ndofs, index_base=0):
         conn = np.ascontiguousarray(conn, dtype=np.int64)
         coords = np.ascontiguousarray(coords, dtype=np.float64)

@@ -467,6 +467,190 @@ extern "C" int32_t tb_mesh_set_ownership(tb_mesh *m, int64_t ndofs_owned, int64_
     return TB_OK;
 }
 
+// =====================================================================================================
+// Structured grids, local part only: what tb_mesh_extract_local(tb_mesh_generate_grid(...), lo, hi) returns, built
+// WITHOUT ever holding the global grid in HBM.  Ferrite's first-touch numbering of a
+// Quadrilateral / Hexahedron grid has a closed form: node (a, b, c) is first touched by cell (max(a-1,0), max(b-1,0),
+// max(c-1,0)) -- the lexicographically first cell that contains it -- and its id is the number of nodes introduced by the
+// cells before that one plus its rank among the cell's new vertices in local vertex order.  All temporaries are sized by
+// the slab of cell layers that can touch [lo, hi).
+// =====================================================================================================
+__host__ __device__ __forceinline__ int64_t tb_grid_dof(const GridDesc &g, int64_t a, int64_t b, int64_t c) {
+    const bool d3 = g.dim == 3;
+    const int64_t i = a > 0 ? a - 1 : 0, j = b > 0 ? b - 1 : 0, k = d3 ? (c > 0 ? c - 1 : 0) : 0;
+    const int64_t Ck = (d3 && k == 0) ? 2 : 1, Bj = j == 0 ? 2 : 1;
+    int64_t n = 0;
+    if (d3 && k >= 1) n += g.nn[0] * g.nn[1] * (k + 1);
+    if (j >= 1) n += g.nn[0] * (j + 1) * Ck;
+    if (i >= 1) n += (i + 1) * Bj * Ck;
+    const int da = (int)(a - i), db = (int)(b - j), dc = d3 ? (int)(c - k) : 0;
+    // rank among the new vertices of cell (i, j, k) in local vertex order (--,+-,++,-+ bottom, then top)
+    const int oa[8] = {0, 1, 1, 0, 0, 1, 1, 0}, ob[8] = {0, 0, 1, 1, 0, 0, 1, 1}, oc[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    const int nvl = d3 ? 8 : 4;
+    int pos = 0;
+    for (int v = 0; v < nvl; v++) {
+        if (oa[v] == da && ob[v] == db && oc[v] == dc) break;
+        pos += ((oa[v] == 1 || i == 0) && (ob[v] == 1 || j == 0) && (!d3 || oc[v] == 1 || k == 0)) ? 1 : 0;
+    }
+    return n + pos;
+}
+
+struct SlabDesc {
+    GridDesc g;
+    int64_t k0, k1;          // cell layers of the outermost direction
+    int64_t cells_per_layer, nodes_per_layer;
+    int64_t ncells, nnodes;  // of the slab
+    int64_t node_base, dof_base, ndofs_slab;
+    int64_t lo, hi;
+};
+// slab cell id -> its vertices' global (a, b, c); vertex v
+__device__ __forceinline__ void slab_cell_vertex(const SlabDesc &S, int64_t sc, int v, int64_t &a, int64_t &b, int64_t &c) {
+    const GridDesc &g = S.g;
+    const int oa[8] = {0, 1, 1, 0, 0, 1, 1, 0}, ob[8] = {0, 0, 1, 1, 0, 0, 1, 1}, oc[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    if (g.dim == 3) {
+        const int64_t i = sc % g.nel[0], j = (sc / g.nel[0]) % g.nel[1], k = S.k0 + sc / (g.nel[0] * g.nel[1]);
+        a = i + oa[v]; b = j + ob[v]; c = k + oc[v];
+    } else {
+        const int64_t i = sc % g.nel[0], j = S.k0 + sc / g.nel[0];
+        a = i + oa[v]; b = j + ob[v]; c = 0;
+    }
+}
+__global__ void k_slab_mark_cells(SlabDesc S, int nv, int *cellflag) {
+    for (int64_t sc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sc < S.ncells; sc += (int64_t)gridDim.x * blockDim.x) {
+        int f = 0;
+        for (int v = 0; v < nv; v++) {
+            int64_t a, b, c;
+            slab_cell_vertex(S, sc, v, a, b, c);
+            const int64_t d = tb_grid_dof(S.g, a, b, c);
+            f |= (d >= S.lo && d < S.hi);
+        }
+        cellflag[sc] = f;
+    }
+}
+__global__ void k_slab_mark_nodes_dofs(SlabDesc S, int nv, const int *cellflag, int *nodeflag, int *dofflag) {
+    for (int64_t sc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sc < S.ncells; sc += (int64_t)gridDim.x * blockDim.x) {
+        if (!cellflag[sc]) continue;
+        for (int v = 0; v < nv; v++) {
+            int64_t a, b, c;
+            slab_cell_vertex(S, sc, v, a, b, c);
+            const int64_t node = (c * S.g.nn[1] + b) * S.g.nn[0] + a;
+            nodeflag[node - S.node_base] = 1;
+            const int64_t d = tb_grid_dof(S.g, a, b, c);
+            if (d < S.lo || d >= S.hi) dofflag[d - S.dof_base] = 1;
+        }
+    }
+}
+__global__ void k_slab_ghost_list(SlabDesc S, const int *dofflag, const int *dofscan, int64_t *ghost_global) {
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < S.ndofs_slab; d += (int64_t)gridDim.x * blockDim.x)
+        if (dofflag[d]) ghost_global[dofscan[d]] = d + S.dof_base;
+}
+__global__ void k_slab_compact_cells(SlabDesc S, int nv, const int *cellflag, const int *cellscan, const int *nodescan,
+                                     const int *dofscan, int nowned, int *lconn, int *ldofs) {
+    for (int64_t sc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sc < S.ncells; sc += (int64_t)gridDim.x * blockDim.x) {
+        if (!cellflag[sc]) continue;
+        const int64_t lc = cellscan[sc];
+        for (int v = 0; v < nv; v++) {
+            int64_t a, b, c;
+            slab_cell_vertex(S, sc, v, a, b, c);
+            const int64_t node = (c * S.g.nn[1] + b) * S.g.nn[0] + a;
+            lconn[lc * nv + v] = nodescan[node - S.node_base];
+            const int64_t d = tb_grid_dof(S.g, a, b, c);
+            ldofs[lc * nv + v] = (d >= S.lo && d < S.hi) ? (int)(d - S.lo) : nowned + dofscan[d - S.dof_base];
+        }
+    }
+}
+__global__ void k_slab_compact_nodes(SlabDesc S, const int *nodeflag, const int *nodescan, const int *dofscan, int nowned,
+                                     double *lcoords, int *lnode2dof) {
+    const GridDesc &g = S.g;
+    for (int64_t sn = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sn < S.nnodes; sn += (int64_t)gridDim.x * blockDim.x) {
+        if (!nodeflag[sn]) continue;
+        const int64_t n = sn + S.node_base;
+        const int64_t a = n % g.nn[0], b = (n / g.nn[0]) % g.nn[1], c = n / (g.nn[0] * g.nn[1]);
+        const int ln = nodescan[sn];
+        lcoords[(int64_t)ln * g.dim + 0] = grid_coord(g.left[0], g.right[0], a, g.nel[0]);
+        lcoords[(int64_t)ln * g.dim + 1] = grid_coord(g.left[1], g.right[1], b, g.nel[1]);
+        if (g.dim == 3) lcoords[(int64_t)ln * g.dim + 2] = grid_coord(g.left[2], g.right[2], c, g.nel[2]);
+        const int64_t d = tb_grid_dof(g, a, b, c);
+        lnode2dof[ln] = (d >= S.lo && d < S.hi) ? (int)(d - S.lo) : nowned + dofscan[d - S.dof_base];
+    }
+}
+
+extern "C" int32_t tb_mesh_generate_grid_local(tb_ctx *ctx, int32_t celltype, const int64_t *nel3, const double *left3,
+                                               const double *right3, int64_t dof_lo, int64_t dof_hi, tb_mesh **out, int64_t *nghost) {
+    TB_REQUIRE(ctx && nel3 && left3 && right3 && out, "tb_mesh_generate_grid_local: NULL argument");
+    TB_REQUIRE(celltype == TB_QUAD4 || celltype == TB_HEX8, "tb_mesh_generate_grid_local: closed-form numbering exists for Quadrilateral and Hexahedron grids only");
+    TB_DEV(ctx);
+    *out = nullptr;
+    SlabDesc S;
+    GridDesc &g = S.g;
+    g.celltype = celltype;
+    g.dim = dim_of(celltype);
+    for (int d = 0; d < 3; d++) {
+        g.nel[d] = d < g.dim ? nel3[d] : 1;
+        g.nn[d] = d < g.dim ? nel3[d] + 1 : 1;
+        g.left[d] = left3[d];
+        g.right[d] = right3[d];
+        TB_REQUIRE(g.nel[d] >= 1, "tb_mesh_generate_grid_local: nel[%d] must be >= 1", d);
+    }
+    const int od = g.dim - 1;                                     // outermost loop direction
+    const int64_t L = od == 2 ? g.nn[0] * g.nn[1] : g.nn[0];      // nodes per outer layer
+    const int64_t CL = od == 2 ? g.nel[0] * g.nel[1] : g.nel[0];  // cells per outer layer
+    const int64_t ndofs_global = g.nn[0] * g.nn[1] * g.nn[2];
+    TB_REQUIRE(0 <= dof_lo && dof_lo < dof_hi && dof_hi <= ndofs_global, "tb_mesh_generate_grid_local: bad dof range");
+    // node layers 0 and 1 share the ids [0, 2L); layer c >= 2 holds [cL, (c+1)L)
+    const int64_t c_lo = dof_lo < 2 * L ? 0 : dof_lo / L, c_hi = (dof_hi - 1) < 2 * L ? 1 : (dof_hi - 1) / L;
+    S.k0 = c_lo > 0 ? c_lo - 1 : 0;
+    S.k1 = c_hi < g.nel[od] ? c_hi : g.nel[od] - 1;
+    S.cells_per_layer = CL;
+    S.nodes_per_layer = L;
+    S.ncells = (S.k1 - S.k0 + 1) * CL;
+    S.nnodes = (S.k1 - S.k0 + 2) * L;
+    S.node_base = S.k0 * L;
+    S.dof_base = S.k0 <= 1 ? 0 : S.k0 * L;
+    S.ndofs_slab = (S.k1 + 2) * L - S.dof_base;
+    S.lo = dof_lo;
+    S.hi = dof_hi;
+    TB_REQUIRE(S.ncells < INT32_MAX && S.nnodes < INT32_MAX, "tb_mesh_generate_grid_local: slab too large for one GPU");
+    const int nv = nv_of(celltype);
+    const int grid = ctx->sm_count * 8;
+    int *cellflag, *cellscan, *dofflag, *dofscan, *nodeflag, *nodescan;
+    TB_CUDA(cudaMalloc(&cellflag, sizeof(int) * (size_t)S.ncells));
+    TB_CUDA(cudaMalloc(&cellscan, sizeof(int) * (size_t)S.ncells));
+    TB_CUDA(cudaMalloc(&dofflag, sizeof(int) * (size_t)S.ndofs_slab));
+    TB_CUDA(cudaMalloc(&dofscan, sizeof(int) * (size_t)S.ndofs_slab));
+    TB_CUDA(cudaMalloc(&nodeflag, sizeof(int) * (size_t)S.nnodes));
+    TB_CUDA(cudaMalloc(&nodescan, sizeof(int) * (size_t)S.nnodes));
+    TB_CUDA(cudaMemsetAsync(dofflag, 0, sizeof(int) * (size_t)S.ndofs_slab, ctx->stream));
+    TB_CUDA(cudaMemsetAsync(nodeflag, 0, sizeof(int) * (size_t)S.nnodes, ctx->stream));
+    TB_LAUNCH(ctx, k_slab_mark_cells, grid, 256, 0, S, nv, cellflag);
+    TB_LAUNCH(ctx, k_slab_mark_nodes_dofs, grid, 256, 0, S, nv, cellflag, nodeflag, dofflag);
+    int64_t lcells = 0, lghost = 0, lnodes = 0;
+    TB_TRY(scan_flags(ctx, cellflag, cellscan, S.ncells, &lcells));
+    TB_TRY(scan_flags(ctx, dofflag, dofscan, S.ndofs_slab, &lghost));
+    TB_TRY(scan_flags(ctx, nodeflag, nodescan, S.nnodes, &lnodes));
+    TB_REQUIRE(lcells > 0, "tb_mesh_generate_grid_local: no cell touches dofs [%lld,%lld)", (long long)dof_lo, (long long)dof_hi);
+    tb_mesh *m = nullptr;
+    int32_t st = mesh_alloc(ctx, celltype, lcells, lnodes, &m);
+    if (st != TB_OK) {
+        tb_mesh_destroy(m);
+        return st;
+    }
+    const int nowned = (int)(dof_hi - dof_lo);
+    m->ndofs_owned = nowned;
+    m->ndofs = nowned + lghost;
+    m->nghost = lghost;
+    m->dof_lo = dof_lo;
+    TB_CUDA(cudaMalloc(&m->d_ghost_global, sizeof(int64_t) * (size_t)(lghost + 1)));
+    TB_LAUNCH(ctx, k_slab_ghost_list, grid, 256, 0, S, dofflag, dofscan, m->d_ghost_global);
+    TB_LAUNCH(ctx, k_slab_compact_cells, grid, 256, 0, S, nv, cellflag, cellscan, nodescan, dofscan, nowned, m->d_conn, m->d_celldofs);
+    TB_LAUNCH(ctx, k_slab_compact_nodes, grid, 256, 0, S, nodeflag, nodescan, dofscan, nowned, m->d_coords, m->d_node2dof);
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(cellflag); cudaFree(cellscan); cudaFree(dofflag); cudaFree(dofscan); cudaFree(nodeflag); cudaFree(nodescan);
+    if (nghost) *nghost = lghost;
+    *out = m;
+    return TB_OK;
+}
+
 extern "C" int32_t tb_mesh_ghosts(const tb_mesh *m, int64_t *ghost_global) {
     TB_REQUIRE(m && ghost_global, "tb_mesh_ghosts: NULL argument");
     if (m->nghost == 0) return TB_OK;

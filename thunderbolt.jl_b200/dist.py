@@ -149,6 +149,19 @@ class Partition:
         A.set_halo_fused(self.fused)
 
 
+def partition_structured_grid(dev: B200Device, celltype, nel, left, right, dist, plane: int | None = None) -> Partition:
+    """partition_mesh for a structured Quadrilateral / Hexahedron grid WITHOUT the global grid in HBM: every rank generates
+    only its own cells from the closed-form first-touch numbering (tb_mesh_generate_grid_local)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ndofs = int(np.prod([n + 1 for n in nel]))
+    bounds = dof_bounds(ndofs, world, plane)
+    local = DeviceMesh.generate_grid_local(dev, celltype, nel, left, right, int(bounds[rank]), int(bounds[rank + 1]))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local.ghost_global)
+    plan = build_halo_plan(rank, bounds, local.ghost_global, gathered)
+    return Partition(local, bounds, plan, rank, world, dist)
+
+
 def partition_mesh(dev: B200Device, mesh: DeviceMesh, dist, plane: int | None = None) -> Partition:
     """Split `mesh` (the full grid, present on every rank) by dof ownership and build the halo plan."""
     rank, world = dist.get_rank(), dist.get_world_size()
