@@ -217,3 +217,70 @@ def test_blocked_cell_sweep_layouts_and_models(tb, dev, oracle):
             assert abs(R.value - Ro) <= 1e-12 * abs(Ro)
         assert np.abs(u.to_host() - uo).max() <= 1e-11 * np.abs(uo).max()
         u.free()
+
+
+@pytest.mark.gpu
+def test_subdomains_with_different_cell_models(tb, dev, oracle):
+    """test/test_solution_variables.jl:162-215 ("Subdomains with different cell models": FHN with 2 states next to PCG2019
+    with 7) -- the index contract -- and then 5 split steps of that mixed problem against the oracle's composition."""
+    import ctypes as C
+    O = oracle
+    g = O.generate_grid(O.QUAD4, (8, 8), (-1.0, -1.0), (1.0, 1.0))
+    xc = g.coords[g.conn]
+    fast = np.flatnonzero((np.abs(xc).max(axis=2) <= 0.5).all(axis=1))
+    slow = np.setdiff1d(np.arange(g.ncells), fast)
+    grid = tb.insert_interfaces(tb.Quadrilateral, g.conn, g.coords, {"Fast": fast, "Slow": slow}, ("Fast", "Slow"))
+    coeff = tb.ConstantCoefficient(tb.SymmetricTensor(2, (1.0e-4, 0, 1.0e-4)))
+    one = tb.ConstantCoefficient(1.0)
+    models = {"Fast": tb.MonodomainModel(one, one, coeff, tb.NoStimulationProtocol(), tb.FHNModel(), "φₘ", "sfast"),
+              "Slow": tb.MonodomainModel(one, one, coeff, tb.NoStimulationProtocol(), tb.PCG2019(), "φₘ", "sslow"),
+              "interfaces": tb.InterfaceDiffusionModel(tb.ConstantCoefficient(1.0), "φₘ", "φₘi")}
+    form = tb.semidiscretize(tb.ReactionDiffusionSplit(models),
+                             tb.FiniteElementDiscretization({"φₘ": tb.LagrangeCollection(1), "φₘi": tb.LagrangeCollection(1)}), grid)
+    heat, ionic = form.functions
+    n = heat.ndofs
+    md = tb.multidomain
+    iφ = md.solution_indices(form, "φₘ", tb.api)
+    assert iφ.size == n and np.array_equal(iφ, np.asarray(form.solution_indices[0]))
+    nf, ns_ = ionic.functions[0].block.npoints, ionic.functions[1].block.npoints
+    assert tb.solution_size(form) == 2 * nf + 7 * ns_ and nf + ns_ == n
+    ifast, islow = md.solution_indices(form, "sfast", tb.api), md.solution_indices(form, "sslow", tb.api)
+    assert ifast.size == nf and islow.size == 6 * ns_
+    assert np.intersect1d(ifast, islow).size == 0 and np.intersect1d(ifast, iφ).size == 0 and np.intersect1d(islow, iφ).size == 0
+    assert np.array_equal(np.sort(np.concatenate([iφ, ifast, islow])), np.arange(1, tb.solution_size(form) + 1))
+    u0 = tb.create_initial_condition(form)
+    exp = tb.default_initial_state(tb.PCG2019())
+    assert np.allclose(u0[islow - 1].reshape(-1, 6), exp[1:])             # point major: (ncomponents per point)
+    before = u0[islow - 1].copy()
+    u0[ifast - 1] = -1.0                                                   # writing one subdomain's state ...
+    assert np.array_equal(u0[islow - 1], before)                           # ... does not touch the other's
+    u0[ifast - 1] = 0.0
+    # a depolarised patch inside the FHN block, PCG2019 tissue at rest around it
+    xd = heat.dof_coords
+    blk0 = ionic.functions[0]
+    u0[iφ[blk0.subdofs] - 1] = np.maximum(1.0 - 2.0 * np.linalg.norm(xd[blk0.subdofs], axis=1), 0.0)
+    tol = dict(atol=1e-14, rtol=1e-13)
+    integ = tb.init(tb.OperatorSplittingProblem(form, u0.copy(), (0.0, 0.05)),
+                    tb.LieTrotterGodunov((tb.BackwardEulerSolver(inner_solver=tb.B200CG(**tol)), tb.AdaptiveForwardEulerSubstepper())), dt=0.01)
+    rowptr, colidx = heat.rowptr, heat.colidx
+    D2 = np.array([[1.0e-4, 0.0], [0.0, 1.0e-4]])
+    Mo, Ko = _oracle_operators(O, grid, ["Fast", "Slow"], heat.celldofs, n, rowptr, colidx, D2, 1.0)
+    name, d, xh, xt, G, q = heat.interfaces[0]
+    assert O.lib().orc_assemble_interface_diffusion(2, 2, q, d.shape[0], np.ascontiguousarray(d), np.ascontiguousarray(xh),
+                                                    np.ascontiguousarray(xt), G, rowptr, colidx, Ko) == 0
+    L_ = O.lib()
+    f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    L_.orc_cell_step_strided.argtypes = [C.c_int, f64, f64, f64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int]
+    uo, du = u0.copy(), np.zeros_like(u0)
+    Ao = O.axpby_values(Mo, Ko, 0.01)
+    for step in range(5):
+        assert tb.step_(integ)
+        x, ito, rno, convo = O.cg(rowptr, colidx, Ao, O.spmv(rowptr, colidx, Mo, uo[iφ - 1].copy()), **tol)
+        uo[iφ - 1] = x
+        for f, om in zip(ionic.functions, (O.FHN, O.PCG2019)):
+            b = f.block
+            seg, dseg = uo[b.offset:b.offset + b.nstates * b.npoints], du[b.offset:b.offset + b.nstates * b.npoints]
+            L_.orc_cell_step_strided(om, O.default_params(om), seg, dseg, b.npoints, b.nstates, 1, 0.01 * step, 0.01, 10, 0.1, 0)
+    h = integ.u.to_host()
+    scale = np.maximum(np.abs(uo), 1.0)
+    assert (np.abs(h - uo) / scale).max() <= 1e-9

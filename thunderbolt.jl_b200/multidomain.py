@@ -211,6 +211,7 @@ def semidiscretize_multidomain(split_models: dict, discretization, grid: Subdoma
         npoints = subdofs.size
         f = api.PointwiseODEFunction(ep.ion, None, range(offset + 1, offset + ns * npoints + 1), ep.internal_state_symbol)
         f.layout = PointBlockedLayout()
+        f.phi_symbol = ep.transmembrane_solution_symbol
         f.block = StateBlock(offset, npoints, ns, PointBlockedLayout())
         f.subdofs = subdofs
         inner.append(f)
@@ -220,6 +221,23 @@ def semidiscretize_multidomain(split_models: dict, discretization, grid: Subdoma
     if (heat_dofrange == 0).any():
         raise ValueError("The transmembrane potential field carries dofs that no bulk model claims")
     return api.GenericSplitFunction((heat, PointwiseMultiODEFunction(inner, None)), (heat_dofrange, range(1, offset + 1)))
+
+
+def solution_indices(f, sym: str, api) -> np.ndarray:
+    """1-based slots of a solution variable of a multi-subdomain split (solution_variables.jl): the shared transmembrane
+    potential symbol -> heat_dofrange (ordered by dof of the heat problem); a subdomain's internal-state symbol -> the
+    non-phi slots of that block, point major (all internal states of point 1, then point 2, ...)."""
+    heat, ionic = f.functions
+    if any(getattr(fn, "phi_symbol", None) == sym for fn in ionic.functions):
+        return np.asarray(f.solution_indices[0]).copy()
+    for fn in ionic.functions:
+        if fn.state_symbol == sym:
+            b = fn.block
+            φ = api.transmembranepotential_index(fn.ode)
+            k = np.arange(b.npoints)[:, None] * b.nstates
+            s = np.array([j for j in range(1, b.nstates + 1) if j != φ])[None, :]
+            return (b.offset + k + s).ravel()
+    raise KeyError(f"unknown solution variable {sym}")
 
 
 def create_initial_condition_multidomain(f, api) -> np.ndarray:
