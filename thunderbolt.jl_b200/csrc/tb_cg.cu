@@ -76,6 +76,7 @@ __global__ void k_cg_set_tol(CGState *st, double atol, double rtol, long long it
     st->done = 0;
     st->solved = 0;
     st->iter = 0;
+    st->beta = 0.0;   // the fused-p SpMV forms p = r + beta p_old: beta = 0 on the first iteration gives p0 = r0
 }
 
 // finishing step shared by the reducing kernels: single GPU -> advance the scalars here;
@@ -202,6 +203,56 @@ __global__ void __launch_bounds__(1024, 1)
     const tb_acc<X> bs = tb_block_sum_acc<X>(acc, sm);
     if (INIT) cg_finish<0, X>(bs, st, partials, ticket, sm, dist, ar);
     else cg_finish<1, X>(bs, st, partials, ticket, sm, dist, ar);
+}
+
+// ---- experiment: the p update inside the SpMV's gather (TB_SPMV_FUSEP=1; single GPU, unpreconditioned) ----------------
+// Ap = A (r + beta p_old), p_new = r + beta p_old for the own rows, p_new.Ap.  One launch less and 16 B/row less vector traffic
+// per iteration, paid with a second gather per matrix entry.  Same bits as k_cg_spmv_tma + k_cg_p.
+template <bool CC>
+__global__ void __launch_bounds__(1024, 1)
+    k_cg_spmv_fp(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col, const int *__restrict__ cstream,
+                 const int64_t *__restrict__ cptr, const double *__restrict__ val, const double *__restrict__ r,
+                 const double *__restrict__ p_old, double *__restrict__ p_new, double *__restrict__ Ap, int64_t nrows, int64_t nslices,
+                 unsigned val_bytes, unsigned col_bytes, CGState *st, double *partials, unsigned *ticket, const tb_wide_list wide) {
+    if (st->done) return;
+    extern __shared__ __align__(128) unsigned char tb_dyn_smem[];
+    __shared__ double sm[64];
+    const double beta = st->beta;
+    tb_acc<false> acc;
+    auto epi = [&](int64_t row, double v) {
+        if (row < nrows) {
+            const double pn = r[row] + beta * p_old[row];
+            p_new[row] = pn;
+            Ap[row] = v;
+            acc.add_prod(pn, v);
+        }
+    };
+    tb_sell_sweep_tma<1, CC, decltype(epi), true>(slice_ptr, val, cstream, cptr, r, nslices, val_bytes, col_bytes, tb_dyn_smem, epi, nullptr,
+                                                  col, wide, p_old, beta);
+    tb_ar_args ar;
+    ar.wins = nullptr;
+    cg_finish<1, false>(tb_block_sum_acc<false>(acc, sm), st, partials, ticket, sm, false, ar);
+}
+
+static int32_t launch_spmv_fp(tb_ctx *ctx, const tb_pattern *pat, const double *val, const double *r, const double *p_old, double *p_new,
+                              double *Ap, CGState *st, double *part, unsigned *tick) {
+    const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? pat->max_ccol_ints : 32 * pat->max_width_tma, 1, 0);
+    const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
+    const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);
+    tb_wide_list wide;
+    wide.slices = pat->d_wide_slices;
+    wide.n = (int)pat->n_wide;
+    if (cc) {
+        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_fp<true>, g.smem));
+        TB_LAUNCH(ctx, k_cg_spmv_fp<true>, grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_ccol, pat->d_cptr, val, r, p_old,
+                  p_new, Ap, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, wide);
+    } else {
+        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_cg_spmv_fp<false>, g.smem));
+        TB_LAUNCH(ctx, k_cg_spmv_fp<false>, grid, g.warps * 32, g.smem, pat->d_slice_ptr, pat->d_col, pat->d_col, nullptr, val, r, p_old,
+                  p_new, Ap, pat->nrows, pat->nslices, g.val_bytes, g.col_bytes, st, part, tick, wide);
+    }
+    return TB_OK;
 }
 
 template <int STAGES, bool INIT>
@@ -682,7 +733,18 @@ int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_c
             if (X) TB_LAUNCH(ctx, k_cg_p_fused<true>, grid_pf, 256, 0, r, p, n, sin, sout, ar2, dinv, pa, ctx->d_ticket + 6);
             else TB_LAUNCH(ctx, k_cg_p_fused<false>, grid_pf, 256, 0, r, p, n, sin, sout, ar2, dinv, pa, ctx->d_ticket + 6);
         }
-        for (int64_t k = 0; k < chunk && !fused; k++) {
+        const bool fusep = ctx->spmv_fusep && !dist && !gen_pc && !dinv && !X && tma;
+        for (int64_t k = 0; k < chunk && fusep; k++) {
+            const int64_t it = enq + k;
+            double *pp[2] = {p, ctx->d_cgwork + 3 * ctx->cgwork_ld};
+            const bool prof = ctx->profile && it < TB_PROF_MAX;
+            if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * it], ctx->stream));
+            TB_TRY(launch_spmv_fp(ctx, pat, A->d_val, r, pp[it & 1], pp[(it + 1) & 1], Ap, st, part, tick));
+            if (prof) TB_CUDA(cudaEventRecord(ctx->prof_ev[2 * it + 1], ctx->stream));
+            const tb_ar_args ar2 = cg_next_ar(ctx, false);
+            TB_LAUNCH(ctx, k_cg_xr<false>, grid_xr, 256, 0, x, r, pp[(it + 1) & 1], Ap, n, st, part + TB_MAX_PARTIALS, tick + 1, false, ar2, nullptr);
+        }
+        for (int64_t k = 0; k < chunk && !fused && !fusep; k++) {
             tb_hwait_args hw = nowait;
             if (peer_halo) TB_TRY(tb_halo_push(ctx, pat, p, st, &hw));
             else if (pat->halo.nneigh > 0) TB_TRY(tb_halo_exchange(ctx, pat, p));

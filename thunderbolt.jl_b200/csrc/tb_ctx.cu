@@ -78,6 +78,7 @@ static int32_t ctx_init(tb_ctx *ctx, int32_t device, void *stream) {
     if (const char *v = getenv("TB_CG_PERSISTENT")) ctx->cg_persistent = atoi(v) < 0 ? 0 : atoi(v) > 2 ? 2 : atoi(v);
     if (const char *v = getenv("TB_P2P_FUSED")) ctx->p2p_fused = atoi(v);
     if (const char *v = getenv("TB_DOT_EXACT")) ctx->exact_dot = atoi(v) != 0;
+    if (const char *v = getenv("TB_SPMV_FUSEP")) ctx->spmv_fusep = atoi(v) != 0;
     if (const char *v = getenv("TB_CG_PERSISTENT_MAX_ROWS")) ctx->cg_persistent_max_rows = atoll(v);
     if (const char *v = getenv("TB_ASSEMBLY_MODE")) ctx->assembly_mode = atoi(v) == 0 ? 0 : 2;
     if (const char *v = getenv("TB_EA_BUDGET_MB")) ctx->ea_budget_bytes = (size_t)(atof(v) * 1048576.0);
@@ -178,8 +179,8 @@ int32_t tb_ctx_ensure_cgwork(tb_ctx *ctx, int64_t n) {
         TB_CUDA(cudaFree(ctx->d_cgwork));
         ctx->d_cgwork = nullptr;
     }
-    TB_CUDA(cudaMalloc(&ctx->d_cgwork, sizeof(double) * 3 * (size_t)ld));
-    TB_CUDA(cudaMemsetAsync(ctx->d_cgwork, 0, sizeof(double) * 3 * (size_t)ld, ctx->stream));
+    TB_CUDA(cudaMalloc(&ctx->d_cgwork, sizeof(double) * 4 * (size_t)ld));   // r | p | Ap | p' (ping-pong partner of the fused-p experiment)
+    TB_CUDA(cudaMemsetAsync(ctx->d_cgwork, 0, sizeof(double) * 4 * (size_t)ld, ctx->stream));
     ctx->cgwork_ld = ld;
     return TB_OK;
 }

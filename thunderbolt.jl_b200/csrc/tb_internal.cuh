@@ -177,6 +177,7 @@ struct tb_ctx {
     int64_t last_cg_iters = 4;        // launch-ahead hint for the next solve
     int cg_persistent = 1;            // 0: never; 1: auto (small: register-resident kernel, mid-size: TMA kernel); 2: TMA kernel whenever eligible (tests); env TB_CG_PERSISTENT
     int last_cg_persistent = 0;       // path of the last solve: 0 multi-kernel, 1 persistent (registers), 2 persistent (TMA sweep, vectors in L2)
+    int spmv_fusep = 0;               // experiment (env TB_SPMV_FUSEP): p = r + beta p formed inside the SpMV's gather, no k_cg_p launch
     int exact_dot = 0;                // 1: CG dot products accumulated in double-double (order-independent after rounding; env TB_DOT_EXACT)
     int p2p_fused = 1;                // multi-GPU peer path: 1 = collects and halo push inside the CG kernels (3 launches per iteration), 0 = separate tiny kernels (env TB_P2P_FUSED)
     int64_t cg_persistent_max_rows = 4000000;   // above this the multi-kernel path is used (env TB_CG_PERSISTENT_MAX_ROWS)

@@ -16,13 +16,23 @@
 
 #define TB_CCOL_EXPLICIT INT32_MIN   // header value of a slot whose 32 column ids are stored explicitly
 
+// Gathered operand of the SpMV.  FP = false: x[c].  FP = true ("fused p update", experiment of VERDICT r1 item 10): the CG
+// direction p = r + beta p_old is formed on the fly from r (= x) and p_old (= x2) -- the same unfused multiply and add
+// k_cg_p performs, hence the same bits -- so that the separate p-update kernel and its 24 B/row disappear.
+template <bool FP>
+__device__ __forceinline__ double tb_gx(const double *__restrict__ x, const double *__restrict__ x2, double beta, int64_t c) {
+    if (FP) return x[c] + beta * x2[c];
+    return x[c];
+}
+
 // Row (s*32 + lane) of y = A x.  Entry j of the row is at slice_ptr[s] + j*32 + lane, so one warp
 // streams 256 B of values + 128 B of column ids per j, fully coalesced; the dependent x gathers hit
 // L1/L2 (neighbouring rows share columns).  The additions stay strictly left to right (and unfused,
 // -fmad=false) so the sum is bitwise the reference's.
+template <bool FP = false>
 __device__ __forceinline__ double tb_sell_row(const int64_t *__restrict__ slice_ptr, const int *__restrict__ col,
                                               const double *__restrict__ val, const double *__restrict__ x, int64_t s,
-                                              int lane) {
+                                              int lane, const double *__restrict__ x2 = nullptr, double beta = 0.0) {
     const int64_t base = slice_ptr[s];
     const int w = (int)((slice_ptr[s + 1] - base) >> 5);
     const int *c = col + base + lane;
@@ -32,13 +42,13 @@ __device__ __forceinline__ double tb_sell_row(const int64_t *__restrict__ slice_
     for (; j + 4 <= w; j += 4) {
         const int c0 = c[(j + 0) * 32], c1 = c[(j + 1) * 32], c2 = c[(j + 2) * 32], c3 = c[(j + 3) * 32];
         const double v0 = v[(j + 0) * 32], v1 = v[(j + 1) * 32], v2 = v[(j + 2) * 32], v3 = v[(j + 3) * 32];
-        const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
-        acc += v0 * x0;
-        acc += v1 * x1;
-        acc += v2 * x2;
-        acc += v3 * x3;
+        const double g0 = tb_gx<FP>(x, x2, beta, c0), g1 = tb_gx<FP>(x, x2, beta, c1), g2 = tb_gx<FP>(x, x2, beta, c2), g3 = tb_gx<FP>(x, x2, beta, c3);
+        acc += v0 * g0;
+        acc += v1 * g1;
+        acc += v2 * g2;
+        acc += v3 * g3;
     }
-    for (; j < w; j++) acc += v[j * 32] * x[c[j * 32]];
+    for (; j < w; j++) acc += v[j * 32] * tb_gx<FP>(x, x2, beta, c[j * 32]);
     return acc;
 }
 
@@ -120,13 +130,14 @@ struct tb_wide_list {
     int n = 0;
 };
 
-template <int STAGES, bool CC, class Epilogue>
+template <int STAGES, bool CC, class Epilogue, bool FP = false>
 __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ slice_ptr, const double *__restrict__ val,
                                                   const int *__restrict__ cstream, const int64_t *__restrict__ cptr,
                                                   const double *__restrict__ x, int64_t nslices, unsigned val_bytes,
                                                   unsigned col_bytes, unsigned char *smem, Epilogue epi,
                                                   tb_tma_ring *ring = nullptr, const int *__restrict__ col = nullptr,
-                                                  const tb_wide_list wide = tb_wide_list()) {
+                                                  const tb_wide_list wide = tb_wide_list(), const double *__restrict__ x2 = nullptr,
+                                                  double beta = 0.0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const size_t stage_bytes = (size_t)val_bytes + col_bytes;
     unsigned char *wbase = smem + (size_t)warp * STAGES * stage_bytes;
@@ -196,7 +207,7 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         for (int j0 = 0; j0 < w; j0 += 32) {
             const int j = j0 + lane;
             double prod = 0.0;
-            if (j < w) prod = v[(int64_t)j * 32] * x[c[(int64_t)j * 32]];
+            if (j < w) prod = v[(int64_t)j * 32] * tb_gx<FP>(x, x2, beta, c[(int64_t)j * 32]);
             const int m = w - j0 < 32 ? w - j0 : 32;
             for (int k = 0; k < m; k++) acc += __shfl_sync(0xffffffffu, prod, k);
         }
@@ -212,7 +223,7 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         double acc = 0.0;
         const bool wide_done = w > TB_TMA_WCAP && wide.n > 0;   // handled row by row above
         if (w > TB_TMA_WCAP) {
-            if (!wide_done) acc = tb_sell_row(slice_ptr, CC ? col : cstream, val, x, s, lane);   // not staged (see `issue`)
+            if (!wide_done) acc = tb_sell_row<FP>(slice_ptr, CC ? col : cstream, val, x, s, lane, x2, beta);   // not staged (see `issue`)
         } else if (CC) {
             // header: one int per slot (uniform offset or EXPLICIT); explicit blocks follow the padded header
             const int hdr_ints = (w + 3) & ~3;
@@ -223,13 +234,13 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
                 for (; j + 9 <= w; j += 9) {
                     double xv[9], vv[9];
 #pragma unroll
-                    for (int k = 0; k < 9; k++) xv[k] = x[row + sc[j + k]];
+                    for (int k = 0; k < 9; k++) xv[k] = tb_gx<FP>(x, x2, beta, row + sc[j + k]);
 #pragma unroll
                     for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
 #pragma unroll
                     for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
                 }
-                for (; j < w; j++) acc += sv[j * 32] * x[row + sc[j]];
+                for (; j < w; j++) acc += sv[j * 32] * tb_gx<FP>(x, x2, beta, row + sc[j]);
             }
             for (; j + 9 <= w; j += 9) {
                 double xv[9], vv[9];
@@ -238,7 +249,7 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
                     const int h = sc[j + k];                                  // broadcast read
                     int c = row + h;
                     if (h == TB_CCOL_EXPLICIT) c = sexp[(e++) * 32];          // warp-uniform branch
-                    xv[k] = x[c];
+                    xv[k] = tb_gx<FP>(x, x2, beta, c);
                 }
 #pragma unroll
                 for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
@@ -249,7 +260,7 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
                 const int h = sc[j];
                 int c = row + h;
                 if (h == TB_CCOL_EXPLICIT) c = sexp[(e++) * 32];
-                acc += sv[j * 32] * x[c];
+                acc += sv[j * 32] * tb_gx<FP>(x, x2, beta, c);
             }
         } else {
             const int *scl = sc + lane;
@@ -257,13 +268,13 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             for (; j + 9 <= w; j += 9) {
                 double xv[9], vv[9];
 #pragma unroll
-                for (int k = 0; k < 9; k++) xv[k] = x[scl[(j + k) * 32]];
+                for (int k = 0; k < 9; k++) xv[k] = tb_gx<FP>(x, x2, beta, scl[(j + k) * 32]);
 #pragma unroll
                 for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
 #pragma unroll
                 for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
             }
-            for (; j < w; j++) acc += sv[j * 32] * x[scl[j * 32]];
+            for (; j < w; j++) acc += sv[j * 32] * tb_gx<FP>(x, x2, beta, scl[j * 32]);
         }
         if (!wide_done) epi(s * TB_SLICE + lane, acc);
         // every lane has consumed its shared-memory operands (acc depends on all of them): the stage may be refilled
