@@ -207,9 +207,14 @@ def run_b200(args):
         # structured grid: every rank generates only its own cells from the closed-form first-touch numbering -- the global
         # grid never exists in HBM (tb_mesh_generate_grid_local)
         plane = (nel[0] + 1) * (nel[1] + 1) if dim == 3 else nel[0] + 1
-        part = tbd.partition_structured_grid(dev, ct, nel, (0.0,) * dim, lengths, dist, plane=plane if args.cut == "planes" else None)
-        mesh = part.mesh
         N_global = int(np.prod([n + 1 for n in nel]))
+        if os.environ.get("TB_BENCH_LOCAL_GRID", "1") != "0":
+            part = tbd.partition_structured_grid(dev, ct, nel, (0.0,) * dim, lengths, dist, plane=plane if args.cut == "planes" else None)
+        else:   # round-1 path: the global grid on every rank, cut on the device
+            full = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
+            part = tbd.partition_mesh(dev, full, dist, plane=plane if args.cut == "planes" else None)
+            full.free()
+        mesh = part.mesh
     else:
         mesh = tb.generate_mesh(ct, nel, (0.0,) * dim, lengths, device=dev)
         N_global = mesh.ndofs
