@@ -65,7 +65,7 @@ def hostmath():
     d = ROOT / "tests" / "hostmath"
     so = d / "libhostmath.so"
     srcs = [d / "hostmath.cpp", ROOT / "thunderbolt.jl_b200" / "csrc" / "tb_cells.cuh",
-            ROOT / "thunderbolt.jl_b200" / "csrc" / "tb_elements.cuh"]
+            ROOT / "thunderbolt.jl_b200" / "csrc" / "tb_elements.cuh", ROOT / "thunderbolt.jl_b200" / "csrc" / "tb_grid.cuh"]
     if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas",
                         "-shared", "-o", str(so), str(srcs[0])], check=True)
@@ -76,6 +76,8 @@ def hostmath():
     L.hm_tables.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), f64, f64, f64, f64]
     L.hm_element_matrix.argtypes = [C.c_int, C.c_int, C.c_int, f64, C.c_double, C.c_int, f64, C.c_double, C.c_int64, f64]
     L.hm_element_diffusion_full.argtypes = [C.c_int, C.c_int, f64, C.c_int, f64, C.c_double, C.c_int64, f64]
+    L.hm_grid_dofs.argtypes = [C.c_int, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
+                               np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
     L.hm_element_source.argtypes = [C.c_int, C.c_int, f64, C.c_int, f64, C.c_double, C.c_void_p, f64]
     return L
 

@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../thunderbolt.jl_b200/csrc/tb_cells.cuh"
 #include "../../thunderbolt.jl_b200/csrc/tb_elements.cuh"
+#include "../../thunderbolt.jl_b200/csrc/tb_grid.cuh"
 
 template <int NV> static void unpack(const double *acc, double *full) {
     for (int i = 0; i < NV; i++)
@@ -11,6 +12,22 @@ template <int NV> static void unpack(const double *acc, double *full) {
 }
 
 extern "C" {
+
+// closed-form first-touch dof id of every node of a structured Quadrilateral (dim 2) / Hexahedron (dim 3) grid
+void hm_grid_dofs(int dim, const int64_t *nel, int64_t *node2dof) {
+    GridDesc g;
+    g.celltype = dim == 2 ? 0 : 1;
+    g.dim = dim;
+    for (int d = 0; d < 3; d++) {
+        g.nel[d] = d < dim ? nel[d] : 1;
+        g.nn[d] = d < dim ? nel[d] + 1 : 1;
+        g.left[d] = 0.0;
+        g.right[d] = 1.0;
+    }
+    for (int64_t c = 0; c < g.nn[2]; c++)
+        for (int64_t b = 0; b < g.nn[1]; b++)
+            for (int64_t a = 0; a < g.nn[0]; a++) node2dof[(c * g.nn[1] + b) * g.nn[0] + a] = tb_grid_dof(g, a, b, c);
+}
 
 double hm_cell_node_step(int model, int adaptive, const double *prm, double *u, double t, double dt, int substeps, double thr) {
     tb_cell_params P;

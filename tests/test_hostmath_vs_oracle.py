@@ -153,3 +153,15 @@ def test_pcg2019_node_step(oracle, hostmath):
             d = hostmath.hm_cell_node_step(1, int(sub > 1), prm, b, 0.0, 0.01, sub, 0.1)
             assert np.array_equal(a, b)          # same libm exp on the host: bitwise
             assert d == du[0]
+
+
+@pytest.mark.parametrize("nel", [(4, 3, 5), (1, 1, 1), (2, 5, 1), (7, 1, 3), (5, 4), (1, 3), (6, 1)])
+def test_closed_form_first_touch_numbering(hostmath, oracle, nel):
+    """tb_grid_dof (the numbering tb_mesh_generate_grid_local builds local meshes from, no global grid in HBM) against the
+    oracle's close! restatement on the whole grid"""
+    O = oracle
+    dim = len(nel)
+    m = O.generate_grid(O.HEX8 if dim == 3 else O.QUAD4, nel, (0,) * dim, (1,) * dim)
+    got = np.empty(m.nnodes, dtype=np.int64)
+    hostmath.hm_grid_dofs(dim, np.array(list(nel) + [1] * (3 - dim), dtype=np.int64), got)
+    assert np.array_equal(got, m.node2dof)
