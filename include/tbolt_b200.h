@@ -363,6 +363,15 @@ int32_t tb_csr_diagonal(const tb_csr *A, tb_vec *d, int32_t col);
 int32_t tb_csr_apply_zero(tb_csr *A, const tb_index *constrained, double diag_value);
 int32_t tb_vec_fill_at(tb_vec *v, int32_t col, const tb_index *ix, double value);
 
+/* ---- output staging for store_timestep_field! (src/ferrite-addons/io.jl:18-93) -----------------------------------------
+ * A snapshot of one state column is copied to PINNED host memory on a dedicated copy stream, ordered after the work already
+ * queued on the compute stream; the call returns at once, later kernels that overwrite the column wait for the copy, the
+ * host writer reads the buffer after tb_stage_wait.  The hot path never blocks on I/O. */
+int32_t tb_host_alloc(int64_t bytes, void **out);   /* cudaMallocHost */
+int32_t tb_host_free(void *p);
+int32_t tb_vec_stage_col(const tb_vec *v, int32_t col, double *pinned_host);
+int32_t tb_stage_wait(tb_ctx *ctx);
+
 /* ---- fused LieTrotterGodunov step -------------------------------------------------------------
  * One OS.LieTrotterGodunov((BackwardEulerSolver, cell solver)) step (operatorsplitting-interface.jl:23-232;
  * perform_backward_euler_step!, euler.jl:71-101; partitioned_solver.jl:14-21): refresh A when dt

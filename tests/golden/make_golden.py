@@ -171,7 +171,9 @@ def c4_mid_1000():
     N = m.ndofs
     print("dofs", N, "tets", tets.shape[0], flush=True)
     u = np.repeat(O.default_initial_state(O.PCG2019), N)
-    orc = O.MonodomainOracle(m, O.PCG2019, O.default_params(O.PCG2019), M, K, threaded_blas1=True)
+    # dot mode 2: order-free (double-double) dot products, so that the iteration counts do not depend on a summation order
+    # no other implementation could reproduce; the GPU test runs tb_cg_set_exact_dot against this golden
+    orc = O.MonodomainOracle(m, O.PCG2019, O.default_params(O.PCG2019), M, K, threaded_blas1=2)
     SRC = [0.0, 0.2, 0.3, 0.25]
     out, t, dt = {}, 0.0, 0.01
     act = np.full(u[:N:13].size, -1, dtype=np.int16)

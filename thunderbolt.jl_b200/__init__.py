@@ -8,6 +8,6 @@ from . import _lib
 from ._lib import TBError, build, declared_symbols
 from .core import *  # noqa: F401,F403
 from .api import *  # noqa: F401,F403
-from . import core, api, multidomain, ecg
+from . import core, api, multidomain, ecg, io
 from .multidomain import (InterfaceDiffusionModel, PointBlockedLayout, PointwiseMultiODEFunction, StateBlock,  # noqa: F401
                           StateBlockedLayout, SubdomainGrid, insert_interfaces, state_range)

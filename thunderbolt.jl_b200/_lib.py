@@ -160,6 +160,10 @@ _SIGNATURES = {
     "tb_csr_diagonal": [_vp, _vp, C.c_int32],
     "tb_csr_apply_zero": [_vp, _vp, C.c_double],
     "tb_vec_fill_at": [_vp, C.c_int32, _vp, C.c_double],
+    "tb_host_alloc": [C.c_int64, _pp],
+    "tb_host_free": [_vp],
+    "tb_vec_stage_col": [_vp, C.c_int32, _vp],
+    "tb_stage_wait": [_vp],
     "tb_monodomain_create": [_vp, _vp, _vp, C.c_int32, _f64p, C.c_int32, C.c_int32, _pp],
     "tb_monodomain_destroy": [_vp],
     "tb_monodomain_set_cg": [_vp, C.c_double, C.c_double, C.c_int64],

@@ -109,6 +109,10 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2 * TB_PROF_MAX; i++)
         if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
+    if (ctx->stage_stream) {
+        cudaStreamDestroy(ctx->stage_stream);
+        cudaEventDestroy(ctx->stage_ev);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TB_OK;

@@ -170,6 +170,8 @@ struct tb_ctx {
     size_t ea_budget_bytes = (size_t)8 << 30;   // scratch for element matrices per chunk (env TB_EA_BUDGET_MB)
     struct tb_elem_tables *d_tables[4][5] = {};   // quadrature/shape tables per (cell type, order), uploaded once (tb_assembly.cu)
     int tables_nq[4][5] = {};
+    cudaStream_t stage_stream = nullptr;   // output staging (tb_vec_stage_col)
+    cudaEvent_t stage_ev = nullptr;
     void *d_ea = nullptr;             // cached scratch of the vector (per-step source) assembly
     size_t ea_bytes = 0;
     int spmv_variant = 1;             // 0: LDG kernel, 1..: bulk-async (TMA) staged kernel configurations (env TB_SPMV_VARIANT)

@@ -451,3 +451,39 @@ extern "C" int32_t tb_vec_fill_at(tb_vec *v, int32_t col, const tb_index *ix, do
     if (ix->n) TB_LAUNCH(ctx, k_fill_at, tb_grid_for(ctx, ix->n, 256, 4), 256, 0, v->d + (size_t)col * v->ld, ix->d, ix->n, value);
     return TB_OK;
 }
+
+// ---- output staging (store_timestep_field!, src/ferrite-addons/io.jl:18-93) ----------------------------------------------------
+// A snapshot of one state column leaves the device on its own copy stream, ordered after the work already queued on the
+// compute stream, into caller-provided PINNED host memory (tb_host_alloc); stepping continues while the copy and the
+// writer (host) run.  tb_stage_wait blocks until every staged snapshot has landed.
+extern "C" int32_t tb_host_alloc(int64_t bytes, void **out) {
+    TB_REQUIRE(out && bytes > 0, "tb_host_alloc: bad argument");
+    *out = nullptr;
+    TB_CUDA(cudaMallocHost(out, (size_t)bytes));
+    return TB_OK;
+}
+extern "C" int32_t tb_host_free(void *p) {
+    if (p) TB_CUDA(cudaFreeHost(p));
+    return TB_OK;
+}
+extern "C" int32_t tb_vec_stage_col(const tb_vec *v, int32_t col, double *pinned_host) {
+    TB_REQUIRE(v && pinned_host && col >= 0 && col < v->ncols, "tb_vec_stage_col: bad argument");
+    tb_ctx *ctx = v->ctx;
+    TB_DEV(ctx);
+    if (!ctx->stage_stream) {
+        TB_CUDA(cudaStreamCreateWithFlags(&ctx->stage_stream, cudaStreamNonBlocking));
+        TB_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+    }
+    TB_CUDA(cudaEventRecord(ctx->stage_ev, ctx->stream));                 // the state as of the work queued so far
+    TB_CUDA(cudaStreamWaitEvent(ctx->stage_stream, ctx->stage_ev, 0));
+    TB_CUDA(cudaMemcpyAsync(pinned_host, v->d + (size_t)col * v->ld, sizeof(double) * (size_t)v->n, cudaMemcpyDeviceToHost, ctx->stage_stream));
+    // the compute stream must not overwrite the column before the copy has read it
+    TB_CUDA(cudaEventRecord(ctx->stage_ev, ctx->stage_stream));
+    TB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_ev, 0));
+    return TB_OK;
+}
+extern "C" int32_t tb_stage_wait(tb_ctx *ctx) {
+    TB_REQUIRE(ctx, "tb_stage_wait: ctx is NULL");
+    if (ctx->stage_stream) TB_CUDA(cudaStreamSynchronize(ctx->stage_stream));
+    return TB_OK;
+}
