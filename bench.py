@@ -373,6 +373,24 @@ def run_b200(args):
         else:
             bytes_step = ns * n_local * 8
         t += (ke + 1) * dt
+        sweep = None
+        if args.e2e_chunk_sweep:      # experiment: pieces of the phi column in the chunk-chased round trip
+            sweep = {}
+            for nch in (int(v) for v in args.e2e_chunk_sweep.split(",")):
+                st.set_host_chunks(nch)
+                st.run_host(u, hout.numpy(), hin.numpy(), t, dt, 1)
+                barrier()
+                t0 = time.perf_counter()
+                st.run_host(u, hin.numpy(), hout.numpy(), t + dt, dt, ke)
+                dev.sync()
+                ts = time.perf_counter() - t0
+                if world > 1:
+                    tt = torch.tensor([ts], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    ts = float(tt.item())
+                sweep[str(nch)] = ts / ke * 1e3
+                t += (ke + 1) * dt
+            st.set_host_chunks(16)
         # what the host link gives each rank while ALL ranks copy at once, both directions at once (the platform bound of e2e)
         nb_probe = min(ns * n_local, 1 << 25)
         dprobe = [torch.empty(nb_probe, dtype=torch.float64, device="cuda") for _ in range(2)]
@@ -399,6 +417,7 @@ def run_b200(args):
                "exposed_ms_measured": te / ke * 1e3 - ms / args.steps,
                "value": N_global * ke / te, "unit": "DoF*steps/s", "h2d_bytes_per_step": bytes_step,
                "d2h_bytes_per_step": bytes_step, "steps": ke, "ms_per_step": te / ke * 1e3,
+               **({"ms_per_step_by_phi_chunks": sweep} if sweep else {}),
                "api": "tb_monodomain_run_host (C ABI): state in pinned host buffers between steps, full state H2D + D2H every "
                       "step, copies pipelined on two copy streams (phi download/upload full duplex in chunks, other columns under CG); exposed time per step = the phi column's "
                       "round trip over the host link (download of step n, upload as step n+1's input), which no schedule can hide because "
@@ -553,6 +572,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--grid", default="", help="override cells per direction, e.g. 128,128,32")
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end (host-buffer) measurement; -1 = same as --steps, 0 = skip")
+    ap.add_argument("--e2e-chunk-sweep", default="", help="experiment: also time the e2e loop with these phi chunk counts, e.g. 2,4,8,32")
     ap.add_argument("--cpu-layers", type=int, default=48,
                     help="z-layers of cells in the --impl reference sample (48 = the 1/8 slab of C5 BASELINE.md states)")
     ap.add_argument("--cpu-inline-layers", type=int, default=16, help="z-layers of the cpu_baseline sample printed by the b200 arm")

@@ -77,6 +77,7 @@ extern "C" {
 #define TB_SRC_COSEXP 3
 #define TB_SRC_NORMT 4
 #define TB_SRC_ENDO 5
+#define TB_SRC_PROGRAM 6 /* a traced closure, see tb_assemble_source_program */
 
 typedef struct tb_ctx tb_ctx;
 typedef struct tb_vec tb_vec;
@@ -226,7 +227,15 @@ int32_t tb_assemble_diffusion(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, 
                               int64_t ndata, double cm_chi, tb_csr *K);
 int32_t tb_assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, int32_t kind, const double *prm,
                            int32_t nprm, double t, tb_vec *b, int32_t bcol);
-/* general closure path: fq[cell*nq + q] = f(x_q, t) evaluated by the host */
+/* Traced closure: the AnalyticalCoefficient's f(x, t) (analytical_coefficient.jl:80-101 evaluates it at every quadrature
+ * point) is called ONCE on the host with tracing numbers and shipped as a postfix program, code[i] = op | arg << 8 with
+ * op one of (in this order, from 0): X(arg = coordinate) T CONST(arg = index into consts) | ADD SUB MUL DIV MIN MAX POW
+ * LT LE GT GE EQ NE AND OR (binary; comparisons give 1.0 / 0.0) | NEG ABS SQRT EXP LOG SIN COS TANH NOT (unary) |
+ * SELECT (cond a b -> cond != 0 ? a : b).  At most 96 instructions, 24 constants, stack depth 16.  Evaluated on the
+ * device in plain IEEE fp64 in program order: nothing but the 400-byte program crosses the host link, per call. */
+int32_t tb_assemble_source_program(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, const int32_t *code, int32_t ncode,
+                                   const double *consts, int32_t nconsts, double t, tb_vec *b, int32_t bcol);
+/* general closure path (anything the tracer cannot express): fq[cell*nq + q] = f(x_q, t) evaluated by the host */
 int32_t tb_assemble_source_qp(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, const double *fq, tb_vec *b,
                               int32_t bcol);
 /* Assembly strategy (FerriteOperators' strategies: sequential / per-colour / per-element, SURVEY a-10):
@@ -290,6 +299,9 @@ int32_t tb_cg_set_chebyshev(tb_ctx *ctx, int32_t degree, double ratio);
  * mode 0 = never, 1 = auto (default), 2 = path 2 whenever it is eligible (lets the tests reach it on tiny systems).
  * tb_cg_last_path reports the path of the last solve. */
 int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t mode);
+/* register-resident persistent kernel (operators up to ~300 k rows): 2 (default) = two flag barriers per iteration, the
+ * direction of the gathered columns formed on the fly; 1 = three cooperative grid barriers.  Bitwise equal results. */
+int32_t tb_cg_set_persistent_variant(tb_ctx *ctx, int32_t variant);
 int32_t tb_cg_last_path(tb_ctx *ctx, int32_t *path);
 /* Order-independent dot products (off by default; env TB_DOT_EXACT=1).  Krylov's cg! forms r.r and p.Ap with BLAS `dot`
  * (euler.jl:94 -> KrylovJL_CG); any two implementations differ in summation order, and on ill-conditioned operators
@@ -405,6 +417,9 @@ int32_t tb_monodomain_step_host(tb_monodomain *md, tb_vec *u_dev, const double *
  * columns travel while CG runs (the diffusion solve only needs phi).  Pinned buffers are required for the overlap. */
 int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u_dev, double *buf0, double *buf1, double t0, double dt,
                                int64_t nsteps, int64_t *iters_total, int32_t *all_converged);
+/* number of pieces (1..64, default 16 or env TB_RUNHOST_CHUNKS) the phi column is cut into for the chunk-chased
+ * download / upload of tb_monodomain_run_host */
+int32_t tb_monodomain_set_host_chunks(tb_monodomain *md, int32_t nchunks);
 /* per-section CUDA-event timings of the last step, ms: [0] "b = M u", [1] "inner solve",
  * [2] "reaction solve" (the reference's TimerOutputs labels, euler.jl:85,94; partitioned_solver.jl:20) */
 int32_t tb_monodomain_section_ms(tb_monodomain *md, double *ms3);

@@ -12,6 +12,7 @@ Timed on the library's stream with CUDA events (tb_timer_*), after one warm-up c
 import argparse
 import json
 import sys
+import time
 from pathlib import Path
 
 import numpy as np
@@ -27,6 +28,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--modes", default="2,0")
     ap.add_argument("--cells", default="hex,tet")
+    ap.add_argument("--warm-s", type=float, default=0.4, help="seconds of untimed repetitions before each timed loop")
     args = ap.parse_args()
     nel = tuple(int(v) for v in args.grid.split(","))
     dev = tb.B200Device(0)
@@ -53,6 +55,11 @@ def main():
             for fname, (fn, bytes_per_el) in forms.items():
                 fn()                                   # warm-up (builds the adjacency cache in mode 2)
                 dev.sync()
+                t_w = time.perf_counter()              # keep the GPU busy until its clocks have left the idle state (a box
+                while time.perf_counter() - t_w < args.warm_s:   # that sat idle during host-side setup ramps up over ~0.1 s)
+                    for _ in range(args.reps):
+                        fn()
+                    dev.sync()
                 dev.timer_start()
                 for _ in range(args.reps):
                     fn()

@@ -79,6 +79,8 @@ def hostmath():
     L.hm_grid_dofs.argtypes = [C.c_int, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
                                np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
     L.hm_element_source.argtypes = [C.c_int, C.c_int, f64, C.c_int, f64, C.c_double, C.c_void_p, f64]
+    L.hm_program_eval.argtypes = [C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_int, f64, C.c_int,
+                                  f64, C.c_int, C.c_double, f64]
     return L
 
 

@@ -97,4 +97,15 @@ int hm_element_source(int celltype, int qorder, const double *X, int kind, const
     }
     return 0;
 }
+
+// traced source program (tb_program_build + tb_program_eval) at npts points; returns tb_program_build's code
+int hm_program_eval(int dim, const int32_t *code, int ncode, const double *consts, int nconsts, const double *x, int npts,
+                    double t, double *out) {
+    tb_src_program P;
+    const int rc = tb_program_build(code, ncode, consts, nconsts, dim, &P);
+    if (rc) return rc;
+    for (int i = 0; i < npts; i++)
+        out[i] = dim == 2 ? tb_program_eval<2>(P, x + 2 * i, t) : tb_program_eval<3>(P, x + 3 * i, t);
+    return 0;
+}
 }

@@ -149,3 +149,45 @@ def test_jacobi_pcg_matches_oracle(tb, dev, oracle, ct, nel, dt, cg_path):
     assert it <= it_plain + 2      # (near-)uniform diagonals: Jacobi must at least not hurt
     for h in (M, K, A, bd, xd, md):
         h.free()
+
+
+@pytest.mark.parametrize("ct,nel", [(0, (64, 48)), (0, (256, 256)), (1, (50, 50, 50)), (1, (64, 64, 60))])
+def test_persistent_variants_bitwise(tb, dev, oracle, ct, nel, cg_path):
+    """The register-resident persistent CG with two flag barriers per iteration (direction of the gathered columns formed on the
+    fly) against the three-grid.sync kernel: same partial-sum order, same unfused p = z + beta p, hence the same bits -- x,
+    iteration count and residual norm -- at 1, 2 and 4 rows per lane, plain and Jacobi-preconditioned, from b and fused
+    with b = M u."""
+    if cg_path != "persistent":
+        pytest.skip("register-resident kernels only")
+    md = tb.generate_mesh([tb.Quadrilateral, tb.Hexahedron][ct], nel, (0.0,) * len(nel), tuple(0.25 * n for n in nel), device=dev)
+    M = tb.B200CSRMatrix.from_mesh(dev, md)
+    K, A = M.like(), M.like()
+    tb.core.assemble_mass(dev, md, M, 2, 1.0)
+    tb.core.assemble_diffusion(dev, md, K, 2, tb._lib.D_TENSOR, np.diag([0.13, 0.02, 0.02][:len(nel)]), 1.0)
+    A.axpby_values(M, K, 0.7)
+    n = md.ndofs
+    rng = np.random.default_rng(4)
+    bd, xd = tb.B200Vector.from_host(dev, rng.standard_normal(n)), tb.B200Vector(dev, n)
+    res = {}
+    for variant in (1, 2):
+        dev.cg_set_persistent_variant(variant)
+        for precond in (tb._lib.PRECOND_NONE, tb._lib.PRECOND_JACOBI):
+            for tol in ((oracle.SQRT_EPS, oracle.SQRT_EPS), (1e-13, 1e-13)):
+                it, rn, conv = tb.core.cg_solve(dev, A, bd, xd, *tol, precond=precond)
+                assert conv and dev.cg_last_path() == 1
+                res[(variant, precond, tol)] = (it, rn, xd.to_host().copy())
+        ion = tb.ParametrizedFHNModel()
+        st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+        u = tb.B200Vector.from_host(dev, np.concatenate([rng.uniform(0, 1, n), np.zeros(n)]) if variant == 1 else res["u0"], 2)
+        if variant == 1:
+            res["u0"] = u.to_host().copy()
+        its = [st.step(u, float(k), 0.7)[0] for k in range(5)]
+        res[(variant, "step")] = (its, u.to_host().copy())
+        st.free(); u.free()
+    dev.cg_set_persistent_variant(2)
+    for key in [k for k in res if isinstance(k, tuple) and k[0] == 1 and k[1] != "step"]:
+        a, b = res[key], res[(2,) + key[1:]]
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]), key
+    assert res[(1, "step")][0] == res[(2, "step")][0] and np.array_equal(res[(1, "step")][1], res[(2, "step")][1])
+    for h in (M, K, A, bd, xd, md):
+        h.free()

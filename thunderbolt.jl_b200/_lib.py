@@ -134,6 +134,7 @@ _SIGNATURES = {
     "tb_assemble_diffusion": [_vp, _vp, C.c_int32, C.c_int32, _f64p, C.c_int64, C.c_double, _vp],
     "tb_assemble_source": [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_double, _vp, C.c_int32],
     "tb_assemble_source_qp": [_vp, _vp, C.c_int32, _f64p, _vp, C.c_int32],
+    "tb_assemble_source_program": [_vp, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_double, _vp, C.c_int32],
     "tb_assembly_set_mode": [_vp, C.c_int32],
     "tb_assembly_info": [_vp, _pi32, _pi32, _pi32],
     "tb_assembly_set_scratch_budget": [_vp, C.c_int64],
@@ -144,6 +145,7 @@ _SIGNATURES = {
     "tb_cg_solve_pc": [_vp, _vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int64, _pi64, _pf64, _pi32],
     "tb_monodomain_set_preconditioner": [_vp, C.c_int32],
     "tb_cg_set_persistent": [_vp, C.c_int32],
+    "tb_cg_set_persistent_variant": [_vp, C.c_int32],
     "tb_cg_last_path": [_vp, _pi32],
     "tb_cg_set_exact_dot": [_vp, C.c_int32],
     "tb_cg_set_block_jacobi": [_vp, C.c_int64, C.c_int64, _vp],
@@ -173,6 +175,7 @@ _SIGNATURES = {
     "tb_monodomain_step_rt": [_vp, _vp, C.c_double, C.c_double, _pi64, _pf64, _pi32, _pf64],
     "tb_monodomain_run": [_vp, _vp, C.c_double, C.c_double, C.c_int64, _pi64, _pi32],
     "tb_monodomain_run_host": [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int64, _pi64, _pi32],
+    "tb_monodomain_set_host_chunks": [_vp, C.c_int32],
     "tb_monodomain_step_host": [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _pi64, _pf64, _pi32],
     "tb_monodomain_section_ms": [_vp, _pf64],
     "tb_monodomain_enable_timing": [_vp, C.c_int32],

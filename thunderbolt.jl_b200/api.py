@@ -22,7 +22,10 @@ import numpy as np
 
 from . import _lib as L
 from . import core
+from . import trace
 from .core import B200CSRMatrix, B200Device, B200Vector, DeviceMesh, SQRT_EPS
+
+TRACE_CLOSURES = True      # False: every closure takes the host-evaluated path (tests compare the two)
 
 # ---------------------------------------------------------------------------------------------
 # cells
@@ -596,14 +599,24 @@ def update_operator_(op, t):
     f = op.integrator.integrand.f.f
     if hasattr(f, "kind"):
         core.assemble_source(dev, dh, op.b, q, f.kind, f.prm(), t)
-    else:
-        # arbitrary closure: evaluate at the quadrature points on the host (a closure cannot cross the C ABI)
+        return
+    # a closure cannot cross the C ABI, its expression can: trace it once into a postfix program the element kernel
+    # evaluates at every quadrature point (trace.py); nothing but the program travels per update
+    if not hasattr(op, "_program"):
+        op._program = trace.trace_source(f, dh.dim) if TRACE_CLOSURES else None
+    if op._program is not None:
+        core.assemble_source_program(dev, dh, op.b, q, op._program.code, op._program.consts, t)
+        return
+    # untraceable closure (Python control flow on x or t): evaluate at the quadrature points on the host; the points are
+    # computed once per operator
+    if getattr(op, "_xq", None) is None:
         conn, coords, _ = dh.download()
         pts, _w = core.quadrature(dh.celltype, q)
         N = _shape_values(dh.celltype, pts)                       # nq x nv
-        xq = np.einsum("qa,cad->cqd", N, coords[conn])            # ncells x nq x dim
-        fq = np.array([[f(xq[c, k], t) for k in range(xq.shape[1])] for c in range(xq.shape[0])])
-        core.assemble_source_qp(dev, dh, op.b, q, fq)
+        op._xq = np.einsum("qa,cad->cqd", N, coords[conn])        # ncells x nq x dim
+    xq = op._xq
+    fq = np.array([[f(xq[c, k], t) for k in range(xq.shape[1])] for c in range(xq.shape[0])])
+    core.assemble_source_qp(dev, dh, op.b, q, fq)
 
 
 def _shape_values(celltype, pts):

@@ -63,6 +63,10 @@ class B200Device:
         return ms.value, n.value
 
     # ---- CG execution model ----
+    def cg_set_persistent_variant(self, variant):
+        """register-resident persistent CG: 2 (default) two flag barriers per iteration, 1 three grid-wide barriers"""
+        L.call("tb_cg_set_persistent_variant", self.h, int(variant))
+
     def cg_set_persistent(self, mode):
         """whole CG solve in one cooperative kernel: 0/False never, 1/True auto (default), 2 the TMA-staged variant
         whenever eligible (single GPU only)"""
@@ -416,6 +420,14 @@ def assemble_source(dev, mesh, b: B200Vector, qorder, kind, prm, t, col=0):
     L.call("tb_assemble_source", dev.h, mesh.h, int(qorder), int(kind), L.ptr(prm), prm.size, float(t), b.h, int(col))
 
 
+def assemble_source_program(dev, mesh, b: B200Vector, qorder, code, consts, t, col=0):
+    """f(x, t) as a traced postfix program (api.trace_source): evaluated on the device at every quadrature point."""
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    consts = np.ascontiguousarray(np.atleast_1d(np.asarray(consts, dtype=np.float64)).ravel())
+    L.call("tb_assemble_source_program", dev.h, mesh.h, int(qorder), L.ptr(code), code.size, L.ptr(consts), consts.size,
+           float(t), b.h, int(col))
+
+
 def assemble_source_qp(dev, mesh, b: B200Vector, qorder, fq, col=0):
     fq = np.ascontiguousarray(fq, dtype=np.float64).ravel()
     L.call("tb_assemble_source_qp", dev.h, mesh.h, int(qorder), fq, b.h, int(col))
@@ -503,6 +515,9 @@ class MonodomainStepper:
         L.call("tb_monodomain_run_host", self.h, u_dev.h, L.ptr(buf0), L.ptr(buf1), float(t0), float(dt), int(nsteps),
                C.byref(it), C.byref(cv))
         return it.value, bool(cv.value)
+
+    def set_host_chunks(self, nchunks: int):
+        L.call("tb_monodomain_set_host_chunks", self.h, int(nchunks))
 
     def step_host(self, u_dev: B200Vector, u_in: np.ndarray, u_out: np.ndarray, t, dt):
         it, rn, cv = C.c_int64(), C.c_double(), C.c_int32()

@@ -50,9 +50,16 @@ extern "C" int32_t tb_quadrature(int32_t celltype, int32_t qorder, int32_t *nq, 
     return TB_OK;
 }
 
-struct SrcParams {
+struct SrcParams {      // travels by value as a kernel argument
     double p[8];
+    tb_src_program prog;   // used when kind == TB_SRC_PROGRAM
 };
+__device__ __forceinline__ void stage_program(const SrcParams &prm, int kind, tb_src_program *sprog) {
+    if (kind != TB_SRC_PROGRAM) return;
+    const int *src = reinterpret_cast<const int *>(&prm.prog);
+    int *dst = reinterpret_cast<int *>(sprog);
+    for (int i = threadIdx.x; i < (int)(sizeof(tb_src_program) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+}
 
 struct SellView {
     const int64_t *rowptr;
@@ -155,7 +162,10 @@ __global__ void __launch_bounds__(AS_BLOCK)
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
     const tb_tables_view sT{nq, sW, sN, sdN};
     __shared__ double sprm[8];
+    __shared__ tb_src_program sprog;
     if (threadIdx.x < 8) sprm[threadIdx.x] = prm.p[threadIdx.x];
+    stage_program(prm, kind, &sprog);
+    const tb_src_program *prog = kind == TB_SRC_PROGRAM ? &sprog : nullptr;
     const int64_t ntiles = (ncells + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t e0 = tile * AS_BLOCK;
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
         const int64_t e = e0 + threadIdx.x;
         if (e < ncells) {
             double be[NV];
-            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * nq : nullptr, be);
+            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * nq : nullptr, be, prog);
 #pragma unroll
             for (int j = 0; j < NV; j++) {
                 const int d = sDof[threadIdx.x * NV + j];
@@ -394,6 +404,182 @@ __global__ void __launch_bounds__(AS_BLOCK)
     }
 }
 
+// ---- phase 1, split form (default): geometry per (element, point), then one thread per element-matrix column group ----
+// One thread per element keeps the whole NV x NV matrix in registers (hex: 64 accumulators + 24 gradients = the 255
+// register limit, 8 warps per SM, fp64 pipe 62 % busy waiting on its own dependent instructions).  Here a CTA works on a
+// tile of TE elements in two alternating phases over batches of qb quadrature points:
+//   A  one thread per (element, point): J, det J, J^-1, the NV spatial gradients and dOmega (and the diffusion tensor when
+//      it varies per point) -> shared memory, element index fastest (bank-conflict free);
+//   B  NV / CPT threads per element, each owning CPT adjacent columns j of Ke (NV * CPT accumulators): for every point of
+//      the batch it reads the element's gradients (broadcast within the element's threads), forms gradN_j . D once per
+//      column and subtracts ((gradN_j . D) . gradN_i) dOmega for all i -- the same operations in the same order as the
+//      one-thread kernel (tb_element_diffusion_full), so Ke is bit for bit the same; only the leading "0.0 +" of each
+//      short dot product is dropped (it can only change the sign of an exact zero, which no accumulator can observe:
+//      they start at +0.0 and x - (+-0) = x, (+0) - (+-0) = +0).
+// The element's threads hold adjacent columns, so EA[cell][i][j0..j0+CPT) leaves as 16 B (CPT = 2) stores that fill whole
+// sectors; no transposition tile is needed.
+template <int NV, int DIM, int OP, int CPT, int TE>
+__global__ void __launch_bounds__(TE *(NV / CPT), 2)
+    k_element_matrices_split(const int *__restrict__ conn, const double *__restrict__ coords, int64_t c0, int64_t c1,
+                             const tb_elem_tables *__restrict__ gT, int nq, int qb, double rho, int kind,
+                             const double *__restrict__ ddata, double cmchi, double *__restrict__ EA, int64_t ea_si, int ea_sc) {
+    static_assert(NV % CPT == 0, "columns per thread must divide the element size");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TPE = NV / CPT, BLOCK = TE * TPE, NG = NV * DIM;
+    constexpr int GS = OP == 1 ? NG + 1 : 1;            // doubles per (element, point): gradients + dOmega | dOmega
+    double *sW = reinterpret_cast<double *>(smem_raw);
+    double *sN = sW + nq;
+    double *sdN = sN + nq * NV;
+    double *sX = sdN + nq * NV * DIM;
+    double *sG = sX + NG * TE;
+    double *sDq = sG + (size_t)qb * GS * TE;            // per-point tensors (kind >= 2 only)
+    for (int i = threadIdx.x; i < nq; i += BLOCK) sW[i] = gT->w[i];
+    for (int i = threadIdx.x; i < nq * NV; i += BLOCK) sN[i] = gT->N[i];
+    for (int i = threadIdx.x; i < nq * NV * DIM; i += BLOCK) sdN[i] = gT->dN[i];
+    __shared__ double sD[9];                            // constant diffusion tensor, evaluated once per CTA
+    if (OP == 1 && kind < 2 && threadIdx.x == 0) tb_eval_D<NV, DIM>(kind, ddata, cmchi, 0, nullptr, sD);
+    const int jj = threadIdx.x % TPE, el = threadIdx.x / TPE;
+    const int64_t ncl = c1 - c0;
+    const int64_t ntiles = (ncl + TE - 1) / TE;
+    // vertex coordinates of a tile: TE * NV (element, vertex) pairs, CPT per thread; the NEXT tile's are fetched into
+    // registers while this tile is integrated, so the dependent conn -> coords loads never sit in front of a barrier
+    double pre[CPT * DIM];
+    auto fetch = [&](int64_t tile) {
+        const int64_t e0 = c0 + tile * TE;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int idx = threadIdx.x + k * BLOCK;
+            if (tile < ntiles && e0 + idx / NV < c1) {
+                const int64_t node = conn[e0 * NV + idx];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) pre[k * DIM + d] = coords[node * DIM + d];
+            }
+        }
+    };
+    fetch(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t e0 = c0 + tile * TE;
+        // (no barrier here: phase B of the previous tile reads sG only, and every thread passed the barrier that followed
+        // its last phase A -- the only reader of sX -- before it can arrive here)
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int idx = threadIdx.x + k * BLOCK;
+            const int e = idx / NV, a = idx - e * NV;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) sX[(a * DIM + d) * TE + e] = pre[k * DIM + d];
+        }
+        __syncthreads();
+        fetch(tile + gridDim.x);
+        double acc[NV * CPT];
+#pragma unroll
+        for (int i = 0; i < NV * CPT; i++) acc[i] = 0.0;
+        for (int q0 = 0; q0 < nq; q0 += qb) {
+            const int nqb = nq - q0 < qb ? nq - q0 : qb;
+            if (q0 > 0) __syncthreads();                // phase B of the previous batch is done with sG
+            for (int task = threadIdx.x; task < TE * nqb; task += BLOCK) {
+                const int ql = task / TE, e = task - ql * TE, q = q0 + ql;
+                if (e0 + e >= c1) continue;
+                double *g = sG + (size_t)ql * GS * TE + e;
+                if constexpr (OP == 1) {
+                    double G[NG];
+                    const double dO = tb_map_qp<NV, DIM, TE, true>(sX + e, sdN + q * NG, G) * sW[q];
+#pragma unroll
+                    for (int c = 0; c < NG; c++) g[c * TE] = G[c];
+                    g[NG * TE] = dO;
+                    if (kind >= 2) {
+                        double Dq[DIM * DIM];
+                        tb_eval_D<NV, DIM>(kind, ddata, cmchi, e0 + e, sN + q * NV, Dq);
+#pragma unroll
+                        for (int c = 0; c < DIM * DIM; c++) sDq[((size_t)ql * DIM * DIM + c) * TE + e] = Dq[c];
+                    }
+                } else {
+                    g[0] = tb_map_qp<NV, DIM, TE, false>(sX + e, sdN + q * NG, nullptr) * sW[q];
+                }
+            }
+            __syncthreads();
+            if (e0 + el < c1) {
+                for (int ql = 0; ql < nqb; ql++) {
+                    const double *g = sG + (size_t)ql * GS * TE + el;
+                    if constexpr (OP == 0) {
+                        const double dO = g[0];
+                        const double *Nq = sN + (q0 + ql) * NV;
+#pragma unroll
+                        for (int c = 0; c < CPT; c++) {
+                            const double Nj = Nq[jj * CPT + c];
+#pragma unroll
+                            for (int i = 0; i < NV; i++) acc[i * CPT + c] += rho * (Nq[i] * Nj) * dO;
+                        }
+                    } else {
+                        // gradN_j . D for this thread's columns first (the tensor is only live here), then row by row so
+                        // that only one gradN_i is in registers at a time
+                        const double dO = g[NG * TE];
+                        double gD[CPT][DIM];
+                        {
+                            double Dq[DIM * DIM];
+                            if (kind >= 2) {
+#pragma unroll
+                                for (int c = 0; c < DIM * DIM; c++) Dq[c] = sDq[((size_t)ql * DIM * DIM + c) * TE + el];
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < DIM * DIM; c++) Dq[c] = sD[c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < CPT; c++) {
+                                const int j = jj * CPT + c;
+                                double Gj[DIM];
+#pragma unroll
+                                for (int d = 0; d < DIM; d++) Gj[d] = g[(j * DIM + d) * TE];
+                                if (kind == 0) {
+                                    // _inner_product_helper(a, B::AbstractFloat, c) = (a . c) * B: keep gradN_j, scale later
+#pragma unroll
+                                    for (int d = 0; d < DIM; d++) gD[c][d] = Gj[d];
+                                } else {
+#pragma unroll
+                                    for (int l = 0; l < DIM; l++) {
+                                        double s = Gj[0] * Dq[l];
+#pragma unroll
+                                        for (int k = 1; k < DIM; k++) s += Gj[k] * Dq[k * DIM + l];
+                                        gD[c][l] = s;
+                                    }
+                                }
+                            }
+                        }
+                        const double D0 = sD[0];
+                        double Gi[NG];      // all loads issued before the arithmetic that consumes them
+#pragma unroll
+                        for (int c = 0; c < NG; c++) Gi[c] = g[c * TE];
+#pragma unroll
+                        for (int i = 0; i < NV; i++) {
+#pragma unroll
+                            for (int c = 0; c < CPT; c++) {
+                                double s = gD[c][0] * Gi[i * DIM];
+#pragma unroll
+                                for (int l = 1; l < DIM; l++) s += gD[c][l] * Gi[i * DIM + l];
+                                if (kind == 0) acc[i * CPT + c] -= (s * D0) * dO;
+                                else acc[i * CPT + c] -= s * dO;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // EA[i][cell][j] (row-of-the-element major, ea_si = cells of the chunk * NV): the rows that gather local row i of
+        // neighbouring cells -- neighbouring matrix rows on a structured grid -- read one contiguous run
+        if (e0 + el < c1) {
+            double *out = EA + (e0 - c0 + el) * ea_sc + jj * CPT;
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                if constexpr (CPT == 2) {
+                    *reinterpret_cast<double2 *>(out + i * ea_si) = make_double2(acc[i * 2], acc[i * 2 + 1]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPT; c++) out[i * ea_si + c] = acc[i * CPT + c];
+                }
+            }
+        }
+    }
+}
+
 template <int NV, int DIM>
 __global__ void __launch_bounds__(AS_BLOCK)
     k_element_vectors(const int *__restrict__ conn, const double *__restrict__ coords, int64_t c0, int64_t c1,
@@ -409,7 +595,10 @@ __global__ void __launch_bounds__(AS_BLOCK)
     for (int i = threadIdx.x; i < nq * NV * DIM; i += AS_BLOCK) sdN[i] = gT->dN[i];
     const tb_tables_view sT{nq, sW, sN, sdN};
     __shared__ double sprm[8];
+    __shared__ tb_src_program sprog;
     if (threadIdx.x < 8) sprm[threadIdx.x] = prm.p[threadIdx.x];
+    stage_program(prm, kind, &sprog);
+    const tb_src_program *prog = kind == TB_SRC_PROGRAM ? &sprog : nullptr;
     const int64_t ncl = c1 - c0;
     const int64_t ntiles = (ncl + AS_BLOCK - 1) / AS_BLOCK;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -427,7 +616,7 @@ __global__ void __launch_bounds__(AS_BLOCK)
         const int64_t e = e0 + threadIdx.x;
         if (e < c1) {
             double be[NV];
-            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * nq : nullptr, be);
+            tb_element_source<NV, DIM, AS_BLOCK>(sT, sX + threadIdx.x, kind, sprm, t, fq ? fq + e * nq : nullptr, be, prog);
 #pragma unroll
             for (int j = 0; j < NV; j++) EAb[(e - c0) * NV + j] = be[j];
         }
@@ -445,11 +634,11 @@ template <int NV> struct GatherCell {
 };
 template <int NV>
 __device__ __forceinline__ void gather_load(GatherCell<NV> &g, unsigned p, const int *__restrict__ celldofs,
-                                            const double *__restrict__ EA, int64_t c0) {
+                                            const double *__restrict__ EA, int64_t c0, int64_t ea_si, int ea_sc) {
     const unsigned c = p / (unsigned)NV;
     const int a = (int)(p - c * (unsigned)NV);
     const int *cd = celldofs + (int64_t)c * NV;
-    const double *ke = EA + ((int64_t)c - c0) * (NV * NV) + a * NV;
+    const double *ke = EA + ((int64_t)c - c0) * ea_sc + a * ea_si;   // row a of the cell's matrix: (NV*NV, NV) or (NV, plane)
     if constexpr (NV % 4 == 0) {
 #pragma unroll
         for (int b = 0; b < NV; b += 4) {
@@ -476,8 +665,8 @@ __device__ __forceinline__ void gather_load(GatherCell<NV> &g, unsigned p, const
 template <int NV>
 __global__ void __launch_bounds__(256)
     k_gather_rows(const int64_t *__restrict__ adjptr, const unsigned *__restrict__ adj, const int *__restrict__ celldofs,
-                  const double *__restrict__ EA, int64_t c0, SellView S, int64_t slice0, int64_t slice1, int maxw, int top_step,
-                  int wlo) {
+                  const double *__restrict__ EA, int64_t c0, int64_t ea_si, int ea_sc, SellView S, int64_t slice0, int64_t slice1,
+                  int maxw, int top_step, int wlo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     double *acc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * maxw * TB_SLICE + lane;
@@ -497,10 +686,10 @@ __global__ void __launch_bounds__(256)
             int64_t q = adjptr[r];
             const int64_t q1 = adjptr[r + 1];
             GatherCell<NV> cur, nxt;
-            if (q < q1) gather_load<NV>(nxt, adj[q], celldofs, EA, c0);
+            if (q < q1) gather_load<NV>(nxt, adj[q], celldofs, EA, c0, ea_si, ea_sc);
             for (; q < q1; q++) {
                 cur = nxt;
-                if (q + 1 < q1) gather_load<NV>(nxt, adj[q + 1], celldofs, EA, c0);
+                if (q + 1 < q1) gather_load<NV>(nxt, adj[q + 1], celldofs, EA, c0, ea_si, ea_sc);
                 int lo[NV];
 #pragma unroll
                 for (int b = 0; b < NV; b++) lo[b] = 0;
@@ -539,14 +728,63 @@ static size_t element_matrix_smem(int nv, int dim, int nq) {
     return element_smem(nv, dim, nq) + sizeof(double) * (size_t)(AS_BLOCK / 32) * nv * nv * EA_PAD;
 }
 
+// Launch geometry of the split element kernel: columns per thread and elements per tile by element size, the batch of
+// quadrature points sized so that two CTAs fit an SM (TB_ELEMENT_QB overrides; TB_ELEMENT_SPLIT=0 selects the
+// one-thread-per-element kernel).
+template <int NV> struct SplitGeom {
+    static constexpr int CPT = NV % 2 == 0 ? 2 : 1;
+    static constexpr int TE = NV == 8 ? 64 : NV == 4 ? 128 : 64;
+    static constexpr int BLOCK = TE * (NV / CPT);
+};
+static int element_split_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TB_ELEMENT_SPLIT");
+        v = e ? atoi(e) != 0 : 1;
+    }
+    return v;
+}
+static int ea_planes_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TB_EA_PLANES");
+        v = e ? atoi(e) != 0 : 1;
+    }
+    return v;
+}
+template <int NV, int DIM, int OP>
+static size_t element_split_smem(int nq, int kind, int *qb_out) {
+    constexpr int TE = SplitGeom<NV>::TE;
+    const size_t fixed = sizeof(double) * ((size_t)nq * (1 + NV + NV * DIM) + (size_t)NV * DIM * TE);
+    const size_t per_q = sizeof(double) * (size_t)TE * ((OP == 1 ? NV * DIM + 1 : 1) + (OP == 1 && kind >= 2 ? DIM * DIM : 0));
+    int qb = (int)(((size_t)100 * 1024 - fixed) / per_q);   // two CTAs per SM (the kernel is compiled for <= 128 registers)
+    if (qb > nq) qb = nq;
+    if (qb < 1) qb = 1;
+    qb = (nq + (nq + qb - 1) / qb - 1) / ((nq + qb - 1) / qb);   // balanced batches
+    const char *e = getenv("TB_ELEMENT_QB");
+    if (e && atoi(e) > 0) qb = atoi(e) < nq ? atoi(e) : nq;
+    while (qb > 1 && fixed + per_q * qb > (size_t)200 * 1024) qb--;
+    *qb_out = qb;
+    return fixed + per_q * qb;
+}
+
 template <int NV, int DIM, int OP>
 static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_tables *d_T, int nq, double rho, int kind,
                                  const double *d_data, double cmchi, const tb_pattern *pat, const SellView &S,
                                  const GatherPlan &plan, double *EA) {
-    const size_t smem1 = element_matrix_smem(NV, DIM, nq);
-    TB_CUDA(cudaFuncSetAttribute(k_element_matrices<NV, DIM, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    using SG = SplitGeom<NV>;
+    const bool split = element_split_enabled();
+    int qb = nq;
+    const size_t smem1 = split ? element_split_smem<NV, DIM, OP>(nq, kind, &qb) : element_matrix_smem(NV, DIM, nq);
+    const int block1 = split ? SG::BLOCK : AS_BLOCK, tile1 = split ? SG::TE : AS_BLOCK;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_matrices<NV, DIM, OP>, AS_BLOCK, smem1);
+    if (split) {
+        TB_CUDA(cudaFuncSetAttribute((k_element_matrices_split<NV, DIM, OP, SG::CPT, SG::TE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_element_matrices_split<NV, DIM, OP, SG::CPT, SG::TE>), block1, smem1);
+    } else {
+        TB_CUDA(cudaFuncSetAttribute(k_element_matrices<NV, DIM, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_element_matrices<NV, DIM, OP>, AS_BLOCK, smem1);
+    }
     if (per_sm < 1) per_sm = 1;
     // Two width classes: the bulk of the slices (<= TB_TMA_WCAP entries per row) and the few wide ones a high-valence
     // vertex produces (LV apex: 2*nc + 3).  Sizing the shared-memory row image for the widest slice would leave one
@@ -587,22 +825,31 @@ static int32_t gather_bilinear_t(tb_ctx *ctx, const tb_mesh *m, const tb_elem_ta
         const int64_t r0 = (int64_t)ch * plan.rows_per_chunk;
         const int64_t r1 = r0 + plan.rows_per_chunk < pat->nrows ? r0 + plan.rows_per_chunk : pat->nrows;
         const int64_t s0 = r0 / TB_SLICE, s1 = (r1 + TB_SLICE - 1) / TB_SLICE;
-        int64_t c0 = 0;
+        int64_t c0 = 0, ea_si = NV;
+        int ea_sc = NV * NV;
         if (plan.cmax[ch] >= plan.cmin[ch]) {
             c0 = plan.cmin[ch];
             const int64_t c1 = (int64_t)plan.cmax[ch] + 1;
-            const int64_t ntiles = (c1 - c0 + AS_BLOCK - 1) / AS_BLOCK;
+            if (split && ea_planes_enabled()) {
+                ea_si = (c1 - c0) * NV;
+                ea_sc = NV;
+            }
+            const int64_t ntiles = (c1 - c0 + tile1 - 1) / tile1;
             const int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
-            TB_LAUNCH(ctx, (k_element_matrices<NV, DIM, OP>), grid, AS_BLOCK, smem1, m->d_conn, m->d_coords, c0, c1, d_T, nq,
-                      rho, kind, d_data, cmchi, EA);
+            if (split)
+                TB_LAUNCH(ctx, (k_element_matrices_split<NV, DIM, OP, SG::CPT, SG::TE>), grid, block1, smem1, m->d_conn, m->d_coords,
+                          c0, c1, d_T, nq, qb, rho, kind, d_data, cmchi, EA, ea_si, ea_sc);
+            else
+                TB_LAUNCH(ctx, (k_element_matrices<NV, DIM, OP>), grid, AS_BLOCK, smem1, m->d_conn, m->d_coords, c0, c1, d_T, nq,
+                          rho, kind, d_data, cmchi, EA);
         }
         for (int k = 0; k < ngeom; k++) {
             const GatherGeom &G = gg[k];
             const int64_t need = (s1 - s0 + G.warps - 1) / G.warps;
             const int grid2 = (int)(need < (int64_t)ctx->sm_count * G.per_sm ? need : (int64_t)ctx->sm_count * G.per_sm);
             if (grid2 > 0)
-                TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, G.warps * 32, G.smem, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, S, s0,
-                          s1, G.maxw, G.top_step, G.wlo);
+                TB_LAUNCH(ctx, k_gather_rows<NV>, grid2, G.warps * 32, G.smem, m->d_adjptr, m->d_adj, m->d_celldofs, EA, c0, ea_si,
+                          ea_sc, S, s0, s1, G.maxw, G.top_step, G.wlo);
         }
     }
     return TB_OK;
@@ -796,17 +1043,22 @@ static int32_t launch_element_vectors(tb_ctx *ctx, const tb_mesh *m, const tb_el
 }
 
 static int32_t assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int qorder, int kind, const double *prm, int nprm,
-                               double t, const double *fq, tb_vec *b, int bcol) {
+                               double t, const double *fq, tb_vec *b, int bcol, const tb_src_program *prog = nullptr) {
     TB_REQUIRE(ctx && mesh && b, "tb_assemble_source: NULL argument");
     TB_REQUIRE(bcol >= 0 && bcol < b->ncols && b->n >= mesh->ndofs_owned, "tb_assemble_source: vector too small");
-    TB_REQUIRE(fq || (kind >= TB_SRC_NONE && kind <= TB_SRC_ENDO), "tb_assemble_source: unknown source kind %d", kind);
+    TB_REQUIRE(fq || prog || (kind >= TB_SRC_NONE && kind <= TB_SRC_ENDO), "tb_assemble_source: unknown source kind %d", kind);
     TB_REQUIRE(nprm >= 0 && nprm <= 8, "tb_assemble_source: at most 8 parameters");
     TB_DEV(ctx);
     const tb_elem_tables *d_T = nullptr;
     int nq = 0;
     TB_TRY(tb_get_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
     SrcParams d_prm;                      // travels as a kernel argument: no allocation, no copy, nothing to free
+    memset(&d_prm, 0, sizeof(d_prm));
     for (int i = 0; i < 8; i++) d_prm.p[i] = i < nprm ? prm[i] : 0.0;
+    if (prog) {
+        d_prm.prog = *prog;
+        kind = TB_SRC_PROGRAM;
+    }
     double *d_fq = nullptr;
     if (fq) {
         const size_t bytes = sizeof(double) * (size_t)(mesh->ncells * nq);
@@ -895,6 +1147,19 @@ extern "C" int32_t tb_assemble_source(tb_ctx *ctx, const tb_mesh *mesh, int32_t 
                                       int32_t nprm, double t, tb_vec *b, int32_t bcol) {
     TB_REQUIRE(kind == TB_SRC_NONE || prm || nprm == 0, "tb_assemble_source: prm is NULL");
     return assemble_source(ctx, mesh, qorder, kind, prm, nprm, t, nullptr, b, bcol);
+}
+
+extern "C" int32_t tb_assemble_source_program(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, const int32_t *code,
+                                              int32_t ncode, const double *consts, int32_t nconsts, double t, tb_vec *b,
+                                              int32_t bcol) {
+    TB_REQUIRE(mesh && code && (consts || nconsts == 0), "tb_assemble_source_program: NULL argument");
+    tb_src_program P;
+    memset(&P, 0, sizeof(P));
+    const int rc = tb_program_build(code, ncode, consts, nconsts, mesh->dim, &P);
+    static const char *why[] = {"", "too long (or too many constants)", "unknown opcode", "operand out of range",
+                                "stack underflow or overflow", "must leave exactly one value"};
+    if (rc) return tb_fail(TB_ERR_INVALID, "tb_assemble_source_program: invalid program: %s", why[-rc]);
+    return assemble_source(ctx, mesh, qorder, TB_SRC_PROGRAM, nullptr, 0, t, nullptr, b, bcol, &P);
 }
 
 extern "C" int32_t tb_assemble_source_qp(tb_ctx *ctx, const tb_mesh *mesh, int32_t qorder, const double *fq, tb_vec *b,

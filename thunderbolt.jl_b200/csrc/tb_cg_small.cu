@@ -186,6 +186,253 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two barriers per iteration instead of three, and cheaper ones (default; TB_PCG_V=1 selects the kernel above).
+//
+//   * All-reduce and barrier are ONE operation: a CTA stores its partial sum, then raises its flag to the current epoch
+//     (st.release.gpu); warp 0 of every CTA polls all flags (ld.acquire.gpu -- which also drops the SM's stale L1 lines) and
+//     adds the partials in slot order, so every CTA holds the same bits.  One L2 round trip after the last arrival,
+//     against grid.sync() (arrive + release + L1 invalidate) followed by a second round trip to read the partials.
+//     Slots are double-buffered by epoch parity: a CTA can only write epoch e+2 after every CTA has published e+1, i.e.
+//     after every CTA has finished reading epoch e.
+//   * The third barrier ("p complete before anyone gathers it") is gone: the SpMV forms the direction at the gathered
+//     columns itself, p_c = z_c + beta * p_old_c, from the z published before the r.z barrier and the PREVIOUS direction,
+//     which has been globally visible for a whole iteration -- the same unfused multiply and add the owner of row c
+//     performs, hence the same bits.  The owner writes its new p into the other half of a ping-pong pair; the two
+//     barriers of the next iteration publish it before it becomes "previous".  On the 101 M-row operator this trade
+//     (two gathers per entry for one kernel) LOSES because the gather is the bandwidth bottleneck (DESIGN, fused-p
+//     experiment); here everything is L2 resident and the iteration is latency bound, so a barrier is worth more than
+//     nine extra L2 hits per row.
+//   Write-after-read hazards: z_c of iteration k+1 overwrites z_c of iteration k after the p.Ap barrier of iteration k+1,
+//   which every CTA reaches only after its SpMV -- the last reader of the old z; the same barrier separates the last
+//   read of p_{k-1} from the write of p_{k+1} into its slot.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pcg_st_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pcg_ld_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+struct PcgBar {
+    double *vals;                 // [2][gridDim.x]
+    unsigned long long *flags;    // [gridDim.x], zeroed before the launch
+    unsigned long long epoch;
+    bool dead;
+};
+__device__ __forceinline__ double pcg_allsum2(double v, PcgBar &B, double *sm) {
+    const double bs = tb_block_sum(v, sm);          // valid in warp 0; the __syncthreads inside order the CTA's earlier global stores before thread 0
+    B.epoch++;
+    double *slot = B.vals + (B.epoch & 1) * gridDim.x;
+    if (threadIdx.x == 0) {
+        slot[blockIdx.x] = bs;
+        pcg_st_release(B.flags + blockIdx.x, B.epoch);
+    }
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) {
+            if (pcg_ld_acquire(B.flags + i) < B.epoch) {
+                // a CTA that never arrives must not hang the GPU: give up after 10 s, poison the sum (NaN ends the solve
+                // as "not converged") and let every later wait fall through at once
+                const unsigned long long t0 = tb_globaltimer();
+                unsigned spins = 0;
+                while (pcg_ld_acquire(B.flags + i) < B.epoch) {
+                    if ((++spins & 1023u) == 0 && (B.dead || tb_globaltimer() - t0 > 10000000000ull)) {
+                        B.dead = true;
+                        break;
+                    }
+                }
+            }
+            s += B.dead ? __longlong_as_double(0x7ff8000000000000ll) : __ldcg(slot + i);
+        }
+        s = tb_warp_sum(s);
+        if (threadIdx.x == 0) sm[32] = s;
+    }
+    __syncthreads();
+    const double out = sm[32];
+    __syncthreads();
+    return out;
+}
+
+// gathered operand: the direction at column c (FUSED: formed on the fly, see above); L2 loads, never a stale L1 line
+template <bool FUSED>
+__device__ __forceinline__ double pcg_dir(const double *__restrict__ zg, const double *__restrict__ pold, double beta, int c) {
+    if (FUSED) return __ldcg(zg + c) + beta * __ldcg(pold + c);
+    return __ldcg(pold + c);
+}
+template <bool FUSED>
+__device__ __forceinline__ double pcg_row2(const PcgMat &P, const double *__restrict__ val, const double *__restrict__ zg,
+                                           const double *__restrict__ pold, double beta, int64_t s, int lane) {
+    const int64_t base = P.slice_ptr[s];
+    const int w = (int)((P.slice_ptr[s + 1] - base) >> 5);
+    const double *v = val + base + lane;
+    double acc = 0.0;
+    if (P.ccol) {
+        const int *hdr = P.ccol + P.cptr[s];
+        const int *ex = hdr + ((w + 3) & ~3) + lane;
+        const int row = (int)(s * TB_SLICE) + lane;
+        int e = 0, j = 0;
+        for (; j + 4 <= w; j += 4) {
+            int c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int h = hdr[j + k];
+                c[k] = row + h;
+                if (h == TB_CCOL_EXPLICIT) c[k] = ex[(e++) * 32];
+            }
+            const double v0 = v[(j + 0) * 32], v1 = v[(j + 1) * 32], v2 = v[(j + 2) * 32], v3 = v[(j + 3) * 32];
+            const double x0 = pcg_dir<FUSED>(zg, pold, beta, c[0]), x1 = pcg_dir<FUSED>(zg, pold, beta, c[1]),
+                         x2 = pcg_dir<FUSED>(zg, pold, beta, c[2]), x3 = pcg_dir<FUSED>(zg, pold, beta, c[3]);
+            acc += v0 * x0;
+            acc += v1 * x1;
+            acc += v2 * x2;
+            acc += v3 * x3;
+        }
+        for (; j < w; j++) {
+            const int h = hdr[j];
+            int c = row + h;
+            if (h == TB_CCOL_EXPLICIT) c = ex[(e++) * 32];
+            acc += v[j * 32] * pcg_dir<FUSED>(zg, pold, beta, c);
+        }
+    } else {
+        const int *c = P.col + base + lane;
+        int j = 0;
+        for (; j + 4 <= w; j += 4) {
+            const int c0 = c[(j + 0) * 32], c1 = c[(j + 1) * 32], c2 = c[(j + 2) * 32], c3 = c[(j + 3) * 32];
+            const double v0 = v[(j + 0) * 32], v1 = v[(j + 1) * 32], v2 = v[(j + 2) * 32], v3 = v[(j + 3) * 32];
+            const double x0 = pcg_dir<FUSED>(zg, pold, beta, c0), x1 = pcg_dir<FUSED>(zg, pold, beta, c1),
+                         x2 = pcg_dir<FUSED>(zg, pold, beta, c2), x3 = pcg_dir<FUSED>(zg, pold, beta, c3);
+            acc += v0 * x0;
+            acc += v1 * x1;
+            acc += v2 * x2;
+            acc += v3 * x3;
+        }
+        for (; j < w; j++) acc += v[j * 32] * pcg_dir<FUSED>(zg, pold, beta, c[j * 32]);
+    }
+    return acc;
+}
+
+template <int RPL, bool FROM_B>
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+    k_cg_persistent2(const PcgMat P, const double *__restrict__ Aval, const double *__restrict__ Mval,
+                     const double *__restrict__ src, const double *__restrict__ bS, double *__restrict__ x_out,
+                     double *zglob, double *pg0, double *pg1, int64_t nrows, int64_t nslices, CGState *st, double *barvals,
+                     unsigned long long *barflags, const double *__restrict__ dinv) {
+    __shared__ double sm[34];
+    PcgBar B{barvals, barflags, 0ull, false};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * PCG_WARPS + warp, nw = (int64_t)gridDim.x * PCG_WARPS;
+    double x[RPL], r[RPL], p[RPL], Ap[RPL], di[RPL];   // di = 1/a_ii (Jacobi) or 1
+    bool own[RPL];
+    double *pg[2] = {pg0, pg1};
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < RPL; k++) {
+        const int64_t s = gw + k * nw;
+        const int64_t row = s * TB_SLICE + lane;
+        own[k] = s < nslices && row < nrows;
+        x[k] = 0.0;
+        r[k] = p[k] = Ap[k] = 0.0;
+        di[k] = (dinv && own[k]) ? dinv[row] : 1.0;
+        if (s < nslices) {
+            double v;
+            if (FROM_B) v = own[k] ? src[row] : 0.0;
+            else {
+                v = pcg_row(P, Mval, src, s, lane);     // src is never written here: cached loads are fine
+                if (own[k] && bS) v += bS[row];
+            }
+            if (own[k]) {
+                const double z = dinv ? di[k] * v : v;         // z = M r, p = z, gamma = r.z
+                r[k] = v;
+                p[k] = z;
+                pg0[row] = z;
+                acc += v * z;
+            }
+        }
+    }
+    double gamma = pcg_allsum2(acc, B, sm);                    // also publishes pg0 = p_0
+    double rn = sqrt(gamma);
+    const double eps = st->atol + st->rtol * rn;
+    const long long itmax = st->itmax;
+    bool solved = rn <= eps;
+    long long iter = 0;
+    double beta = 0.0;
+    int cur = 0;                                               // pg[cur]: the direction every CTA can see (p_k, or p_{k-1} when FUSED)
+    while (!solved && iter < itmax) {
+        acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < RPL; k++) {
+            const int64_t s = gw + k * nw;
+            if (s < nslices) {
+                const double v = iter == 0 ? pcg_row2<false>(P, Aval, zglob, pg[cur], beta, s, lane)
+                                           : pcg_row2<true>(P, Aval, zglob, pg[cur], beta, s, lane);
+                if (own[k]) {
+                    Ap[k] = v;
+                    acc += p[k] * v;
+                }
+            }
+        }
+        // the direction used above is now "previous" for everybody; own rows' current p goes into the other slot -- nobody
+        // reads that slot before the second barrier after this point
+        if (iter > 0) cur ^= 1;
+        const double pAp = pcg_allsum2(acc, B, sm);
+        const double alpha = gamma / pAp;
+        acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < RPL; k++)
+            if (own[k]) {
+                x[k] += alpha * p[k];
+                r[k] -= alpha * Ap[k];
+                const double z = dinv ? di[k] * r[k] : r[k];
+                zglob[(gw + k * nw) * TB_SLICE + lane] = z;
+                acc += r[k] * z;
+            }
+        const double gnext = pcg_allsum2(acc, B, sm);          // publishes z
+        rn = sqrt(gnext);
+        solved = rn <= eps;
+        iter++;
+        if (rn != rn) iter = itmax;   // NaN never recovers: what the reference reports after grinding through itmax iterations
+        if (!solved && iter < itmax) {
+            beta = gnext / gamma;
+            gamma = gnext;
+#pragma unroll
+            for (int k = 0; k < RPL; k++)
+                if (own[k]) {
+                    p[k] = (dinv ? di[k] * r[k] : r[k]) + beta * p[k];
+                    pg[cur ^ 1][(gw + k * nw) * TB_SLICE + lane] = p[k];
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; k++)
+        if (own[k]) x_out[(gw + k * nw) * TB_SLICE + lane] = x[k];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->gamma = gamma;
+        st->rnorm = rn;
+        st->eps = eps;
+        st->iter = iter;
+        st->solved = solved;
+        st->done = 1;
+    }
+}
+
+template <int RPL, bool FROM_B>
+static int32_t launch_pcg2(tb_ctx *ctx, int grid, const PcgMat &P, const double *Aval, const double *Mval, const double *src,
+                           const double *bS, double *x, int64_t nrows, int64_t nslices, const double *dinv) {
+    CGState *st = ctx->d_cg;
+    double *zglob = ctx->d_cgwork, *pg0 = zglob + ctx->cgwork_ld, *pg1 = pg0 + ctx->cgwork_ld;
+    double *barvals = ctx->d_partials;
+    unsigned long long *barflags = reinterpret_cast<unsigned long long *>(ctx->d_partials + 2 * TB_MAX_PARTIALS);
+    TB_CUDA(cudaMemsetAsync(barflags, 0, sizeof(unsigned long long) * (size_t)grid, ctx->stream));
+    void *args[] = {(void *)&P, (void *)&Aval, (void *)&Mval, (void *)&src, (void *)&bS, (void *)&x, (void *)&zglob, (void *)&pg0,
+                    (void *)&pg1, (void *)&nrows, (void *)&nslices, (void *)&st, (void *)&barvals, (void *)&barflags, (void *)&dinv};
+    // cooperative launch: the hand-made barrier needs every CTA resident, which only this launch mode guarantees
+    TB_CUDA(cudaLaunchCooperativeKernel((void *)k_cg_persistent2<RPL, FROM_B>, dim3(grid), dim3(PCG_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    return TB_OK;
+}
+
 template <int RPL, bool FROM_B>
 static int32_t launch_pcg(tb_ctx *ctx, int grid, const PcgMat &P, const double *Aval, const double *Mval, const double *src,
                           const double *bS, double *x, double *pglob, int64_t nrows, int64_t nslices, const double *dinv) {
@@ -461,8 +708,17 @@ int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const doubl
 #define PCG_GO(R)                                                                                                              \
     (b ? launch_pcg<R, true>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices, dinv)                  \
        : launch_pcg<R, false>(ctx, grid, P, A->d_val, Mval, src, bS, x, pglob, pat->nrows, pat->nslices, dinv))
-    int32_t st = rpl <= 1 ? PCG_GO(1) : rpl <= 2 ? PCG_GO(2) : PCG_GO(4);
+#define PCG_GO2(R)                                                                                                             \
+    (b ? launch_pcg2<R, true>(ctx, grid, P, A->d_val, Mval, src, bS, x, pat->nrows, pat->nslices, dinv)                        \
+       : launch_pcg2<R, false>(ctx, grid, P, A->d_val, Mval, src, bS, x, pat->nrows, pat->nslices, dinv))
+    if (ctx->pcg_variant == 0) {
+        const char *e = getenv("TB_PCG_V");
+        ctx->pcg_variant = e && atoi(e) == 1 ? 1 : 2;
+    }
+    int32_t st = ctx->pcg_variant == 1 ? (rpl <= 1 ? PCG_GO(1) : rpl <= 2 ? PCG_GO(2) : PCG_GO(4))
+                            : (rpl <= 1 ? PCG_GO2(1) : rpl <= 2 ? PCG_GO2(2) : PCG_GO2(4));
 #undef PCG_GO
+#undef PCG_GO2
     if (st != TB_OK) return st;
     if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[1], ctx->stream));
     CGState *h = ctx->h_cg;
@@ -487,6 +743,12 @@ extern "C" int32_t tb_cg_set_persistent(tb_ctx *ctx, int32_t mode) {
     TB_REQUIRE(ctx, "tb_cg_set_persistent: ctx is NULL");
     TB_REQUIRE(mode >= 0 && mode <= 2, "tb_cg_set_persistent: mode must be 0 (off), 1 (auto) or 2 (TMA kernel whenever eligible)");
     ctx->cg_persistent = mode;
+    return TB_OK;
+}
+
+extern "C" int32_t tb_cg_set_persistent_variant(tb_ctx *ctx, int32_t variant) {
+    TB_REQUIRE(ctx && (variant == 1 || variant == 2), "tb_cg_set_persistent_variant: 1 (three grid.sync per iteration) or 2 (two flag barriers)");
+    ctx->pcg_variant = variant;
     return TB_OK;
 }
 

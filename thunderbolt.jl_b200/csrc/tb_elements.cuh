@@ -347,6 +347,108 @@ TB_HD void tb_element_diffusion_full(const tb_tables_view T, const double *X, in
     }
 }
 
+// ---- source programs: a closure f(x, t) traced into postfix code (tbolt_b200.h TB_SRC_PROGRAM) ---------------
+// A stimulus closure cannot cross a C ABI, but its expression can: the host binding calls f once with tracing numbers
+// and ships the resulting postfix program (<= TB_PROG_MAXCODE instructions, <= TB_PROG_MAXCONST constants); the
+// element kernels evaluate it at every quadrature point.  All arithmetic is plain IEEE fp64 in program order (no
+// contraction), so +,-,*,/,sqrt,abs,min,max and the comparisons give the bits the closure itself would give on the
+// host; exp/log/sin/cos/tanh/pow agree to the ulp of the two math libraries.
+#define TB_PROG_MAXCODE 96
+#define TB_PROG_MAXCONST 24
+#define TB_PROG_MAXSTACK 16
+enum tb_prog_op {
+    TB_OP_X = 0,      // push x[arg]
+    TB_OP_T,          // push t
+    TB_OP_CONST,      // push c[arg]
+    TB_OP_ADD, TB_OP_SUB, TB_OP_MUL, TB_OP_DIV, TB_OP_MIN, TB_OP_MAX, TB_OP_POW,        // binary: a = pop-under, b = top
+    TB_OP_LT, TB_OP_LE, TB_OP_GT, TB_OP_GE, TB_OP_EQ, TB_OP_NE, TB_OP_AND, TB_OP_OR,    // binary, result 1.0 / 0.0
+    TB_OP_NEG, TB_OP_ABS, TB_OP_SQRT, TB_OP_EXP, TB_OP_LOG, TB_OP_SIN, TB_OP_COS, TB_OP_TANH, TB_OP_NOT,   // unary
+    TB_OP_SELECT,     // ternary: cond, a, b -> cond != 0 ? a : b
+    TB_OP_COUNT
+};
+struct tb_src_program {
+    int n;
+    unsigned char op[TB_PROG_MAXCODE];
+    unsigned char arg[TB_PROG_MAXCODE];
+    double c[TB_PROG_MAXCONST];
+};
+
+// Validates code (op | arg << 8 per instruction) and fills P; returns 0, or a negative code: -1 too long, -2 unknown
+// opcode, -3 bad operand, -4 stack underflow/overflow, -5 does not leave exactly one value.
+static inline int tb_program_build(const int32_t *code, int ncode, const double *consts, int nconsts, int dim,
+                                   tb_src_program *P) {
+    if (ncode < 1 || ncode > TB_PROG_MAXCODE || nconsts < 0 || nconsts > TB_PROG_MAXCONST) return -1;
+    int sp = 0;
+    for (int i = 0; i < ncode; i++) {
+        const int op = code[i] & 0xff, arg = (code[i] >> 8) & 0xff;
+        if (op < 0 || op >= TB_OP_COUNT) return -2;
+        if (op == TB_OP_X && arg >= dim) return -3;
+        if (op == TB_OP_CONST && arg >= nconsts) return -3;
+        const int pops = op <= TB_OP_CONST ? 0 : op <= TB_OP_OR ? 2 : op <= TB_OP_NOT ? 1 : 3;
+        if (sp < pops) return -4;
+        sp += 1 - pops;
+        if (sp > TB_PROG_MAXSTACK) return -4;
+        P->op[i] = (unsigned char)op;
+        P->arg[i] = (unsigned char)arg;
+    }
+    if (sp != 1) return -5;
+    P->n = ncode;
+    for (int i = 0; i < nconsts; i++) P->c[i] = consts[i];
+    for (int i = nconsts; i < TB_PROG_MAXCONST; i++) P->c[i] = 0.0;
+    return 0;
+}
+
+template <int DIM> TB_HD double tb_program_eval(const tb_src_program &P, const double *x, double t) {
+    double st[TB_PROG_MAXSTACK];
+    int sp = 0;
+    for (int pc = 0; pc < P.n; pc++) {
+        const int op = P.op[pc];
+        if (op <= TB_OP_CONST) {
+            st[sp++] = op == TB_OP_X ? x[P.arg[pc] < DIM ? P.arg[pc] : 0] : op == TB_OP_T ? t : P.c[P.arg[pc]];
+        } else if (op <= TB_OP_OR) {
+            const double b = st[--sp], a = st[sp - 1];
+            double r;
+            switch (op) {
+            case TB_OP_ADD: r = a + b; break;
+            case TB_OP_SUB: r = a - b; break;
+            case TB_OP_MUL: r = a * b; break;
+            case TB_OP_DIV: r = a / b; break;
+            case TB_OP_MIN: r = b < a ? b : a; break;
+            case TB_OP_MAX: r = a < b ? b : a; break;
+            case TB_OP_POW: r = pow(a, b); break;
+            case TB_OP_LT: r = a < b ? 1.0 : 0.0; break;
+            case TB_OP_LE: r = a <= b ? 1.0 : 0.0; break;
+            case TB_OP_GT: r = a > b ? 1.0 : 0.0; break;
+            case TB_OP_GE: r = a >= b ? 1.0 : 0.0; break;
+            case TB_OP_EQ: r = a == b ? 1.0 : 0.0; break;
+            case TB_OP_NE: r = a != b ? 1.0 : 0.0; break;
+            case TB_OP_AND: r = (a != 0.0 && b != 0.0) ? 1.0 : 0.0; break;
+            default: r = (a != 0.0 || b != 0.0) ? 1.0 : 0.0; break;
+            }
+            st[sp - 1] = r;
+        } else if (op <= TB_OP_NOT) {
+            const double a = st[sp - 1];
+            double r;
+            switch (op) {
+            case TB_OP_NEG: r = -a; break;
+            case TB_OP_ABS: r = fabs(a); break;
+            case TB_OP_SQRT: r = sqrt(a); break;
+            case TB_OP_EXP: r = exp(a); break;
+            case TB_OP_LOG: r = log(a); break;
+            case TB_OP_SIN: r = sin(a); break;
+            case TB_OP_COS: r = cos(a); break;
+            case TB_OP_TANH: r = tanh(a); break;
+            default: r = a == 0.0 ? 1.0 : 0.0; break;
+            }
+            st[sp - 1] = r;
+        } else {
+            const double b = st[--sp], a = st[--sp], c = st[sp - 1];
+            st[sp - 1] = c != 0.0 ? a : b;
+        }
+    }
+    return st[0];
+}
+
 // ---- built-in stimulus families (see tbolt_b200.h TB_SRC_*) --------------------------------------------
 template <int DIM> TB_HD double tb_source_eval(int kind, const double *prm, const double *x, double t) {
     double n2 = 0.0, mx = -INFINITY;
@@ -365,10 +467,10 @@ template <int DIM> TB_HD double tb_source_eval(int kind, const double *prm, cons
     }
 }
 
-// fq != nullptr: host-evaluated f at this cell's quadrature points
+// fq != nullptr: host-evaluated f at this cell's quadrature points; prog != nullptr: traced closure
 template <int NV, int DIM, int XS>
 TB_HD void tb_element_source(const tb_tables_view T, const double *X, int kind, const double *prm, double t,
-                             const double *fq, double *be) {
+                             const double *fq, double *be, const tb_src_program *prog = nullptr) {
 #pragma unroll
     for (int j = 0; j < NV; j++) be[j] = 0.0;
     for (int q = 0; q < T.nq; q++) {
@@ -385,7 +487,7 @@ TB_HD void tb_element_source(const tb_tables_view T, const double *X, int kind, 
             for (int a = 0; a < NV; a++)
 #pragma unroll
                 for (int d = 0; d < DIM; d++) x[d] += Nq[a] * X[(a * DIM + d) * XS];
-            fx = tb_source_eval<DIM>(kind, prm, x, t);
+            fx = prog ? tb_program_eval<DIM>(*prog, x, t) : tb_source_eval<DIM>(kind, prm, x, t);
         }
 #pragma unroll
         for (int j = 0; j < NV; j++) be[j] += fx * Nq[j] * dO;

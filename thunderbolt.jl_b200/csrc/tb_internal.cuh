@@ -148,6 +148,7 @@ struct tb_ctx {
     // CG workspace (grown on demand): r, p, Ap as one tb_vec-like allocation
     double *d_cgwork = nullptr;
     int64_t cgwork_ld = 0;
+    int pcg_variant = 0;              // register-resident persistent CG: 1 = three grid.sync per iteration, 2 = two flag barriers (0: env TB_PCG_V, default 2)
     struct CGState *d_cg = nullptr;   // device scalars of the running solve
     struct CGState *h_cg = nullptr;   // pinned mirror
     double *d_scalar = nullptr;       // small device scratch (16 doubles)
@@ -326,7 +327,8 @@ struct tb_monodomain {
     double section_ms[3];
     // tb_monodomain_run_host: copy streams and events (created on first use)
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t e_phi = nullptr, e_s = nullptr, e_done = nullptr, o_s = nullptr, e_chunk[16] = {};
+    cudaEvent_t e_phi = nullptr, e_s = nullptr, e_done = nullptr, o_s = nullptr, e_chunk[64] = {};
+    int rh_chunks = 16;            // pieces of the phi column in tb_monodomain_run_host (download / chasing upload)
 };
 
 // ionic model tables (tb_cells.cuh traits, host side)

@@ -69,8 +69,8 @@ extern "C" int32_t tb_monodomain_destroy(tb_monodomain *md) {
     if (md->s_out) cudaStreamDestroy(md->s_out);
     for (cudaEvent_t e : {md->e_phi, md->e_s, md->e_done, md->o_s})
         if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 16; i++)
-        if (md->e_chunk[i]) cudaEventDestroy(md->e_chunk[i]);
+    for (cudaEvent_t e : md->e_chunk)
+        if (e) cudaEventDestroy(e);
     delete md;
     return TB_OK;
 }
@@ -226,7 +226,12 @@ extern "C" int32_t tb_monodomain_step_host(tb_monodomain *md, tb_vec *u_dev, con
     return TB_OK;
 }
 
-#define RH_CHUNKS 16
+#define RH_CHUNKS_MAX 64
+extern "C" int32_t tb_monodomain_set_host_chunks(tb_monodomain *md, int32_t nchunks) {
+    TB_REQUIRE(md && nchunks >= 1 && nchunks <= RH_CHUNKS_MAX, "tb_monodomain_set_host_chunks: 1 <= nchunks <= 64");
+    md->rh_chunks = nchunks;
+    return TB_OK;
+}
 #define RH_TRACE_MAX 64
 extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *buf0, double *buf1, double t0, double dt,
                                           int64_t nsteps, int64_t *iters_total, int32_t *all_converged) {
@@ -238,11 +243,13 @@ extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *
         TB_CUDA(cudaStreamCreateWithFlags(&md->s_in, cudaStreamNonBlocking));
         TB_CUDA(cudaStreamCreateWithFlags(&md->s_out, cudaStreamNonBlocking));
         for (cudaEvent_t *e : {&md->e_phi, &md->e_s, &md->e_done, &md->o_s}) TB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        for (int i = 0; i < RH_CHUNKS; i++) TB_CUDA(cudaEventCreateWithFlags(&md->e_chunk[i], cudaEventDisableTiming));
+        for (int i = 0; i < RH_CHUNKS_MAX; i++) TB_CUDA(cudaEventCreateWithFlags(&md->e_chunk[i], cudaEventDisableTiming));
+        if (const char *e = getenv("TB_RUNHOST_CHUNKS")) md->rh_chunks = atoi(e);
     }
     const int64_t n = u->n, ld = u->ld;
     const int nc = u->ncols, phic = md->phi_idx;
-    const int64_t csz = tb_round_up((n + RH_CHUNKS - 1) / RH_CHUNKS, 32);
+    const int nchunks = md->rh_chunks < 1 ? 1 : md->rh_chunks > RH_CHUNKS_MAX ? RH_CHUNKS_MAX : md->rh_chunks;
+    const int64_t csz = tb_round_up((n + nchunks - 1) / nchunks, 32);
     // TB_RUNHOST_TRACE=<file>: per-step timeline from CUDA events on the three streams (ms since the first step started):
     // compute start | CG + cells done | phi download done | phi upload (next step's input) done | other columns down | up
     const char *trace_path = getenv("TB_RUNHOST_TRACE");
@@ -281,7 +288,7 @@ extern "C" int32_t tb_monodomain_run_host(tb_monodomain *md, tb_vec *u, double *
         const bool more = s + 1 < nsteps;
         // download of this step's result; the upload of the next step's input chases it chunk by chunk (full duplex)
         TB_CUDA(cudaStreamWaitEvent(md->s_out, md->e_done, 0));
-        for (int k = 0; k < RH_CHUNKS; k++) {
+        for (int k = 0; k < nchunks; k++) {
             const int64_t o = k * csz, len = o + csz <= n ? csz : n - o;
             if (len <= 0) break;
             TB_CUDA(cudaMemcpyAsync(out + (size_t)phic * n + o, u->d + (size_t)phic * ld + o, sizeof(double) * (size_t)len, cudaMemcpyDeviceToHost, md->s_out));

@@ -14,7 +14,7 @@ import Thunderbolt: create_system_vector, create_system_matrix, adapt_vector_typ
     AdaptiveForwardEulerSubstepperCache, ForwardEulerCellSolverCache, BilinearMassIntegrator, BilinearDiffusionIntegrator,
     LinearIntegrator, AnalyticalTransmembraneStimulationProtocol, ParametrizedFHNModel, ParametrizedPCG2019Model,
     ConductivityToDiffusivityCoefficient, ConstantCoefficient, ElementAssemblyStrategy, AbstractGPUDevice, num_states
-import Ferrite
+import Ferrite, Tensors
 
 const LIB = Ref{String}("libtbolt_b200.so")
 
@@ -183,8 +183,78 @@ function evaluate_at_quadrature_points(f, dh::Ferrite.DofHandler, qorder::Intege
     end
     return fq
 end
+# ... but its EXPRESSION can.  `f(x, t)` is called once with tracing numbers; the recorded expression tree becomes the postfix
+# program of tb_assemble_source_program (tbolt_b200.h, TB_SRC_PROGRAM: the opcode order below is the header's) that the
+# element kernel evaluates at every quadrature point -- per update only the ~400-byte program crosses the host link, not
+# ncells × nq doubles.  `&&` / `||` / `if` on x or t need a Bool and throw a TypeError while tracing (use `ifelse`, `&`, `|`,
+# `min`, `max`): then, or when the program would exceed 96 instructions, the closure keeps the host-evaluated path above.
+const TB_OPS = (:X, :T, :CONST, :ADD, :SUB, :MUL, :DIV, :MIN, :MAX, :POW, :LT, :LE, :GT, :GE, :EQ, :NE, :AND, :OR,
+                :NEG, :ABS, :SQRT, :EXP, :LOG, :SIN, :COS, :TANH, :NOT, :SELECT)
+const TB_OPCODE = Dict(op => Int32(i - 1) for (i, op) in enumerate(TB_OPS))
+struct TracedReal <: Real
+    op::Symbol
+    args::Tuple
+end
+TracedReal(v::Real) = v isa TracedReal ? v : TracedReal(:CONST, (Float64(v),))
+Base.promote_rule(::Type{TracedReal}, ::Type{<:Real}) = TracedReal
+Base.convert(::Type{TracedReal}, v::Real) = TracedReal(v)
+Base.convert(::Type{TracedReal}, v::TracedReal) = v
+for (fn, op) in ((:+, :ADD), (:-, :SUB), (:*, :MUL), (:/, :DIV), (:min, :MIN), (:max, :MAX), (:^, :POW),
+                 (:<, :LT), (:<=, :LE), (:(==), :EQ), (:&, :AND), (:|, :OR))
+    @eval Base.$fn(a::TracedReal, b::TracedReal) = TracedReal($(QuoteNode(op)), (a, b))
+end
+Base.:>(a::TracedReal, b::TracedReal) = TracedReal(:GT, (a, b))
+Base.:>=(a::TracedReal, b::TracedReal) = TracedReal(:GE, (a, b))
+Base.:!=(a::TracedReal, b::TracedReal) = TracedReal(:NE, (a, b))
+Base.literal_pow(::typeof(^), a::TracedReal, ::Val{2}) = a * a               # what Julia does for Float64
+Base.literal_pow(::typeof(^), a::TracedReal, ::Val{3}) = a * a * a
+for (fn, op) in ((:-, :NEG), (:abs, :ABS), (:sqrt, :SQRT), (:exp, :EXP), (:log, :LOG), (:sin, :SIN), (:cos, :COS),
+                 (:tanh, :TANH), (:!, :NOT))
+    @eval Base.$fn(a::TracedReal) = TracedReal($(QuoteNode(op)), (a,))
+end
+Base.ifelse(c::TracedReal, a::Real, b::Real) = TracedReal(:SELECT, (c, TracedReal(a), TracedReal(b)))
+Base.abs2(a::TracedReal) = a * a
+Base.zero(::Type{TracedReal}) = TracedReal(0.0); Base.one(::Type{TracedReal}) = TracedReal(1.0)
+function emit!(code::Vector{Int32}, consts::Vector{Float64}, n::TracedReal)
+    if n.op === :X
+        push!(code, TB_OPCODE[:X] | Int32(n.args[1]) << 8)
+    elseif n.op === :T
+        push!(code, TB_OPCODE[:T])
+    elseif n.op === :CONST
+        k = findfirst(c -> c === n.args[1], consts)
+        k === nothing && (push!(consts, n.args[1]); k = length(consts))
+        push!(code, TB_OPCODE[:CONST] | Int32(k - 1) << 8)
+    else
+        foreach(a -> emit!(code, consts, a), n.args)
+        push!(code, TB_OPCODE[n.op])
+    end
+    return code
+end
+const TRACED_SOURCES = IdDict{Any, Any}()        # closure => (code, consts) | nothing
+"postfix program of `f(x::Vec{dim}, t)`, or `nothing` if f cannot be traced"
+function trace_source(f, dim::Integer)
+    try
+        x = Tensors.Vec{dim, TracedReal}(ntuple(d -> TracedReal(:X, (d - 1,)), dim))
+        root = TracedReal(f(x, TracedReal(:T, ())))
+        code, consts = Int32[], Float64[]
+        emit!(code, consts, root)
+        (length(code) > 96 || length(consts) > 24) && return nothing
+        return code, consts            # the library validates the stack depth (tb_assemble_source_program)
+    catch err
+        err isa Union{TypeError, MethodError} || rethrow()
+        return nothing
+    end
+end
 function update_operator!(op::B200LinearOperator, t)
     proto = op.integrator.integrand::AnalyticalTransmembraneStimulationProtocol
+    prog = get!(() -> trace_source(proto.f.f, Ferrite.getspatialdim(Ferrite.get_grid(op.dh))), TRACED_SOURCES, proto.f.f)
+    if prog !== nothing
+        code, consts = prog
+        rc = ccall((:tb_assemble_source_program, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Float64, Ptr{Cvoid}, Int32),
+                   op.b.dev.h, op.mesh.h, Int32(qorder(op.integrator)), code, length(code), consts, length(consts), Float64(t), op.b.h, Int32(0))
+        rc == 0 && return
+        TRACED_SOURCES[proto.f.f] = nothing          # e.g. deeper than the 16-entry stack: host-evaluated from now on
+    end
     fq = evaluate_at_quadrature_points(proto.f.f, op.dh, qorder(op.integrator), t)
     @tb tb_assemble_source_qp (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Cvoid}, Int32) op.b.dev.h op.mesh.h Int32(qorder(op.integrator)) fq op.b.h Int32(0)
 end
