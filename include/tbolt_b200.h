@@ -8,8 +8,10 @@
  * owned by the library behind the handles and released by the matching *_destroy.  A tb_ctx is
  * used from one host thread at a time; all work is ordered on the context's CUDA stream (a non-blocking
  * stream unless the caller supplies one); only *_download, the solves and steps that return scalars
- * (tb_cg_solve*, tb_monodomain_step*, tb_monodomain_run*, tb_ecg_plonsey), the matrix assemblies and
- * tb_sync block the host -- tb_assemble_source with a built-in stimulus family is fully stream-ordered.
+ * (tb_cg_solve*, tb_monodomain_step*, tb_monodomain_run*, tb_ecg_plonsey), assemblies that ship per-cell
+ * or per-point host data (coefficient fields, tb_assemble_source_qp) and tb_sync block the host -- tb_assemble_mass,
+ * tb_assemble_diffusion with a constant coefficient and tb_assemble_source[_program] are fully stream-ordered (an
+ * asynchronous kernel failure then surfaces at the next blocking call on the context).
  *
  * Each declaration cites the reference interface (file:line under JuliaHealth/Thunderbolt.jl
  * v0.0.4) that a Julia `ccall` of it replaces; INTEGRATION.md shows those bindings.

@@ -919,14 +919,23 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     const tb_elem_tables *d_T = nullptr;
     int nq = 0;
     TB_TRY(tb_get_tables(ctx, mesh->celltype, qorder, &d_T, &nq));
+    // Constant coefficients (a scalar or one tensor) go through a small buffer owned by the context: the upload is
+    // stream-ordered (the driver stages pageable host memory before cudaMemcpyAsync returns), nothing is allocated or freed
+    // and the call does not block.  Coefficient FIELDS (per-cell data) get a buffer for the duration of the call, which then
+    // has to wait for its kernels.
     double *d_data = nullptr;
+    const bool own_data = op == 1 && ndata > 16;
     if (op == 1) {
-        if (cudaMalloc(&d_data, sizeof(double) * (size_t)ndata) != cudaSuccess) {
-            cudaGetLastError();
-            return tb_fail(TB_ERR_NOMEM, "tb_assemble_diffusion: cannot allocate %lld coefficient values", (long long)ndata);
+        if (own_data) {
+            if (cudaMalloc(&d_data, sizeof(double) * (size_t)ndata) != cudaSuccess) {
+                cudaGetLastError();
+                return tb_fail(TB_ERR_NOMEM, "tb_assemble_diffusion: cannot allocate %lld coefficient values", (long long)ndata);
+            }
+        } else {
+            d_data = ctx->d_dconst;
         }
         if (cudaMemcpyAsync(d_data, data, sizeof(double) * (size_t)ndata, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
-            cudaFree(d_data);
+            if (own_data) cudaFree(d_data);
             return tb_fail(TB_ERR_CUDA, "tb_assemble_diffusion: coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
     }
@@ -940,11 +949,16 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
         double *EA = nullptr;
         st = mesh_ensure_adjacency(ctx, mesh);
         if (st == TB_OK) {
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            size_t budget = ctx->ea_budget_bytes;
-            if (budget > free_b / 2) budget = free_b / 2;
             const int64_t per_cell = (int64_t)mesh->nv * mesh->nv * (int64_t)sizeof(double);
+            size_t budget = ctx->ea_budget_bytes;
+            // the scratch of an earlier call that is large enough for the whole mesh settles it; otherwise ask the driver how
+            // much memory there is (cudaMemGetInfo costs a fraction of a millisecond: not on every call)
+            if (ctx->ea_bytes < (size_t)mesh->ncells * (size_t)per_cell || budget < ctx->ea_bytes) {
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                free_b += ctx->ea_bytes;                 // what the cached scratch holds would be reused
+                if (budget > free_b / 2) budget = free_b / 2;
+            }
             st = plan_gather(ctx, mesh, (int64_t)(budget / (size_t)per_cell), 0, &planp);
             ok = st == TB_OK && planp->ok;
             if (ok) {
@@ -981,6 +995,7 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
             ctx->assembly_last_chunks = (int)plan.cmin.size();
         }
         if (gathered || st != TB_OK) {
+            if (!own_data) return st;         // stream-ordered: a failing kernel surfaces at the next blocking call on this stream
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
             cudaFree(d_data);
             if (st != TB_OK) return st;
@@ -1002,6 +1017,7 @@ static int32_t assemble_bilinear(tb_ctx *ctx, const tb_mesh *mesh, int qorder, i
     default: DISPATCH(4, 3); break;
     }
 #undef DISPATCH
+    if (!own_data) return st;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_data);
     if (st != TB_OK) return st;

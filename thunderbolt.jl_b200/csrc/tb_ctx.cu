@@ -72,6 +72,7 @@ static int32_t ctx_init(tb_ctx *ctx, int32_t device, void *stream) {
     TB_CUDA(cudaMemsetAsync(ctx->d_cg, 0, 2 * sizeof(CGState), ctx->stream));
     TB_CUDA(cudaMallocHost(&ctx->h_cg, sizeof(CGState)));
     TB_CUDA(cudaMalloc(&ctx->d_scalar, sizeof(double) * 16));
+    TB_CUDA(cudaMalloc(&ctx->d_dconst, sizeof(double) * 16));
     TB_CUDA(cudaMallocHost(&ctx->h_scalar, sizeof(double) * 16));
     if (const char *v = getenv("TB_SPMV_VARIANT")) ctx->spmv_variant = atoi(v);
     if (const char *v = getenv("TB_SPMV_COMPRESS")) ctx->spmv_compress = atoi(v);
@@ -97,6 +98,7 @@ extern "C" int32_t tb_ctx_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_cg);
     cudaFreeHost(ctx->h_cg);
     cudaFree(ctx->d_scalar);
+    cudaFree(ctx->d_dconst);
     cudaFreeHost(ctx->h_scalar);
     for (int a = 0; a < 4; a++)
         for (int b = 0; b < 5; b++) cudaFree(ctx->d_tables[a][b]);

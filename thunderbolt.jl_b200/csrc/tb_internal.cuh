@@ -152,6 +152,7 @@ struct tb_ctx {
     struct CGState *d_cg = nullptr;   // device scalars of the running solve
     struct CGState *h_cg = nullptr;   // pinned mirror
     double *d_scalar = nullptr;       // small device scratch (16 doubles)
+    double *d_dconst = nullptr;       // constant diffusion coefficient of the running assembly (<= 16 doubles, stream-ordered uploads)
     double *h_scalar = nullptr;       // pinned
     double *d_dinv = nullptr;         // Jacobi preconditioner: 1/diag(A) of the operator being solved
     int64_t dinv_len = 0;
