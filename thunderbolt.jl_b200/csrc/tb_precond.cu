@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(512) k_bj_invert(const int64_t *__restrict__ b
 // the 32 lanes fetch 256 contiguous bytes per term; r_b never touches shared memory -- a warp keeps 32 entries in
 // registers and broadcasts them with shuffles.  No barriers, eight independent 256-byte loads in flight per warp: the
 // kernel streams sum(n_b^2) * 8 bytes per application and is HBM bound.
+// (Round-2 experiment, removed: stream only the lower triangle of the -- symmetrised -- inverse into a padded shared-memory
+// image and walk that instead: half the DRAM bytes (350 vs 494 MB on C4 with 64-row blocks), but the load / barrier / compute
+// phases of a CTA serialise and the index arithmetic fills the issue slots: 196 us against this kernel's 102 us.)
 __global__ void __launch_bounds__(256) k_bj_apply(const double *__restrict__ r, double *__restrict__ z, const int *__restrict__ perm,
                                                   const int64_t *__restrict__ bptr, const int64_t *__restrict__ iptr,
                                                   const double *__restrict__ inv, int64_t nblocks, const CGState *st) {
@@ -295,62 +298,6 @@ __global__ void __launch_bounds__(256) k_bj_apply(const double *__restrict__ r, 
     }
 }
 
-// The inverse of an SPD block is symmetric; Gauss-Jordan returns it symmetric only up to rounding.  Copy the lower triangle
-// over the upper one so that (i, j) and (j, i) are the same bits -- the apply kernels may then read either.
-__global__ void __launch_bounds__(256) k_bj_symmetrize(const int64_t *__restrict__ bptr, const int64_t *__restrict__ iptr,
-                                                       double *__restrict__ inv, int64_t nblocks) {
-    for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        const int n = (int)(bptr[b + 1] - bptr[b]);
-        double *a = inv + iptr[b];
-        for (int64_t e = threadIdx.x; e < (int64_t)n * n; e += blockDim.x) {
-            const int i = (int)(e / n), j = (int)(e % n);
-            if (j > i) a[e] = a[(int64_t)j * n + i];
-        }
-    }
-}
-
-// Same product, half the traffic: a CTA streams only the LOWER triangle of its block (row j: the j + 1 leading entries, one
-// contiguous run) into a padded shared-memory image, mirroring every entry, and the lanes then walk their column of that
-// image exactly like k_bj_apply walks global memory -- same terms, same left-to-right order, same bits (the stored inverse
-// is exactly symmetric, k_bj_symmetrize).  Every load of the triangle is issued before the first use, so a CTA has its
-// whole 8 * n (n + 1) / 2 bytes in flight at once.
-__global__ void __launch_bounds__(128) k_bj_apply_sym(const double *__restrict__ r, double *__restrict__ z, const int *__restrict__ perm,
-                                                      const int64_t *__restrict__ bptr, const int64_t *__restrict__ iptr,
-                                                      const double *__restrict__ inv, int64_t nblocks, const CGState *st) {
-    if (st && st->done) return;
-    extern __shared__ double s_a[];                 // n x (n + 1): element (j, i) at j * (n + 1) + i
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-        const int64_t p0 = bptr[b];
-        const int n = (int)(bptr[b + 1] - p0);
-        const int ld = n + 1;
-        const double *a = inv + iptr[b];
-        __syncthreads();                            // the previous block's image is no longer read
-        // lower triangle, row by row: a warp takes rows j = warp, warp + nw, ...; its lanes the entries i = lane, lane + 32, ... <= j
-        for (int j = warp; j < n; j += nw) {
-            const double *row = a + (int64_t)j * n;
-            for (int i = lane; i <= j; i += 32) {
-                const double v = row[i];
-                s_a[j * ld + i] = v;
-                s_a[i * ld + j] = v;
-            }
-        }
-        __syncthreads();
-        for (int i0 = warp * 32; i0 < n; i0 += nw * 32) {
-            const int i = i0 + lane;
-            const int ic = i < n ? i : n - 1;
-            double acc = 0.0;
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int jj = j0 + lane;
-                const double xv = jj < n ? r[perm[p0 + jj]] : 0.0;
-                const int jn = n - j0 < 32 ? n - j0 : 32;
-                for (int j = 0; j < jn; j++) acc += s_a[(j0 + j) * ld + ic] * __shfl_sync(0xffffffffu, xv, j);
-            }
-            if (i < n) z[perm[p0 + i]] = acc;
-        }
-    }
-}
-
 // update!(P, A): rebuild the dense inverses from the current values of A
 int32_t tb_pc_bj_update(tb_ctx *ctx, const tb_csr *A) {
     tb_bj *B = ctx->bj;
@@ -365,7 +312,6 @@ int32_t tb_pc_bj_update(tb_ctx *ctx, const tb_csr *A) {
     const size_t smem = sizeof(double) * 2 * (size_t)B->max_bs;
     const int grid = (int)(B->nblocks < (int64_t)ctx->sm_count * 2 ? B->nblocks : (int64_t)ctx->sm_count * 2);
     TB_LAUNCH(ctx, k_bj_invert, grid, 512, smem, B->d_bptr, B->d_iptr, B->d_inv, B->nblocks, d_fail);
-    TB_LAUNCH(ctx, k_bj_symmetrize, grid, 256, 0, B->d_bptr, B->d_iptr, B->d_inv, B->nblocks);
     int fail = 0;
     TB_CUDA(cudaMemcpyAsync(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     TB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -375,23 +321,6 @@ int32_t tb_pc_bj_update(tb_ctx *ctx, const tb_csr *A) {
 
 int32_t tb_pc_bj_apply(tb_ctx *ctx, const double *r, double *z, const CGState *st) {
     tb_bj *B = ctx->bj;
-    // blocks whose padded image fits shared memory: stream the lower triangle only (TB_BJ_SYM=0 keeps the full-matrix kernel)
-    static int use_sym = -1;
-    if (use_sym < 0) {
-        const char *e = getenv("TB_BJ_SYM");
-        use_sym = e ? atoi(e) != 0 : 1;
-    }
-    const size_t smem_sym = sizeof(double) * (size_t)B->max_bs * (size_t)(B->max_bs + 1);
-    if (use_sym && smem_sym <= (size_t)100 * 1024) {
-        TB_CUDA(tb_ensure_smem(ctx, (const void *)k_bj_apply_sym, smem_sym));
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bj_apply_sym, 128, smem_sym);
-        if (per_sm < 1) per_sm = 1;
-        const int64_t cap = (int64_t)ctx->sm_count * per_sm;
-        const int grid = (int)(B->nblocks < cap ? B->nblocks : cap);
-        TB_LAUNCH(ctx, k_bj_apply_sym, grid, 128, smem_sym, r, z, B->d_perm, B->d_bptr, B->d_iptr, B->d_inv, B->nblocks, st);
-        return TB_OK;
-    }
     int threads = (B->max_bs + 31) / 32 * 32;          // one warp per 32-row tile of the largest block, at most 8 warps
     if (threads > 256) threads = 256;
     const int64_t cap = (int64_t)ctx->sm_count * (2048 / threads);
