@@ -109,6 +109,20 @@ static inline tb_tma_geom tb_tma_geometry(int max_width, int col_ints, int stage
     return g;
 }
 
+// Shared-memory column stage of the compressed stream, in ints.  Default: the slot headers only (one int per slot, padded to
+// 4) -- slices that also carry explicit 32-id blocks read their ids from the uncompressed SELL array, see tb_sell_sweep_tma.
+// TB_SPMV_HDRONLY=0 sizes the stage for the largest stream of the operator instead (round-1 behaviour: 21 instead of 31 warps
+// per SM on the 27-point operator).
+static inline int tb_ccol_stage_ints(int max_width, int max_ccol_ints) {
+    static int hdr_only = -1;
+    if (hdr_only < 0) {
+        const char *e = getenv("TB_SPMV_HDRONLY");
+        hdr_only = e ? atoi(e) != 0 : 1;
+    }
+    const int hdr = ((max_width < 1 ? 1 : max_width) + 3) & ~3;
+    return hdr_only && hdr < max_ccol_ints ? hdr : max_ccol_ints;
+}
+
 // One warp = one private ring of STAGES slices.  `epi(row, acc)` is called by every lane with the
 // finished row sum (rows >= nrows included: the caller masks).
 // CC = false: cstream = SELL column ids, cptr unused.  CC = true: cstream/cptr = compressed column stream.
@@ -165,11 +179,12 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         }
         if (CC) {
             const int64_t cb = cptr[s];
-            const unsigned cn = (unsigned)(cptr[s + 1] - cb);      // ints, multiple of 4
+            unsigned cn = (unsigned)(cptr[s + 1] - cb);            // ints, multiple of 4
+            if (cn * 4u > col_bytes) cn = 0;                       // stream larger than the stage: its ids are read from `col` (below)
             tb_mbar_expect_tx(bar, n * 8u + cn * 4u);
             if (n) {
                 tb_bulk_g2s(tb_smem_addr(dst), val + base, n * 8u, bar);
-                tb_bulk_g2s(tb_smem_addr(dst + val_bytes), cstream + cb, cn * 4u, bar);
+                if (cn) tb_bulk_g2s(tb_smem_addr(dst + val_bytes), cstream + cb, cn * 4u, bar);
             }
         } else {
             tb_mbar_expect_tx(bar, n * 12u);
@@ -229,7 +244,24 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             const int hdr_ints = (w + 3) & ~3;
             const int *sexp = sc + hdr_ints + lane;
             int e = 0, j = 0;
-            if ((int)(cptr[s + 1] - cptr[s]) == hdr_ints) {
+            const int cn = (int)(cptr[s + 1] - cptr[s]);
+            if ((unsigned)cn * 4u > col_bytes) {
+                // The column stage holds headers only (tb_ccol_stage_ints): a slice with explicit blocks -- on a structured grid
+                // the one slice in sixteen that straddles a grid line -- takes its ids from the SELL array instead, 128
+                // coalesced bytes per slot; its values were staged like everybody's.  Sizing the stage for these slices costs
+                // a third of the warps an SM can hold.
+                const int *gc = col + slice_ptr[s] + lane;
+                for (; j + 9 <= w; j += 9) {
+                    double xv[9], vv[9];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) xv[k] = tb_gx<FP>(x, x2, beta, gc[(int64_t)(j + k) * 32]);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) vv[k] = sv[(j + k) * 32];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) acc += vv[k] * xv[k];
+                }
+                for (; j < w; j++) acc += sv[j * 32] * tb_gx<FP>(x, x2, beta, gc[(int64_t)j * 32]);
+            } else if (cn == hdr_ints) {
                 // fast path (most slices of a structured mesh): every slot is a uniform offset
                 for (; j + 9 <= w; j += 9) {
                     double xv[9], vv[9];
