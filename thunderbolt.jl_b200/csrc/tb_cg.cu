@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(1024, 1)
 static int32_t launch_spmv_fp(tb_ctx *ctx, const tb_pattern *pat, const double *val, const double *r, const double *p_old, double *p_new,
                               double *Ap, CGState *st, double *part, unsigned *tick) {
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
-    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? tb_ccol_stage_ints(pat->max_width_tma, pat->max_ccol_ints) : 32 * pat->max_width_tma, 1, 0);
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? tb_ccol_stage_ints(pat) : 32 * pat->max_width_tma, 1, 0);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);
     tb_wide_list wide;
@@ -260,7 +260,7 @@ static int32_t launch_spmv_tma(tb_ctx *ctx, int warps_override, const tb_pattern
                                const double *bS, double *xout, double *r, double *pout, CGState *st, double *part,
                                unsigned *tick, bool dist, const tb_ar_args &ar, const tb_hwait_args &hw, const double *dinv) {
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
-    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? tb_ccol_stage_ints(pat->max_width_tma, pat->max_ccol_ints) : 32 * pat->max_width_tma, STAGES, warps_override);
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? tb_ccol_stage_ints(pat) : 32 * pat->max_width_tma, STAGES, warps_override);
     const int64_t need = (pat->nslices + g.warps - 1) / g.warps;
     const int grid = (int)(need < ctx->sm_count ? need : ctx->sm_count);   // one CTA per SM, one balanced wave
     tb_wide_list wide;

@@ -654,7 +654,7 @@ int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const d
     TB_TRY(tb_ctx_ensure_cgwork(ctx, pat->ncols));
     double *r = ctx->d_cgwork, *p = r + ctx->cgwork_ld, *Ap = p + ctx->cgwork_ld;
     const bool cc = ctx->spmv_compress && pat->d_ccol != nullptr;
-    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? tb_ccol_stage_ints(pat->max_width_tma, pat->max_ccol_ints) : 32 * pat->max_width_tma, 1, 0);
+    const tb_tma_geom g = tb_tma_geometry(pat->max_width_tma, cc ? tb_ccol_stage_ints(pat) : 32 * pat->max_width_tma, 1, 0);
     PcgTmaArgs P{pat->d_slice_ptr, pat->d_col, cc ? pat->d_ccol : pat->d_col, pat->d_cptr, g.val_bytes, g.col_bytes, tb_wide_list()};
     P.wide.slices = pat->d_wide_slices;
     P.wide.n = (int)pat->n_wide;
