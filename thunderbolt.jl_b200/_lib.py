@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "lib" / "libtbolt_b200.so"
+LIB_PATH = Path(os.environ.get("TB_LIB", PKG_DIR / "lib" / "libtbolt_b200.so"))   # TB_LIB: A/B runs against another build
 HEADER = PKG_DIR.parent / "include" / "tbolt_b200.h"
 
 TB_OK = 0

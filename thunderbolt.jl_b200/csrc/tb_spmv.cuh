@@ -171,9 +171,29 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
 
     const int64_t gw = (int64_t)blockIdx.x * nwarp + warp, nw = (int64_t)gridDim.x * nwarp;
 
-    auto issue = [&](int stage, int64_t s) {   // lane 0 only
-        const int64_t base = slice_ptr[s];
-        const unsigned n = (unsigned)(slice_ptr[s + 1] - base);   // stored entries of the slice (32 * width)
+    // Where a slice lives: loaded by every lane (one broadcast transaction each) ONE ITERATION AHEAD of its use, so that neither
+    // the bulk copies of the next slice nor the loop over the current one start behind an L2 round trip (ncu source view of
+    // the round-1 form: 15 % of the stall samples on `slice_ptr[s + 1] - slice_ptr[s]`, and the empty stage waited as long
+    // again before its copy was even issued).
+    struct Meta {
+        int64_t base, cb;
+        unsigned n, cn;      // stored entries (32 * width); ints of the compressed column stream
+    };
+    auto load_meta = [&](int64_t s) {
+        Meta m{0, 0, 0u, 0u};
+        if (s < nslices) {
+            m.base = slice_ptr[s];
+            m.n = (unsigned)(slice_ptr[s + 1] - m.base);
+            if (CC) {
+                m.cb = cptr[s];
+                m.cn = (unsigned)(cptr[s + 1] - m.cb);
+            }
+        }
+        return m;
+    };
+    auto issue = [&](int stage, const Meta &m) {   // lane 0 only
+        const int64_t base = m.base;
+        const unsigned n = m.n;
         const unsigned bar = tb_smem_addr(bars + stage);
         unsigned char *dst = wbase + (size_t)stage * stage_bytes;
         if (n > TB_TMA_WCAP * 32u) {            // wide slice: nothing is staged, the phase completes at once
@@ -181,8 +201,8 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             return;
         }
         if (CC) {
-            const int64_t cb = cptr[s];
-            unsigned cn = (unsigned)(cptr[s + 1] - cb);            // ints, multiple of 4
+            const int64_t cb = m.cb;
+            unsigned cn = m.cn;                                    // ints, multiple of 4
             if (cn * 4u > col_bytes) cn = 0;                       // stream larger than the stage: its ids are read from `col` (below)
             tb_mbar_expect_tx(bar, n * 8u + cn * 4u);
             if (n) {
@@ -202,16 +222,19 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
     int stage = ring ? ring->stage : 0;
     unsigned parity = ring ? ring->parity : 0;
     int64_t s_issue = gw;
-    if (lane == 0) {
+    Meta held[STAGES];                     // metadata of the slices in flight, by ring position (consumption order)
+    {
         int st = stage;
 #pragma unroll
         for (int k = 0; k < STAGES; k++) {
-            if (s_issue < nslices) issue(st, s_issue);
+            held[k] = load_meta(s_issue);
+            if (lane == 0 && s_issue < nslices) issue(st, held[k]);
             s_issue += nw;
             if (++st == STAGES) st = 0;
         }
     }
     s_issue = gw + (int64_t)STAGES * nw;   // same value in every lane
+    Meta ahead = load_meta(s_issue);       // the slice that will be issued when the first stage is free
 
     // wide rows first (the first staged slices are already in flight): one warp per row
     for (int64_t q = gw; q < (int64_t)wide.n * TB_SLICE; q += nw) {
@@ -233,7 +256,8 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
     }
 
     for (int64_t s = gw; s < nslices; s += nw) {
-        const int w = (int)((slice_ptr[s + 1] - slice_ptr[s]) >> 5);
+        const Meta cur = held[0];
+        const int w = (int)(cur.n >> 5);
         const int row = (int)(s * TB_SLICE) + lane;
         tb_mbar_wait(tb_smem_addr(bars + stage), parity);
         const double *sv = reinterpret_cast<const double *>(wbase + (size_t)stage * stage_bytes) + lane;
@@ -247,13 +271,13 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
             const int hdr_ints = (w + 3) & ~3;
             const int *sexp = sc + hdr_ints + lane;
             int e = 0, j = 0;
-            const int cn = (int)(cptr[s + 1] - cptr[s]);
+            const int cn = (int)cur.cn;
             if ((unsigned)cn * 4u > col_bytes) {
                 // The column stage holds headers only (tb_ccol_stage_ints): a slice with explicit blocks -- on a structured grid
                 // the one slice in sixteen that straddles a grid line -- takes its ids from the SELL array instead, 128
                 // coalesced bytes per slot; its values were staged like everybody's.  Sizing the stage for these slices costs
                 // a third of the warps an SM can hold.
-                const int *gc = col + slice_ptr[s] + lane;
+                const int *gc = col + cur.base + lane;
                 for (; j + 9 <= w; j += 9) {
                     double xv[9], vv[9];
 #pragma unroll
@@ -314,8 +338,12 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         if (!wide_done) epi(s * TB_SLICE + lane, acc);
         // every lane has consumed its shared-memory operands (acc depends on all of them): the stage may be refilled
         __syncwarp();
-        if (lane == 0 && s_issue < nslices) issue(stage, s_issue);
+        if (lane == 0 && s_issue < nslices) issue(stage, ahead);
+#pragma unroll
+        for (int k = 0; k + 1 < STAGES; k++) held[k] = held[k + 1];
+        held[STAGES - 1] = ahead;
         s_issue += nw;
+        ahead = load_meta(s_issue);        // in flight while the next slice is waited for and consumed
         if (++stage == STAGES) {
             stage = 0;
             parity ^= 1u;
