@@ -235,6 +235,25 @@ def test_lv_high_valence_apex_rows(tb, dev, oracle, nc, nr, nl, cg_mode):
             assert dev.cg_last_path() == (2 if cg_mode == 1 else cg_mode)     # rows bound to lanes (path 1) never take a wide slice
             assert conv and convo and abs(it - ito) <= 2
             assert np.abs(yv.to_host() - xo).max() <= 1e-9 * np.abs(xo).max()
+        if cg_mode != 1:
+            # the fused start (b = M u inside the solve) and the solve from a given b sum r.r over the same rows in the
+            # same threads -- wide rows included, which one warp per row handles in both -- so the two entry points give the
+            # same BITS however ill-conditioned the operator (bench.py's fused_vs_unfused check on the 966 k-dof LV)
+            ion = tb.ParametrizedFHNModel()
+            st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+            st.set_cg(*tight)
+            u0 = np.concatenate([0.5 + 0.5 * np.sin(np.arange(mo.ndofs) * 0.37), np.zeros(mo.ndofs)])
+            uf, uu = tb.B200Vector.from_host(dev, u0, 2), tb.B200Vector.from_host(dev, u0, 2)
+            it_f, _, conv_f = st.step(uf, 0.0, 0.01)
+            phi = tb.B200Vector.from_host(dev, u0[:mo.ndofs])
+            M.mul(bv, phi)
+            it_u, _, conv_u = tb.core.cg_solve(dev, A, bv, yv, *tight)
+            uu.copy_from(yv, scol=0, dcol=0)
+            tb.core.cell_step(dev, ion.model_id, ion.params(), uu, 0.0, 0.01, 1, 0.1, phi_idx=0)
+            assert conv_f and conv_u and it_f == it_u
+            assert np.array_equal(uf.to_host(), uu.to_host())
+            for h in (st, uf, uu, phi):
+                h.free()
     finally:
         dev.cg_set_persistent(1)
     for h in (M, K, A, xv, yv, bv, mesh):

@@ -196,6 +196,8 @@ def lib():
         L.tb_version.restype = C.c_int32
         L.tb_last_error.restype = C.c_char_p
         for name, args in _SIGNATURES.items():
+            if not hasattr(L, name) and "TB_LIB" in os.environ:
+                continue                      # an older build under test: calls to what it lacks fail loudly
             f = getattr(L, name)
             f.argtypes = args
             f.restype = C.c_int32

@@ -516,13 +516,27 @@ __global__ void __launch_bounds__(1024, 1)
     tb_tma_ring ring;
     double acc = 0.0;
     if (FROM_B) {
-        for (int64_t i = tid; i < nrows; i += nth) {
+        // Row i = tid + k * nth is the row this thread's lane gets in the sweep below (warp gw takes slices gw, gw + nw, ...),
+        // so the partial sums of r.z -- and with them every bit of the solve -- are those of the fused "b = M u" start.  Rows of
+        // wide slices are the exception in the sweep (one warp per row, summed by its lane 0), hence also here.
+        const int lane = threadIdx.x & 31;
+        const int64_t gw = tid >> 5, nw = nth >> 5;
+        auto start = [&](int64_t i) {
             const double v = src[i];
             const double z = dinv ? dinv[i] * v : v;
             x[i] = 0.0;
             r[i] = v;
             p[i] = z;
             acc += v * z;
+        };
+        for (int64_t q = gw; q < (int64_t)P.wide.n * TB_SLICE; q += nw) {
+            const int64_t i = P.wide.slices[q >> 5] * TB_SLICE + (q & 31);
+            if (lane == 0 && i < nrows) start(i);
+        }
+        for (int64_t i = tid; i < nrows; i += nth) {
+            const int64_t s = i >> 5;
+            if (P.wide.n > 0 && P.slice_ptr[s + 1] - P.slice_ptr[s] > (int64_t)TB_TMA_WCAP * TB_SLICE) continue;
+            start(i);
         }
     } else {
         tb_sell_sweep_tma<1, CC>(P.slice_ptr, Mval, P.cstream, P.cptr, src, nslices, P.val_bytes, P.col_bytes, tb_dyn_smem,

@@ -245,12 +245,23 @@ __device__ __forceinline__ void tb_sell_sweep_tma(const int64_t *__restrict__ sl
         const int *c = (CC ? col : cstream) + base + rl;
         const double *v = val + base + rl;
         double acc = 0.0;
-        for (int j0 = 0; j0 < w; j0 += 32) {
-            const int j = j0 + lane;
-            double prod = 0.0;
-            if (j < w) prod = v[(int64_t)j * 32] * tb_gx<FP>(x, x2, beta, c[(int64_t)j * 32]);
-            const int m = w - j0 < 32 ? w - j0 : 32;
-            for (int k = 0; k < m; k++) acc += __shfl_sync(0xffffffffu, prod, k);
+        // eight chunks of 32 entries are fetched before the first of them is added: the (column id -> x) load chains of a
+        // chunk are two dependent L2 round trips, and a 483-entry apex row walked one chunk at a time kept its warp -- and with
+        // it the end of the sweep -- busy for ~27 us.  The additions stay in entry order.
+        constexpr int WU = 8;
+        for (int j0 = 0; j0 < w; j0 += 32 * WU) {
+            double prod[WU];
+#pragma unroll
+            for (int u = 0; u < WU; u++) {
+                const int j = j0 + u * 32 + lane;
+                prod[u] = j < w ? v[(int64_t)j * 32] * tb_gx<FP>(x, x2, beta, c[(int64_t)j * 32]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < WU; u++) {
+                const int left = w - (j0 + u * 32);
+                const int m = left < 32 ? left : 32;
+                for (int k = 0; k < m; k++) acc += __shfl_sync(0xffffffffu, prod[u], k);
+            }
         }
         if (lane == 0) epi(s * TB_SLICE + rl, acc);
     }
