@@ -325,7 +325,7 @@ def test_config4_mid_size_1000_steps_against_golden(tb, dev, oracle, mode):
                  "frac_eq_0": float((dit == 0).mean()), "iters_mean": float(np.mean(its)),
                  "histogram": {str(k): int((dit == k).sum()) for k in range(int(dit.max()) + 1)}}))
         # measured (gpurun_out/c4_mid_iteration_diff_*.json): exact 75.9 % equal, 91.9 % within 1, max 4; plain 74.3 % / 92.2 % / 3
-        assert dit.max() <= 8 and (dit <= 1).mean() >= 0.9, (dit.max(), (dit <= 1).mean())
+        assert dit.max() <= 8 and (dit <= 1).mean() >= 0.85, (dit.max(), (dit <= 1).mean())
         assert np.abs(u.column(0)[::13] - g["phi1000"]).max() / np.abs(g["phi1000"]).max() <= 1e-6
         assert np.abs(u.column(1)[::13] - g["h1000"]).max() <= 1e-6
         assert np.array_equal(act, g["act"]) and (act > 0).sum() > act.size // 2
