@@ -158,6 +158,7 @@ static int32_t pattern_from_device_csr(tb_ctx *ctx, int64_t nrows, int64_t ncols
                                        const int *d_colidx, tb_pattern **out) {
     tb_pattern *p = new (std::nothrow) tb_pattern();
     if (!p) return tb_fail(TB_ERR_NOMEM, "tb_pattern: host allocation failed");
+    p->uid = tb_next_uid();
     p->ctx = ctx;
     p->nrows = nrows;
     p->ncols = ncols;

@@ -243,6 +243,9 @@ struct tb_mesh {
     // (tb_assembly.cu): entry = cell*nv + a, each list sorted ascending = the reference's element order
     mutable int64_t *d_adjptr = nullptr;   // ndofs_owned + 1
     mutable unsigned *d_adj = nullptr;
+    mutable unsigned char *d_adjpos = nullptr;   // per adjacency entry (row, cell, a): slot of each of the cell's nv dofs in the row (gather assembly)
+    mutable uint64_t adjpos_pat_uid = 0;         // pattern the slots were computed for
+    mutable int adjpos_state = 0;                // 0 not tried, 1 built, -1 not applicable (rows wider than 255, or over budget)
     mutable int64_t nadj = 0;
     // per 32-row slice: smallest / largest adjacent cell (host copy), and the chunk plans derived from it
     mutable std::vector<int> slice_cmin, slice_cmax;
@@ -293,6 +296,7 @@ struct tb_pattern {
     int64_t ccol_len = 0;
     int max_ccol_ints = 0;        // largest per-slice stream (sizes the shared-memory stage)
     int refcount = 1;
+    uint64_t uid = 0;             // identity of the pattern (the mesh caches data computed against it)
     int *d_diag_slot = nullptr;   // per row: entry slot of the diagonal (-1: none); built on first use by the Jacobi preconditioner
     tb_halo halo;
     // element colouring cache (assembly mode 1)

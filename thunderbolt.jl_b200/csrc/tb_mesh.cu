@@ -187,6 +187,7 @@ extern "C" int32_t tb_mesh_destroy(tb_mesh *m) {
     cudaFree(m->d_ghost_global);
     cudaFree(m->d_adjptr);
     cudaFree(m->d_adj);
+    cudaFree(m->d_adjpos);
     delete m;
     return TB_OK;
 }
