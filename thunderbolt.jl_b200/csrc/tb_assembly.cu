@@ -747,6 +747,7 @@ __global__ void __launch_bounds__(256)
                       int64_t slice1, int maxw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PS = NV == 3 ? 4 : NV;
+    constexpr int GB = 4;                              // adjacency entries in flight per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     double *acc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * maxw * TB_SLICE + lane;
     struct Entry {
@@ -777,15 +778,20 @@ __global__ void __launch_bounds__(256)
         for (int j = 0; j < w; j++) acc[j * TB_SLICE] = 0.0;
         const int64_t r = s * TB_SLICE + lane;
         if (r < S.nrows) {
-            int64_t q = adjptr[r];
+            // GB adjacency entries at a time: their (cell, a) words first, then all GB matrix rows and slot words -- two
+            // round trips per batch instead of two per entry -- and the additions in adjacency order as always
             const int64_t q1 = adjptr[r + 1];
-            Entry cur, nxt;
-            if (q < q1) load(nxt, q);
-            for (; q < q1; q++) {
-                cur = nxt;
-                if (q + 1 < q1) load(nxt, q + 1);
+            for (int64_t q = adjptr[r]; q < q1; q += GB) {
+                Entry e[GB];
 #pragma unroll
-                for (int b = 0; b < NV; b++) acc[cur.pos[b] * TB_SLICE] += cur.kv[b];
+                for (int k = 0; k < GB; k++)
+                    if (q + k < q1) load(e[k], q + k);
+#pragma unroll
+                for (int k = 0; k < GB; k++)
+                    if (q + k < q1) {
+#pragma unroll
+                        for (int b = 0; b < NV; b++) acc[e[k].pos[b] * TB_SLICE] += e[k].kv[b];
+                    }
             }
         }
         double *dst = S.val + base + lane;
@@ -869,9 +875,7 @@ static int32_t mesh_ensure_adjpos(tb_ctx *ctx, const tb_mesh *m, const tb_patter
     constexpr int PS = NV == 3 ? 4 : NV;
     const size_t bytes = (size_t)m->nadj * PS;
     const size_t cap = ctx->ea_budget_bytes / 4;          // C5 (6.4 GB of slots) keeps the searching kernel: setup runs once there
-    // hexahedra only: 8 searches per (row, cell) there; with 4 searches (tetrahedra: 24 cells per row) the walk is bound by
-    // its one-deep prefetch chain either way and the table measured no gain (gather 2.14 vs 2.21 ms on 30 M tets)
-    if (!enabled || NV != 8 || pat->max_width > 255 || bytes > cap || m->nadj == 0) return TB_OK;
+    if (!enabled || pat->max_width > 255 || bytes > cap || m->nadj == 0) return TB_OK;
     if (cudaMalloc(&m->d_adjpos, bytes + 16) != cudaSuccess) {
         cudaGetLastError();
         m->d_adjpos = nullptr;
