@@ -244,9 +244,12 @@ def test_random_inputs_one_step_vs_oracle(tb, dev, oracle):
         b1 = torch.empty(u.size, dtype=torch.float64, pin_memory=True).numpy()
         b0[:] = u
         b1[:] = np.nan
+        st.set_host_chunks({1: 16, 4: 3, 5: 64}[nsteps])         # pieces of the phi round trip: any count, same bits
         tot2, conv3 = st.run_host(ud, b0, b1, 0.0, 0.5, nsteps)
         res = b1 if nsteps % 2 else b0
         assert conv3 and tot2 == tot and np.array_equal(res, want) and np.array_equal(ud.to_host(), want)
+    with pytest.raises(tb.TBError):
+        st.set_host_chunks(65)
     for x in (st, ud, bS, M, K, md):
         x.free()
 
