@@ -22,6 +22,9 @@ KERNELS = {
     "k_cell_step<PCG2019,true,false>": r"_Z11k_cell_stepILi1ELb1ELb0EE",
     "k_bj_apply": r"_Z10k_bj_apply",
     "k_element_matrices<8,3,1>": r"_Z18k_element_matricesILi8ELi3ELi1EE",
+    "k_element_matrices_split<8,3,1,2,64> (round 2 default)": r"_Z24k_element_matrices_splitILi8ELi3ELi1ELi2ELi64EE",
+    "k_gather_rows_pos<8>": r"_Z17k_gather_rows_posILi8EE",
+    "k_cg_persistent2<1,false> (two ticket barriers per iteration)": r"_Z16k_cg_persistent2ILi1ELb0EE",
 }
 WATCH = ["UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "DFMA", "DMUL", "DADD", "MUFU", "SHFL", "RED", "ATOM", "MEMBAR", "CCTL",
          "ERRBAR", "BAR", "LDGSTS", "UTMALDG", "LD.E.64.STRONG.SYS", "ST.E.64.STRONG.SYS"]
