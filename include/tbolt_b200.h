@@ -407,6 +407,8 @@ int32_t tb_monodomain_step(tb_monodomain *md, tb_vec *u, double t, double dt, in
 int32_t tb_monodomain_step_rt(tb_monodomain *md, tb_vec *u, double t, double dt, int64_t *iters, double *rnorm,
                               int32_t *converged, double *reaction_tangent);
 /* `nsteps` steps back to back with one host round trip at the end (iters = total, converged = all) */
+/* (tb_monodomain_run: when the inner solve is one persistent kernel -- operators up to ~4 M rows, no block-Jacobi / Chebyshev --
+ * the whole run is enqueued without a host read-back; iteration counts and convergence flags are accumulated on the device) */
 int32_t tb_monodomain_run(tb_monodomain *md, tb_vec *u, double t0, double dt, int64_t nsteps, int64_t *iters_total,
                           int32_t *all_converged);
 /* end-to-end variant on HOST buffers: uploads u_in, steps, downloads into u_out (may alias u_in) */

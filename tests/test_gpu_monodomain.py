@@ -387,3 +387,41 @@ def test_c2_full_size_properties(tb, dev):
     assert np.isfinite(u.to_host()).all()
     for h in (st, u, bS, A, phi, b, y, xs, M, K, md):
         h.free()
+
+
+@pytest.mark.parametrize("mode,nel", [(1, (48, 40)), (2, (48, 40)), (0, (48, 40)), (1, (40, 36, 30))])
+def test_run_without_readbacks_matches_stepping(tb, dev, mode, nel):
+    """tb_monodomain_run: with a persistent CG kernel (mode 1: register-resident, mode 2: TMA sweep) the whole run is enqueued
+    without a read-back, iteration counts and convergence flags folded on the device (k_pcg_fold); with the multi-kernel path
+    (mode 0) it is the per-step loop.  Either way: the state and the total iteration count of stepping one by one, to the bit."""
+    ct = tb.Quadrilateral if len(nel) == 2 else tb.Hexahedron
+    md = tb.generate_mesh(ct, nel, (0.0,) * len(nel), tuple(0.25 * n for n in nel), device=dev)
+    M = tb.B200CSRMatrix.from_mesh(dev, md)
+    K = M.like()
+    tb.core.assemble_mass(dev, md, M, 2, 1.0)
+    tb.core.assemble_diffusion(dev, md, K, 2, tb._lib.D_TENSOR, np.diag([0.13, 0.02, 0.02][:len(nel)]), 1.0)
+    ion = tb.ParametrizedFHNModel()
+    st = tb.MonodomainStepper(dev, M, K, ion.model_id, ion.params())
+    n = md.ndofs
+    rng = np.random.default_rng(8)
+    u0 = np.concatenate([rng.uniform(0, 1, n), 0.1 * rng.uniform(0, 1, n)])
+    dev.cg_set_persistent(mode)
+    try:
+        for precond in (tb._lib.PRECOND_NONE, tb._lib.PRECOND_JACOBI):
+            st.set_preconditioner(precond)
+            ua, ub = tb.B200Vector.from_host(dev, u0, 2), tb.B200Vector.from_host(dev, u0, 2)
+            tot, t = 0, 0.0
+            for _ in range(7):
+                it, _rn, conv = st.step(ua, t, 0.7)
+                assert conv and dev.cg_last_path() == mode
+                tot += it
+                t += 0.7
+            tot2, conv2 = st.run(ub, 0.0, 0.7, 7)
+            assert conv2 and tot2 == tot and np.array_equal(ua.to_host(), ub.to_host())
+            it, _rn, conv = st.step(ub, t, 0.7)                       # and the per-step entry point still reports afterwards
+            assert conv and it > 0
+            ua.free(); ub.free()
+    finally:
+        dev.cg_set_persistent(1)
+    for h in (st, M, K, md):
+        h.free()

@@ -462,6 +462,31 @@ static int32_t launch_pcg(tb_ctx *ctx, int grid, const PcgMat &P, const double *
     return TB_OK;
 }
 
+// deferred read-back (tb_monodomain_run): totals of a run of solves stay on the device
+__global__ void k_pcg_totals_reset(CGState *st) {
+    st->iter_sum = 0;
+    st->all_solved = 1;
+}
+__global__ void k_pcg_fold(CGState *st) {
+    st->iter_sum += st->iter;
+    st->all_solved &= st->solved;
+}
+int32_t tb_cg_deferred_begin(tb_ctx *ctx) {
+    TB_LAUNCH(ctx, k_pcg_totals_reset, 1, 1, 0, ctx->d_cg);
+    ctx->cg_deferred = true;
+    return TB_OK;
+}
+int32_t tb_cg_deferred_end(tb_ctx *ctx, int64_t *iters_total, int32_t *all_solved) {
+    ctx->cg_deferred = false;
+    CGState *h = ctx->h_cg;
+    TB_CUDA(cudaMemcpyAsync(h, ctx->d_cg, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (iters_total) *iters_total = h->iter_sum;
+    if (all_solved) *all_solved = h->all_solved;
+    ctx->last_cg_iters = h->iter;
+    return TB_OK;
+}
+
 __global__ void k_pcg_set_tol(CGState *st, double atol, double rtol, long long itmax) {
     st->atol = atol;
     st->rtol = rtol;
@@ -684,6 +709,14 @@ int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const d
     else st = cc ? launch_pcg_tma<false, true>(ctx, grid, g.warps * 32, g.smem, P, A->d_val, Mval, src, bS, x, r, p, Ap, pat->nrows, pat->nslices, dinv)
                  : launch_pcg_tma<false, false>(ctx, grid, g.warps * 32, g.smem, P, A->d_val, Mval, src, bS, x, r, p, Ap, pat->nrows, pat->nslices, dinv);
     if (st != TB_OK) return st;
+    if (ctx->cg_deferred) {               // tb_monodomain_run: fold into the device-side totals, nothing comes back now
+        TB_LAUNCH(ctx, k_pcg_fold, 1, 1, 0, ctx->d_cg);
+        ctx->last_cg_persistent = 2;
+        if (iters) *iters = 0;
+        if (rnorm) *rnorm = 0.0;
+        if (converged) *converged = 1;
+        return TB_OK;
+    }
     if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[1], ctx->stream));
     CGState *h = ctx->h_cg;
     TB_CUDA(cudaMemcpyAsync(h, ctx->d_cg, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -751,6 +784,14 @@ int32_t tb_cg_run_persistent(tb_ctx *ctx, int grid, const tb_csr *A, const doubl
 #undef PCG_GO
 #undef PCG_GO2
     if (st != TB_OK) return st;
+    if (ctx->cg_deferred) {
+        TB_LAUNCH(ctx, k_pcg_fold, 1, 1, 0, ctx->d_cg);
+        ctx->last_cg_persistent = 1;
+        if (iters) *iters = 0;
+        if (rnorm) *rnorm = 0.0;
+        if (converged) *converged = 1;
+        return TB_OK;
+    }
     if (ctx->profile) TB_CUDA(cudaEventRecord(ctx->prof_ev[1], ctx->stream));
     CGState *h = ctx->h_cg;
     TB_CUDA(cudaMemcpyAsync(h, ctx->d_cg, sizeof(CGState), cudaMemcpyDeviceToHost, ctx->stream));

@@ -187,6 +187,7 @@ struct tb_ctx {
     int64_t cg_persistent_max_rows = 4000000;   // above this the multi-kernel path is used (env TB_CG_PERSISTENT_MAX_ROWS)
     // per-kernel profiling of the dominant kernel (SpMV inside CG): CUDA events around each launch
     bool profile = false;
+    bool cg_deferred = false;         // tb_monodomain_run: the persistent CG paths leave their scalars on the device (no read-back per solve)
     cudaEvent_t prof_ev[2 * TB_PROF_MAX] = {};
     double prof_spmv_ms = 0.0;
     int64_t prof_spmv_n = 0;
@@ -215,7 +216,9 @@ struct CGState {
     long long itmax;
     int done;           // solved || tired
     int solved;
-    int pad[2];
+    int all_solved;     // tb_monodomain_run (deferred read-back): AND of `solved` over the run's solves
+    int pad;
+    long long iter_sum; // ... and the sum of their iteration counts (k_pcg_fold)
 };
 
 struct tb_vec {
@@ -606,6 +609,8 @@ int32_t tb_pc_bj_apply(tb_ctx *ctx, const double *r, double *z, const struct CGS
 int32_t tb_cg_run_impl(tb_ctx *ctx, const tb_csr *A, const double *b, const tb_csr *M, double *phi, const double *bS,
                        double *x, double atol, double rtol, int64_t itmax, int64_t *iters, double *rnorm,
                        int32_t *converged, int precond = 0);
+int32_t tb_cg_deferred_begin(tb_ctx *ctx);
+int32_t tb_cg_deferred_end(tb_ctx *ctx, int64_t *iters_total, int32_t *all_solved);
 int tb_cg_persistent_grid(tb_ctx *ctx, const tb_pattern *pat);
 int tb_cg_persistent_kind(tb_ctx *ctx, const tb_pattern *pat, int *grid_out);
 int32_t tb_cg_run_persistent_tma(tb_ctx *ctx, int grid, const tb_csr *A, const double *b, const tb_csr *M, const double *phi,

@@ -195,6 +195,31 @@ extern "C" int32_t tb_monodomain_run(tb_monodomain *md, tb_vec *u, double t0, do
     TB_REQUIRE(md && u && nsteps >= 0, "tb_monodomain_run: bad argument");
     int64_t total = 0;
     int32_t all = 1;
+    // Small and mid-size operators solve in ONE persistent kernel that needs nothing from the host: then the whole run is
+    // enqueued without a single read-back -- iteration counts and convergence flags are folded into device-side totals
+    // (k_pcg_fold) and fetched once at the end.  At C1 size a third of a step was the blocking scalar read-back and the
+    // launch gaps behind it.  (The multi-kernel path polls the host by design and keeps the per-step loop below.)
+    {
+        tb_ctx *ctx = md->ctx;
+        int pgrid = 0;
+        const bool gen_pc = md->precond == TB_PRECOND_BLOCK_JACOBI || md->precond == TB_PRECOND_CHEBYSHEV;
+        if (nsteps > 1 && !gen_pc && !ctx->exact_dot && !md->timing && !ctx->profile &&
+            tb_cg_persistent_kind(ctx, md->M->pat, &pgrid) != 0) {
+            TB_DEV(ctx);
+            TB_TRY(tb_cg_deferred_begin(ctx));
+            int32_t st = TB_OK;
+            for (int64_t s = 0; s < nsteps && st == TB_OK; s++) {
+                st = tb_monodomain_step(md, u, t0, dt, nullptr, nullptr, nullptr);
+                t0 += dt;
+            }
+            const int32_t st2 = tb_cg_deferred_end(ctx, &total, &all);
+            if (st != TB_OK) return st;
+            if (st2 != TB_OK) return st2;
+            if (iters_total) *iters_total = total;
+            if (all_converged) *all_converged = all;
+            return TB_OK;
+        }
+    }
     for (int64_t s = 0; s < nsteps; s++) {
         int64_t it = 0;
         int32_t conv = 0;
