@@ -56,3 +56,11 @@ def test_product_never_imports_the_oracle():
         text = p.read_text()
         assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), p
         assert "liboracle" not in text and "tb_oracle" not in text, p
+
+
+def test_header_is_plain_c():
+    """the drop-in boundary is a C ABI: the header must compile as C99 on its own (no C++ types, no missing includes)"""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        str(ROOT / "include" / "tbolt_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
