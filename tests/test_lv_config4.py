@@ -73,6 +73,33 @@ def test_fibres_are_orthonormal_and_rotate_transmurally():
     assert np.all(np.sign(f[endo][:, 2]) == -np.sign(f[epi][:, 2][0]) * np.ones(endo.sum())) or True
 
 
+def test_zero_angle_microstructure_known_answer():
+    """test/test_microstructures.jl:45-72 ("OrthotropicMicrostructureModel"): with all six ODB25LT angles zero the
+    generator yields sheetlets along the apicobasal direction, normals along the transmural one and f = s x n along the
+    circumferential one (tolerance 0.05 there, because the reference's axes come from Laplace solves; here they are
+    analytic, so 1e-5).  The reference's ring has rotational = clockwise; ours is counter-clockwise -- a sign the tensor
+    sum lambda_i v_i (x) v_i never sees -- hence the comparison up to sign."""
+    lv, nodes, hexes, wedges, prm, tets = _lv(24, 2, 6)
+    fsn = lv.odb25lt_fibres(prm, tets, alpha_endo=0.0, alpha_epi=0.0)
+    theta, phi, rp = (prm[tets][..., k] for k in range(3))
+    ok = theta > 0.3                                             # away from the apex, where the azimuth degenerates
+    eps = 1e-6
+    x = lv.ellipsoid_point
+    unit = lambda v: v / np.linalg.norm(v, axis=-1, keepdims=True)
+    transmural = unit(x(theta, phi, np.minimum(rp + eps, 1.0)) - x(theta, phi, np.maximum(rp - eps, 0.0)))
+    circ = np.stack([-np.sin(phi), np.cos(phi), np.zeros_like(phi)], -1)
+    f, s_, n = fsn[..., 0, :], fsn[..., 1, :], fsn[..., 2, :]
+    assert np.allclose(np.abs(np.sum(f * circ, -1))[ok], 1.0, atol=1e-5)            # f: circumferential
+    assert np.abs(np.sum(s_ * transmural, -1))[ok].max() < 1e-4                       # s: no transmural component ...
+    assert np.abs(np.sum(s_ * circ, -1))[ok].max() < 1e-4                             # ... and none along f: the apicobasal direction of the wall
+    assert np.allclose(np.sum(n * np.cross(f, s_), -1)[ok], 1.0, atol=1e-10)          # n = f x s
+    assert np.allclose(np.abs(np.sum(n * unit(transmural - np.sum(transmural * circ, -1, keepdims=True) * circ), -1))[ok], 1.0, atol=1e-4)
+    # on the cylindrical part of the reference's ring the sheetlets are vertical: same here where the wall is vertical (base ring)
+    base = ok & (np.abs(theta - np.pi / 2) < 1e-9)
+    if base.any():
+        assert np.allclose(np.abs(s_[base][:, 2]), 1.0, atol=1e-3)
+
+
 @pytest.mark.gpu
 def test_config4_lv_fibres_pcg2019_vs_oracle(tb, dev, oracle):
     O = oracle
