@@ -32,6 +32,23 @@ def test_lv_generator_matches_reference_counts():
     assert tets.shape == (6 * 48 + 3 * 16, 4)
 
 
+def test_lv_cells_have_positive_jacobians_like_the_reference_test():
+    """test/test_mesh.jl:8-21,82-87 ("Linear Mixed LV to Hex"): det J > 0 at xi = (0.1, 0.1, 0.1) for every hexahedron and
+    wedge of generate_ideal_lv_mesh(8, 4, 4) -- pins the vertex order / orientation of the restated generator."""
+    lv, nodes, hexes, wedges, prm, tets = _lv(8, 4, 4)
+    xi = np.array([0.1, 0.1, 0.1])
+    sx, sy, sz = (np.array(v, dtype=float) for v in ([-1, 1, 1, -1, -1, 1, 1, -1], [-1, -1, 1, 1, -1, -1, 1, 1], [-1, -1, -1, -1, 1, 1, 1, 1]))
+    dN_hex = 0.125 * np.stack([sx * (1 + sy * xi[1]) * (1 + sz * xi[2]), (1 + sx * xi[0]) * sy * (1 + sz * xi[2]),
+                               (1 + sx * xi[0]) * (1 + sy * xi[1]) * sz], axis=1)                     # [8, 3], Ferrite's RefHexahedron
+    # Lagrange{RefPrism, 1}: vertices (0,0,0) (1,0,0) (0,1,0) (0,0,1) (1,0,1) (0,1,1); N = tri(x, y) * (1 - z | z)
+    x, y, z = xi
+    tri, dtri = np.array([1 - x - y, x, y]), np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+    dN_wedge = np.concatenate([np.column_stack([dtri * (1 - z), -tri]), np.column_stack([dtri * z, tri])])   # [6, 3]
+    for cells, dN in ((hexes, dN_hex), (wedges, dN_wedge)):
+        J = np.einsum("cad,ae->cde", nodes[cells], dN)           # J = sum_a x_a (x) dN_a
+        assert cells.shape[0] > 0 and np.all(np.linalg.det(J) > 0)
+
+
 def test_lv_tet_split_is_conforming_and_positive():
     lv, nodes, hexes, wedges, prm, tets = _lv()
     X = nodes[tets]
