@@ -284,3 +284,36 @@ def test_subdomains_with_different_cell_models(tb, dev, oracle):
     h = integ.u.to_host()
     scale = np.maximum(np.abs(uo), 1.0)
     assert (np.abs(h - uo) / scale).max() <= 1e-9
+
+
+@pytest.mark.gpu
+def test_gather_scatter_properties_of_the_reference(tb, dev):
+    """tb_vec_gather / tb_vec_scatter against the properties the reference asserts of its own gather! / scatter!
+    (test/test_solution_vector_mapping.jl:82-110): gather then scatter is a round trip on the wired entries and leaves
+    zeros elsewhere in a wiped source; scatter touches nothing outside the wiring."""
+    import ctypes as C
+    from thunderbolt_jl_b200 import _lib as L
+    rng = np.random.default_rng(12)
+    nsource, ntarget = 1000, 317
+    wiring = np.sort(rng.choice(nsource, ntarget, replace=False)).astype(np.int64) + 1          # 1-based like the reference's dof ids
+    h = C.c_void_p()
+    L.call("tb_index_create", dev.h, L.ptr(wiring), int(wiring.size), 1, C.byref(h))
+    try:
+        original = np.arange(1.0, nsource + 1)
+        source, target = tb.B200Vector.from_host(dev, original), tb.B200Vector(dev, ntarget)
+        L.call("tb_vec_gather", target.h, 0, source.h, 0, h)
+        assert np.array_equal(target.to_host(), original[wiring - 1])
+        source.fill(0.0)                                                                          # a scatter that failed to write shows as a zero
+        L.call("tb_vec_scatter", source.h, 0, h, target.h, 0)
+        got = source.to_host()
+        assert np.array_equal(got[wiring - 1], original[wiring - 1])
+        untouched = np.setdiff1d(np.arange(nsource), wiring - 1)
+        assert np.all(got[untouched] == 0.0)
+        source.upload(original)
+        target.fill(-1.0)
+        L.call("tb_vec_scatter", source.h, 0, h, target.h, 0)
+        got = source.to_host()
+        assert np.array_equal(got[untouched], original[untouched]) and np.all(got[wiring - 1] == -1.0)
+        source.free(); target.free()
+    finally:
+        L.call("tb_index_destroy", h)
