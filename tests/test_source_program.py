@@ -26,6 +26,12 @@ CLOSURES = {
     "endo": lambda x, t: T.where((t <= 2.0) & (x[0] < 0.15), 0.5 / 0.25 * T.exp(t / 0.25), 0.0),
     "poly": lambda x, t: (x[0] - 0.3) ** 2 * x[1] - x[2] ** 3 / (1.0 + t) + abs(x[0] - x[1]),
     "mixed": lambda x, t: T.minimum(x[0] * t, 2.0) + np.tanh(x[1]) - np.sqrt(abs(x[2]) + 1.0) + (x[0] > x[1]) * 0.25,
+    # closures written with plain numpy: ufuncs on tracing numbers dispatch through __array_ufunc__, reductions over the
+    # coordinate vector (np.linalg.norm, x @ x) through the object loops
+    "numpy_minmax": lambda x, t: np.maximum(x[0], 1.0) + np.minimum(x[1], t) * np.where(False, 0.0, 1.0),
+    "numpy_norm": lambda x, t: np.linalg.norm(x) + t,
+    "numpy_dot": lambda x, t: np.exp(-(x @ x)) * np.cos(2 * np.pi * t),
+    "numpy_logic": lambda x, t: (np.less(x[0], 0.5) & np.greater_equal(t, 0.1)) * 0.5 + np.power(x[1], 2) + np.square(x[2]),
 }
 EXACT = {"cv_box", "ball", "normt"}     # +,-,*,/,sqrt,abs,min,max,compare only: bitwise on every side (poly: Python's
                                         # float ** 2 is libm pow, the trace lowers it to x*x like Julia's literal_pow)
@@ -90,7 +96,7 @@ def test_program_matches_host_evaluated_path(dev, ct, nel):
     xq = np.einsum("qa,cad->cqd", tb.api._shape_values(mesh.celltype, pts), coords[conn])
     b1, b2 = tb.B200Vector(dev, mesh.ndofs, 1), tb.B200Vector(dev, mesh.ndofs, 1)
     for name, f3 in CLOSURES.items():
-        f = f3 if dim == 3 else (lambda x, t, f3=f3: f3([x[0], x[1], 0.5 * x[0]], t))
+        f = f3 if dim == 3 else (lambda x, t, f3=f3: f3(np.array([x[0], x[1], 0.5 * x[0]], dtype=object if isinstance(x[0], T.Sym) else float), t))
         prog = T.trace_source(f, dim)
         assert prog is not None
         for t in (0.3, 2.5):

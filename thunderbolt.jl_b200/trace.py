@@ -6,7 +6,9 @@ calls f ONCE with tracing numbers, linearises the recorded expression into postf
 TB_SRC_PROGRAM) and checks the program against f itself at a few sample points.  What cannot be traced -- Python control
 flow on x or t (`if`, `and`, `max(...)` go through `bool()`), math.* functions, more than 96 instructions -- returns None and
 the caller keeps the host-evaluated path (tb_assemble_source_qp).  Branch-free forms are available as `where`, `minimum`,
-`maximum`, `norm`, `&`, `|`, `~` and numpy's ufuncs (np.exp(sym) dispatches to sym.exp()).
+`maximum`, `norm`, `&`, `|`, `~`; closures written with plain numpy trace as well: ufuncs on a tracing number
+(np.maximum(x[0], 1.0), np.exp(-r), np.less(t, 2.0), np.power(x[1], 2) ...) dispatch through `__array_ufunc__`, reductions
+over the coordinate vector (np.linalg.norm(x), x @ x) through numpy's object loops.
 
 The Julia binding does the same with a `TracedReal <: Real` number type.
 """
@@ -43,6 +45,8 @@ class Sym:
             return Sym("CONST", 1.0 if v else 0.0)
         if isinstance(v, (int, float, np.integer, np.floating)):
             return Sym("CONST", float(v))
+        if isinstance(v, np.ndarray) and v.ndim == 0 and v.dtype != object:
+            return Sym.lift(v.item())
         raise TraceError(f"cannot trace a value of type {type(v).__name__}")
 
     def _bin(self, op, other, swap=False):
@@ -86,7 +90,26 @@ class Sym:
     def __bool__(self):
         raise TraceError("the closure branches on x or t (if / and / or / max()); use where(), minimum(), maximum(), &, |")
 
-    # numpy ufuncs on object scalars call the method of the same name
+    # numpy ufuncs applied to a tracing number (np.maximum(x[0], 1.0), np.exp(-r), np.less(t, 2.0) ...) land here
+    _UFUNCS = {"add": "ADD", "subtract": "SUB", "multiply": "MUL", "true_divide": "DIV", "divide": "DIV", "maximum": "MAX",
+               "minimum": "MIN", "fmax": "MAX", "fmin": "MIN", "less": "LT", "less_equal": "LE", "greater": "GT",
+               "greater_equal": "GE", "equal": "EQ", "not_equal": "NE", "logical_and": "AND", "logical_or": "OR",
+               "negative": "NEG", "absolute": "ABS", "fabs": "ABS", "sqrt": "SQRT", "exp": "EXP", "log": "LOG", "sin": "SIN",
+               "cos": "COS", "tanh": "TANH", "logical_not": "NOT"}
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        if ufunc.__name__ in ("power", "float_power") and len(inputs) == 2 and inputs[0] is self:
+            return self.__pow__(inputs[1])
+        if ufunc.__name__ == "square" and len(inputs) == 1:
+            return self * self
+        op = Sym._UFUNCS.get(ufunc.__name__)
+        if op is None:
+            raise TraceError(f"numpy.{ufunc.__name__} cannot be traced")
+        return Sym(op, *(Sym.lift(v) for v in inputs))
+
+    # numpy ufuncs on object ARRAYS of tracing numbers call the method of the same name, element by element
     def sqrt(self): return Sym("SQRT", self)
     def exp(self): return Sym("EXP", self)
     def log(self): return Sym("LOG", self)
