@@ -98,6 +98,40 @@ def test_forward_euler_and_adaptive_agree_but_differ(oracle):
     assert not np.allclose(res[0], res[1], rtol=1e-8, atol=0)
 
 
+def test_forward_euler_and_adaptive_agree_on_the_lv(oracle):
+    """test/integration/test_electrophysiology.jl:101-121: the same wave-propagation case on generate_ideal_lv_mesh(4, 1, 1),
+    kappa = (4.5e-4, 2e-4, 2e-4), where the reference asserts FE ~ adaptive to rtol 1e-4 (isapprox on the whole solution
+    vector: |u - v| <= rtol max(|u|, |v|) in the 2-norm).  The reference's mesh is hexahedra + wedges; here its conforming
+    tetrahedral split (this project's addition, lv.tetrahedralize) carries the same nodes."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from thunderbolt_jl_b200 import lv
+    O = oracle
+    nodes, hexes, wedges, prm = lv.generate_ideal_lv_mesh(4, 1, 1)
+    tets = lv.tetrahedralize(nodes, hexes, wedges)
+    m = O.Mesh(O.TET4, tets, nodes)
+    M = O.assemble_mass(m, 2)
+    K = O.assemble_diffusion(m, 2, O.D_TENSOR, np.diag([4.5e-4, 2.0e-4, 2.0e-4]).ravel())
+    x = m.dof_coords
+    res = []
+    for sub in (1, 10):
+        orc = O.MonodomainOracle(m, O.FHN, O.default_params(O.FHN), M, K, substeps=sub)
+        u = np.zeros(2 * m.ndofs)
+        u[:m.ndofs] = np.maximum(1.0 - np.linalg.norm(x, axis=1), 0.0)            # simple_initializer!, :8-27
+        u0 = u.copy()
+        for s in range(10):
+            t = float(s)
+            if 0.0 <= t + 1.0 <= 2.1:
+                orc.bS = O.assemble_source(m, 2, O.SRC_BALL, [0.1, 2.0, 0.01], t + 1.0)
+            it, rn, conv = orc.step(u, t, 1.0)
+            assert conv
+        assert not np.allclose(u, u0)                                               # `integrator.u ≉ u₀`, :60
+        res.append(u.copy())
+    a, b = res
+    assert np.linalg.norm(a - b) <= 1e-4 * max(np.linalg.norm(a), np.linalg.norm(b))
+
+
 def test_distorted_hex_geometry(oracle):
     """test/test_coefficients.jl:239-279 compares two implementations of the mapping on this fixture;
     here: partition of unity, gradient of a linear field, detJ*w sums to the volume (independent facts)."""
