@@ -132,6 +132,30 @@ def test_forward_euler_and_adaptive_agree_on_the_lv(oracle):
     assert np.linalg.norm(a - b) <= 1e-4 * max(np.linalg.norm(a), np.linalg.norm(b))
 
 
+def test_cartesian_coordinate_and_analytical_coefficient_values(oracle, hostmath):
+    """test/test_coefficients.jl:73-105: on generate_grid(Line, (2,)) the Cartesian coordinate at xi = 0 / 0.1 is -0.5 / -0.45 in
+    cell 1 and 0.5 / 0.55 in cell 2, and AnalyticalCoefficient((x, t) -> norm(x) + t) is 0.5 / 0.45 / 0.5 / 0.55 (+ t).  This
+    library has no 1-D cells: the same numbers on the x coordinate of the two-quadrilateral strip [-1, 1] x [0, 1] (first
+    reference coordinate = the Line's), through the oracle's shape functions (x_q = sum_a N_a x_a, coefficients.jl:279-292)
+    and through the product's traced-program evaluator for f."""
+    from thunderbolt_jl_b200 import trace as T
+    O = oracle
+    m = O.generate_grid(O.QUAD4, (2, 1), (-1.0, 0.0), (1.0, 1.0))
+    want_x = {(0, 0.0): -0.5, (0, 0.1): -0.45, (1, 0.0): 0.5, (1, 0.1): 0.55}
+    prog = T.trace_source(lambda x, t: abs(x[0]) + t, 2)                       # norm of the Line's 1-vector
+    assert prog is not None
+    for (cell, xi1), xw in want_x.items():
+        for eta in (-0.3, 0.0, 0.7):
+            N, _ = O.shape(O.QUAD4, [xi1, eta])
+            xq = N @ m.coords[m.conn[cell]]
+            assert np.isclose(xq[0], xw, rtol=0, atol=1e-15)
+            for t in (0.0, 1.0):
+                out = np.zeros(1)
+                rc = hostmath.hm_program_eval(2, prog.code, len(prog), np.ascontiguousarray(prog.consts) if prog.consts.size else np.zeros(1),
+                                              prog.consts.size, np.ascontiguousarray(xq), 1, t, out)
+                assert rc == 0 and np.isclose(out[0], abs(xw) + t, rtol=0, atol=1e-15)
+
+
 def test_distorted_hex_geometry(oracle):
     """test/test_coefficients.jl:239-279 compares two implementations of the mapping on this fixture;
     here: partition of unity, gradient of a linear field, detJ*w sums to the volume (independent facts)."""
